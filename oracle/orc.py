@@ -1,0 +1,249 @@
+"""ctypes front-end of the CPU oracle (``blokus_oracle.c``).
+
+TEST INFRASTRUCTURE ONLY -- see the header of ``blokus_oracle.c``.  Imported by ``tests/``,
+``__graft_entry__.smoke()`` and the CPU-baseline legs of ``bench.py``; never by the product
+package.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liborc.so")
+
+PASS_ID = 0xFFFF
+MAX_TURNS = 96
+STATE_BYTES = 256
+
+STATE_DTYPE = np.dtype(
+    [
+        ("bits", "<u8", (4, 7)),
+        ("used", "<u4", (4,)),
+        ("to_move", "u1"),
+        ("first_mask", "u1"),
+        ("move_count", "<u2"),
+        ("reserved", "u1", (12,)),
+    ]
+)
+assert STATE_DTYPE.itemsize == STATE_BYTES
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "blokus_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liborc.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        vp, i32, u32, u64 = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64
+        L.orc_init.restype = None
+        L.orc_num_orientations.restype = i32
+        L.orc_orientation_info.argtypes = [i32, vp]
+        L.orc_board_sizeof.restype = i32
+        L.orc_board_reset.argtypes = [vp]
+        L.orc_can_place.argtypes = [vp, i32, vp, vp, i32]
+        L.orc_pass.argtypes = [vp]
+        L.orc_place.argtypes = [vp, i32, i32, i32, i32, i32]
+        L.orc_legal_moves_naive.argtypes = [vp, i32, vp, i32]
+        L.orc_legal_moves_frontier.argtypes = [vp, i32, vp, i32]
+        L.orc_has_legal_moves.argtypes = [vp, i32]
+        L.orc_is_move_legal.argtypes = [vp, i32, i32]
+        L.orc_check_game_over.argtypes = [vp]
+        L.orc_make_move.argtypes = [vp, i32, i32]
+        L.orc_board_score.argtypes = [vp, i32]
+        L.orc_game_score.argtypes = [vp, i32]
+        L.orc_pack.argtypes = [vp, vp]
+        L.orc_unpack.argtypes = [vp, vp]
+        L.orc_get_grid.argtypes = [vp, vp]
+        L.orc_get_current_player.argtypes = [vp]
+        L.orc_get_game_over.argtypes = [vp]
+        L.orc_get_move_count.argtypes = [vp]
+        L.orc_get_used.argtypes = [vp, i32]
+        L.orc_get_used.restype = u32
+        L.orc_get_frontier.argtypes = [vp, i32, vp]
+        L.orc_philox4x32_10.argtypes = [vp, vp, vp]
+        L.orc_heuristic_score.argtypes = [vp, i32, i32]
+        L.orc_heuristic_score.restype = C.c_double
+        L.orc_playout.argtypes = [vp, u64, u64, i32, i32, vp, vp, vp, vp, vp]
+        L.orc_zobrist_table.argtypes = [u32, vp]
+        L.orc_zobrist_hash.argtypes = [vp, vp]
+        L.orc_zobrist_hash.restype = u64
+        L.orc_init()
+        _lib = L
+    return _lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OracleBoard:
+    """A reference-rules board living in C memory (restates engine/board.py:43-78)."""
+
+    def __init__(self):
+        L = lib()
+        self._buf = C.create_string_buffer(L.orc_board_sizeof())
+        L.orc_board_reset(self._buf)
+
+    # -- construction -----------------------------------------------------------------------
+    @classmethod
+    def from_packed(cls, state: np.ndarray) -> "OracleBoard":
+        b = cls()
+        s = np.ascontiguousarray(state, dtype=STATE_DTYPE).reshape(())
+        lib().orc_unpack(_ptr(np.atleast_1d(s)), b._buf)
+        return b
+
+    def copy(self) -> "OracleBoard":
+        b = OracleBoard.__new__(OracleBoard)
+        b._buf = C.create_string_buffer(self._buf.raw, len(self._buf))
+        return b
+
+    def pack(self) -> np.ndarray:
+        out = np.zeros(1, dtype=STATE_DTYPE)
+        lib().orc_pack(self._buf, _ptr(out))
+        return out[0]
+
+    # -- state getters ----------------------------------------------------------------------
+    @property
+    def grid(self) -> np.ndarray:
+        g = np.zeros((20, 20), dtype=np.int8)
+        lib().orc_get_grid(self._buf, _ptr(g))
+        return g
+
+    @property
+    def current_player(self) -> int:
+        return lib().orc_get_current_player(self._buf)
+
+    @property
+    def game_over(self) -> bool:
+        return bool(lib().orc_get_game_over(self._buf))
+
+    @property
+    def move_count(self) -> int:
+        return lib().orc_get_move_count(self._buf)
+
+    def used(self, player: int) -> int:
+        return lib().orc_get_used(self._buf, player)
+
+    def frontier(self, player: int) -> List[Tuple[int, int]]:
+        f = np.zeros(400, dtype=np.uint8)
+        lib().orc_get_frontier(self._buf, player, _ptr(f))
+        return [(int(i) // 20, int(i) % 20) for i in np.nonzero(f)[0]]
+
+    # -- rules ------------------------------------------------------------------------------
+    def legal_moves(self, player: int, naive: bool = False) -> np.ndarray:
+        out = np.zeros(4096, dtype=np.uint16)
+        fn = lib().orc_legal_moves_naive if naive else lib().orc_legal_moves_frontier
+        n = fn(self._buf, player, _ptr(out), out.size)
+        assert n <= out.size
+        return out[:n].copy()
+
+    def has_legal_moves(self, player: int) -> bool:
+        return bool(lib().orc_has_legal_moves(self._buf, player))
+
+    def is_move_legal(self, player: int, move_id: int) -> bool:
+        return bool(lib().orc_is_move_legal(self._buf, player, int(move_id)))
+
+    def can_place(self, player: int, cells: Sequence[Tuple[int, int]]) -> bool:
+        r = np.array([c[0] for c in cells], dtype=np.int32)
+        c = np.array([c[1] for c in cells], dtype=np.int32)
+        return bool(lib().orc_can_place(self._buf, player, _ptr(r), _ptr(c), len(cells)))
+
+    def place(self, player: int, move_id: int, validate: bool = True) -> bool:
+        g, cell = divmod(int(move_id), 400)
+        return bool(lib().orc_place(self._buf, player, g, cell // 20, cell % 20, int(validate)))
+
+    def make_move(self, player: int, move_id: int) -> bool:
+        return bool(lib().orc_make_move(self._buf, player, int(move_id)))
+
+    def pass_turn(self) -> None:
+        lib().orc_pass(self._buf)
+
+    def check_game_over(self) -> bool:
+        lib().orc_check_game_over(self._buf)
+        return self.game_over
+
+    def board_score(self, player: int) -> int:
+        return lib().orc_board_score(self._buf, player)
+
+    def game_score(self, player: int) -> int:
+        return lib().orc_game_score(self._buf, player)
+
+    def heuristic_score(self, player: int, move_id: int) -> float:
+        return lib().orc_heuristic_score(self._buf, player, int(move_id))
+
+    def zobrist_hash(self, table: np.ndarray) -> int:
+        t = np.ascontiguousarray(table, dtype=np.uint64)
+        return int(lib().orc_zobrist_hash(_ptr(t), self._buf))
+
+
+def orientation_table() -> List[dict]:
+    L = lib()
+    out = []
+    for g in range(L.orc_num_orientations()):
+        info = np.zeros(15, dtype=np.int32)
+        L.orc_orientation_info(g, _ptr(info))
+        n = int(info[2])
+        out.append(
+            {
+                "piece_id": int(info[0]),
+                "index": int(info[1]),
+                "h": int(info[3]),
+                "w": int(info[4]),
+                "cells": [(int(info[5 + 2 * i]), int(info[6 + 2 * i])) for i in range(n)],
+            }
+        )
+    return out
+
+
+def philox4x32_10(ctr: Sequence[int], key: Sequence[int]) -> Tuple[int, int, int, int]:
+    c = np.array(ctr, dtype=np.uint32)
+    k = np.array(key, dtype=np.uint32)
+    o = np.zeros(4, dtype=np.uint32)
+    lib().orc_philox4x32_10(_ptr(c), _ptr(k), _ptr(o))
+    return tuple(int(x) for x in o)
+
+
+def zobrist_table(seed: int) -> np.ndarray:
+    t = np.zeros(2088, dtype=np.uint64)
+    lib().orc_zobrist_table(int(seed) & 0xFFFFFFFF, _ptr(t))
+    return t
+
+
+def playout(
+    seed: int,
+    game_index: int,
+    start: Optional[np.ndarray] = None,
+    max_turns: int = 0,
+    fast: bool = True,
+    want_final: bool = False,
+):
+    """One Philox-driven random game; returns dict(game_scores, board_scores, trace, choice, turns)."""
+    gs = np.zeros(4, dtype=np.int32)
+    bs = np.zeros(4, dtype=np.int32)
+    tr = np.zeros(MAX_TURNS, dtype=np.uint16)
+    ch = np.zeros(MAX_TURNS, dtype=np.uint16)
+    fin = np.zeros(1, dtype=STATE_DTYPE) if want_final else None
+    st = None
+    if start is not None:
+        st = np.ascontiguousarray(np.atleast_1d(start), dtype=STATE_DTYPE)
+    turns = lib().orc_playout(_ptr(st), int(seed), int(game_index), int(max_turns), int(fast),
+                              _ptr(gs), _ptr(bs), _ptr(tr), _ptr(ch), _ptr(fin))
+    res = {"game_scores": gs, "board_scores": bs, "trace": tr, "choice": ch, "turns": int(turns)}
+    if want_final:
+        res["final"] = fin[0]
+    return res

@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the UNMODIFIED Python reference.
+
+Run in the build container only (the reference lives at /root/reference, read-only, and is not
+available on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/generate_golden.py
+
+Everything written here is an *output of the reference* (engine/, agents/, mcts/): tables, legal
+move sets, replayed games, scores, Zobrist keys, heuristic scores.  The only non-reference
+ingredient is the Philox4x32-10 index stream (numpy implementation below) that replaces
+RandomAgent's MT19937 draw, so CPU oracle and GPU kernels can replay the very same games.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import random
+import sys
+
+sys.dont_write_bytecode = True
+REF = os.environ.get("BLOKUS_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+
+import numpy as np  # noqa: E402
+
+from engine.board import Board, Player  # noqa: E402
+from engine.game import BlokusGame  # noqa: E402
+from engine.move_generator import LegalMoveGenerator, Move  # noqa: E402
+from engine.pieces import ALL_PIECE_ORIENTATIONS  # noqa: E402
+from agents.heuristic_agent import HeuristicAgent  # noqa: E402
+from mcts.zobrist import ZobristHash  # noqa: E402
+from tests.utils_game_states import generate_random_valid_state  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GEN = LegalMoveGenerator()
+
+STATE_DTYPE = np.dtype(
+    [("bits", "<u8", (4, 7)), ("used", "<u4", (4,)), ("to_move", "u1"), ("first_mask", "u1"),
+     ("move_count", "<u2"), ("reserved", "u1", (12,))]
+)
+
+FIRST = {}
+_g = 0
+for _pid in range(1, 22):
+    FIRST[_pid] = _g
+    _g += len(ALL_PIECE_ORIENTATIONS[_pid])
+
+
+def move_id(m: Move) -> int:
+    return (FIRST[m.piece_id] + m.orientation) * 400 + m.anchor_row * 20 + m.anchor_col
+
+
+def id_to_move(i: int) -> Move:
+    g, cell = divmod(int(i), 400)
+    pid = max(p for p in FIRST if FIRST[p] <= g)
+    return Move(pid, g - FIRST[pid], cell // 20, cell % 20)
+
+
+def pack(board: Board) -> np.ndarray:
+    s = np.zeros((), dtype=STATE_DTYPE)
+    for p in range(4):
+        pl = Player(p + 1)
+        raw = int(board.player_bits[pl]).to_bytes(56, "little")
+        s["bits"][p] = np.frombuffer(raw, dtype="<u8")
+        s["used"][p] = sum(1 << (pid - 1) for pid in board.player_pieces_used[pl])
+        if board.player_first_move[pl]:
+            s["first_mask"] |= 1 << p
+    s["to_move"] = board.current_player.value - 1
+    s["move_count"] = board.move_count
+    return s
+
+
+def sorted_ids(board: Board, player: Player, naive: bool = False) -> np.ndarray:
+    moves = GEN._get_legal_moves_naive(board, player) if naive else GEN.get_legal_moves(board, player)
+    return np.array(sorted(move_id(m) for m in moves), dtype=np.uint16)
+
+
+def philox4x32_10(ctr, key):
+    c = [np.uint64(x) for x in ctr]
+    k = [int(key[0]), int(key[1])]
+    M0, M1 = 0xD2511F53, 0xCD9E8D57
+    c = [int(x) for x in c]
+    for _ in range(10):
+        p0 = M0 * c[0]
+        p1 = M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xFFFFFFFF, p1 & 0xFFFFFFFF,
+             ((p0 >> 32) ^ c[3] ^ k[1]) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
+        k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
+    return c
+
+
+def draw(seed: int, g: int, t: int, stream: int = 0) -> int:
+    return philox4x32_10([g & 0xFFFFFFFF, g >> 32, t, stream], [seed & 0xFFFFFFFF, seed >> 32])[0]
+
+
+# ---------------------------------------------------------------------------------------------
+def gen_tables():
+    rows = []
+    for pid in range(1, 22):
+        for o in ALL_PIECE_ORIENTATIONS[pid]:
+            rows.append({"piece_id": pid, "index": o.orientation_id, "cells": [list(c) for c in o.offsets]})
+            # the generator's own cache must agree (engine/move_generator.py:119-128)
+            assert [list(c) for c in GEN.piece_position_cache[pid][o.orientation_id]] == rows[-1]["cells"]
+    assert len(rows) == 91
+    with open(os.path.join(HERE, "tables.json"), "w") as f:
+        json.dump({"source": "engine/pieces.py ALL_PIECE_ORIENTATIONS", "orientations": rows}, f)
+
+
+def describe_state(board: Board) -> dict:
+    d = {
+        "grid": board.grid.astype(int).tolist(),
+        "to_move": board.current_player.value - 1,
+        "move_count": int(board.move_count),
+        "used": [sorted(board.player_pieces_used[Player(p + 1)]) for p in range(4)],
+        "first_move": [bool(board.player_first_move[Player(p + 1)]) for p in range(4)],
+        "frontier": [sorted([list(x) for x in board.get_frontier(Player(p + 1))]) for p in range(4)],
+        "has_legal_moves": [bool(GEN.has_legal_moves(board, Player(p + 1))) for p in range(4)],
+        "board_score": [int(board.get_score(Player(p + 1))) for p in range(4)],
+    }
+    g = BlokusGame(enable_telemetry=False)
+    g.board = board
+    d["game_score"] = [int(g.get_score(Player(p + 1))) for p in range(4)]
+    return d
+
+
+def gen_kat1():
+    """benchmarks/benchmark_move_generation.py:163 states: generate_random_valid_state(n, seed=n)."""
+    out = []
+    for n in (5, 10, 20, 30, 40):
+        board, _ = generate_random_valid_state(n, seed=n)
+        d = describe_state(board)
+        d["n"] = n
+        d["legal"] = []
+        for p in range(4):
+            ids = sorted_ids(board, Player(p + 1))
+            naive = sorted_ids(board, Player(p + 1), naive=True)
+            assert np.array_equal(ids, naive)
+            d["legal"].append(ids.tolist())
+        d["packed_hex"] = pack(board).tobytes().hex()
+        out.append(d)
+        print("kat1", n, [len(x) for x in d["legal"]])
+    with open(os.path.join(HERE, "kat1_states.json"), "w") as f:
+        json.dump(out, f)
+
+
+def gen_kat2():
+    """tests/fixtures/advanced_metrics_snapshot.json: the reference's recorded 20-move game."""
+    with open(os.path.join(REF, "tests/fixtures/advanced_metrics_snapshot.json")) as f:
+        snap = json.load(f)
+    hist = snap["history"]
+    game = BlokusGame(enable_telemetry=False)
+    moves = []
+    for h in hist:
+        a = h["action"] if "action" in h else h
+        pl = Player[h["player"]]
+        m = Move(a["piece_id"], a["orientation"], a["anchor_row"], a["anchor_col"])
+        assert game.board.current_player == pl
+        assert game.make_move(m, pl)
+        moves.append({"player": pl.value - 1, "move_id": move_id(m),
+                      "game_score": [int(game.get_score(Player(p + 1))) for p in range(4)]})
+    d = describe_state(game.board)
+    d["moves"] = moves
+    d["legal"] = [sorted_ids(game.board, Player(p + 1)).tolist() for p in range(4)]
+    d["packed_hex"] = pack(game.board).tobytes().hex()
+    with open(os.path.join(HERE, "kat2_game.json"), "w") as f:
+        json.dump(d, f)
+    print("kat2 scores", d["game_score"])
+
+
+def random_state(num_moves: int, seed: int):
+    """Random self-play like tests/utils_game_states.py:12-57 but with the default generator
+    (fast) and passes advanced the way callers do (board._update_current_player)."""
+    rng = random.Random(seed)
+    board = Board()
+    made = 0
+    stall = 0
+    while made < num_moves and stall < 4:
+        pl = board.current_player
+        moves = GEN.get_legal_moves(board, pl)
+        if not moves:
+            board._update_current_player()
+            stall += 1
+            continue
+        stall = 0
+        moves.sort(key=move_id)
+        m = rng.choice(moves)
+        assert board.place_piece(m.get_positions(GEN.piece_orientations_cache[m.piece_id]), pl, m.piece_id)
+        made += 1
+    return board
+
+
+def gen_random_states(count=240):
+    states = np.zeros(count, dtype=STATE_DTYPE)
+    offs = [0]
+    ids_all = []
+    grids = np.zeros((count, 20, 20), dtype=np.int8)
+    has = np.zeros((count, 4), dtype=np.uint8)
+    bscore = np.zeros((count, 4), dtype=np.int32)
+    gscore = np.zeros((count, 4), dtype=np.int32)
+    rng = random.Random(20261018)
+    for i in range(count):
+        depth = rng.choice([0, 1, 2, 3, 4, 6, 9, 13, 18, 24, 31, 39, 48, 56, 64, 72, 80])
+        board = random_state(depth, seed=1000 + i)
+        states[i] = pack(board)
+        grids[i] = board.grid
+        g = BlokusGame(enable_telemetry=False)
+        g.board = board
+        for p in range(4):
+            ids = sorted_ids(board, Player(p + 1))
+            if i % 16 == 0:
+                assert np.array_equal(ids, sorted_ids(board, Player(p + 1), naive=True))
+            ids_all.append(ids)
+            offs.append(offs[-1] + len(ids))
+            has[i, p] = GEN.has_legal_moves(board, Player(p + 1))
+            assert bool(has[i, p]) == (len(ids) > 0)
+            bscore[i, p] = board.get_score(Player(p + 1))
+            gscore[i, p] = g.get_score(Player(p + 1))
+        if i % 40 == 0:
+            print("random state", i, depth, [len(x) for x in ids_all[-4:]])
+    np.savez_compressed(
+        os.path.join(HERE, "random_states.npz"),
+        states=states.view(np.uint8).reshape(count, 256),
+        grids=grids,
+        offsets=np.array(offs, dtype=np.int64),
+        move_ids=np.concatenate(ids_all).astype(np.uint16),
+        has_moves=has, board_scores=bscore, game_scores=gscore,
+    )
+
+
+def gen_games(count=16, seed=42):
+    """Complete games through BlokusGame(enable_telemetry=False) with the loop of
+    analytics/tournament/arena_runner.py:653-695 and Philox-drawn indices into the SORTED list."""
+    traces = np.full((count, 96), 0xFFFF, dtype=np.uint16)
+    choices = np.full((count, 96), 0xFFFF, dtype=np.uint16)
+    gsc = np.zeros((count, 4), dtype=np.int32)
+    bsc = np.zeros((count, 4), dtype=np.int32)
+    turns = np.zeros(count, dtype=np.int32)
+    finals = np.zeros(count, dtype=STATE_DTYPE)
+    for gi in range(count):
+        game = BlokusGame(enable_telemetry=False)
+        t = 0
+        while not game.is_game_over() and t < 96:
+            pl = game.get_current_player()
+            legal = game.get_legal_moves(pl)
+            if not legal:
+                game.board._update_current_player()
+                game._check_game_over()
+                t += 1
+                continue
+            legal.sort(key=move_id)
+            idx = (draw(seed, gi, t) * len(legal)) >> 32
+            assert game.make_move(legal[idx], pl)
+            traces[gi, t] = move_id(legal[idx])
+            choices[gi, t] = idx
+            t += 1
+        assert game.is_game_over()
+        res = game.get_game_result()
+        for p in range(4):
+            gsc[gi, p] = res.scores[p + 1]
+            bsc[gi, p] = game.board.get_score(Player(p + 1))
+        turns[gi] = t
+        finals[gi] = pack(game.board)
+        print("game", gi, "turns", t, "scores", gsc[gi].tolist())
+    np.savez_compressed(
+        os.path.join(HERE, "games.npz"),
+        seed=np.array([seed], dtype=np.uint64), traces=traces, choices=choices,
+        game_scores=gsc, board_scores=bsc, turns=turns,
+        finals=finals.view(np.uint8).reshape(count, 256),
+    )
+
+
+def gen_zobrist():
+    out = {}
+    boards = [Board()] + [random_state(d, seed=7000 + d) for d in (1, 5, 17, 33, 60)]
+    for seed in (0, 42, 12345):
+        z = ZobristHash(seed=seed)
+        table = np.concatenate([z.position_player_hashes.reshape(-1), z.player_turn_hashes.reshape(-1),
+                                z.piece_used_hashes.reshape(-1)]).astype(np.uint64)
+        assert table.size == 2088
+        out[str(seed)] = {
+            "table_sha256": hashlib.sha256(table.astype("<u8").tobytes()).hexdigest(),
+            "first": [int(x) for x in table[:8]],
+            "turn": [int(x) for x in z.player_turn_hashes],
+            "piece00": int(z.piece_used_hashes[0, 0]),
+            "hashes": [int(z.hash_board(b)) for b in boards],
+        }
+    out["states_hex"] = [pack(b).tobytes().hex() for b in boards]
+    with open(os.path.join(HERE, "zobrist.json"), "w") as f:
+        json.dump(out, f)
+    print("zobrist empty-board hash seed0: %#x" % out["0"]["hashes"][0])
+
+
+def gen_heuristic():
+    agent = HeuristicAgent(seed=0)
+    states, offs, ids_all, sc_all = [], [0], [], []
+    for d, s in ((0, 1), (3, 2), (8, 3), (21, 4), (29, 5), (30, 6), (31, 7), (45, 8), (62, 9)):
+        board = random_state(d, seed=9000 + s)
+        pl = board.current_player
+        legal = GEN.get_legal_moves(board, pl)
+        legal.sort(key=move_id)
+        states.append(pack(board))
+        ids_all.append(np.array([move_id(m) for m in legal], dtype=np.uint16))
+        sc_all.append(np.array([agent._evaluate_move(board, pl, m) for m in legal], dtype=np.float64))
+        offs.append(offs[-1] + len(legal))
+    np.savez_compressed(
+        os.path.join(HERE, "heuristic.npz"),
+        states=np.array(states, dtype=STATE_DTYPE).view(np.uint8).reshape(len(states), 256),
+        offsets=np.array(offs, dtype=np.int64), move_ids=np.concatenate(ids_all),
+        scores=np.concatenate(sc_all),
+    )
+    print("heuristic", offs[-1], "scored moves")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic"]
+    for w in which:
+        {"tables": gen_tables, "kat1": gen_kat1, "kat2": gen_kat2, "random": gen_random_states,
+         "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic}[w]()
