@@ -105,12 +105,12 @@ int bk_is_move_legal(const bk_state* states, const uint8_t* players, const uint1
 /* ---- step: BlokusGame.make_move + caller-side pass (engine/game.py:57-180, board.py:515-560) */
 
 /* For each i: move_ids[i]==BK_PASS advances to_move only (engine/board.py:557-560); otherwise the
- * move is checked for the side to move and, if legal, applied (cells, used, first-move flag,
+ * move is checked for players[i] (NULL: the side to move) and, if legal, applied (cells, used, first-move flag,
  * move_count, to_move).  ok[i] = 1 applied / passed, 0 rejected (state unchanged), mirroring
  * make_move's bool.  alive[i] (optional) = has-moves mask after the step (game over iff 0,
  * engine/game.py:182-214). */
-int bk_step(bk_state* states, const uint16_t* move_ids, int n, uint8_t* ok, uint8_t* alive,
-            void* stream);
+int bk_step(bk_state* states, const uint8_t* players, const uint16_t* move_ids, int n,
+            uint8_t* ok, uint8_t* alive, void* stream);
 
 /* ---- K3: scores (engine/board.py:562-577, engine/game.py:284-349) ------------------------- */
 int bk_scores(const bk_state* states, int n, int32_t* game_scores /*[n][4]*/,
@@ -131,11 +131,10 @@ int bk_playout(const bk_state* start_states, int n, uint64_t seed, uint64_t game
 
 /* ---- K4: Zobrist keys and transposition table (mcts/zobrist.py:20-99, 155-220) ------------ */
 
-/* Upload the 2088-entry table (host pointer) in the reference's draw order:
- * position_player_hashes[20][20][5], player_turn_hashes[4], piece_used_hashes[4][21]. */
-int bk_zobrist_set_table(const uint64_t* table_host);
-/* keys[i] = ZobristHash.hash_board(board_i)  (mcts/zobrist.py:70-99). */
-int bk_zobrist_hash(const bk_state* states, int n, uint64_t* keys, void* stream);
+/* keys[i] = ZobristHash.hash_board(board_i)  (mcts/zobrist.py:70-99).  `table` is a DEVICE array of
+ * BK_ZOBRIST_ENTRIES keys in the reference's draw order: position_player_hashes[20][20][5],
+ * player_turn_hashes[4], piece_used_hashes[4][21] (mcts/zobrist.py:38-68). */
+int bk_zobrist_hash(const bk_state* states, int n, const uint64_t* table, uint64_t* keys, void* stream);
 
 typedef struct bk_tt bk_tt;  /* open-addressing device table {key -> reward} */
 int bk_tt_create(bk_tt** out, uint32_t log2_slots);
@@ -146,33 +145,6 @@ int bk_tt_get(bk_tt* tt, const uint64_t* keys, int n, double* rewards, uint8_t* 
 int bk_tt_put(bk_tt* tt, const uint64_t* keys, const double* rewards, int n, void* stream);
 /* host out: [0]=slots, [1]=occupied */
 int bk_tt_stats(bk_tt* tt, uint64_t* out_host, void* stream);
-
-/* ---- K5: UCT search (mcts/mcts_agent.py:304-582) ------------------------------------------- */
-
-typedef struct bk_mcts_params {
-    int32_t  iterations;        /* MCTSAgent.iterations (mcts_agent.py:204) per tree */
-    int32_t  max_rollout_moves; /* mcts_agent.py:218 (50); 0 = play to the end */
-    int32_t  rollout_policy;    /* bk_policy */
-    int32_t  use_tt;            /* mcts_agent.py:208 */
-    double   exploration;       /* 1.414 */
-    uint64_t seed;
-    uint64_t tree_offset;       /* global index of tree 0 (root-parallel sharding) */
-    int32_t  ucb_variant;       /* 0: sqrt(ln N/n) (mcts_agent.py:86); 1: sqrt(2 ln N/n) (fast_mcts_agent.py:52) */
-    int32_t  reserved;
-} bk_mcts_params;
-
-/* Bytes of device workspace bk_mcts_search needs for n_trees trees (host call). */
-int64_t bk_mcts_workspace_bytes(int n_trees, const bk_mcts_params* params);
-
-/* Run n_trees independent UCT searches; tree k searches roots[k % n_roots] with stream
- * (seed, tree_offset+k).  Outputs per tree, indexed by the root's ascending legal-move rank:
- * root_visits [n_trees][max_root_moves] (int32), root_reward [n_trees][max_root_moves] (int64,
- * rollout rewards are integers), root_counts [n_trees] = number of root moves,
- * root_move_ids [n_trees][max_root_moves]. */
-int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, const bk_mcts_params* params,
-                   bk_tt* tt, void* workspace, int64_t workspace_bytes, int max_root_moves,
-                   int32_t* root_visits, int64_t* root_reward, uint32_t* root_counts,
-                   uint16_t* root_move_ids, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI declared in include/blokus_b200.h.
+
+The shared library is the product: if it is missing or no CUDA device is present, every compute
+call raises.  There is no CPU path behind this module.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libblokus_b200.so")
+
+BK_PASS = 0xFFFF
+BK_MAX_TURNS = 96
+BK_BITMAP_WORDS = 91 * 20
+BK_ZOBRIST_ENTRIES = 2088
+STATE_BYTES = 256
+
+
+class BlokusB200Error(RuntimeError):
+    pass
+
+
+_vp, _i32, _u32, _u64, _i64 = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_int64
+
+#: name -> (restype, argtypes); kept in one place so tests can check the export list against the header
+PROTOTYPES = {
+    "bk_init": (_i32, [_i32]),
+    "bk_last_error": (C.c_char_p, []),
+    "bk_version": (C.c_char_p, []),
+    "bk_movegen_count": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "bk_exclusive_scan_u32": (_i32, [_vp, _i32, _vp, _vp]),
+    "bk_movegen_emit": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
+    "bk_movegen_bitmap": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "bk_has_moves": (_i32, [_vp, _i32, _vp, _vp]),
+    "bk_is_move_legal": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "bk_step": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "bk_scores": (_i32, [_vp, _i32, _vp, _vp, _vp]),
+    "bk_playout": (_i32, [_vp, _i32, _u64, _u64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bk_zobrist_hash": (_i32, [_vp, _i32, _vp, _vp, _vp]),
+    "bk_tt_create": (_i32, [C.POINTER(_vp), _u32]),
+    "bk_tt_clear": (_i32, [_vp, _vp]),
+    "bk_tt_destroy": (_i32, [_vp]),
+    "bk_tt_get": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
+    "bk_tt_put": (_i32, [_vp, _vp, _vp, _i32, _vp]),
+    "bk_tt_stats": (_i32, [_vp, _vp, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+_inited_devices = set()
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library (no compute, safe without a GPU)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise BlokusB200Error(
+                    f"{LIB_PATH} is missing: build it with `python -m reinforcementlearning_blokus_b200.build` "
+                    "(there is no CPU fallback)")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        msg = load().bk_last_error().decode("utf-8", "replace")
+        raise BlokusB200Error(f"blokus_b200 error {code}: {msg}")
+
+
+def init(device: int = 0) -> C.CDLL:
+    """bk_init once per device; raises when no CUDA device is available."""
+    lib = load()
+    with _lock:
+        if device not in _inited_devices:
+            check(lib.bk_init(int(device)))
+            _inited_devices.add(device)
+    return lib

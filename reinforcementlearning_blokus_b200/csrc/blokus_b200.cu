@@ -1,0 +1,559 @@
+// blokus_b200.cu -- kernels and the C ABI of libblokus_b200.so (sm_100a only).
+//
+// One warp owns one game state (see movegen_core.cuh).  All kernels are warp-per-item grid-stride
+// loops launched with a grid that fills the 148 SMs; nothing here uses tensor cores (no dense
+// contraction on this path) and nothing falls back to the CPU.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "movegen_core.cuh"
+
+#define BK_THREADS 256
+#define BK_WARPS (BK_THREADS / 32)
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing / lifecycle
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int g_device = -1;
+static int g_sms = 0;
+
+static int fail(int code, const char* fmt, const char* detail) {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (expr);                                                        \
+        if (e__ != cudaSuccess) return fail(BK_ERR_CUDA, #expr ": %s", cudaGetErrorString(e__)); \
+    } while (0)
+#define REQUIRE_INIT() \
+    do { if (g_device < 0) return fail(BK_ERR_NOT_INIT, "%s", "bk_init has not been called"); } while (0)
+#define REQUIRE(cond, msg) \
+    do { if (!(cond)) return fail(BK_ERR_ARG, "%s", msg); } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int grid_for(int n_items, int ctas_per_sm) {
+    long long need = ((long long)n_items + BK_WARPS - 1) / BK_WARPS;
+    long long cap = (long long)g_sms * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+extern "C" const char* bk_last_error(void) { return g_err; }
+extern "C" const char* bk_version(void) { return "blokus_b200 r1 sm_100a (row-sliced warp-per-game)"; }
+
+extern "C" int bk_init(int device) {
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(BK_ERR_ARG, "%s", "bk_init: no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaMemcpyToSymbol(c_orient_piece, BK_TBL_ORIENT_PIECE, sizeof(BK_TBL_ORIENT_PIECE)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_orient_ncells, BK_TBL_ORIENT_NCELLS, sizeof(BK_TBL_ORIENT_NCELLS)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_orient_cells, BK_TBL_ORIENT_CELLS, sizeof(BK_TBL_ORIENT_CELLS)));
+    g_device = device;
+    return BK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: legal-move generation
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BK_THREADS)
+k_movegen_count(const bk_state* __restrict__ states, const uint8_t* __restrict__ players, int n,
+                uint32_t* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s; load_state(states + i, lane, s);
+        const uint32_t p = players ? (players[i] & 3u) : s.to_move;
+        uint32_t A, C; make_masks(s, p, lane, A, C);
+        CountSink sink; bk_gen_all(A, C, sel4(s.used, p), sink);
+        const uint32_t tot = __reduce_add_sync(BK_FULL, sink.acc);
+        if (lane == 0) counts[i] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ players, int n,
+               const uint32_t* __restrict__ offsets, uint16_t* __restrict__ ids) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s; load_state(states + i, lane, s);
+        const uint32_t p = players ? (players[i] & 3u) : s.to_move;
+        uint32_t A, C; make_masks(s, p, lane, A, C);
+        EmitSink sink; sink.out = ids; sink.pos = offsets[i]; sink.lane = lane;
+        bk_gen_all(A, C, sel4(s.used, p), sink);
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_movegen_bitmap(const bk_state* __restrict__ states, const uint8_t* __restrict__ players, int n,
+                 uint32_t* __restrict__ bitmap) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s; load_state(states + i, lane, s);
+        const uint32_t p = players ? (players[i] & 3u) : s.to_move;
+        uint32_t A, C; make_masks(s, p, lane, A, C);
+        BitmapSink sink; sink.out = bitmap + (size_t)i * BK_BITMAP_WORDS; sink.lane = lane;
+        bk_gen_all(A, C, sel4(s.used, p), sink);
+    }
+}
+
+__device__ __forceinline__ uint32_t alive_mask(const WarpState& s, int lane) {
+    uint32_t mask = 0;
+#pragma unroll 1
+    for (uint32_t p = 0; p < 4; p++) {
+        uint32_t A, C; make_masks(s, p, lane, A, C);
+        // no corner cell at all -> no move (cheap early out, warp-uniform)
+        if (!__any_sync(BK_FULL, C != 0)) continue;
+        AnySink sink; bk_gen_all(A, C, sel4(s.used, p), sink);
+        if (__any_sync(BK_FULL, sink.acc != 0)) mask |= 1u << p;
+    }
+    return mask;
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_has_moves(const bk_state* __restrict__ states, int n, uint8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s; load_state(states + i, lane, s);
+        const uint32_t m = alive_mask(s, lane);
+        if (lane == 0) out[i] = (uint8_t)m;
+    }
+}
+
+// One move for `p`: piece unspent, orientation/anchor in range, bit set in the legal-anchor row.
+__device__ __forceinline__ bool move_is_legal(const WarpState& s, uint32_t p, uint32_t id, int lane,
+                                              int& o, int& row, int& col) {
+    if (id >= (uint32_t)(BK_ORIENTS * BK_CELLS)) return false;
+    o = id / 400; const int cell = id - o * 400; row = cell / 20; col = cell - row * 20;
+    if (sel4(s.used, p) & (1u << (c_orient_piece[o] - 1))) return false;
+    uint32_t A, C; make_masks(s, p, lane, A, C);
+    const uint32_t L = bk_gen_one(A, C, o);
+    return (__shfl_sync(BK_FULL, L, row) >> col) & 1u;
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_is_move_legal(const bk_state* __restrict__ states, const uint8_t* __restrict__ players,
+                const uint16_t* __restrict__ ids, int n, uint8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s; load_state(states + i, lane, s);
+        const uint32_t p = players ? (players[i] & 3u) : s.to_move;
+        int o, row, col;
+        const bool ok = move_is_legal(s, p, ids[i], lane, o, row, col);
+        if (lane == 0) out[i] = ok ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_step(bk_state* __restrict__ states, const uint8_t* __restrict__ players, const uint16_t* __restrict__ ids,
+       int n, uint8_t* __restrict__ okv, uint8_t* __restrict__ alive) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s; load_state(states + i, lane, s);
+        const uint32_t id = ids[i];
+        bool ok = true;
+        if (id == BK_PASS) {
+            s.to_move = (s.to_move + 1) & 3u;
+        } else {
+            const uint32_t p = players ? (players[i] & 3u) : s.to_move;
+            int o, row, col;
+            ok = move_is_legal(s, p, id, lane, o, row, col);
+            if (ok) place_move(s, p, o, row, col, lane);
+        }
+        if (ok) store_state(states + i, lane, s);
+        if (okv && lane == 0) okv[i] = ok ? 1 : 0;
+        if (alive) {
+            const uint32_t m = alive_mask(s, lane);
+            if (lane == 0) alive[i] = (uint8_t)m;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: scores
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BK_THREADS)
+k_scores(const bk_state* __restrict__ states, int n, int32_t* __restrict__ gs, int32_t* __restrict__ bs) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s; load_state(states + i, lane, s);
+        int32_t g[4], b[4]; scores_of(s, lane, g, b);
+        if (lane < 4) {
+            const int32_t gv = lane == 0 ? g[0] : lane == 1 ? g[1] : lane == 2 ? g[2] : g[3];
+            const int32_t bv = lane == 0 ? b[0] : lane == 1 ? b[1] : lane == 2 ? b[2] : b[3];
+            if (gs) gs[(size_t)i * 4 + lane] = gv;
+            if (bs) bs[(size_t)i * 4 + lane] = bv;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: playouts (uniform policy).  One warp plays one whole game in registers.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BK_THREADS)
+k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int max_turns,
+                  int32_t* __restrict__ gs, int32_t* __restrict__ bs, uint16_t* __restrict__ trace,
+                  uint16_t* __restrict__ choice, bk_state* __restrict__ finals) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s;
+        if (start) load_state(start + i, lane, s); else init_empty(s);
+        const uint64_t g = game_offset + (uint64_t)i;
+        uint16_t* tr = trace ? trace + (size_t)i * BK_MAX_TURNS : nullptr;
+        uint16_t* ch = choice ? choice + (size_t)i * BK_MAX_TURNS : nullptr;
+        if (tr) { uint32_t* t32 = reinterpret_cast<uint32_t*>(tr); t32[lane] = 0xFFFFFFFFu; if (lane < 16) t32[32 + lane] = 0xFFFFFFFFu; }
+        if (ch) { uint32_t* c32 = reinterpret_cast<uint32_t*>(ch); c32[lane] = 0xFFFFFFFFu; if (lane < 16) c32[32 + lane] = 0xFFFFFFFFu; }
+        __syncwarp();
+        uint32_t dead = 0;
+        for (uint32_t t = 0; t < (uint32_t)max_turns && dead != 0xFu; t++) {
+            const uint32_t p = s.to_move;
+            bool moved = false;
+            if (!((dead >> p) & 1u)) {
+                uint32_t A, C; make_masks(s, p, lane, A, C);
+                PackSink sink; bk_gen_all(A, C, sel4(s.used, p), sink);
+                const Totals tot = reduce_totals(sink, lane);
+                if (tot.n == 0) {
+                    dead |= 1u << p;      // a player without moves never regains any ("dead stay dead")
+                } else {
+                    const uint32_t r = philox_draw(seed, g, t, 0);
+                    const uint32_t idx = __umulhi(r, tot.n);
+                    int o, row, col;
+                    const uint32_t id = select_move(tot, idx, A, C, lane, o, row, col);
+                    place_move(s, p, o, row, col, lane);
+                    if (lane == 0) { if (tr) tr[t] = (uint16_t)id; if (ch) ch[t] = (uint16_t)idx; }
+                    moved = true;
+                }
+            }
+            if (!moved) s.to_move = (p + 1) & 3u;   // pass: engine/board.py:557-560 via arena_runner.py:662-666
+        }
+        int32_t gsc[4], bsc[4]; scores_of(s, lane, gsc, bsc);
+        if (lane < 4) {
+            const int32_t gv = lane == 0 ? gsc[0] : lane == 1 ? gsc[1] : lane == 2 ? gsc[2] : gsc[3];
+            const int32_t bv = lane == 0 ? bsc[0] : lane == 1 ? bsc[1] : lane == 2 ? bsc[2] : bsc[3];
+            if (gs) gs[(size_t)i * 4 + lane] = gv;
+            if (bs) bs[(size_t)i * 4 + lane] = bv;
+        }
+        if (finals) store_state(finals + i, lane, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of counts (three short kernels; n is at most a few million)
+// ---------------------------------------------------------------------------------------------
+#define SCAN_BLOCK 1024
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& block_total) {
+    __shared__ uint32_t warp_sums[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(BK_FULL, incl, d); if (lane >= d) incl += u; }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = warp_sums[lane], si = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(BK_FULL, si, d); if (lane >= d) si += u; }
+        warp_sums[lane] = si - s;
+        if (lane == 31) block_total = si;
+    }
+    __syncthreads();
+    const uint32_t res = warp_sums[w] + incl - v;
+    return res;
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_partial(const uint32_t* __restrict__ in, int n, uint32_t* __restrict__ out,
+                                                               uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t total;
+    const int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t v = i < n ? in[i] : 0u;
+    const uint32_t ex = block_exclusive_scan(v, total);
+    if (i < n) out[i] = ex;
+    __syncthreads();
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_blocks(uint32_t* __restrict__ block_sums, int nb, uint32_t* __restrict__ grand) {
+    __shared__ uint32_t total;
+    uint32_t carry = 0;
+    for (int base = 0; base < nb; base += SCAN_BLOCK) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < nb ? block_sums[i] : 0u;
+        const uint32_t ex = block_exclusive_scan(v, total);
+        if (i < nb) block_sums[i] = ex + carry;
+        __syncthreads();
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand = carry;
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(uint32_t* __restrict__ out, int n, const uint32_t* __restrict__ block_sums) {
+    const int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    if (i < n) out[i] += block_sums[blockIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: Zobrist keys + open-addressing transposition table
+// ---------------------------------------------------------------------------------------------
+// mcts/zobrist.py:70-99: XOR over all 400 cells of table[row][col][value 0..4], the side to move and
+// every spent piece of every player.
+__device__ __forceinline__ uint64_t zobrist_of(const WarpState& s, const uint64_t* __restrict__ table, int lane) {
+    uint64_t h = 0;
+    if (lane < 20) {
+        const uint64_t* rowt = table + (size_t)lane * 100;
+#pragma unroll 4
+        for (int c = 0; c < 20; c++) {
+            const uint32_t v = ((s.P[0] >> c) & 1u) * 1u + ((s.P[1] >> c) & 1u) * 2u + ((s.P[2] >> c) & 1u) * 3u +
+                               ((s.P[3] >> c) & 1u) * 4u;
+            h ^= __ldg(rowt + c * 5 + v);
+        }
+    }
+    if (lane < 21) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if ((s.used[q] >> lane) & 1u) h ^= __ldg(table + 2004 + q * 21 + lane);
+    }
+    if (lane == 31) h ^= __ldg(table + 2000 + s.to_move);
+    uint32_t lo = __reduce_xor_sync(BK_FULL, (uint32_t)h), hi = __reduce_xor_sync(BK_FULL, (uint32_t)(h >> 32));
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_zobrist(const bk_state* __restrict__ states, int n, const uint64_t* __restrict__ table, uint64_t* __restrict__ keys) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s; load_state(states + i, lane, s);
+        const uint64_t h = zobrist_of(s, table, lane);
+        if (lane == 0) keys[i] = h;
+    }
+}
+
+struct bk_tt {
+    unsigned long long* keys;   // 0 = empty slot
+    double* rewards;
+    uint32_t log2_slots;
+    unsigned long long* occupied;  // device counter
+};
+#define TT_MAX_PROBE 128
+__device__ __forceinline__ uint64_t tt_norm(uint64_t k) { return k ? k : 0x9E3779B97F4A7C15ull; }
+__device__ __forceinline__ uint32_t tt_home(uint64_t k, uint32_t log2_slots) {
+    return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> (64 - log2_slots));
+}
+__device__ __forceinline__ bool tt_lookup(const unsigned long long* keys, const double* rewards, uint32_t log2_slots,
+                                          uint64_t key, double& reward) {
+    key = tt_norm(key);
+    const uint32_t mask = (1u << log2_slots) - 1u;
+    uint32_t slot = tt_home(key, log2_slots);
+    for (int probe = 0; probe < TT_MAX_PROBE; probe++, slot = (slot + 1) & mask) {
+        const unsigned long long k = keys[slot];
+        if (k == key) { reward = rewards[slot]; return true; }
+        if (k == 0ull) return false;
+    }
+    return false;
+}
+__device__ __forceinline__ bool tt_insert(unsigned long long* keys, double* rewards, uint32_t log2_slots,
+                                          unsigned long long* occupied, uint64_t key, double reward) {
+    key = tt_norm(key);
+    const uint32_t mask = (1u << log2_slots) - 1u;
+    uint32_t slot = tt_home(key, log2_slots);
+    for (int probe = 0; probe < TT_MAX_PROBE; probe++, slot = (slot + 1) & mask) {
+        unsigned long long k = keys[slot];
+        if (k == 0ull) {
+            k = atomicCAS(&keys[slot], 0ull, (unsigned long long)key);
+            if (k == 0ull) { rewards[slot] = reward; atomicAdd(occupied, 1ull); return true; }
+        }
+        if (k == key) { rewards[slot] = reward; return true; }   // dict semantics: last put wins
+    }
+    return false;   // neighbourhood full: entry dropped (the reference evicts instead, mcts/zobrist.py:196-200)
+}
+__global__ void k_tt_get(const unsigned long long* keys, const double* rewards, uint32_t log2_slots,
+                         const uint64_t* q, int n, double* out, uint8_t* found) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r = 0.0;
+    const bool hit = tt_lookup(keys, rewards, log2_slots, q[i], r);
+    found[i] = hit ? 1 : 0;
+    if (hit) out[i] = r;
+}
+__global__ void k_tt_put(unsigned long long* keys, double* rewards, uint32_t log2_slots, unsigned long long* occupied,
+                         const uint64_t* q, const double* r, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tt_insert(keys, rewards, log2_slots, occupied, q[i], r[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+#define LAUNCH_CHECK() CUDA_TRY(cudaGetLastError())
+
+extern "C" int bk_movegen_count(const bk_state* states, const uint8_t* players, int n, uint32_t* counts, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && counts)), "bk_movegen_count: null buffer");
+    if (n == 0) return BK_OK;
+    k_movegen_count<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, counts);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_movegen_emit(const bk_state* states, const uint8_t* players, int n, const uint32_t* offsets,
+                               uint16_t* move_ids, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids)), "bk_movegen_emit: null buffer");
+    if (n == 0) return BK_OK;
+    k_movegen_emit<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, offsets, move_ids);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_movegen_bitmap(const bk_state* states, const uint8_t* players, int n, uint32_t* bitmap, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && bitmap)), "bk_movegen_bitmap: null buffer");
+    if (n == 0) return BK_OK;
+    // rows of spent pieces are not visited by the generator: clear first
+    CUDA_TRY(cudaMemsetAsync(bitmap, 0, (size_t)n * BK_BITMAP_WORDS * sizeof(uint32_t), as_stream(stream)));
+    k_movegen_bitmap<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, bitmap);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_has_moves(const bk_state* states, int n, uint8_t* out_mask, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && out_mask)), "bk_has_moves: null buffer");
+    if (n == 0) return BK_OK;
+    k_has_moves<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, n, out_mask);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_is_move_legal(const bk_state* states, const uint8_t* players, const uint16_t* move_ids, int n,
+                                uint8_t* out, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && move_ids && out)), "bk_is_move_legal: null buffer");
+    if (n == 0) return BK_OK;
+    k_is_move_legal<<<grid_for(n, 4), BK_THREADS, 0, as_stream(stream)>>>(states, players, move_ids, n, out);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_step(bk_state* states, const uint8_t* players, const uint16_t* move_ids, int n, uint8_t* ok,
+                       uint8_t* alive, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && move_ids)), "bk_step: null buffer");
+    if (n == 0) return BK_OK;
+    k_step<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, players, move_ids, n, ok, alive);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_scores(const bk_state* states, int n, int32_t* game_scores, int32_t* board_scores, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || states), "bk_scores: null buffer");
+    if (n == 0) return BK_OK;
+    k_scores<<<grid_for(n, 4), BK_THREADS, 0, as_stream(stream)>>>(states, n, game_scores, board_scores);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_playout(const bk_state* start_states, int n, uint64_t seed, uint64_t game_offset, int policy,
+                          int max_turns, int32_t* game_scores, int32_t* board_scores, uint16_t* trace,
+                          uint16_t* choice, bk_state* final_states, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0, "bk_playout: negative n");
+    REQUIRE(max_turns >= 0 && max_turns <= BK_MAX_TURNS, "bk_playout: max_turns out of range");
+    if (policy != BK_POLICY_UNIFORM) return fail(BK_ERR_ARG, "%s", "bk_playout: unknown policy");
+    if (n == 0) return BK_OK;
+    if (max_turns == 0) max_turns = BK_MAX_TURNS;
+    k_playout_uniform<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(
+        start_states, n, seed, game_offset, max_turns, game_scores, board_scores, trace, choice, final_states);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_exclusive_scan_u32(const uint32_t* counts, int n, uint32_t* offsets, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && offsets && (n == 0 || counts), "bk_exclusive_scan_u32: null buffer");
+    cudaStream_t st = as_stream(stream);
+    if (n == 0) { CUDA_TRY(cudaMemsetAsync(offsets, 0, sizeof(uint32_t), st)); return BK_OK; }
+    const int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    uint32_t* block_sums = nullptr;
+    CUDA_TRY(cudaMallocAsync(&block_sums, (size_t)nb * sizeof(uint32_t), st));
+    k_scan_partial<<<nb, SCAN_BLOCK, 0, st>>>(counts, n, offsets, block_sums);
+    k_scan_blocks<<<1, SCAN_BLOCK, 0, st>>>(block_sums, nb, offsets + n);
+    k_scan_add<<<nb, SCAN_BLOCK, 0, st>>>(offsets, n, block_sums);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(block_sums, st);
+    if (e != cudaSuccess) return fail(BK_ERR_CUDA, "scan launch: %s", cudaGetErrorString(e));
+    return BK_OK;
+}
+
+extern "C" int bk_zobrist_hash(const bk_state* states, int n, const uint64_t* table, uint64_t* keys, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && table && (n == 0 || (states && keys)), "bk_zobrist_hash: null buffer");
+    if (n == 0) return BK_OK;
+    k_zobrist<<<grid_for(n, 4), BK_THREADS, 0, as_stream(stream)>>>(states, n, table, keys);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_tt_create(bk_tt** out, uint32_t log2_slots) {
+    REQUIRE_INIT(); REQUIRE(out && log2_slots >= 4 && log2_slots <= 30, "bk_tt_create: log2_slots must be in [4,30]");
+    bk_tt* t = new (std::nothrow) bk_tt();
+    if (!t) return fail(BK_ERR_ARG, "%s", "bk_tt_create: out of host memory");
+    const size_t slots = (size_t)1 << log2_slots;
+    t->log2_slots = log2_slots; t->keys = nullptr; t->rewards = nullptr; t->occupied = nullptr;
+    cudaError_t e = cudaMalloc(&t->keys, slots * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&t->rewards, slots * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&t->occupied, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(t->keys, 0, slots * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(t->occupied, 0, sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        cudaFree(t->keys); cudaFree(t->rewards); cudaFree(t->occupied); delete t;
+        return fail(BK_ERR_CUDA, "bk_tt_create: %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return BK_OK;
+}
+extern "C" int bk_tt_clear(bk_tt* tt, void* stream) {
+    REQUIRE_INIT(); REQUIRE(tt, "bk_tt_clear: null table");
+    CUDA_TRY(cudaMemsetAsync(tt->keys, 0, ((size_t)1 << tt->log2_slots) * sizeof(unsigned long long), as_stream(stream)));
+    CUDA_TRY(cudaMemsetAsync(tt->occupied, 0, sizeof(unsigned long long), as_stream(stream)));
+    return BK_OK;
+}
+extern "C" int bk_tt_destroy(bk_tt* tt) {
+    if (!tt) return BK_OK;
+    cudaFree(tt->keys); cudaFree(tt->rewards); cudaFree(tt->occupied);
+    delete tt;
+    return BK_OK;
+}
+extern "C" int bk_tt_get(bk_tt* tt, const uint64_t* keys, int n, double* rewards, uint8_t* found, void* stream) {
+    REQUIRE_INIT(); REQUIRE(tt && n >= 0 && (n == 0 || (keys && rewards && found)), "bk_tt_get: null buffer");
+    if (n == 0) return BK_OK;
+    k_tt_get<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(tt->keys, tt->rewards, tt->log2_slots, keys, n, rewards, found);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+extern "C" int bk_tt_put(bk_tt* tt, const uint64_t* keys, const double* rewards, int n, void* stream) {
+    REQUIRE_INIT(); REQUIRE(tt && n >= 0 && (n == 0 || (keys && rewards)), "bk_tt_put: null buffer");
+    if (n == 0) return BK_OK;
+    k_tt_put<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(tt->keys, tt->rewards, tt->log2_slots, tt->occupied, keys, rewards, n);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+extern "C" int bk_tt_stats(bk_tt* tt, uint64_t* out_host, void* stream) {
+    REQUIRE_INIT(); REQUIRE(tt && out_host, "bk_tt_stats: null buffer");
+    unsigned long long occ = 0;
+    CUDA_TRY(cudaMemcpyAsync(&occ, tt->occupied, sizeof(occ), cudaMemcpyDeviceToHost, as_stream(stream)));
+    CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
+    out_host[0] = (uint64_t)1 << tt->log2_slots;
+    out_host[1] = (uint64_t)occ;
+    return BK_OK;
+}

@@ -1,0 +1,309 @@
+// movegen_core.cuh -- row-sliced Blokus legality on one warp per game state (sm_100a).
+//
+// Replaces the per-candidate loop of the reference's generator
+// (engine/move_generator.py:261-559 calling is_placement_legal_bitboard_fast :760-831, which in turn
+// calls shift_mask_fast engine/bitboard.py:173-205 three times per candidate) by a dense bit-parallel
+// evaluation: lane r (0..19) of the warp owns row r of every 20x20 mask as the low 20 bits of a
+// register; lanes 20..31 hold zero rows.  A row shift is one SHFL, a column shift one SHF, and bits
+// 20..31 / lanes 20..31 being zero makes "off the board" fall out as "not allowed" with no wrap masks.
+//
+//   own  = mover's cells, occ = all cells
+//   A    = ~(occ | N(own)|S(own)|E(own)|W(own))          cells the mover may cover (rules 1+2)
+//   C    = first move ? A & start_corner : A & (NE|NW|SE|SW)(own)   cells that satisfy rule 3
+//   legal_o(row, col) = AND_i A[row+r_i][col+c_i]  &  OR_i C[row+r_i][col+c_i]
+//
+// The 91 orientation bodies are generated (orient_gen.cuh) with shared run primitives.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "../../include/blokus_b200.h"
+#include "tables_gen.h"
+
+#define BK_FULL 0xffffffffu
+#define BK_ROWMASK 0xFFFFFu
+#define BK_ALL_PIECES 0x1FFFFFu
+
+__constant__ uint8_t c_orient_piece[BK_TBL_ORIENTS];
+__constant__ uint8_t c_orient_ncells[BK_TBL_ORIENTS];
+__constant__ uint8_t c_orient_cells[BK_TBL_ORIENTS * 5];
+
+// ---- per-warp game state in registers ----------------------------------------------------------
+struct WarpState {
+    uint32_t P[4];     // this lane's row of each player's cells
+    uint32_t used[4];  // warp-uniform
+    uint32_t to_move, first_mask, move_count;  // warp-uniform
+};
+
+__device__ __forceinline__ uint32_t sel4(const uint32_t (&v)[4], uint32_t i) {
+    uint32_t a = (i & 1) ? v[1] : v[0];
+    uint32_t b = (i & 1) ? v[3] : v[2];
+    return (i & 2) ? b : a;
+}
+
+__device__ __forceinline__ void init_empty(WarpState& s) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) { s.P[q] = 0; s.used[q] = 0; }
+    s.to_move = 0; s.first_mask = 0xF; s.move_count = 0;
+}
+
+// 256-byte packed state -> rows.  Lane i reads 64-bit word i (two coalesced 128-byte lines per warp).
+__device__ __forceinline__ void load_state(const bk_state* __restrict__ sp, int lane, WarpState& s) {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(sp);
+    uint64_t word = __ldg(w + lane);
+    const int bitpos = lane * 20;
+    const int wi = bitpos >> 6, off = bitpos & 63;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint64_t lo = __shfl_sync(BK_FULL, word, (q * 7 + wi) & 31);
+        uint64_t hi = __shfl_sync(BK_FULL, word, (q * 7 + wi + 1) & 31);
+        uint64_t v = lo >> off;
+        if (off) v |= hi << (64 - off);
+        s.P[q] = (lane < 20) ? ((uint32_t)v & BK_ROWMASK) : 0u;
+    }
+    uint64_t u01 = __shfl_sync(BK_FULL, word, 28), u23 = __shfl_sync(BK_FULL, word, 29);
+    uint64_t meta = __shfl_sync(BK_FULL, word, 30);
+    s.used[0] = (uint32_t)u01; s.used[1] = (uint32_t)(u01 >> 32);
+    s.used[2] = (uint32_t)u23; s.used[3] = (uint32_t)(u23 >> 32);
+    s.to_move = (uint32_t)meta & 3u;
+    s.first_mask = (uint32_t)(meta >> 8) & 0xFu;
+    s.move_count = (uint32_t)(meta >> 16) & 0xFFFFu;
+}
+
+// rows -> 256-byte packed state.  Lane i assembles 64-bit word i.
+__device__ __forceinline__ void store_state(bk_state* __restrict__ sp, int lane, const WarpState& s) {
+    uint64_t word = 0;
+    const int q = lane / 7, w = lane - q * 7;         // valid for lane < 28
+    const int r0 = (64 * w) / 20;                      // first row overlapping this word
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const int rr = r0 + j;
+        uint32_t v0 = __shfl_sync(BK_FULL, s.P[0], rr & 31);
+        uint32_t v1 = __shfl_sync(BK_FULL, s.P[1], rr & 31);
+        uint32_t v2 = __shfl_sync(BK_FULL, s.P[2], rr & 31);
+        uint32_t v3 = __shfl_sync(BK_FULL, s.P[3], rr & 31);
+        uint32_t v = (q == 0) ? v0 : (q == 1) ? v1 : (q == 2) ? v2 : v3;
+        const int d = 20 * rr - 64 * w;                // bit offset of row rr inside this word
+        if (rr < 20 && d < 64) word |= (d >= 0) ? ((uint64_t)v << d) : ((uint64_t)v >> (-d));
+    }
+    if (lane == 28) word = (uint64_t)s.used[0] | ((uint64_t)s.used[1] << 32);
+    if (lane == 29) word = (uint64_t)s.used[2] | ((uint64_t)s.used[3] << 32);
+    if (lane == 30) word = (uint64_t)(s.to_move & 3u) | ((uint64_t)(s.first_mask & 0xFu) << 8) |
+                           ((uint64_t)(s.move_count & 0xFFFFu) << 16);
+    if (lane == 31) word = 0;
+    reinterpret_cast<uint64_t*>(sp)[lane] = word;
+}
+
+// allowed (A) and corner (C) rows for `player` -- the rules of engine/board.py:136-220.
+__device__ __forceinline__ void make_masks(const WarpState& s, uint32_t player, int lane,
+                                           uint32_t& A, uint32_t& C) {
+    const uint32_t own = sel4(s.P, player);
+    const uint32_t occ = s.P[0] | s.P[1] | s.P[2] | s.P[3];
+    const uint32_t h = ((own << 1) | (own >> 1)) & BK_ROWMASK;      // E/W neighbours
+    uint32_t up_own = __shfl_up_sync(BK_FULL, own, 1), dn_own = __shfl_down_sync(BK_FULL, own, 1);
+    uint32_t up_h = __shfl_up_sync(BK_FULL, h, 1), dn_h = __shfl_down_sync(BK_FULL, h, 1);
+    if (lane == 0) { up_own = 0; up_h = 0; }
+    if (lane >= 19) { dn_own = 0; dn_h = 0; }
+    const uint32_t orth = h | up_own | dn_own;
+    const uint32_t diag = up_h | dn_h;
+    A = (lane < 20) ? (~(occ | orth) & BK_ROWMASK) : 0u;
+    if ((s.first_mask >> player) & 1u) {
+        // start corners RED(0,0) BLUE(0,19) YELLOW(19,19) GREEN(19,0): engine/board.py:56-61
+        const int crow = (player >= 2) ? 19 : 0;
+        const uint32_t cbit = (player == 1 || player == 2) ? (1u << 19) : 1u;
+        C = (lane == crow) ? (A & cbit) : 0u;
+    } else {
+        C = A & diag;
+    }
+}
+
+// Evaluate every orientation of every unspent piece; sink.put<O>(row_of_legal_anchors).
+template <class Sink>
+__device__ __forceinline__ void bk_gen_all(const uint32_t A, const uint32_t C, const uint32_t used, Sink& sink) {
+#include "orient_gen.cuh"
+}
+
+// One orientation, table-driven (used after a move has been chosen, and by is_move_legal).
+__device__ __forceinline__ uint32_t bk_gen_one(const uint32_t A, const uint32_t C, const int o) {
+    uint32_t fit = BK_ROWMASK, touch = 0;
+    const int n = c_orient_ncells[o];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        if (i < n) {
+            const uint32_t rc = c_orient_cells[o * 5 + i];
+            const uint32_t a = __shfl_down_sync(BK_FULL, A, rc >> 4) >> (rc & 15);
+            const uint32_t c = __shfl_down_sync(BK_FULL, C, rc >> 4) >> (rc & 15);
+            fit &= a; touch |= c;
+        }
+    }
+    return fit & touch;
+}
+
+// ---- sinks ------------------------------------------------------------------------------------
+struct CountSink {                 // per-lane move count
+    uint32_t acc = 0;
+    template <int O> __device__ __forceinline__ void put(uint32_t L) { acc += __popc(L); }
+};
+
+struct AnySink {                   // does any move exist
+    uint32_t acc = 0;
+    template <int O> __device__ __forceinline__ void put(uint32_t L) { acc |= L; }
+};
+
+// Per-lane counts of three orientations per register in 10-bit fields (a row holds <= 20 anchors, a
+// warp-wide field sum <= 400 < 1024), so one REDUX yields three per-orientation totals.
+struct PackSink {
+    uint32_t pk[31];
+    __device__ __forceinline__ PackSink() {
+#pragma unroll
+        for (int i = 0; i < 31; i++) pk[i] = 0;
+    }
+    template <int O> __device__ __forceinline__ void put(uint32_t L) {
+        pk[O / 3] += (uint32_t)__popc(L) << (10 * (O % 3));
+    }
+};
+
+struct BitmapSink {                // legal-anchor bitmap rows straight to memory
+    uint32_t* out; int lane;
+    template <int O> __device__ __forceinline__ void put(uint32_t L) {
+        if (lane < 20) out[O * 20 + lane] = L;
+    }
+};
+
+struct EmitSink {                  // ascending move ids
+    uint16_t* out; uint32_t pos; int lane;
+    template <int O> __device__ __forceinline__ void put(uint32_t L) {
+        if (!__any_sync(BK_FULL, L != 0)) return;
+        const uint32_t c = __popc(L);
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(BK_FULL, incl, d);
+            if (lane >= d) incl += v;
+        }
+        uint32_t w = pos + incl - c;
+        uint32_t bits = L;
+        const uint32_t base = O * 400 + lane * 20;
+        while (bits) {
+            const int col = __ffs(bits) - 1;
+            bits &= bits - 1;
+            out[w++] = (uint16_t)(base + col);
+        }
+        pos += __shfl_sync(BK_FULL, incl, 31);
+    }
+};
+
+// ---- choosing the idx-th legal move in ascending id order ----------------------------------------
+// After PackSink: lane j (< 31) receives the warp totals of orientations 3j..3j+2.
+struct Totals {
+    uint32_t mine;    // packed totals owned by this lane (10-bit fields)
+    uint32_t incl;    // inclusive prefix of this lane's three totals over lanes
+    uint32_t n;       // total number of legal moves
+};
+
+__device__ __forceinline__ Totals reduce_totals(const PackSink& s, int lane) {
+    Totals t; t.mine = 0;
+#pragma unroll
+    for (int j = 0; j < 31; j++) {
+        const uint32_t v = __reduce_add_sync(BK_FULL, s.pk[j]);
+        if (lane == j) t.mine = v;
+    }
+    uint32_t sum = (t.mine & 1023u) + ((t.mine >> 10) & 1023u) + ((t.mine >> 20) & 1023u);
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(BK_FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    t.incl = incl;
+    t.n = __shfl_sync(BK_FULL, incl, 31);
+    return t;
+}
+
+// Locate move number idx (0-based, idx < t.n): returns the move id; A/C are the masks used for the count.
+__device__ __forceinline__ uint32_t select_move(const Totals& t, uint32_t idx, uint32_t A, uint32_t C, int lane,
+                                                int& o_out, int& row_out, int& col_out) {
+    // lane holding the orientation triple that contains idx
+    const uint32_t vote = __ballot_sync(BK_FULL, t.incl > idx);
+    const int j = __ffs(vote) - 1;
+    const uint32_t mine = __shfl_sync(BK_FULL, t.mine, j);
+    const uint32_t incl = __shfl_sync(BK_FULL, t.incl, j);
+    const uint32_t f0 = mine & 1023u, f1 = (mine >> 10) & 1023u, f2 = (mine >> 20) & 1023u;
+    uint32_t rem = idx - (incl - f0 - f1 - f2);
+    int o = 3 * j;
+    if (rem >= f0) { rem -= f0; o++; if (rem >= f1) { rem -= f1; o++; } }
+    // rows of that orientation
+    const uint32_t L = bk_gen_one(A, C, o);
+    const uint32_t c = __popc(L);
+    uint32_t rincl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(BK_FULL, rincl, d);
+        if (lane >= d) rincl += v;
+    }
+    const uint32_t rvote = __ballot_sync(BK_FULL, rincl > rem);
+    const int row = __ffs(rvote) - 1;
+    const uint32_t Lr = __shfl_sync(BK_FULL, L, row);
+    const uint32_t before = __shfl_sync(BK_FULL, rincl - c, row);
+    uint32_t k = rem - before;          // k-th set bit of Lr
+    uint32_t bits = Lr;
+    while (k--) bits &= bits - 1;
+    const int col = __ffs(bits) - 1;
+    o_out = o; row_out = row; col_out = col;
+    return (uint32_t)(o * 400 + row * 20 + col);
+}
+
+// Apply a placement for the side `player` -- engine/board.py:515-555 (cells, used, first-move flag,
+// move_count, next player).  The frontier sets of the reference are not state here: A and C are
+// recomputed from the cells each turn.
+__device__ __forceinline__ void place_move(WarpState& s, uint32_t player, int o, int row, int col, int lane) {
+    uint32_t add = 0;
+    const int n = c_orient_ncells[o];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        if (i < n) {
+            const uint32_t rc = c_orient_cells[o * 5 + i];
+            if (lane == row + (int)(rc >> 4)) add |= 1u << (col + (rc & 15));
+        }
+    }
+    const uint32_t pbit = 1u << (c_orient_piece[o] - 1);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (q == (int)player) { s.P[q] |= add; s.used[q] |= pbit; }
+    }
+    s.first_mask &= ~(1u << player);
+    s.move_count += 1;
+    s.to_move = (s.to_move + 1) & 3u;   // advances from current_player (engine/board.py:552,557-560)
+}
+
+// ---- scores ---------------------------------------------------------------------------------------
+// Board.get_score (engine/board.py:562-577) and BlokusGame.get_score (engine/game.py:284-349).
+__device__ __forceinline__ void scores_of(const WarpState& s, int lane, int32_t (&game)[4], int32_t (&board)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t row = s.P[q];
+        uint32_t cells = __popc(row);
+        uint32_t bonus = 0;
+        if (lane == 0 || lane == 19) bonus += 5 * ((row & 1u) + ((row >> 19) & 1u));   // four board corners
+        if (lane >= 8 && lane <= 11) bonus += 2 * __popc(row & 0xF00u);                 // rows/cols 8..11
+        const uint32_t tot_cells = __reduce_add_sync(BK_FULL, cells);
+        const uint32_t tot_bonus = __reduce_add_sync(BK_FULL, bonus);
+        const uint32_t all = ((s.used[q] & BK_ALL_PIECES) == BK_ALL_PIECES) ? 15u : 0u;
+        board[q] = (int32_t)(tot_cells + all);
+        game[q] = (int32_t)(tot_cells + all + tot_bonus);
+    }
+}
+
+// ---- Philox4x32-10 (same stream as oracle/blokus_oracle.c:orc_philox4x32_10) -------------------------
+__device__ __forceinline__ uint32_t philox_draw(uint64_t seed, uint64_t g, uint32_t t, uint32_t stream) {
+    uint32_t c0 = (uint32_t)g, c1 = (uint32_t)(g >> 32), c2 = t, c3 = stream;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c0;
+}

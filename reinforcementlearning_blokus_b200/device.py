@@ -1,0 +1,258 @@
+"""Batched device API: torch tensors in, torch tensors out, CUDA kernels in between.
+
+Thin layer over the C ABI (include/blokus_b200.h).  PyTorch is used for device memory and
+streams only; every function launches on torch's current stream.  States are ``uint8[N, 256]``
+CUDA tensors holding packed ``bk_state`` records (see ``state.py``).
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BK_BITMAP_WORDS, BK_MAX_TURNS, BK_PASS, STATE_BYTES, check
+
+POLICY_UNIFORM = 0
+POLICY_HEURISTIC = 1
+
+_launches = 0  # kernels launched through this module (bench.py reports it)
+
+
+def launches() -> int:
+    return _launches
+
+
+def _count(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def _lib_for(t: Optional[torch.Tensor] = None):
+    if not torch.cuda.is_available():
+        raise _lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
+    dev = t.device.index if (t is not None and t.is_cuda) else torch.cuda.current_device()
+    return _lib.init(dev)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check_states(states: torch.Tensor) -> int:
+    if not (states.is_cuda and states.dtype == torch.uint8 and states.dim() == 2
+            and states.shape[1] == STATE_BYTES and states.is_contiguous()):
+        raise ValueError("states must be a contiguous CUDA uint8 tensor of shape [N, 256]")
+    if states.data_ptr() % 8:
+        raise ValueError("states must be 8-byte aligned")
+    return states.shape[0]
+
+
+def _check_players(players: Optional[torch.Tensor], n: int) -> None:
+    if players is None:
+        return
+    if not (players.is_cuda and players.dtype == torch.uint8 and players.numel() == n and players.is_contiguous()):
+        raise ValueError("players must be a contiguous CUDA uint8 tensor of length N (values 0..3)")
+
+
+def to_device(states_np: np.ndarray, device: Optional[torch.device] = None) -> torch.Tensor:
+    """numpy packed states (STATE_DTYPE or uint8[N,256]) -> CUDA uint8[N,256]."""
+    raw = np.ascontiguousarray(states_np).view(np.uint8).reshape(-1, STATE_BYTES)
+    return torch.from_numpy(raw.copy()).to(device or torch.device("cuda", torch.cuda.current_device()))
+
+
+# ---- K1 --------------------------------------------------------------------------------------
+def movegen_count(states: torch.Tensor, players: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """len(get_legal_moves(board, player)) per state (engine/move_generator.py:130)."""
+    n = _check_states(states)
+    _check_players(players, n)
+    lib = _lib_for(states)
+    counts = torch.empty(n, dtype=torch.int32, device=states.device)
+    check(lib.bk_movegen_count(_ptr(states), _ptr(players), n, _ptr(counts), _stream()))
+    _count()
+    return counts
+
+
+def movegen(states: torch.Tensor, players: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Legal moves of every state as CSR: (counts int32[N], offsets int32[N+1], move_ids uint16[total]),
+    ids ascending = the (piece, orientation, row, col) order of the reference's naive generator."""
+    n = _check_states(states)
+    _check_players(players, n)
+    lib = _lib_for(states)
+    counts = torch.empty(n, dtype=torch.int32, device=states.device)
+    offsets = torch.empty(n + 1, dtype=torch.int32, device=states.device)
+    st = _stream()
+    check(lib.bk_movegen_count(_ptr(states), _ptr(players), n, _ptr(counts), st))
+    check(lib.bk_exclusive_scan_u32(_ptr(counts), n, _ptr(offsets), st))
+    _count(4)
+    total = int(offsets[n].item())
+    ids = torch.empty(max(total, 1), dtype=torch.uint16, device=states.device)
+    check(lib.bk_movegen_emit(_ptr(states), _ptr(players), n, _ptr(offsets), _ptr(ids), st))
+    _count()
+    return counts, offsets, ids[:total]
+
+
+def movegen_bitmap(states: torch.Tensor, players: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int32[N, 91*20]: word o*20+row has bit col set iff move (o,row,col) is legal."""
+    n = _check_states(states)
+    _check_players(players, n)
+    lib = _lib_for(states)
+    bitmap = torch.empty((n, BK_BITMAP_WORDS), dtype=torch.int32, device=states.device)
+    check(lib.bk_movegen_bitmap(_ptr(states), _ptr(players), n, _ptr(bitmap), _stream()))
+    _count()
+    return bitmap
+
+
+def has_moves(states: torch.Tensor) -> torch.Tensor:
+    """uint8[N]: bit p set iff player p has a legal move (engine/move_generator.py:961)."""
+    n = _check_states(states)
+    lib = _lib_for(states)
+    out = torch.empty(n, dtype=torch.uint8, device=states.device)
+    check(lib.bk_has_moves(_ptr(states), n, _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def is_move_legal(states: torch.Tensor, move_ids: torch.Tensor, players: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n = _check_states(states)
+    _check_players(players, n)
+    if not (move_ids.is_cuda and move_ids.dtype == torch.uint16 and move_ids.numel() == n):
+        raise ValueError("move_ids must be a CUDA uint16 tensor of length N")
+    lib = _lib_for(states)
+    out = torch.empty(n, dtype=torch.uint8, device=states.device)
+    check(lib.bk_is_move_legal(_ptr(states), _ptr(players), _ptr(move_ids), n, _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def step(states: torch.Tensor, move_ids: torch.Tensor, players: Optional[torch.Tensor] = None,
+         want_alive: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """In-place make_move / pass per state (engine/game.py:57, engine/board.py:557).  Returns (ok, alive)."""
+    n = _check_states(states)
+    _check_players(players, n)
+    if not (move_ids.is_cuda and move_ids.dtype == torch.uint16 and move_ids.numel() == n):
+        raise ValueError("move_ids must be a CUDA uint16 tensor of length N")
+    lib = _lib_for(states)
+    ok = torch.empty(n, dtype=torch.uint8, device=states.device)
+    alive = torch.empty(n, dtype=torch.uint8, device=states.device) if want_alive else None
+    check(lib.bk_step(_ptr(states), _ptr(players), _ptr(move_ids), n, _ptr(ok), _ptr(alive), _stream()))
+    _count()
+    return ok, alive
+
+
+def scores(states: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(BlokusGame.get_score, Board.get_score) as int32[N,4] each (engine/game.py:284, engine/board.py:562)."""
+    n = _check_states(states)
+    lib = _lib_for(states)
+    gs = torch.empty((n, 4), dtype=torch.int32, device=states.device)
+    bs = torch.empty((n, 4), dtype=torch.int32, device=states.device)
+    check(lib.bk_scores(_ptr(states), n, _ptr(gs), _ptr(bs), _stream()))
+    _count()
+    return gs, bs
+
+
+# ---- K2 --------------------------------------------------------------------------------------
+def playout(n: int, seed: int, game_offset: int = 0, start_states: Optional[torch.Tensor] = None,
+            policy: int = POLICY_UNIFORM, max_turns: int = 0, want_trace: bool = False,
+            want_choice: bool = False, want_final: bool = False, want_board_scores: bool = True,
+            out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """Play n games to the end on the device.  Game i has global index game_offset+i (its Philox stream).
+
+    `out` may carry preallocated tensors from a previous call (keys as returned) to avoid reallocation.
+    """
+    if start_states is not None:
+        if _check_states(start_states) != n:
+            raise ValueError("start_states must have N rows")
+    lib = _lib_for(start_states)
+    dev = start_states.device if start_states is not None else torch.device("cuda", torch.cuda.current_device())
+    res = out if out is not None else {}
+
+    def buf(key, shape, dtype, want=True):
+        if not want:
+            return None
+        t = res.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            res[key] = t
+        return t
+
+    gs = buf("game_scores", (n, 4), torch.int32)
+    bs = buf("board_scores", (n, 4), torch.int32, want_board_scores)
+    tr = buf("trace", (n, BK_MAX_TURNS), torch.uint16, want_trace)
+    ch = buf("choice", (n, BK_MAX_TURNS), torch.uint16, want_choice)
+    fin = buf("final_states", (n, STATE_BYTES), torch.uint8, want_final)
+    check(lib.bk_playout(_ptr(start_states), n, int(seed) & (2**64 - 1), int(game_offset), int(policy), int(max_turns),
+                         _ptr(gs), _ptr(bs), _ptr(tr), _ptr(ch), _ptr(fin), _stream()))
+    _count()
+    return res
+
+
+# ---- K4 --------------------------------------------------------------------------------------
+def zobrist_hash(states: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """uint64 keys (returned as int64 bit patterns) of ZobristHash.hash_board (mcts/zobrist.py:70)."""
+    n = _check_states(states)
+    if not (table.is_cuda and table.dtype in (torch.int64, torch.uint64) and table.numel() == _lib.BK_ZOBRIST_ENTRIES):
+        raise ValueError("table must be a CUDA 64-bit tensor with 2088 entries")
+    lib = _lib_for(states)
+    keys = torch.empty(n, dtype=torch.int64, device=states.device)
+    check(lib.bk_zobrist_hash(_ptr(states), n, _ptr(table), _ptr(keys), _stream()))
+    _count()
+    return keys
+
+
+class DeviceTranspositionTable:
+    """Open-addressing device table key -> reward (mcts/zobrist.py:155-220 TranspositionTable)."""
+
+    def __init__(self, log2_slots: int = 20):
+        import ctypes as C
+
+        self._lib = _lib_for(None)
+        h = C.c_void_p()
+        check(self._lib.bk_tt_create(C.byref(h), int(log2_slots)))
+        self._h = h
+        self.log2_slots = int(log2_slots)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def clear(self) -> None:
+        check(self._lib.bk_tt_clear(self._h, _stream()))
+
+    def put(self, keys: torch.Tensor, rewards: torch.Tensor) -> None:
+        n = keys.numel()
+        rewards = rewards.to(torch.float64).contiguous()
+        check(self._lib.bk_tt_put(self._h, _ptr(keys), _ptr(rewards), n, _stream()))
+        _count()
+
+    def get(self, keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        n = keys.numel()
+        rewards = torch.zeros(n, dtype=torch.float64, device=keys.device)
+        found = torch.empty(n, dtype=torch.uint8, device=keys.device)
+        check(self._lib.bk_tt_get(self._h, _ptr(keys), n, _ptr(rewards), _ptr(found), _stream()))
+        _count()
+        return rewards, found
+
+    def stats(self) -> Dict[str, int]:
+        import ctypes as C
+
+        out = (C.c_uint64 * 2)()
+        check(self._lib.bk_tt_stats(self._h, out, _stream()))
+        return {"max_size": int(out[0]), "size": int(out[1])}
+
+    def close(self) -> None:
+        if self._h is not None:
+            self._lib.bk_tt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
