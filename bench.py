@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Blokus simulation core.
+
+Workload (BASELINE.json configs[1]): batched uniform-random 4-player self-play, 65,536 concurrent
+games from the empty board to terminal score per GPU.  One "step" = one such batch.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # CUDA arm (this repo)
+  python bench.py --impl reference [...]                          # CPU arm: the oracle port of the
+                                                                  # reference engine on all host cores
+
+For N > 1 the driver launches one rank per GPU with torch.distributed.run; games are sharded by global
+game index (rank r plays games [r*G, (r+1)*G) of every step: weak scaling, no data-path collective).
+Rank 0 prints ONE JSON line.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+GAMES_PER_GPU = 65536
+SEED = 42                      # configs/stage3_selfplay_gpu.yaml:3 of the reference
+METRIC = "random_playouts_per_sec"
+UNIT = "playouts/s"
+WORKLOAD = "uniform-random 4-player self-play, 65536 concurrent games/GPU, empty board to terminal score"
+
+# Algorithmic constants of one playout (DESIGN.md "Roofline"): bytes that must cross HBM and the
+# warp-level instructions the row-sliced algorithm issues (ncu smsp__inst_executed.sum / games,
+# profiles/r01_playout_ncu.md).
+ALG_BYTES_PER_PLAYOUT_DEVICE = 16            # int32 game_scores[4] written; no input (empty board start)
+ALG_WARP_INSTR_PER_PLAYOUT = None            # filled from profiles/ when known; see _int_roofline
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = samples in the upper half of what was seen (idle samples at the edges drop out)
+        load = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference engine (oracle/blokus_oracle.c), all host threads
+# ------------------------------------------------------------------------------------------------
+def _cpu_playouts(n_games: int, threads: int, game_offset: int) -> float:
+    """Plays n_games oracle games on `threads` threads; returns elapsed seconds."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import orc
+
+    orc.lib()
+    t0 = time.perf_counter()
+    if threads <= 1:
+        for g in range(n_games):
+            orc.playout(SEED, game_offset + g)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:   # ctypes releases the GIL inside the C call
+            list(ex.map(lambda g: orc.playout(SEED, game_offset + g), range(n_games)))
+    return time.perf_counter() - t0
+
+
+def run_reference(args) -> None:
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = max(cores * 16, 64)                      # games per step: a bounded sample of the workload
+    for w in range(args.warmup):
+        _cpu_playouts(max(cores, 8), cores, 10_000_000 + w * 1000)
+    t = 0.0
+    for k in range(args.steps):
+        t += _cpu_playouts(sample, cores, k * sample)
+    value = sample * args.steps / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "games_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} games/step x {args.steps} steps of the same workload "
+                                   "(oracle/blokus_oracle.c: C restatement of the reference's default "
+                                   "frontier+bitboard engine; the Python reference itself cannot travel "
+                                   "to the GPU box and runs 2.5 playouts/s/core, BASELINE.md section 2)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------
+def run_cuda(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from reinforcementlearning_blokus_b200 import device as dev
+    from reinforcementlearning_blokus_b200 import _lib
+    from reinforcementlearning_blokus_b200.state import empty_states
+
+    rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this framework has no CPU fallback; use --impl reference "
+                         "for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.games
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
+
+    def step_device(k):
+        # global game index = (k * world + rank) * n + i : disjoint Philox streams over steps and ranks
+        dev.playout(n, seed=SEED, game_offset=(k * world + rank) * n, out=out, want_board_scores=False)
+
+    for w in range(args.warmup):
+        step_device(1_000_000 + w)
+    launches0 = dev.launches()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                      # L2 flush between timed iterations (untimed)
+        ev[k][0].record(stream)
+        step_device(k)
+        ev[k][1].record(stream)
+    barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = dev.launches() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop()
+    value = n * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the public API; H2D of the start states and D2H of the scores inside
+    host_states = torch.from_numpy(empty_states(n).view(np.uint8).reshape(n, 256).copy()).pin_memory()
+    host_scores = torch.empty((n, 4), dtype=torch.int32).pin_memory()
+    dstates = torch.empty((n, 256), dtype=torch.uint8, device="cuda")
+    out2 = {}
+
+    def step_e2e(k):
+        dstates.copy_(host_states, non_blocking=True)
+        r = dev.playout(n, seed=SEED, game_offset=(k * world + rank) * n, start_states=dstates, out=out2,
+                        want_board_scores=False)
+        host_scores.copy_(r["game_scores"], non_blocking=True)
+
+    for w in range(max(1, args.warmup // 2)):
+        step_e2e(2_000_000 + w)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        step_e2e(k)
+    e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = n * world * args.steps / (ms_e2e * 1e-3)
+    mean_score = float(host_scores.float().mean())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_playout_uniform; one launch per step)
+    hbm_peak, peak_src, sm_max = _measured_peaks()
+    per_launch_s = ms * 1e-3 / args.steps
+    hbm_achieved = ALG_BYTES_PER_PLAYOUT_DEVICE * n / per_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": hbm_achieved / hbm_peak, "traffic": _traffic_from_profiles(),
+                "peak_source": peak_src, "kernel": "k_playout_uniform",
+                "note": "integer-ALU bound by design: HBM fraction is expected to be tiny; see int_roofline"}
+    int_roofline = _int_roofline(n, per_launch_s, clocks, sm_max)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "games_per_gpu": n, "seed": SEED, "rng": "philox4x32-10",
+                   "l2": "256 MiB buffer written between timed steps (flush)", "parallelism": f"games sharded x{world}"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 256, "d2h_bytes_per_step": n * 16,
+                "ms_per_step": ms_e2e / args.steps, "mean_game_score": mean_score},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "int_roofline": int_roofline,
+        "lib": _lib.load().bk_version().decode(),
+    }
+    if world == 1 and not args.no_extras:
+        line["extras"] = _extras(dev, torch, n)
+        line["cpu_baseline"] = _cpu_baseline()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _traffic_from_profiles():
+    p = os.path.join(ROOT, "profiles", "r01_playout_traffic.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def _int_roofline(n, per_launch_s, clocks, sm_max):
+    """Issue-slot roofline: warp instructions issued per second vs 148 SMs x 4 schedulers x 1 instr/clk."""
+    import ctypes as C
+
+    res = {"bound": "int_issue", "unit": "warp-instr/s"}
+    sm_mhz = clocks.get("sm_mhz") or sm_max
+    peak = 148 * 4 * sm_mhz * 1e6
+    res["peak"] = peak
+    res["peak_source"] = f"148 SMs x 4 SMSP x 1 warp-instr/clk x {sm_mhz:.0f} MHz (median under load)"
+    p = os.path.join(ROOT, "profiles", "r01_playout_traffic.json")
+    wi = ALG_WARP_INSTR_PER_PLAYOUT
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                wi = json.load(f).get("warp_instr_per_playout", wi)
+        except Exception:
+            pass
+    if wi:
+        res["warp_instr_per_playout"] = wi
+        res["achieved"] = wi * n / per_launch_s
+        res["frac"] = res["achieved"] / peak
+    # measured pipe throughput (csrc/probe.cu), warp-instr/clk/SMSP
+    probe = os.path.join(ROOT, "reinforcementlearning_blokus_b200", "libbk_probe.so")
+    if os.path.exists(probe):
+        try:
+            L = C.CDLL(probe)
+            L.bk_probe_int.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+            per_trip = {0: 192, 1: 120}     # SASS instructions per loop trip (cuobjdump of libbk_probe.so)
+            blocks, iters = 148 * 8, 20000
+            for mode, key in ((0, "probe_alu_only_ipc"), (1, "probe_alu_fma_mix_ipc")):
+                msf = C.c_float()
+                if L.bk_probe_int(mode, blocks, iters, C.byref(msf)) == 0:
+                    warp_instr = blocks * 8 * iters * per_trip[mode]
+                    res[key] = warp_instr / (msf.value * 1e-3) / (148 * 4 * sm_mhz * 1e6)
+        except Exception as e:  # measurement aid only
+            res["probe_error"] = str(e)
+    return res
+
+
+def _extras(dev, torch, n):
+    """The other two parts of BASELINE.json's metric: legal-move generations/s (and later MCTS sims/s)."""
+    def timeit(fn, reps=5):
+        fn(); fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # mid-game corpus (BASELINE configs[0] flavour): random self-play stopped after k turns
+    parts = []
+    for k in (8, 16, 24, 32, 40, 48):
+        parts.append(dev.playout(n // 4, seed=7, game_offset=k * 1_000_000, max_turns=k, want_final=True)["final_states"])
+    corpus = torch.cat(parts).contiguous()
+    m = corpus.shape[0]
+    ex = {"movegen_states": m, "movegen_mean_legal_moves": float(dev.movegen_count(corpus).float().mean())}
+    ms = timeit(lambda: dev.movegen_count(corpus))
+    ex["movegen_count_gens_per_sec"] = m / ms * 1e3
+    ms = timeit(lambda: dev.movegen_bitmap(corpus))
+    ex["movegen_bitmap_gens_per_sec"] = m / ms * 1e3
+    ms = timeit(lambda: dev.movegen(corpus))
+    ex["movegen_csr_gens_per_sec"] = m / ms * 1e3
+    try:
+        from reinforcementlearning_blokus_b200 import mcts as _m
+        ex.update(_m.bench_extras())
+    except Exception:
+        pass
+    return ex
+
+
+def _cpu_baseline():
+    """Oracle port on ONE host core, bounded sample (~10-15 s)."""
+    budget = float(os.environ.get("BLOKUS_CPU_BASELINE_SECONDS", "12"))
+    from oracle import orc
+    orc.lib()
+    t0 = time.perf_counter()
+    g = 0
+    while time.perf_counter() - t0 < budget:
+        orc.playout(SEED, g)
+        g += 1
+    dt = time.perf_counter() - t0
+    return {"value": g / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{g} games of the same workload in {dt:.1f} s (oracle/blokus_oracle.c, default "
+                      "frontier+bitboard generator, game-over check after every move as engine/game.py:182)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -11,7 +11,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libblokus_b200.so")
+# BLOKUS_B200_LIB points at an alternative build of the SAME library (kernel tuning experiments only)
+LIB_PATH = os.environ.get("BLOKUS_B200_LIB") or os.path.join(HERE, "libblokus_b200.so")
 
 BK_PASS = 0xFFFF
 BK_MAX_TURNS = 96

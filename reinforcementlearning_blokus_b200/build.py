@@ -39,15 +39,24 @@ def needs_build() -> bool:
     return False
 
 
+PROBE_LIB = os.path.join(HERE, "libbk_probe.so")
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
-    if verbose:
-        sys.stderr.write(proc.stderr)
+    """Compile libblokus_b200.so (and the bench-only pipe-throughput probe) if stale."""
+    if force or needs_build():
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+        proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+        if verbose:
+            sys.stderr.write(proc.stderr)
+    probe_src = os.path.join(CSRC, "probe.cu")
+    if force or not os.path.exists(PROBE_LIB) or os.path.getmtime(PROBE_LIB) < os.path.getmtime(probe_src):
+        proc = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-o", PROBE_LIB, "probe.cu"], cwd=CSRC,
+                              capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed (probe):\n" + proc.stdout + proc.stderr)
     return LIB
 
 

@@ -44,6 +44,10 @@ static inline int grid_for(int n_items, int ctas_per_sm) {
 extern "C" const char* bk_last_error(void) { return g_err; }
 extern "C" const char* bk_version(void) { return "blokus_b200 r1 sm_100a (row-sliced warp-per-game)"; }
 
+__global__ void k_movegen_emit(const bk_state* __restrict__, const uint8_t* __restrict__, int, const uint32_t* __restrict__,
+                               uint16_t* __restrict__);
+#define BK_EMIT_SMEM_BYTES (8 * (32 * 57 * 4 + 2048 * 2))
+
 extern "C" int bk_init(int device) {
     int count = 0;
     CUDA_TRY(cudaGetDeviceCount(&count));
@@ -53,6 +57,7 @@ extern "C" int bk_init(int device) {
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_piece, BK_TBL_ORIENT_PIECE, sizeof(BK_TBL_ORIENT_PIECE)));
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_ncells, BK_TBL_ORIENT_NCELLS, sizeof(BK_TBL_ORIENT_NCELLS)));
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_cells, BK_TBL_ORIENT_CELLS, sizeof(BK_TBL_ORIENT_CELLS)));
+    CUDA_TRY(cudaFuncSetAttribute(k_movegen_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
     g_device = device;
     return BK_OK;
 }
@@ -76,18 +81,68 @@ k_movegen_count(const bk_state* __restrict__ states, const uint8_t* __restrict__
     }
 }
 
+// Ascending move ids.  Phase 1 writes the legal-anchor rows of all 91 orientations to shared memory
+// (word w = o*20 + row, so a set bit `col` of word w is move id 20*w + col); phase 2 gives every lane a
+// contiguous slice of 57 words, so one warp scan orders the whole list; phase 3 stages the ids in shared
+// memory and copies them out with coalesced stores.
+#define EMIT_WORDS_PER_LANE 57            /* 32 * 57 = 1824 >= 1820 */
+#define EMIT_ROW_WORDS (32 * EMIT_WORDS_PER_LANE)
+#define EMIT_STAGE 2048                   /* ids staged per state; longer lists are written directly */
+#define EMIT_SMEM_PER_WARP (EMIT_ROW_WORDS * 4 + EMIT_STAGE * 2)
+static_assert(BK_EMIT_SMEM_BYTES == BK_WARPS * EMIT_SMEM_PER_WARP, "emit shared-memory size");
+
+struct SmemRowSink {
+    uint32_t* rows; int lane;
+    template <int O> __device__ __forceinline__ void put(uint32_t L) {
+        if (lane < 20) rows[O * 20 + lane] = L;
+    }
+};
+
 __global__ void __launch_bounds__(BK_THREADS)
 k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ players, int n,
                const uint32_t* __restrict__ offsets, uint16_t* __restrict__ ids) {
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + (size_t)wib * EMIT_SMEM_PER_WARP);
+    uint16_t* stage = reinterpret_cast<uint16_t*>(rows + EMIT_ROW_WORDS);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int i = warp; i < n; i += nwarps) {
         WarpState s; load_state(states + i, lane, s);
         const uint32_t p = players ? (players[i] & 3u) : s.to_move;
         uint32_t A, C; make_masks(s, p, lane, A, C);
-        EmitSink sink; sink.out = ids; sink.pos = offsets[i]; sink.lane = lane;
+#pragma unroll
+        for (int k = 0; k < EMIT_WORDS_PER_LANE; k++) rows[k * 32 + lane] = 0;   // spent pieces are never visited
+        __syncwarp();
+        SmemRowSink sink; sink.rows = rows; sink.lane = lane;
         bk_gen_all(A, C, sel4(s.used, p), sink);
+        __syncwarp();
+        const uint32_t* mine = rows + lane * EMIT_WORDS_PER_LANE;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < EMIT_WORDS_PER_LANE; k++) cnt += __popc(mine[k]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(BK_FULL, incl, d); if (lane >= d) incl += v; }
+        const uint32_t total = __shfl_sync(BK_FULL, incl, 31);
+        uint32_t pos = incl - cnt;
+        const uint32_t base = offsets[i];
+        const bool staged = total <= EMIT_STAGE;
+        uint16_t* dst = staged ? stage : ids + base;
+        for (int k = 0; k < EMIT_WORDS_PER_LANE; k++) {
+            uint32_t bits = mine[k];
+            const uint32_t idb = (uint32_t)(lane * EMIT_WORDS_PER_LANE + k) * 20u;
+            while (bits) {
+                const int col = __ffs(bits) - 1;
+                bits &= bits - 1;
+                dst[pos++] = (uint16_t)(idb + col);
+            }
+        }
+        __syncwarp();
+        if (staged) {
+            for (uint32_t k = lane; k < total; k += 32) ids[base + k] = stage[k];
+        }
+        __syncwarp();
     }
 }
 
@@ -207,7 +262,10 @@ k_scores(const bk_state* __restrict__ states, int n, int32_t* __restrict__ gs, i
 // ---------------------------------------------------------------------------------------------
 // K2: playouts (uniform policy).  One warp plays one whole game in registers.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BK_THREADS)
+#ifndef BK_PLAYOUT_MIN_BLOCKS
+#define BK_PLAYOUT_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(BK_THREADS, BK_PLAYOUT_MIN_BLOCKS)
 k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int max_turns,
                   int32_t* __restrict__ gs, int32_t* __restrict__ bs, uint16_t* __restrict__ trace,
                   uint16_t* __restrict__ choice, bk_state* __restrict__ finals) {
@@ -224,7 +282,17 @@ k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint
         if (ch) { uint32_t* c32 = reinterpret_cast<uint32_t*>(ch); c32[lane] = 0xFFFFFFFFu; if (lane < 16) c32[32 + lane] = 0xFFFFFFFFu; }
         __syncwarp();
         uint32_t dead = 0;
-        for (uint32_t t = 0; t < (uint32_t)max_turns && dead != 0xFu; t++) {
+        // The reference loop stops the moment nobody can move (engine/game.py:182-214 runs after every
+        // move and pass).  Here a player's death is discovered lazily on its own turn, which is the same
+        // game as long as it runs to the end.  When max_turns cuts it short, up to four extra "probe" turns
+        // (no placement) decide whether the game had in fact ended with the last placement, so that the
+        // returned side-to-move equals the reference's in both cases.
+        uint32_t resume_to_move = s.to_move;   // side to move right after the last placement
+        uint32_t cut_to_move = s.to_move;      // side to move when max_turns was reached
+        bool still_alive = false;
+        for (uint32_t t = 0; dead != 0xFu; t++) {
+            const bool probing = t >= (uint32_t)max_turns;
+            if (t == (uint32_t)max_turns) cut_to_move = s.to_move;
             const uint32_t p = s.to_move;
             bool moved = false;
             if (!((dead >> p) & 1u)) {
@@ -233,18 +301,23 @@ k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint
                 const Totals tot = reduce_totals(sink, lane);
                 if (tot.n == 0) {
                     dead |= 1u << p;      // a player without moves never regains any ("dead stay dead")
+                } else if (probing) {
+                    still_alive = true;
+                    break;
                 } else {
                     const uint32_t r = philox_draw(seed, g, t, 0);
                     const uint32_t idx = __umulhi(r, tot.n);
                     int o, row, col;
                     const uint32_t id = select_move(tot, idx, A, C, lane, o, row, col);
                     place_move(s, p, o, row, col, lane);
+                    resume_to_move = s.to_move;
                     if (lane == 0) { if (tr) tr[t] = (uint16_t)id; if (ch) ch[t] = (uint16_t)idx; }
                     moved = true;
                 }
             }
             if (!moved) s.to_move = (p + 1) & 3u;   // pass: engine/board.py:557-560 via arena_runner.py:662-666
         }
+        s.to_move = still_alive ? cut_to_move : resume_to_move;
         int32_t gsc[4], bsc[4]; scores_of(s, lane, gsc, bsc);
         if (lane < 4) {
             const int32_t gv = lane == 0 ? gsc[0] : lane == 1 ? gsc[1] : lane == 2 ? gsc[2] : gsc[3];
@@ -417,7 +490,7 @@ extern "C" int bk_movegen_emit(const bk_state* states, const uint8_t* players, i
                                uint16_t* move_ids, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids)), "bk_movegen_emit: null buffer");
     if (n == 0) return BK_OK;
-    k_movegen_emit<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, offsets, move_ids);
+    k_movegen_emit<<<grid_for(n, 2), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, offsets, move_ids);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -474,7 +547,7 @@ extern "C" int bk_playout(const bk_state* start_states, int n, uint64_t seed, ui
     if (policy != BK_POLICY_UNIFORM) return fail(BK_ERR_ARG, "%s", "bk_playout: unknown policy");
     if (n == 0) return BK_OK;
     if (max_turns == 0) max_turns = BK_MAX_TURNS;
-    k_playout_uniform<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(
+    k_playout_uniform<<<grid_for(n, BK_PLAYOUT_MIN_BLOCKS), BK_THREADS, 0, as_stream(stream)>>>(
         start_states, n, seed, game_offset, max_turns, game_scores, board_scores, trace, choice, final_states);
     LAUNCH_CHECK();
     return BK_OK;
