@@ -91,6 +91,11 @@ int bk_exclusive_scan_u32(const uint32_t* counts, int n, uint32_t* offsets, void
 int bk_movegen_emit(const bk_state* states, const uint8_t* players, int n,
                     const uint32_t* offsets, uint16_t* move_ids, void* stream);
 
+/* One-kernel variant with a fixed capacity per state: ids of state i go to move_ids[i*cap ..], at most
+ * cap of them; counts[i] is the full count (so counts[i] > cap tells the caller the list was cut). */
+int bk_movegen_fixed(const bk_state* states, const uint8_t* players, int n, uint32_t cap,
+                     uint32_t* counts, uint16_t* move_ids, void* stream);
+
 /* Legal-anchor bitmap: bitmap[i][o*20+row] has bit col set iff move (o,row,col) is legal. */
 int bk_movegen_bitmap(const bk_state* states, const uint8_t* players, int n,
                       uint32_t* bitmap, void* stream);
@@ -101,6 +106,13 @@ int bk_has_moves(const bk_state* states, int n, uint8_t* out_mask, void* stream)
 /* is_move_legal (engine/move_generator.py:912-946): out[i] = 1 if move_ids[i] is legal for players[i]. */
 int bk_is_move_legal(const bk_state* states, const uint8_t* players, const uint16_t* move_ids,
                      int n, uint8_t* out, void* stream);
+
+/* Board.can_place_piece (engine/board.py:136-220) for an arbitrary cell set: cell_masks[i] is a 400-bit
+ * mask (7 words, bit row*20+col) of the cells to cover; out[i] = 1 if players[i] may place exactly those
+ * cells (all empty, none edge-adjacent to own cells, one on an own corner -- or on the start corner for
+ * the first move).  The piece inventory is not consulted, as in the reference. */
+int bk_can_place_mask(const bk_state* states, const uint8_t* players, const uint64_t* cell_masks, int n,
+                      uint8_t* out, void* stream);
 
 /* ---- step: BlokusGame.make_move + caller-side pass (engine/game.py:57-180, board.py:515-560) */
 
@@ -118,15 +130,16 @@ int bk_scores(const bk_state* states, int n, int32_t* game_scores /*[n][4]*/,
 
 /* ---- K2: playouts to terminal score (loop of analytics/tournament/arena_runner.py:653-695) - */
 
-/* Game i (global index game_offset+i) starts from start_states[i] (NULL: the empty board) and is
- * played to the end: turn t (passes count) of game g draws r = philox4x32_10(key=seed,
- * ctr=(g_lo,g_hi,t,0)).x and plays the ((uint64)r*n_legal)>>32-th move of the ascending list; a
- * player with no move passes; the game stops once no player can move or after max_turns turns
- * (0 = BK_MAX_TURNS).  Outputs (each may be NULL): game_scores/board_scores [n][4],
- * trace [n][BK_MAX_TURNS] move ids (BK_PASS = pass/pad), choice [n][BK_MAX_TURNS] chosen indices,
- * final_states [n]. */
+/* Game i (global index game_offset+i) starts from start_states[i] (NULL: the empty board) and plays
+ * turns first_turn, first_turn+1, ... (passes count as turns): turn t of game g draws
+ * r = philox4x32_10(key=seed, ctr=(g_lo,g_hi,t,0)).x and plays the ((uint64)r*n_legal)>>32-th move of the
+ * ascending list; a player with no move passes; the game stops once no player can move or when
+ * t reaches max_turns (0 = BK_MAX_TURNS).  A game played in segments [0,a), [a,b), ... through
+ * final_states is the same game as one call.  Outputs (each may be NULL): game_scores/board_scores [n][4],
+ * trace [n][BK_MAX_TURNS] move ids by turn (BK_PASS = pass/pad; slots < first_turn are left untouched),
+ * choice [n][BK_MAX_TURNS] chosen indices, final_states [n]. */
 int bk_playout(const bk_state* start_states, int n, uint64_t seed, uint64_t game_offset,
-               int policy, int max_turns, int32_t* game_scores, int32_t* board_scores,
+               int policy, int first_turn, int max_turns, int32_t* game_scores, int32_t* board_scores,
                uint16_t* trace, uint16_t* choice, bk_state* final_states, void* stream);
 
 /* ---- K4: Zobrist keys and transposition table (mcts/zobrist.py:20-99, 155-220) ------------ */
@@ -145,6 +158,46 @@ int bk_tt_get(bk_tt* tt, const uint64_t* keys, int n, double* rewards, uint8_t* 
 int bk_tt_put(bk_tt* tt, const uint64_t* keys, const double* rewards, int n, void* stream);
 /* host out: [0]=slots, [1]=occupied */
 int bk_tt_stats(bk_tt* tt, uint64_t* out_host, void* stream);
+
+/* ---- N1: HeuristicAgent move scores (agents/heuristic_agent.py:68-198) ---------------------- */
+
+/* scores[k] for every move_ids[k], k in [offsets[i], offsets[i+1]), evaluated on states[i] for players[i]
+ * (NULL: side to move): 1.0*size + 2.0*corner_creation - 1.5*edge + 0.5*centre in float64, bit-identical to
+ * HeuristicAgent._evaluate_move.  The softmax draw over them stays with the caller (:222-244, :65). */
+int bk_heuristic_scores(const bk_state* states, const uint8_t* players, const uint32_t* offsets,
+                        const uint16_t* move_ids, int n, double* scores, void* stream);
+
+/* ---- K5: UCT search (mcts/mcts_agent.py:304-582; flat variant agents/fast_mcts_agent.py:112-338) -- */
+
+typedef struct bk_mcts_params {
+    int32_t  iterations;        /* iterations to run in THIS call (MCTSAgent.iterations, mcts_agent.py:204) */
+    int32_t  iterations_total;  /* capacity of the whole search (>= sum over resumed calls); sizes the workspace */
+    int32_t  max_rollout_moves; /* mcts_agent.py:218 (50); 0 = roll out until the side to move has no move */
+    int32_t  rollout_policy;    /* bk_policy */
+    int32_t  max_depth;         /* 0 = full UCT tree; 1 = flat bandit over the root moves (FastMCTSAgent) */
+    int32_t  ucb_variant;       /* 0: c*sqrt(ln N/n) (mcts_agent.py:86); 1: c*sqrt(2 ln N/n) (fast_mcts_agent.py:52) */
+    int32_t  resume;            /* 0: build a fresh tree from the root; 1: continue the trees in `workspace` */
+    int32_t  reward_mode;       /* 0: gain of the player to move at the leaf, from the leaf (mcts_agent.py:470-521);
+                                   1: gain of the ROOT player measured from the root position (flat bandit) */
+    double   exploration;       /* 1.414 */
+    uint64_t seed;
+    uint64_t tree_offset;       /* global index of tree 0 (root-parallel sharding across GPUs) */
+} bk_mcts_params;
+
+/* Bytes of device workspace per tree for a search of params->iterations_total iterations (host call). */
+int64_t bk_mcts_workspace_bytes(const bk_mcts_params* params);
+
+/* Run n_trees independent UCT searches, one warp each; tree k searches roots[k % n_roots] (side to move =
+ * the root player) with random stream (seed, tree_offset+k).  `tt` (may be NULL) caches rollout rewards by
+ * Zobrist key of `zobrist_table` (device, BK_ZOBRIST_ENTRIES; required when tt != NULL).  Outputs per tree,
+ * indexed by the rank of the move in the root's ascending legal-move list:
+ *   root_visits [n_trees][max_root_moves] int32, root_reward [n_trees][max_root_moves] int64 (rollout
+ *   rewards are integers), root_move_ids [n_trees][max_root_moves] (BK_PASS where not expanded),
+ *   root_counts [n_trees] = number of legal root moves, status [n_trees] = 1 if the tree ran out of workspace. */
+int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, const bk_mcts_params* params,
+                   bk_tt* tt, const uint64_t* zobrist_table, void* workspace, int64_t workspace_bytes,
+                   int max_root_moves, int32_t* root_visits, int64_t* root_reward, uint32_t* root_counts,
+                   uint16_t* root_move_ids, uint32_t* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -78,10 +78,16 @@ def lib() -> C.CDLL:
         L.orc_philox4x32_10.argtypes = [vp, vp, vp]
         L.orc_heuristic_score.argtypes = [vp, i32, i32]
         L.orc_heuristic_score.restype = C.c_double
-        L.orc_playout.argtypes = [vp, u64, u64, i32, i32, vp, vp, vp, vp, vp]
+        L.orc_playout.argtypes = [vp, u64, u64, i32, i32, i32, vp, vp, vp, vp, vp]
         L.orc_zobrist_table.argtypes = [u32, vp]
         L.orc_zobrist_hash.argtypes = [vp, vp]
         L.orc_zobrist_hash.restype = u64
+        L.orc_tt_create.argtypes = [i32]
+        L.orc_tt_create.restype = vp
+        L.orc_tt_destroy.argtypes = [vp]
+        L.orc_tt_size.argtypes = [vp]
+        L.orc_tt_size.restype = u64
+        L.orc_mcts_search.argtypes = [vp, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, vp, vp]
         L.orc_init()
         _lib = L
     return _lib
@@ -230,20 +236,51 @@ def playout(
     start: Optional[np.ndarray] = None,
     max_turns: int = 0,
     fast: bool = True,
+    first_turn: int = 0,
     want_final: bool = False,
 ):
     """One Philox-driven random game; returns dict(game_scores, board_scores, trace, choice, turns)."""
     gs = np.zeros(4, dtype=np.int32)
     bs = np.zeros(4, dtype=np.int32)
-    tr = np.zeros(MAX_TURNS, dtype=np.uint16)
-    ch = np.zeros(MAX_TURNS, dtype=np.uint16)
+    tr = np.full(MAX_TURNS, PASS_ID, dtype=np.uint16)
+    ch = np.full(MAX_TURNS, PASS_ID, dtype=np.uint16)
     fin = np.zeros(1, dtype=STATE_DTYPE) if want_final else None
     st = None
     if start is not None:
         st = np.ascontiguousarray(np.atleast_1d(start), dtype=STATE_DTYPE)
-    turns = lib().orc_playout(_ptr(st), int(seed), int(game_index), int(max_turns), int(fast),
+    turns = lib().orc_playout(_ptr(st), int(seed), int(game_index), int(first_turn), int(max_turns), int(fast),
                               _ptr(gs), _ptr(bs), _ptr(tr), _ptr(ch), _ptr(fin))
     res = {"game_scores": gs, "board_scores": bs, "trace": tr, "choice": ch, "turns": int(turns)}
     if want_final:
         res["final"] = fin[0]
     return res
+
+
+class OracleTT:
+    """Host transposition table for the oracle UCT (mcts/zobrist.py:155-220)."""
+
+    def __init__(self, log2_slots: int = 20):
+        self.h = lib().orc_tt_create(int(log2_slots))
+
+    def size(self) -> int:
+        return int(lib().orc_tt_size(self.h))
+
+    def close(self):
+        if self.h:
+            lib().orc_tt_destroy(self.h)
+            self.h = None
+
+
+def mcts_search(root: np.ndarray, iterations: int, seed: int, tree_id: int = 0, max_rollout_moves: int = 50,
+                max_depth: int = 0, ucb_variant: int = 0, reward_mode: int = 0, exploration: float = 1.414, tt: Optional[OracleTT] = None,
+                zobrist: Optional[np.ndarray] = None, max_root_moves: int = 2048):
+    """Sequential UCT with canonical untried order and Philox rollouts; returns dict(n_root, visits, reward, moves)."""
+    st = np.ascontiguousarray(np.atleast_1d(root), dtype=STATE_DTYPE)
+    vis = np.zeros(max_root_moves, dtype=np.int32)
+    rew = np.zeros(max_root_moves, dtype=np.int64)
+    mov = np.zeros(max_root_moves, dtype=np.uint16)
+    zt = None if zobrist is None else np.ascontiguousarray(zobrist, dtype=np.uint64)
+    n = lib().orc_mcts_search(_ptr(st), int(iterations), int(max_rollout_moves), int(max_depth), int(ucb_variant),
+                              int(reward_mode), float(exploration), int(seed), int(tree_id), tt.h if tt else None, _ptr(zt),
+                              int(max_root_moves), _ptr(vis), _ptr(rew), _ptr(mov))
+    return {"n_root": int(n), "visits": vis, "reward": rew, "moves": mov}

@@ -1,0 +1,35 @@
+"""B200-native Blokus simulation core: a drop-in for the hot path of TGALLOWAY1/ReinforcementLearning_Blokus.
+
+Object API (same names and semantics as the reference's ``engine`` / ``agents`` / ``mcts`` packages):
+    Board, Player, Position, Move, LegalMoveGenerator, get_shared_generator, BlokusGame, GameResult,
+    RandomAgent, HeuristicAgent, FastMCTSAgent, GameplayFastMCTSAgent, MCTSAgent, ZobristHash, TranspositionTable
+Batched device API (the throughput path): ``device`` (tensors in/out), ``batched.BatchedBlokus``, ``mcts.DeviceUCT``,
+``dist`` (game sharding and root-parallel search across GPUs).
+
+Importing this package needs neither a GPU nor the compiled library; the first compute call loads
+``libblokus_b200.so`` and raises if it or a CUDA device is missing (there is no CPU fallback).
+"""
+
+from .pieces import BOARD_SIZE, NUM_ORIENTATIONS, NUM_PIECES, ORIENTATIONS, PASS_ID, decode_move, encode_move  # noqa: F401
+from .state import STATE_BYTES, STATE_DTYPE, empty_states  # noqa: F401
+
+_LAZY = {
+    "Board": "board", "Player": "board", "Position": "board",
+    "Move": "move_generator", "LegalMoveGenerator": "move_generator", "get_shared_generator": "move_generator",
+    "BlokusGame": "game", "GameResult": "game",
+    "RandomAgent": "agents", "HeuristicAgent": "agents", "FastMCTSAgent": "agents", "GameplayFastMCTSAgent": "agents",
+    "MCTSAgent": "mcts", "ZobristHash": "mcts", "TranspositionTable": "mcts", "DeviceUCT": "mcts",
+    "BatchedBlokus": "batched",
+}
+
+
+def __getattr__(name):
+    mod = _LAZY.get(name)
+    if mod is None:
+        raise AttributeError(name)
+    import importlib
+
+    return getattr(importlib.import_module(f".{mod}", __name__), name)
+
+
+__version__ = "0.1.0"

@@ -35,12 +35,14 @@ PROTOTYPES = {
     "bk_movegen_count": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "bk_exclusive_scan_u32": (_i32, [_vp, _i32, _vp, _vp]),
     "bk_movegen_emit": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
+    "bk_movegen_fixed": (_i32, [_vp, _vp, _i32, _u32, _vp, _vp, _vp]),
+    "bk_can_place_mask": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "bk_movegen_bitmap": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "bk_has_moves": (_i32, [_vp, _i32, _vp, _vp]),
     "bk_is_move_legal": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "bk_step": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bk_scores": (_i32, [_vp, _i32, _vp, _vp, _vp]),
-    "bk_playout": (_i32, [_vp, _i32, _u64, _u64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bk_playout": (_i32, [_vp, _i32, _u64, _u64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bk_zobrist_hash": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "bk_tt_create": (_i32, [C.POINTER(_vp), _u32]),
     "bk_tt_clear": (_i32, [_vp, _vp]),
@@ -48,7 +50,21 @@ PROTOTYPES = {
     "bk_tt_get": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "bk_tt_put": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "bk_tt_stats": (_i32, [_vp, _vp, _vp]),
+    "bk_heuristic_scores": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "bk_mcts_workspace_bytes": (_i64, [_vp]),
+    "bk_mcts_search": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
+
+
+class MctsParams(C.Structure):
+    """bk_mcts_params of include/blokus_b200.h."""
+
+    _fields_ = [
+        ("iterations", C.c_int32), ("iterations_total", C.c_int32), ("max_rollout_moves", C.c_int32),
+        ("rollout_policy", C.c_int32), ("max_depth", C.c_int32), ("ucb_variant", C.c_int32),
+        ("resume", C.c_int32), ("reward_mode", C.c_int32), ("exploration", C.c_double),
+        ("seed", C.c_uint64), ("tree_offset", C.c_uint64),
+    ]
 
 _lock = threading.Lock()
 _lib = None

@@ -45,7 +45,7 @@ extern "C" const char* bk_last_error(void) { return g_err; }
 extern "C" const char* bk_version(void) { return "blokus_b200 r1 sm_100a (row-sliced warp-per-game)"; }
 
 __global__ void k_movegen_emit(const bk_state* __restrict__, const uint8_t* __restrict__, int, const uint32_t* __restrict__,
-                               uint16_t* __restrict__);
+                               uint32_t, uint32_t* __restrict__, uint16_t* __restrict__);
 #define BK_EMIT_SMEM_BYTES (8 * (32 * 57 * 4 + 2048 * 2))
 
 extern "C" int bk_init(int device) {
@@ -100,7 +100,8 @@ struct SmemRowSink {
 
 __global__ void __launch_bounds__(BK_THREADS)
 k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ players, int n,
-               const uint32_t* __restrict__ offsets, uint16_t* __restrict__ ids) {
+               const uint32_t* __restrict__ offsets, uint32_t cap, uint32_t* __restrict__ counts_out,
+               uint16_t* __restrict__ ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + (size_t)wib * EMIT_SMEM_PER_WARP);
@@ -126,21 +127,27 @@ k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ 
         for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(BK_FULL, incl, d); if (lane >= d) incl += v; }
         const uint32_t total = __shfl_sync(BK_FULL, incl, 31);
         uint32_t pos = incl - cnt;
-        const uint32_t base = offsets[i];
+        // CSR mode: state i owns ids[offsets[i] .. offsets[i+1]);  fixed mode (offsets == NULL): state i owns
+        // ids[i*cap .. (i+1)*cap) and a longer list is truncated (counts_out still reports the full length).
+        const size_t base = offsets ? (size_t)offsets[i] : (size_t)i * cap;
+        const uint32_t limit = offsets ? 0xFFFFFFFFu : cap;
+        if (counts_out && lane == 0) counts_out[i] = total;
         const bool staged = total <= EMIT_STAGE;
-        uint16_t* dst = staged ? stage : ids + base;
         for (int k = 0; k < EMIT_WORDS_PER_LANE; k++) {
             uint32_t bits = mine[k];
             const uint32_t idb = (uint32_t)(lane * EMIT_WORDS_PER_LANE + k) * 20u;
             while (bits) {
                 const int col = __ffs(bits) - 1;
                 bits &= bits - 1;
-                dst[pos++] = (uint16_t)(idb + col);
+                if (staged) stage[pos] = (uint16_t)(idb + col);
+                else if (pos < limit) ids[base + pos] = (uint16_t)(idb + col);
+                pos++;
             }
         }
         __syncwarp();
         if (staged) {
-            for (uint32_t k = lane; k < total; k += 32) ids[base + k] = stage[k];
+            const uint32_t m = total < limit ? total : limit;
+            for (uint32_t k = lane; k < m; k += 32) ids[base + k] = stage[k];
         }
         __syncwarp();
     }
@@ -212,6 +219,30 @@ k_is_move_legal(const bk_state* __restrict__ states, const uint8_t* __restrict__
     }
 }
 
+// Board.can_place_piece for an arbitrary cell set (engine/board.py:136-220): every cell empty and not
+// edge-adjacent to an own cell (subset of A), and some cell on a corner cell / the start corner (hits C).
+__global__ void __launch_bounds__(BK_THREADS)
+k_can_place_mask(const bk_state* __restrict__ states, const uint8_t* __restrict__ players,
+                 const uint64_t* __restrict__ masks, int n, uint8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s; load_state(states + i, lane, s);
+        const uint32_t p = players ? (players[i] & 3u) : s.to_move;
+        uint32_t A, C; make_masks(s, p, lane, A, C);
+        const uint64_t word = lane < BK_WORDS ? masks[(size_t)i * BK_WORDS + lane] : 0ull;
+        const int bitpos = lane * 20, wi = bitpos >> 6, off = bitpos & 63;
+        const uint64_t lo = __shfl_sync(BK_FULL, word, wi & 31), hi = __shfl_sync(BK_FULL, word, (wi + 1) & 31);
+        uint64_t v = lo >> off;
+        if (off) v |= hi << (64 - off);
+        const uint32_t m = lane < 20 ? ((uint32_t)v & BK_ROWMASK) : 0u;
+        const bool inside = !__any_sync(BK_FULL, (m & ~A) != 0);
+        const bool touches = __any_sync(BK_FULL, (m & C) != 0);
+        if (lane == 0) out[i] = (inside && touches) ? 1 : 0;
+    }
+}
+
 __global__ void __launch_bounds__(BK_THREADS)
 k_step(bk_state* __restrict__ states, const uint8_t* __restrict__ players, const uint16_t* __restrict__ ids,
        int n, uint8_t* __restrict__ okv, uint8_t* __restrict__ alive) {
@@ -266,7 +297,7 @@ k_scores(const bk_state* __restrict__ states, int n, int32_t* __restrict__ gs, i
 #define BK_PLAYOUT_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(BK_THREADS, BK_PLAYOUT_MIN_BLOCKS)
-k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int max_turns,
+k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int first_turn, int max_turns,
                   int32_t* __restrict__ gs, int32_t* __restrict__ bs, uint16_t* __restrict__ trace,
                   uint16_t* __restrict__ choice, bk_state* __restrict__ finals) {
     const int lane = threadIdx.x & 31;
@@ -278,8 +309,7 @@ k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint
         const uint64_t g = game_offset + (uint64_t)i;
         uint16_t* tr = trace ? trace + (size_t)i * BK_MAX_TURNS : nullptr;
         uint16_t* ch = choice ? choice + (size_t)i * BK_MAX_TURNS : nullptr;
-        if (tr) { uint32_t* t32 = reinterpret_cast<uint32_t*>(tr); t32[lane] = 0xFFFFFFFFu; if (lane < 16) t32[32 + lane] = 0xFFFFFFFFu; }
-        if (ch) { uint32_t* c32 = reinterpret_cast<uint32_t*>(ch); c32[lane] = 0xFFFFFFFFu; if (lane < 16) c32[32 + lane] = 0xFFFFFFFFu; }
+        for (int k = first_turn + lane; k < BK_MAX_TURNS; k += 32) { if (tr) tr[k] = BK_PASS; if (ch) ch[k] = BK_PASS; }
         __syncwarp();
         uint32_t dead = 0;
         // The reference loop stops the moment nobody can move (engine/game.py:182-214 runs after every
@@ -290,7 +320,7 @@ k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint
         uint32_t resume_to_move = s.to_move;   // side to move right after the last placement
         uint32_t cut_to_move = s.to_move;      // side to move when max_turns was reached
         bool still_alive = false;
-        for (uint32_t t = 0; dead != 0xFu; t++) {
+        for (uint32_t t = (uint32_t)first_turn; dead != 0xFu; t++) {
             const bool probing = t >= (uint32_t)max_turns;
             if (t == (uint32_t)max_turns) cut_to_move = s.to_move;
             const uint32_t p = s.to_move;
@@ -474,6 +504,64 @@ __global__ void k_tt_put(unsigned long long* keys, double* rewards, uint32_t log
 }
 
 // ---------------------------------------------------------------------------------------------
+// N1: HeuristicAgent move scores (agents/heuristic_agent.py:68-198), float64, evaluated BEFORE the placement:
+//   score = 1.0*size + 2.0*corners - 1.5*edge + 0.5*centre
+//   corners = sum over piece cells, over their in-board diagonal neighbours d: d empty and no orthogonal
+//             neighbour of d owned by the player  ==  d in the allowed mask A (duplicates counted, :118-138)
+//   edge    = #cells with min(r, c, 19-r, 19-c) <= 2, halved once move_count/100 >= 0.3 (:153-173)
+//   centre  = 1 - sqrt((ar-9.5)^2 + (ac-9.5)^2) / sqrt(2*9.5^2), from the ANCHOR (:185-198)
+// Explicit _rn intrinsics keep the compiler from contracting to FMA, so the doubles equal numpy's bit for bit.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double heuristic_score(const uint32_t* __restrict__ arows, uint32_t move_count, uint32_t id) {
+    const int o = id / 400, cell = id - o * 400, ar = cell / 20, ac = cell - ar * 20;
+    const int n = c_orient_ncells[o];
+    int corners = 0, edge = 0;
+    for (int i = 0; i < n; i++) {
+        const uint32_t rc = c_orient_cells[o * 5 + i];
+        const int r = ar + (int)(rc >> 4), c = ac + (int)(rc & 15);
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int nr = r + ((d & 2) ? 1 : -1), nc = c + ((d & 1) ? 1 : -1);
+            if (nr >= 0 && nr < 20 && nc >= 0 && nc < 20) corners += (arows[nr] >> nc) & 1u;
+        }
+        const int m = min(min(r, c), min(19 - r, 19 - c));
+        edge += (m <= 2);
+    }
+    double score = __dadd_rn(0.0, __dmul_rn(1.0, (double)n));
+    score = __dadd_rn(score, __dmul_rn(2.0, (double)corners));
+    const double progress = __ddiv_rn((double)move_count, 100.0);
+    const double edge_score = (progress < 0.3) ? (double)edge : __dmul_rn((double)edge, 0.5);
+    score = __dadd_rn(score, __dmul_rn(-1.5, edge_score));
+    const double dr = __dsub_rn((double)ar, 9.5), dc = __dsub_rn((double)ac, 9.5);
+    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc)));
+    const double maxd = __dsqrt_rn(__dmul_rn(2.0, __dmul_rn(9.5, 9.5)));
+    const double centre = __dsub_rn(1.0, __ddiv_rn(dist, maxd));
+    return __dadd_rn(score, __dmul_rn(0.5, centre));
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_heuristic_scores(const bk_state* __restrict__ states, const uint8_t* __restrict__ players,
+                   const uint32_t* __restrict__ offsets, const uint16_t* __restrict__ ids, int n,
+                   double* __restrict__ out) {
+    __shared__ uint32_t s_a[BK_WARPS][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s; load_state(states + i, lane, s);
+        const uint32_t p = players ? (players[i] & 3u) : s.to_move;
+        uint32_t A, C; make_masks(s, p, lane, A, C);
+        __syncwarp();
+        s_a[wib][lane] = A;
+        __syncwarp();
+        const uint32_t lo = offsets[i], hi = offsets[i + 1];
+        for (uint32_t k = lo + lane; k < hi; k += 32) out[k] = heuristic_score(s_a[wib], s.move_count, ids[k]);
+    }
+}
+
+#include "mcts.cuh"
+
+// ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
 #define LAUNCH_CHECK() CUDA_TRY(cudaGetLastError())
@@ -490,7 +578,16 @@ extern "C" int bk_movegen_emit(const bk_state* states, const uint8_t* players, i
                                uint16_t* move_ids, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids)), "bk_movegen_emit: null buffer");
     if (n == 0) return BK_OK;
-    k_movegen_emit<<<grid_for(n, 2), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, offsets, move_ids);
+    k_movegen_emit<<<grid_for(n, 2), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, offsets, 0u, nullptr, move_ids);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_movegen_fixed(const bk_state* states, const uint8_t* players, int n, uint32_t cap, uint32_t* counts,
+                                uint16_t* move_ids, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && cap > 0 && (n == 0 || (states && counts && move_ids)), "bk_movegen_fixed: bad argument");
+    if (n == 0) return BK_OK;
+    k_movegen_emit<<<grid_for(n, 2), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, nullptr, cap, counts, move_ids);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -522,6 +619,15 @@ extern "C" int bk_is_move_legal(const bk_state* states, const uint8_t* players, 
     return BK_OK;
 }
 
+extern "C" int bk_can_place_mask(const bk_state* states, const uint8_t* players, const uint64_t* cell_masks, int n,
+                                 uint8_t* out, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && cell_masks && out)), "bk_can_place_mask: null buffer");
+    if (n == 0) return BK_OK;
+    k_can_place_mask<<<grid_for(n, 4), BK_THREADS, 0, as_stream(stream)>>>(states, players, cell_masks, n, out);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
 extern "C" int bk_step(bk_state* states, const uint8_t* players, const uint16_t* move_ids, int n, uint8_t* ok,
                        uint8_t* alive, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && move_ids)), "bk_step: null buffer");
@@ -540,15 +646,16 @@ extern "C" int bk_scores(const bk_state* states, int n, int32_t* game_scores, in
 }
 
 extern "C" int bk_playout(const bk_state* start_states, int n, uint64_t seed, uint64_t game_offset, int policy,
-                          int max_turns, int32_t* game_scores, int32_t* board_scores, uint16_t* trace,
+                          int first_turn, int max_turns, int32_t* game_scores, int32_t* board_scores, uint16_t* trace,
                           uint16_t* choice, bk_state* final_states, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0, "bk_playout: negative n");
     REQUIRE(max_turns >= 0 && max_turns <= BK_MAX_TURNS, "bk_playout: max_turns out of range");
     if (policy != BK_POLICY_UNIFORM) return fail(BK_ERR_ARG, "%s", "bk_playout: unknown policy");
     if (n == 0) return BK_OK;
     if (max_turns == 0) max_turns = BK_MAX_TURNS;
+    REQUIRE(first_turn >= 0 && first_turn <= max_turns, "bk_playout: first_turn out of range");
     k_playout_uniform<<<grid_for(n, BK_PLAYOUT_MIN_BLOCKS), BK_THREADS, 0, as_stream(stream)>>>(
-        start_states, n, seed, game_offset, max_turns, game_scores, board_scores, trace, choice, final_states);
+        start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -628,5 +735,42 @@ extern "C" int bk_tt_stats(bk_tt* tt, uint64_t* out_host, void* stream) {
     CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
     out_host[0] = (uint64_t)1 << tt->log2_slots;
     out_host[1] = (uint64_t)occ;
+    return BK_OK;
+}
+
+extern "C" int64_t bk_mcts_workspace_bytes(const bk_mcts_params* params) {
+    if (!params || params->iterations_total <= 0) return 0;
+    return (int64_t)mcts_layout(params->iterations_total).total;
+}
+
+extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, const bk_mcts_params* params, bk_tt* tt,
+                              const uint64_t* zobrist_table, void* workspace, int64_t workspace_bytes, int max_root_moves,
+                              int32_t* root_visits, int64_t* root_reward, uint32_t* root_counts, uint16_t* root_move_ids,
+                              uint32_t* status, void* stream) {
+    REQUIRE_INIT();
+    REQUIRE(roots && params && workspace && n_roots > 0 && n_trees > 0 && max_root_moves >= 0, "bk_mcts_search: bad argument");
+    REQUIRE(params->iterations >= 0 && params->iterations_total > 0 && params->iterations_total <= 60000,
+            "bk_mcts_search: iterations_total must be in [1, 60000]");
+    REQUIRE(params->rollout_policy == BK_POLICY_UNIFORM, "bk_mcts_search: unknown rollout policy");
+    REQUIRE(!tt || zobrist_table, "bk_mcts_search: a transposition table needs a Zobrist table");
+    const MctsLayout L = mcts_layout(params->iterations_total);
+    if ((int64_t)L.total * n_trees > workspace_bytes) return fail(BK_ERR_CAPACITY, "%s", "bk_mcts_search: workspace too small");
+    MctsTT t; t.keys = nullptr; t.rewards = nullptr; t.occupied = nullptr; t.log2_slots = 0; t.zobrist = zobrist_table;
+    if (tt) { t.keys = tt->keys; t.rewards = tt->rewards; t.occupied = tt->occupied; t.log2_slots = tt->log2_slots; }
+    const int cap = g_sms * 16;
+    const int grid = n_trees < cap ? n_trees : cap;
+    k_mcts<<<grid, BK_MCTS_THREADS, 0, as_stream(stream)>>>(roots, n_roots, n_trees, *params, t,
+        reinterpret_cast<unsigned char*>(workspace), params->resume, max_root_moves, root_visits,
+        reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_heuristic_scores(const bk_state* states, const uint8_t* players, const uint32_t* offsets,
+                                   const uint16_t* move_ids, int n, double* scores, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids && scores)), "bk_heuristic_scores: null buffer");
+    if (n == 0) return BK_OK;
+    k_heuristic_scores<<<grid_for(n, 4), BK_THREADS, 0, as_stream(stream)>>>(states, players, offsets, move_ids, n, scores);
+    LAUNCH_CHECK();
     return BK_OK;
 }

@@ -1,0 +1,241 @@
+// mcts.cuh -- K5: UCT search with device rollouts, one warp per tree (root-parallel across warps/GPUs).
+//
+// Mirrors MCTSAgent of the reference (mcts/mcts_agent.py):
+//   iteration (:360-382)  select -> expand one child -> simulate -> back-propagate the same reward to the root
+//   selection (:384-406)  descend while the node has no untried move and has children; child = first argmax of
+//                         Q/n + c*sqrt(ln N_parent / n)   (:68-89; FastMCTS variant c*sqrt(2 ln N / n), fast_mcts_agent.py:45-53)
+//   expansion (:113-145)  pops the LAST untried move; untried moves are the node's legal moves in ascending id
+//                         order here, so the k-th expansion of a node takes legal move number n_legal-1-k
+//   simulation (:408-437) transposition-table probe on the full-board Zobrist key, else rollout and store
+//   rollout (:470-554)    at most max_rollout_moves plies; stops at the first player without a move (no passes);
+//                         reward = Board.get_score(node player) after - before
+//   result (:180-191)     visits / reward sums of the root's children
+// A tree never stores move lists: a node keeps n_legal and n_expanded, and the wanted move is re-derived with
+// the row-sliced generator (count per orientation -> orientation -> row -> column).
+#pragma once
+#include "movegen_core.cuh"
+// (included by blokus_b200.cu after zobrist_of / tt_lookup / tt_insert are defined)
+
+struct MctsLayout {            // byte offsets inside one tree's workspace slice
+    uint32_t max_nodes, pool_slots;
+    size_t off_states, off_parent, off_visits, off_reward, off_child_base, off_n_legal, off_n_expanded,
+           off_move, off_pool, off_header, total;
+};
+
+__host__ __device__ inline size_t bk_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline MctsLayout mcts_layout(int iterations_total) {
+    MctsLayout L;
+    const size_t T = (size_t)(iterations_total > 0 ? iterations_total : 1);
+    L.max_nodes = (uint32_t)(T + 1);
+    // a node first expanded at iteration t can still gain at most T - t children
+    const size_t pool = T * (T + 1) / 2 + 1;
+    L.pool_slots = (uint32_t)(pool > 0xFFFFFF00ull ? 0xFFFFFF00ull : pool);
+    size_t o = 0;
+    L.off_states = o;      o += (size_t)L.max_nodes * sizeof(bk_state);
+    L.off_reward = o;      o += (size_t)L.max_nodes * 8;
+    L.off_parent = o;      o += (size_t)L.max_nodes * 4;
+    L.off_visits = o;      o += (size_t)L.max_nodes * 4;
+    L.off_child_base = o;  o += (size_t)L.max_nodes * 4;
+    L.off_pool = o;        o += (size_t)L.pool_slots * 4;
+    L.off_n_legal = o;     o += (size_t)L.max_nodes * 2;
+    L.off_n_expanded = o;  o += (size_t)L.max_nodes * 2;
+    L.off_move = o;        o += (size_t)L.max_nodes * 2;
+    o = bk_align_up(o, 8);
+    L.off_header = o;      o += 64;
+    L.total = bk_align_up(o, 256);
+    return L;
+}
+
+struct MctsHeader {            // persistent between launches of the same search (resume)
+    uint32_t n_nodes, pool_used, iterations_done, draws, overflow, root_children, root_player;
+    int32_t root_score;
+};
+
+struct MctsTT {                // optional transposition table (mcts/zobrist.py:155-220); keys == nullptr: off
+    unsigned long long* keys; double* rewards; unsigned long long* occupied; uint32_t log2_slots;
+    const uint64_t* zobrist;   // 2088-entry table, reference order
+};
+
+__device__ __noinline__ Totals gen_totals(uint32_t A, uint32_t C, uint32_t used, int lane) {
+    PackSink sink;
+    bk_gen_all(A, C, used, sink);
+    return reduce_totals(sink, lane);
+}
+
+__device__ __forceinline__ int32_t board_score_of(const WarpState& s, uint32_t q) {
+    const uint32_t cells = __reduce_add_sync(BK_FULL, (uint32_t)__popc(sel4(s.P, q)));
+    return (int32_t)(cells + (((sel4(s.used, q) & BK_ALL_PIECES) == BK_ALL_PIECES) ? 15u : 0u));
+}
+
+#define BK_MCTS_THREADS 32   /* one warp = one tree per CTA, so a handful of trees still spreads over the SMs */
+
+__global__ void __launch_bounds__(BK_MCTS_THREADS)
+k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_params prm, MctsTT tt,
+       unsigned char* __restrict__ workspace, int resume, int max_root_moves,
+       int32_t* __restrict__ out_visits, long long* __restrict__ out_reward, uint32_t* __restrict__ out_counts,
+       uint16_t* __restrict__ out_moves, uint32_t* __restrict__ out_status) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const MctsLayout L = mcts_layout(prm.iterations_total);
+    for (int tree = warp; tree < n_trees; tree += nwarps) {
+        unsigned char* base = workspace + (size_t)tree * L.total;
+        bk_state* states = reinterpret_cast<bk_state*>(base + L.off_states);
+        long long* reward = reinterpret_cast<long long*>(base + L.off_reward);
+        int32_t* parent = reinterpret_cast<int32_t*>(base + L.off_parent);
+        int32_t* visits = reinterpret_cast<int32_t*>(base + L.off_visits);
+        uint32_t* child_base = reinterpret_cast<uint32_t*>(base + L.off_child_base);
+        uint32_t* pool = reinterpret_cast<uint32_t*>(base + L.off_pool);
+        uint16_t* n_legal = reinterpret_cast<uint16_t*>(base + L.off_n_legal);
+        uint16_t* n_expanded = reinterpret_cast<uint16_t*>(base + L.off_n_expanded);
+        uint16_t* move_of = reinterpret_cast<uint16_t*>(base + L.off_move);
+        MctsHeader* hdr = reinterpret_cast<MctsHeader*>(base + L.off_header);
+        const uint64_t tree_id = prm.tree_offset + (uint64_t)tree;
+        // per-tree salt keeps concurrently searched trees from reading each other's cached rewards, so the
+        // result of a tree depends on (seed, tree id) only
+        const uint64_t salt = tree_id * 0xD6E8FEB86659FD93ull;
+
+        uint32_t n_nodes, pool_used, iter_done, draws, overflow = 0, root_player;
+        int32_t root_score;
+        WarpState s;
+        if (!resume) {
+            load_state(roots + (tree % n_roots), lane, s);
+            uint32_t A, C; make_masks(s, s.to_move, lane, A, C);
+            const Totals t0 = gen_totals(A, C, sel4(s.used, s.to_move), lane);
+            store_state(states + 0, lane, s);
+            if (lane == 0) {
+                parent[0] = -1; visits[0] = 0; reward[0] = 0; child_base[0] = 0xFFFFFFFFu;
+                n_legal[0] = (uint16_t)t0.n; n_expanded[0] = 0; move_of[0] = 0xFFFF;
+            }
+            n_nodes = 1; pool_used = 0; iter_done = 0; draws = 0;
+            root_player = s.to_move; root_score = board_score_of(s, s.to_move);
+            __syncwarp();
+        } else {
+            n_nodes = hdr->n_nodes; pool_used = hdr->pool_used; iter_done = hdr->iterations_done;
+            draws = hdr->draws; overflow = hdr->overflow; root_player = hdr->root_player; root_score = hdr->root_score;
+        }
+
+        for (int it = 0; it < prm.iterations && !overflow; it++, iter_done++) {
+            // ---- selection (mcts_agent.py:384-406)
+            uint32_t node = 0, depth = 0;
+            while (true) {
+                const uint32_t nl = n_legal[node], ne = n_expanded[node];
+                const bool may_expand = ne < nl && (prm.max_depth <= 0 || (int)depth < prm.max_depth);
+                if (may_expand || ne == 0) break;
+                const double logN = log((double)visits[node]) * (prm.ucb_variant ? 2.0 : 1.0);
+                const uint32_t cb = child_base[node];
+                double best = -1.0; uint32_t best_k = 0xFFFFFFFFu; bool have = false;
+                for (uint32_t k = lane; k < ne; k += 32) {
+                    const uint32_t ch = pool[cb + k];
+                    const double v = (double)visits[ch];
+                    double u;
+                    if (visits[ch] == 0) u = __longlong_as_double(0x7FF0000000000000ll);
+                    else u = __dadd_rn(__ddiv_rn((double)reward[ch], v), __dmul_rn(prm.exploration, sqrt(__ddiv_rn(logN, v))));
+                    if (!have || u > best) { best = u; best_k = k; have = true; }
+                }
+                // warp argmax, ties -> smallest k (Python's max keeps the first maximal child)
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const double ob = __shfl_xor_sync(BK_FULL, best, d);
+                    const uint32_t ok = __shfl_xor_sync(BK_FULL, best_k, d);
+                    const bool oh = ok != 0xFFFFFFFFu;
+                    if (oh && (best_k == 0xFFFFFFFFu || ob > best || (ob == best && ok < best_k))) { best = ob; best_k = ok; }
+                }
+                node = pool[cb + best_k];
+                depth++;
+            }
+            // ---- expansion (mcts_agent.py:113-145): pop the last untried move of `node`
+            load_state(states + node, lane, s);
+            {
+                const uint32_t nl = n_legal[node], ne = n_expanded[node];
+                if (ne < nl && (prm.max_depth <= 0 || (int)depth < prm.max_depth)) {
+                    const uint32_t p = s.to_move;
+                    uint32_t A, C; make_masks(s, p, lane, A, C);
+                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane);
+                    int o, row, col;
+                    const uint32_t id = select_move(tot, nl - 1 - ne, A, C, lane, o, row, col);
+                    place_move(s, p, o, row, col, lane);
+                    uint32_t A2, C2; make_masks(s, s.to_move, lane, A2, C2);
+                    const Totals tc = gen_totals(A2, C2, sel4(s.used, s.to_move), lane);
+                    uint32_t cb = child_base[node];
+                    if (cb == 0xFFFFFFFFu) {
+                        const uint32_t remaining = (uint32_t)prm.iterations_total - iter_done;
+                        const uint32_t want = nl < remaining ? nl : remaining;
+                        cb = pool_used;
+                        if (pool_used + want > L.pool_slots) overflow = 1;
+                        pool_used += want;
+                    }
+                    if (n_nodes >= L.max_nodes) overflow = 1;
+                    if (overflow) break;
+                    const uint32_t child = n_nodes++;
+                    store_state(states + child, lane, s);
+                    if (lane == 0) {
+                        child_base[node] = cb;
+                        pool[cb + ne] = child;
+                        n_expanded[node] = (uint16_t)(ne + 1);
+                        parent[child] = (int32_t)node; visits[child] = 0; reward[child] = 0;
+                        child_base[child] = 0xFFFFFFFFu; n_legal[child] = (uint16_t)tc.n; n_expanded[child] = 0;
+                        move_of[child] = (uint16_t)id;
+                    }
+                    node = child;
+                    depth++;
+                    __syncwarp();
+                }
+            }
+            // ---- simulation (mcts_agent.py:408-437); `s` holds the state of `node`
+            long long r = 0;
+            bool cached = false;
+            uint64_t key = 0;
+            if (tt.keys) {
+                key = zobrist_of(s, tt.zobrist, lane) ^ salt;
+                double rv = 0.0;
+                if (tt_lookup(tt.keys, tt.rewards, tt.log2_slots, key, rv)) { r = (long long)rv; cached = true; }
+            }
+            if (!cached) {
+                const uint32_t me = prm.reward_mode ? root_player : s.to_move;      // node.player (mcts_agent.py:483)
+                const int32_t before = prm.reward_mode ? root_score : board_score_of(s, me);
+                const int limit = prm.max_rollout_moves > 0 ? prm.max_rollout_moves : 1 << 30;
+                for (int ply = 0; ply < limit; ply++) {
+                    const uint32_t p = s.to_move;
+                    uint32_t A, C; make_masks(s, p, lane, A, C);
+                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane);
+                    if (tot.n == 0) break;                       // no passes inside a rollout (:488-489)
+                    const uint32_t rnd = philox_draw(prm.seed, tree_id, draws++, 1);
+                    int o, row, col;
+                    select_move(tot, __umulhi(rnd, tot.n), A, C, lane, o, row, col);
+                    place_move(s, p, o, row, col, lane);
+                }
+                r = (long long)(board_score_of(s, me) - before);
+                if (tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, (double)r);
+            }
+            // ---- back-propagation (mcts_agent.py:572-582)
+            if (lane == 0) {
+                for (int32_t v = (int32_t)node; v >= 0; v = parent[v]) { visits[v] += 1; reward[v] += r; }
+            }
+            __syncwarp();
+        }
+
+        if (lane == 0) {
+            hdr->n_nodes = n_nodes; hdr->pool_used = pool_used; hdr->iterations_done = iter_done;
+            hdr->draws = draws; hdr->overflow = overflow; hdr->root_children = n_expanded[0];
+            hdr->root_player = root_player; hdr->root_score = root_score;
+            if (out_status) out_status[tree] = overflow;
+            if (out_counts) out_counts[tree] = n_legal[0];
+        }
+        __syncwarp();
+        // ---- root statistics by ascending legal-move rank (child k of the root is rank n_legal-1-k)
+        const uint32_t nl0 = n_legal[0], ne0 = n_expanded[0], cb0 = child_base[0];
+        for (uint32_t rank = lane; rank < (uint32_t)max_root_moves; rank += 32) {
+            int32_t v = 0; long long w = 0; uint16_t m = 0xFFFF;
+            if (rank < nl0) {
+                const uint32_t k = nl0 - 1 - rank;
+                if (k < ne0) { const uint32_t ch = pool[cb0 + k]; v = visits[ch]; w = reward[ch]; m = move_of[ch]; }
+            }
+            const size_t oi = (size_t)tree * max_root_moves + rank;
+            if (out_visits) out_visits[oi] = v;
+            if (out_reward) out_reward[oi] = w;
+            if (out_moves) out_moves[oi] = m;
+        }
+    }
+}

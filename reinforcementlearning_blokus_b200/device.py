@@ -98,6 +98,37 @@ def movegen(states: torch.Tensor, players: Optional[torch.Tensor] = None) -> Tup
     return counts, offsets, ids[:total]
 
 
+def movegen_fixed(states: torch.Tensor, cap: int, players: Optional[torch.Tensor] = None,
+                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One-kernel generation into fixed slots: (counts int32[N], ids uint16[N, cap]); a list longer than
+    cap is cut (counts still holds the full length)."""
+    n = _check_states(states)
+    _check_players(players, n)
+    lib = _lib_for(states)
+    if out is None:
+        counts = torch.empty(n, dtype=torch.int32, device=states.device)
+        ids = torch.empty((n, cap), dtype=torch.uint16, device=states.device)
+    else:
+        counts, ids = out
+    check(lib.bk_movegen_fixed(_ptr(states), _ptr(players), n, int(cap), _ptr(counts), _ptr(ids), _stream()))
+    _count()
+    return counts, ids
+
+
+def can_place_mask(states: torch.Tensor, cell_masks: torch.Tensor, players: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Board.can_place_piece for arbitrary cell sets given as 400-bit masks int64[N,7] (engine/board.py:136)."""
+    n = _check_states(states)
+    _check_players(players, n)
+    if not (cell_masks.is_cuda and cell_masks.dtype in (torch.int64, torch.uint64) and tuple(cell_masks.shape) == (n, 7)
+            and cell_masks.is_contiguous()):
+        raise ValueError("cell_masks must be a contiguous CUDA 64-bit tensor of shape [N, 7]")
+    lib = _lib_for(states)
+    out = torch.empty(n, dtype=torch.uint8, device=states.device)
+    check(lib.bk_can_place_mask(_ptr(states), _ptr(players), _ptr(cell_masks), n, _ptr(out), _stream()))
+    _count()
+    return out
+
+
 def movegen_bitmap(states: torch.Tensor, players: Optional[torch.Tensor] = None) -> torch.Tensor:
     """int32[N, 91*20]: word o*20+row has bit col set iff move (o,row,col) is legal."""
     n = _check_states(states)
@@ -159,10 +190,12 @@ def scores(states: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 # ---- K2 --------------------------------------------------------------------------------------
 def playout(n: int, seed: int, game_offset: int = 0, start_states: Optional[torch.Tensor] = None,
-            policy: int = POLICY_UNIFORM, max_turns: int = 0, want_trace: bool = False,
+            policy: int = POLICY_UNIFORM, max_turns: int = 0, first_turn: int = 0, want_trace: bool = False,
             want_choice: bool = False, want_final: bool = False, want_board_scores: bool = True,
             out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     """Play n games to the end on the device.  Game i has global index game_offset+i (its Philox stream).
+    Turns first_turn .. max_turns-1 are played (0 = to the end); segments chained through final_states give
+    the same game as one call.
 
     `out` may carry preallocated tensors from a previous call (keys as returned) to avoid reallocation.
     """
@@ -187,10 +220,22 @@ def playout(n: int, seed: int, game_offset: int = 0, start_states: Optional[torc
     tr = buf("trace", (n, BK_MAX_TURNS), torch.uint16, want_trace)
     ch = buf("choice", (n, BK_MAX_TURNS), torch.uint16, want_choice)
     fin = buf("final_states", (n, STATE_BYTES), torch.uint8, want_final)
-    check(lib.bk_playout(_ptr(start_states), n, int(seed) & (2**64 - 1), int(game_offset), int(policy), int(max_turns),
+    check(lib.bk_playout(_ptr(start_states), n, int(seed) & (2**64 - 1), int(game_offset), int(policy), int(first_turn), int(max_turns),
                          _ptr(gs), _ptr(bs), _ptr(tr), _ptr(ch), _ptr(fin), _stream()))
     _count()
     return res
+
+
+def heuristic_scores(states: torch.Tensor, offsets: torch.Tensor, move_ids: torch.Tensor,
+                     players: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """float64 HeuristicAgent._evaluate_move score of every listed move (agents/heuristic_agent.py:68-103)."""
+    n = _check_states(states)
+    _check_players(players, n)
+    lib = _lib_for(states)
+    out = torch.empty(max(move_ids.numel(), 1), dtype=torch.float64, device=states.device)
+    check(lib.bk_heuristic_scores(_ptr(states), _ptr(players), _ptr(offsets), _ptr(move_ids), n, _ptr(out), _stream()))
+    _count()
+    return out[:move_ids.numel()]
 
 
 # ---- K4 --------------------------------------------------------------------------------------

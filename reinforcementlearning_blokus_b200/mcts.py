@@ -1,0 +1,332 @@
+"""Device UCT search (K5) behind the reference's search interfaces.
+
+``DeviceUCT`` is the batched engine (n_trees root-parallel trees, one warp each, see csrc/mcts.cuh);
+``ZobristHash`` / ``TranspositionTable`` follow ``mcts/zobrist.py``; ``MCTSAgent`` follows
+``mcts/mcts_agent.py:194-341`` (constructor arguments, ``select_action``, ``stats``, ``reset``,
+``set_seed``, ``get_action_info``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import device as dev
+from .board import Board, Player
+from .move_generator import Move, get_shared_generator
+from .state import STATE_BYTES
+
+MAX_ROOT_MOVES = 2048
+
+
+# ---------------------------------------------------------------------------------------------------
+# Zobrist keys and transposition table (mcts/zobrist.py)
+# ---------------------------------------------------------------------------------------------------
+class ZobristHash:
+    """64-bit keys drawn exactly as the reference draws them: ``np.random.RandomState(seed)`` and one
+    ``randint(0, 2**64, dtype=uint64)`` per entry in the order cells[20][20][5], turn[4], pieces[4][21]
+    (mcts/zobrist.py:33-68).  Hashing runs on the device (csrc: zobrist_of)."""
+
+    def __init__(self, board_size: int = 20, num_players: int = 4, seed: Optional[int] = None):
+        if board_size != 20 or num_players != 4:
+            raise ValueError("the device tables are built for the 20x20, 4-player game")
+        self.board_size, self.num_players = board_size, num_players
+        self.rng = np.random.RandomState(seed)
+        n = board_size * board_size * (num_players + 1)
+        flat = np.array([self.rng.randint(0, 2**64, dtype=np.uint64) for _ in range(n + num_players + num_players * 21)],
+                        dtype=np.uint64)
+        self.position_player_hashes = flat[:n].reshape(board_size, board_size, num_players + 1)
+        self.player_turn_hashes = flat[n:n + num_players]
+        self.piece_used_hashes = flat[n + num_players:].reshape(num_players, 21)
+        self.table = flat
+        self._dev: Optional[torch.Tensor] = None
+
+    def device_table(self) -> torch.Tensor:
+        if self._dev is None:
+            self._dev = torch.from_numpy(self.table.view(np.int64).copy()).cuda()
+        return self._dev
+
+    def hash_board(self, board: Board) -> int:
+        st = dev.to_device(np.atleast_1d(board.to_packed()))
+        return int(dev.zobrist_hash(st, self.device_table()).cpu().numpy().view(np.uint64)[0])
+
+    def hash_states(self, states: torch.Tensor) -> torch.Tensor:
+        return dev.zobrist_hash(states, self.device_table())
+
+    def get_hash_info(self) -> Dict[str, Any]:
+        return {"board_size": self.board_size, "num_players": self.num_players, "hash_bits": 64,
+                "total_positions": self.board_size * self.board_size, "total_pieces": 21}
+
+
+class TranspositionTable:
+    """key -> {"reward": r} with the reference's method names (mcts/zobrist.py:155-220), stored in the
+    open-addressing device table the search kernel probes.  ``max_size`` rounds up to a power of two."""
+
+    def __init__(self, max_size: int = 1000000):
+        self.max_size = max_size
+        self._t = dev.DeviceTranspositionTable(max(4, int(np.ceil(np.log2(max(16, 2 * max_size))))))
+        self.access_count = 0
+        self.hit_count = 0
+
+    @property
+    def device(self) -> dev.DeviceTranspositionTable:
+        return self._t
+
+    def get(self, hash_value: int) -> Optional[Dict]:
+        self.access_count += 1
+        k = torch.tensor([np.uint64(hash_value).astype(np.int64)], dtype=torch.int64, device="cuda")
+        r, f = self._t.get(k)
+        if int(f.item()):
+            self.hit_count += 1
+            return {"reward": float(r.item())}
+        return None
+
+    def put(self, hash_value: int, entry: Dict):
+        k = torch.tensor([np.uint64(hash_value).astype(np.int64)], dtype=torch.int64, device="cuda")
+        self._t.put(k, torch.tensor([float(entry["reward"])], dtype=torch.float64, device="cuda"))
+
+    def clear(self):
+        self._t.clear()
+        self.access_count = 0
+        self.hit_count = 0
+
+    def __len__(self):
+        return self._t.stats()["size"]
+
+    def get_stats(self) -> Dict[str, float]:
+        return {"size": len(self), "max_size": self.max_size, "access_count": self.access_count,
+                "hit_count": self.hit_count, "hit_rate": self.hit_count / max(self.access_count, 1)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# the device search engine
+# ---------------------------------------------------------------------------------------------------
+class DeviceUCT:
+    """n_trees independent UCT trees over the same (or a few) roots; results per tree by root-move rank."""
+
+    def __init__(self, iterations_total: int, n_trees: int = 1, max_rollout_moves: int = 50, max_depth: int = 0,
+                 ucb_variant: int = 0, exploration: float = 1.414, seed: int = 0, tree_offset: int = 0,
+                 reward_mode: int = 0, tt: Optional[dev.DeviceTranspositionTable] = None, zobrist: Optional[ZobristHash] = None,
+                 max_root_moves: int = MAX_ROOT_MOVES):
+        if not torch.cuda.is_available():
+            raise _lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
+        self.lib = _lib.init(torch.cuda.current_device())
+        self.p = _lib.MctsParams(iterations=0, iterations_total=int(iterations_total),
+                                 max_rollout_moves=int(max_rollout_moves), rollout_policy=0, max_depth=int(max_depth),
+                                 ucb_variant=int(ucb_variant), resume=0, reward_mode=int(reward_mode), exploration=float(exploration),
+                                 seed=int(seed) & (2**64 - 1), tree_offset=int(tree_offset))
+        self.n_trees = int(n_trees)
+        self.max_root_moves = int(max_root_moves)
+        self.tt, self.zobrist = tt, zobrist
+        if tt is not None and zobrist is None:
+            raise ValueError("a transposition table needs a ZobristHash")
+        per_tree = int(self.lib.bk_mcts_workspace_bytes(C.byref(self.p)))
+        self.ws_bytes = per_tree * self.n_trees
+        d = torch.device("cuda", torch.cuda.current_device())
+        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=d)
+        m = self.max_root_moves
+        self.visits = torch.zeros((self.n_trees, m), dtype=torch.int32, device=d)
+        self.reward = torch.zeros((self.n_trees, m), dtype=torch.int64, device=d)
+        self.moves = torch.zeros((self.n_trees, m), dtype=torch.uint16, device=d)
+        self.counts = torch.zeros(self.n_trees, dtype=torch.int32, device=d)
+        self.status = torch.zeros(self.n_trees, dtype=torch.int32, device=d)
+        self.iterations_done = 0
+        self._roots = None
+
+    def search(self, roots: Optional[torch.Tensor], iterations: int, resume: bool = False) -> Dict[str, torch.Tensor]:
+        """Run `iterations` more iterations on every tree (fresh trees from `roots` unless resume)."""
+        if not resume:
+            if roots is None:
+                raise ValueError("roots required for a fresh search")
+            self._roots = roots.contiguous()
+            self.iterations_done = 0
+        if self.iterations_done + iterations > self.p.iterations_total:
+            raise ValueError("search exceeds iterations_total")
+        self.p.iterations = int(iterations)
+        self.p.resume = 1 if resume else 0
+        n_roots = self._roots.shape[0]
+        check = _lib.check
+        check(self.lib.bk_mcts_search(
+            self._roots.data_ptr(), n_roots, self.n_trees, C.byref(self.p),
+            self.tt.handle if self.tt is not None else None,
+            self.zobrist.device_table().data_ptr() if self.zobrist is not None else None,
+            self.workspace.data_ptr(), self.ws_bytes, self.max_root_moves,
+            self.visits.data_ptr(), self.reward.data_ptr(), self.counts.data_ptr(), self.moves.data_ptr(),
+            self.status.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        dev._count()
+        self.iterations_done += iterations
+        return {"visits": self.visits, "reward": self.reward, "moves": self.moves, "counts": self.counts,
+                "status": self.status}
+
+
+def _root_state(board: Board, player: Player) -> torch.Tensor:
+    s = board.to_packed()
+    s["to_move"] = player.value - 1          # MCTSNode(board, player): the root player moves (mcts_agent.py:325)
+    return dev.to_device(np.atleast_1d(s))
+
+
+def _best_by_visits_creation_order(visits: np.ndarray, n_root: int) -> int:
+    """Rank of the reference's get_best_move(): first child with max visits in creation order; children are
+    created from the last legal move to the first (expand() pops), so ties go to the highest rank."""
+    best, best_v = -1, -1
+    for rank in range(n_root - 1, -1, -1):
+        if visits[rank] > best_v:
+            best, best_v = rank, int(visits[rank])
+    return best
+
+
+# ---------------------------------------------------------------------------------------------------
+# MCTSAgent (mcts/mcts_agent.py:194-632)
+# ---------------------------------------------------------------------------------------------------
+class MCTSAgent:
+    """UCT agent; every simulation (select/expand/rollout/backprop) runs in one device kernel.
+
+    Same constructor arguments as the reference.  Differences, all documented in DESIGN.md: rollouts draw
+    uniformly with Philox (``rollout_agent`` objects are accepted for interface compatibility but only their
+    kind matters); the learned-evaluator options (OUT OF SCOPE in SURVEY.md section 2) raise if enabled;
+    ``num_trees`` > 1 adds root-parallel trees whose root statistics are summed.
+    """
+
+    def __init__(self, iterations: int = 1000, time_limit: Optional[float] = None, exploration_constant: float = 1.414,
+                 rollout_agent=None, use_transposition_table: bool = True, seed: Optional[int] = None,
+                 learned_model_path: Optional[str] = None, leaf_evaluation_enabled: bool = False,
+                 progressive_bias_enabled: bool = False, progressive_bias_weight: float = 0.25,
+                 potential_shaping_enabled: bool = False, potential_shaping_gamma: float = 1.0,
+                 potential_shaping_weight: float = 1.0, potential_mode: str = "prob", max_rollout_moves: int = 50,
+                 num_trees: int = 1):
+        if potential_mode not in {"prob", "logit"}:
+            raise ValueError("potential_mode must be either 'prob' or 'logit'.")
+        if int(max_rollout_moves) <= 0:
+            raise ValueError("max_rollout_moves must be > 0.")
+        if leaf_evaluation_enabled or progressive_bias_enabled or potential_shaping_enabled or learned_model_path:
+            raise NotImplementedError("learned evaluator options are outside the B200 hot path (SURVEY.md section 2)")
+        self.iterations = iterations
+        self.time_limit = time_limit
+        self.exploration_constant = exploration_constant
+        self.use_transposition_table = use_transposition_table
+        self.max_rollout_moves = int(max_rollout_moves)
+        self.num_trees = int(num_trees)
+        self.seed = 0 if seed is None else int(seed)
+        self.move_generator = get_shared_generator()
+        self.zobrist_hash = ZobristHash(seed=seed)
+        self.rollout_agent = rollout_agent
+        self.transposition_table = TranspositionTable() if use_transposition_table else None
+        self._searches = 0
+        self.reset_stats()
+
+    def reset_stats(self):
+        self.stats = {"iterations_run": 0, "time_elapsed": 0.0, "transposition_hits": 0, "rollout_rewards": [],
+                      "leaf_eval_calls": 0, "progressive_bias_updates": 0, "potential_shaping_terms": [],
+                      "evaluator_errors": 0}
+
+    def _engine(self, total: int) -> DeviceUCT:
+        tt = self.transposition_table.device if self.transposition_table is not None else None
+        # every search of this agent gets its own block of Philox streams
+        offset = self._searches * max(self.num_trees, 1)
+        self._searches += 1
+        return DeviceUCT(total, n_trees=self.num_trees, max_rollout_moves=self.max_rollout_moves,
+                         exploration=self.exploration_constant, seed=self.seed, tree_offset=offset, tt=tt,
+                         zobrist=self.zobrist_hash if tt is not None else None)
+
+    def search_root(self, board: Board, player: Player) -> Dict[str, np.ndarray]:
+        """Root statistics (visits, reward sums) by ascending legal-move rank, summed over the trees."""
+        start = time.time()
+        root = _root_state(board, player)
+        if self.time_limit:
+            chunk, cap = 64, 60000
+            eng = self._engine(cap)
+            done = 0
+            res = eng.search(root, chunk)
+            done += chunk
+            torch.cuda.synchronize()
+            while time.time() - start < self.time_limit and done + chunk <= cap:
+                res = eng.search(None, chunk, resume=True)
+                done += chunk
+                torch.cuda.synchronize()
+        else:
+            eng = self._engine(max(1, int(self.iterations)))
+            res = eng.search(root, int(self.iterations))
+            done = int(self.iterations)
+        if int(res["status"].max().item()):
+            raise _lib.BlokusB200Error("MCTS workspace exhausted")
+        n_root = int(res["counts"][0].item())
+        visits = res["visits"][:, :n_root].sum(dim=0).cpu().numpy()
+        reward = res["reward"][:, :n_root].sum(dim=0).cpu().numpy()
+        self.stats["iterations_run"] = done
+        self.stats["time_elapsed"] = time.time() - start
+        return {"visits": visits, "reward": reward, "n_root": n_root}
+
+    def select_action(self, board: Board, player: Player, legal_moves: List[Move]) -> Optional[Move]:
+        if not legal_moves:
+            return None
+        if len(legal_moves) == 1:
+            return legal_moves[0]
+        r = self.search_root(board, player)
+        if self.num_trees == 1:
+            rank = _best_by_visits_creation_order(r["visits"], r["n_root"])
+        else:
+            rank = int(np.argmax(r["visits"]))          # root-parallel: max summed visits, lowest id on ties
+        ids = sorted(m.to_id() for m in legal_moves)            # rank <-> move: ascending canonical id
+        if len(ids) != r["n_root"]:
+            ids = self.move_generator.get_legal_move_ids(board, player)
+        best = Move.from_id(int(ids[rank]))
+        if self.transposition_table is not None and len(self.transposition_table) > 500000:
+            self.transposition_table.clear()             # mcts_agent.py:337-339
+        return best
+
+    def get_action_info(self) -> Dict[str, Any]:
+        info = {"name": "MCTSAgent", "type": "mcts",
+                "description": "Monte Carlo Tree Search with UCT, device rollouts (B200)",
+                "parameters": {"iterations": self.iterations, "time_limit": self.time_limit,
+                               "exploration_constant": self.exploration_constant,
+                               "use_transposition_table": self.use_transposition_table,
+                               "max_rollout_moves": self.max_rollout_moves, "num_trees": self.num_trees},
+                "stats": dict(self.stats)}
+        if self.transposition_table is not None:
+            info["transposition_stats"] = self.transposition_table.get_stats()
+        return info
+
+    def reset(self):
+        self.reset_stats()
+        if self.transposition_table is not None:
+            self.transposition_table.clear()
+
+    def set_seed(self, seed: int):
+        self.seed = int(seed)
+        self.zobrist_hash = ZobristHash(seed=seed)
+        self._searches = 0
+
+
+# ---------------------------------------------------------------------------------------------------
+def smoke() -> None:
+    """Tiny search used by __graft_entry__.smoke(): visits add up and the root count is right."""
+    from .state import empty_states
+
+    eng = DeviceUCT(64, n_trees=2, seed=3)
+    res = eng.search(dev.to_device(empty_states(1)), 64)
+    torch.cuda.synchronize()
+    assert int(res["counts"][0]) == 58
+    assert res["visits"].sum(dim=1).tolist() == [64, 64]
+
+
+def bench_extras(n_trees: int = 1184, iterations: int = 256) -> Dict[str, float]:
+    """MCTS simulations/s for bench.py: root-parallel trees from the empty board, 50-ply rollouts."""
+    from .state import empty_states
+
+    eng = DeviceUCT(iterations, n_trees=n_trees, seed=42)
+    roots = dev.to_device(empty_states(1))
+    eng.search(roots, iterations)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.search(roots, iterations)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"mcts_sims_per_sec": n_trees * iterations / ms * 1e3, "mcts_trees": n_trees,
+            "mcts_iterations_per_tree": iterations, "mcts_rollout_plies": 50}

@@ -1,0 +1,118 @@
+"""Single-board calls for the drop-in (object) API: one 256-byte state up, one kernel, a few bytes back.
+
+These calls are latency-bound by construction (SURVEY.md section 7 "host<->device friction"); the
+throughput path is ``device.py`` / ``batched.py``.  Staging buffers are pinned and reused; a lock makes
+the helpers callable from worker threads (the reference's web API runs agents in an executor thread,
+webapi/app.py:330-333).
+"""
+
+from __future__ import annotations
+
+import threading
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from . import device as dev
+from .state import STATE_BYTES
+
+MAX_MOVES = 4096  # slots for one state's move list; an empty-board first move has 58, mid-game peaks are < 1000
+
+_lock = threading.Lock()
+_ctx = None
+
+
+class _Ctx:
+    def __init__(self):
+        if not torch.cuda.is_available():
+            raise dev._lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
+        d = torch.device("cuda", torch.cuda.current_device())
+        self.h_state = torch.empty((1, STATE_BYTES), dtype=torch.uint8).pin_memory()
+        self.d_state = torch.empty((1, STATE_BYTES), dtype=torch.uint8, device=d)
+        self.d_player = torch.empty(1, dtype=torch.uint8, device=d)
+        self.h_player = torch.empty(1, dtype=torch.uint8).pin_memory()
+        self.d_counts = torch.empty(1, dtype=torch.int32, device=d)
+        self.d_ids = torch.empty((1, MAX_MOVES), dtype=torch.uint16, device=d)
+        self.h_counts = torch.empty(1, dtype=torch.int32).pin_memory()
+        self.h_ids = torch.empty((1, MAX_MOVES), dtype=torch.uint16).pin_memory()
+        self.h_mask = torch.empty((1, 7), dtype=torch.int64).pin_memory()
+        self.d_mask = torch.empty((1, 7), dtype=torch.int64, device=d)
+        self.h_move = torch.empty(1, dtype=torch.uint16).pin_memory()
+        self.d_move = torch.empty(1, dtype=torch.uint16, device=d)
+
+    def upload(self, state_np, player: int) -> None:
+        self.h_state.numpy()[0] = np.frombuffer(np.asarray(state_np).tobytes(), dtype=np.uint8)
+        self.h_player[0] = player
+        self.d_state.copy_(self.h_state, non_blocking=True)
+        self.d_player.copy_(self.h_player, non_blocking=True)
+
+
+def _get() -> _Ctx:
+    global _ctx
+    if _ctx is None:
+        _ctx = _Ctx()
+    return _ctx
+
+
+def legal_move_ids(state_np, player: int) -> np.ndarray:
+    """Ascending move ids of one packed state for `player` (0..3)."""
+    with _lock:
+        c = _get()
+        c.upload(state_np, player)
+        dev.movegen_fixed(c.d_state, MAX_MOVES, c.d_player, out=(c.d_counts, c.d_ids))
+        c.h_counts.copy_(c.d_counts, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n = int(c.h_counts[0])
+        if n > MAX_MOVES:
+            raise dev._lib.BlokusB200Error(f"{n} legal moves exceed the single-state buffer ({MAX_MOVES})")
+        if n == 0:
+            return np.zeros(0, dtype=np.uint16)
+        c.h_ids[:, :n].copy_(c.d_ids[:, :n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return c.h_ids.numpy()[0, :n].copy()
+
+
+def count_moves(state_np, player: int) -> int:
+    with _lock:
+        c = _get()
+        c.upload(state_np, player)
+        return int(dev.movegen_count(c.d_state, c.d_player).item())
+
+
+def has_moves_mask(state_np) -> int:
+    """Bit p set iff player p has a legal move."""
+    with _lock:
+        c = _get()
+        c.upload(state_np, 0)
+        return int(dev.has_moves(c.d_state).item())
+
+
+def is_legal(state_np, player: int, move_id: int) -> bool:
+    if not 0 <= int(move_id) < 0xFFFF:
+        return False
+    with _lock:
+        c = _get()
+        c.upload(state_np, player)
+        c.h_move[0] = int(move_id)
+        c.d_move.copy_(c.h_move, non_blocking=True)
+        return bool(dev.is_move_legal(c.d_state, c.d_move, c.d_player).item())
+
+
+def can_place(state_np, player: int, cell_mask: int) -> bool:
+    with _lock:
+        c = _get()
+        c.upload(state_np, player)
+        c.h_mask.numpy()[0] = np.frombuffer(int(cell_mask).to_bytes(56, "little"), dtype="<i8")
+        c.d_mask.copy_(c.h_mask, non_blocking=True)
+        return bool(dev.can_place_mask(c.d_state, c.d_mask, c.d_player).item())
+
+
+def scores(state_np) -> Tuple[List[int], List[int]]:
+    """(BlokusGame.get_score per player, Board.get_score per player)."""
+    with _lock:
+        c = _get()
+        c.upload(state_np, 0)
+        gs, bs = dev.scores(c.d_state)
+        both = torch.stack([gs[0], bs[0]]).cpu().tolist()
+        return both[0], both[1]

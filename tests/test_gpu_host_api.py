@@ -1,0 +1,183 @@
+"""The object API on a GPU, written the way the reference tests its own engine (tests/test_engine.py,
+tests/test_legality_bitboard_equivalence.py, tests/test_game_over_logic.py, tests/test_game_result.py,
+tests/test_fast_mcts_think.py, tests/test_mcts_diagnostics.py) plus parity against the pinned oracle."""
+
+import math
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import orc  # noqa: E402
+from reinforcementlearning_blokus_b200 import (BlokusGame, Board, FastMCTSAgent, GameplayFastMCTSAgent,  # noqa: E402
+                                               HeuristicAgent, LegalMoveGenerator, Move, Player, Position,
+                                               RandomAgent, get_shared_generator)
+
+
+# ---- tests/test_engine.py:94-153 ---------------------------------------------------------------------
+def test_first_move_corner_rule():
+    board = Board()
+    assert board.can_place_piece([Position(0, 0), Position(0, 1)], Player.RED)
+    assert not board.can_place_piece([Position(1, 1), Position(1, 2)], Player.RED)
+    assert board.can_place_piece([Position(0, 19)], Player.BLUE)
+    assert board.can_place_piece([Position(19, 19), Position(18, 19)], Player.YELLOW)
+    assert board.can_place_piece([Position(19, 0)], Player.GREEN)
+    assert not board.can_place_piece([], Player.RED)
+    assert not board.can_place_piece([Position(-1, 0)], Player.RED)
+
+
+def test_edge_and_corner_adjacency_rules():
+    board = Board()
+    assert board.place_piece([Position(0, 0), Position(0, 1)], Player.RED, 1)
+    assert board.can_place_piece([Position(1, 2), Position(1, 3)], Player.RED)          # corner contact
+    assert not board.can_place_piece([Position(0, 2), Position(0, 3)], Player.RED)      # edge contact
+    assert not board.can_place_piece([Position(5, 5)], Player.RED)                      # no contact
+    assert not board.can_place_piece([Position(0, 1)], Player.RED)                      # occupied
+    board.place_piece([Position(1, 2), Position(1, 3)], Player.RED, 2)
+    assert board.can_place_piece([Position(2, 4), Position(2, 5)], Player.RED)
+    board.assert_bitboard_consistent()
+    assert board.current_player == Player.YELLOW and board.move_count == 2
+
+
+def test_generator_interface_and_first_moves():
+    gen = LegalMoveGenerator()
+    assert len(gen.all_pieces) == 21 and len(gen.piece_orientations_cache) == 21
+    board = Board()
+    for p in Player:
+        moves = gen.get_legal_moves(board, p)
+        assert len(moves) == 58
+        corner = board.player_start_corners[p]
+        for m in moves[::7]:
+            assert gen.is_move_legal(board, p, m)
+            assert corner in m.get_positions(gen.piece_orientations_cache[m.piece_id])
+    assert not gen.is_move_legal(board, Player.RED, Move(1, 0, -1, -1))      # tests/test_engine.py:260-274
+    assert not gen.is_move_legal(board, Player.RED, Move(99, 0, 0, 0))
+    assert not gen.is_move_legal(board, Player.RED, Move(1, 5, 0, 0))
+    assert gen.has_legal_moves(board, Player.RED) and gen.get_move_count(board, Player.RED) == 58
+    assert get_shared_generator() is get_shared_generator()
+
+
+def test_game_flow_matches_oracle_move_by_move():
+    """A BlokusGame driven by RandomAgent; the oracle replays the same moves and must agree on every
+    legal-move list, score and on the game-over moment (engine/game.py:57-214)."""
+    game = BlokusGame(enable_telemetry=False)
+    agent = RandomAgent(seed=11)
+    ob = orc.OracleBoard()
+    assert game.board.current_player == Player.RED and game.move_count == 0 and not game.is_game_over()
+    turns = 0
+    while not game.is_game_over() and turns < 120:
+        p = game.get_current_player()
+        legal = game.get_legal_moves(p)
+        assert [m.to_id() for m in legal] == ob.legal_moves(p.value - 1).tolist()
+        turns += 1
+        if not legal:
+            game.board._update_current_player()
+            game._check_game_over()
+            ob.pass_turn()
+            ob.check_game_over()
+            continue
+        move = agent.select_action(game.board, p, legal)
+        assert game.make_move(move, p)
+        assert ob.make_move(p.value - 1, move.to_id())
+        assert game.is_game_over() == ob.game_over
+        if turns % 9 == 0:
+            for q in Player:
+                assert game.get_score(q) == ob.game_score(q.value - 1)
+                assert game.board.get_score(q) == ob.board_score(q.value - 1)
+    assert game.is_game_over() and ob.game_over
+    res = game.get_game_result()
+    assert res.scores == {q.value: ob.game_score(q.value - 1) for q in Player}
+    top = max(res.scores.values())
+    assert res.winner_ids == [k for k, v in res.scores.items() if v == top] and res.is_tie == (len(res.winner_ids) > 1)
+    assert (game.winner is None) == res.is_tie
+    assert game.board.to_packed().tobytes() == ob.pack().tobytes()
+    assert len(game.game_history) == game.move_count
+    # rebuilt from the packed state, the board is the same board
+    b2 = Board.from_packed(game.board.to_packed())
+    assert np.array_equal(b2.grid, game.board.grid) and b2.player_pieces_used == game.board.player_pieces_used
+
+
+def test_invalid_moves_and_piece_exhaustion():
+    game = BlokusGame()
+    assert not game.make_move(Move(1, 0, -1, -1))
+    assert game.move_count == 0
+    for i in range(1, 22):
+        game.board.player_pieces_used[Player.RED].add(i)
+    assert game.get_legal_moves(Player.RED) == [] and not game.can_player_move(Player.RED)
+    assert game.board.get_score(Player.RED) == 15                         # all-pieces bonus, board.py:574
+    game.reset_game()
+    assert game.move_count == 0 and game.board.current_player == Player.RED and game.winner is None
+    first = game.get_legal_moves()[0]
+    assert game.make_move(first) and game.move_count == 1 and game.board.current_player == Player.BLUE
+    assert not game.make_move(first, Player.RED)                          # piece already spent
+    st = game.get_game_state()
+    assert {"board", "current_player", "move_count", "game_over", "scores"} <= set(st)
+
+
+def test_frontier_is_exact_after_moves():
+    """tests/test_frontier_basic.py:107-164: start corner first, then diagonal cells of the placed piece."""
+    board = Board()
+    assert board.get_frontier(Player.RED) == {(0, 0)}
+    board.place_piece([Position(0, 0)], Player.RED, 1)
+    assert board.get_frontier(Player.RED) == {(1, 1)}
+    board.place_piece([Position(0, 19), Position(0, 18)], Player.BLUE, 2)
+    assert board.get_frontier(Player.BLUE) == {(1, 17)}
+
+
+def test_heuristic_scores_match_reference(golden_dir):
+    """agents/heuristic_agent.py:68-103 scores from the reference itself (tests/golden/heuristic.npz)."""
+    z = np.load(os.path.join(golden_dir, "heuristic.npz"))
+    states = z["states"].view(orc.STATE_DTYPE).reshape(-1)
+    offs = z["offsets"]
+    agent = HeuristicAgent(seed=0)
+    for i, s in enumerate(states):
+        board = Board.from_packed(s)
+        p = Player(int(s["to_move"]) + 1)
+        moves = [Move.from_id(int(m)) for m in z["move_ids"][offs[i]:offs[i + 1]]]
+        got = agent.evaluate_moves(board, p, moves)
+        assert np.array_equal(got, z["scores"][offs[i]:offs[i + 1]]), i          # float64, bit for bit
+        pick = agent.select_action(board, p, moves)
+        assert pick in moves
+    assert agent.select_action(Board(), Player.RED, []) is None
+
+
+def test_fast_mcts_think_schema_and_budget():
+    """tests/test_fast_mcts_think.py and tests/test_mcts_diagnostics.py of the reference."""
+    board = Board()
+    gen = get_shared_generator()
+    legal = gen.get_legal_moves(board, Player.RED)
+    agent = FastMCTSAgent(iterations=5000, time_limit=1.0, seed=7)
+    import time
+    t0 = time.perf_counter()
+    out = agent.think(board, Player.RED, legal, 150)
+    elapsed = (time.perf_counter() - t0) * 1000
+    assert elapsed < 1500
+    assert out["move"] in legal
+    st = out["stats"]
+    for k in ("timeBudgetMs", "timeSpentMs", "nodesEvaluated", "maxDepthReached", "topMoves"):
+        assert k in st
+    assert st["timeBudgetMs"] == 150 and st["nodesEvaluated"] >= 5 and len(st["topMoves"]) <= 10
+    for tm in st["topMoves"]:
+        assert {"piece_id", "orientation", "anchor_row", "anchor_col", "visits", "q_value"} <= set(tm)
+    # diagnostics invariants
+    agent = FastMCTSAgent(iterations=300, time_limit=60.0, seed=7, enable_diagnostics=True, diagnostics_sample_interval=100)
+    out = agent.think(board, Player.RED, legal, 60000)
+    d = out["stats"]["diagnostics"]
+    assert d["version"] == "v1" and d["simulations"] == 300 and d["rootLegalMoves"] == 58
+    assert sum(x["nodes"] for x in d["nodesByDepth"]) == d["nodesExpanded"] + 1
+    assert 0.0 <= d["policyEntropy"] <= math.log(max(d["rootChildrenExpanded"], 1)) + 1e-9
+    assert [t["sim"] for t in d["bestMoveTrace"]] == [100, 200]
+    assert sum(tm["visits"] for tm in d["rootPolicy"]) <= 300
+    # same seed, same search
+    a1 = FastMCTSAgent(iterations=200, time_limit=60.0, seed=3).think(board, Player.RED, legal, 60000)
+    a2 = FastMCTSAgent(iterations=200, time_limit=60.0, seed=3).think(board, Player.RED, legal, 60000)
+    assert a1["move"] == a2["move"] and a1["stats"]["topMoves"] == a2["stats"]["topMoves"]
+    # degenerate inputs
+    assert agent.think(board, Player.RED, [], 10)["move"] is None
+    one = agent.think(board, Player.RED, legal[:1], 10)
+    assert one["move"] == legal[0] and one["stats"]["nodesEvaluated"] == 1
+    mv, stats = GameplayFastMCTSAgent(iterations=64, seed=1).choose_move(board, Player.RED, legal, 200)
+    assert mv in legal and "topMoves" in stats

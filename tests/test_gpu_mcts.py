@@ -1,0 +1,126 @@
+"""K5 parity: the device UCT kernel against the sequential C oracle (same algorithm restated from
+mcts/mcts_agent.py, same canonical untried order, same Philox rollout stream)."""
+
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import orc  # noqa: E402
+from reinforcementlearning_blokus_b200 import Board, MCTSAgent, Move, Player, ZobristHash, get_shared_generator  # noqa: E402
+from reinforcementlearning_blokus_b200 import device as dev  # noqa: E402
+from reinforcementlearning_blokus_b200.mcts import DeviceUCT, TranspositionTable  # noqa: E402
+from reinforcementlearning_blokus_b200.state import STATE_DTYPE, empty_states  # noqa: E402
+
+
+def _roots(golden_dir):
+    z = np.load(os.path.join(golden_dir, "random_states.npz"))
+    states = z["states"].view(STATE_DTYPE).reshape(-1)
+    picks = [s for s in states if 4 <= int(s["move_count"]) <= 40][:3]
+    return [empty_states(1)[0]] + picks
+
+
+@pytest.mark.parametrize("variant", ["uct", "flat"])
+def test_search_matches_oracle(golden_dir, variant):
+    kw = dict(max_depth=0, ucb_variant=0, reward_mode=0) if variant == "uct" else dict(max_depth=1, ucb_variant=1, reward_mode=1)
+    iters = 160
+    for ri, root in enumerate(_roots(golden_dir)):
+        for tree in (0, 5):
+            want = orc.mcts_search(root, iters, seed=99, tree_id=tree, **kw)
+            eng = DeviceUCT(iters, n_trees=1, seed=99, tree_offset=tree, **kw)
+            res = eng.search(dev.to_device(np.atleast_1d(root)), iters)
+            n = int(res["counts"][0])
+            assert n == want["n_root"]
+            assert int(res["status"][0]) == 0
+            assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n]), (variant, ri, tree)
+            assert np.array_equal(res["reward"][0, :n].cpu().numpy(), want["reward"][:n])
+            assert np.array_equal(res["moves"][0, :n].cpu().numpy(), want["moves"][:n])
+            assert int(res["visits"][0, :n].sum()) == iters
+
+
+def test_resume_equals_one_shot_and_trees_are_independent(golden_dir):
+    root = dev.to_device(np.atleast_1d(_roots(golden_dir)[1]))
+    one = DeviceUCT(192, n_trees=4, seed=5).search(root, 192)
+    v1 = one["visits"].clone(); w1 = one["reward"].clone()
+    eng = DeviceUCT(192, n_trees=4, seed=5)
+    eng.search(root, 64)
+    eng.search(None, 64, resume=True)
+    res = eng.search(None, 64, resume=True)
+    assert torch.equal(res["visits"], v1) and torch.equal(res["reward"], w1)
+    # tree k of a 4-tree batch == a single tree with tree_offset k
+    solo = DeviceUCT(192, n_trees=1, seed=5, tree_offset=2).search(root, 192)
+    assert torch.equal(solo["visits"][0], v1[2]) and torch.equal(solo["reward"][0], w1[2])
+    assert not torch.equal(v1[0], v1[1])
+
+
+def test_transposition_table_matches_oracle(golden_dir):
+    """Rewards cached by Zobrist key are reused by a second search of the same agent (mcts_agent.py:418-434)."""
+    root_np = _roots(golden_dir)[2]
+    zob = ZobristHash(seed=42)
+    assert np.array_equal(zob.table, orc.zobrist_table(42))
+    tt = TranspositionTable(max_size=1 << 16)
+    ott = orc.OracleTT(18)
+    root = dev.to_device(np.atleast_1d(root_np))
+    for rep in range(2):                      # second pass hits the entries of the first
+        want = orc.mcts_search(root_np, 120, seed=8, tree_id=0, tt=ott, zobrist=zob.table)
+        res = DeviceUCT(120, n_trees=1, seed=8, tt=tt.device, zobrist=zob).search(root, 120)
+        n = want["n_root"]
+        assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n]), rep
+        assert np.array_equal(res["reward"][0, :n].cpu().numpy(), want["reward"][:n]), rep
+        assert len(tt) == ott.size()
+    ott.close()
+
+
+def test_mcts_agent_interface(golden_dir):
+    board = Board.from_packed(_roots(golden_dir)[1])
+    player = board.current_player
+    gen = get_shared_generator()
+    legal = gen.get_legal_moves(board, player)
+    agent = MCTSAgent(iterations=150, seed=4)
+    mv = agent.select_action(board, player, legal)
+    assert mv in legal
+    assert agent.stats["iterations_run"] == 150
+    info = agent.get_action_info()
+    assert info["type"] == "mcts" and "transposition_stats" in info
+    # the move equals the oracle's best-by-visits with the reference's tie-break (first max in creation order)
+    st = board.to_packed()
+    ott = orc.OracleTT(18)
+    want = orc.mcts_search(st, 150, seed=4, tree_id=0, tt=ott, zobrist=orc.zobrist_table(4))
+    n = want["n_root"]
+    best, best_v = -1, -1
+    for rank in range(n - 1, -1, -1):
+        if want["visits"][rank] > best_v:
+            best, best_v = rank, want["visits"][rank]
+    assert mv.to_id() == sorted(m.to_id() for m in legal)[best]
+    assert agent.select_action(board, player, []) is None
+    assert agent.select_action(board, player, legal[:1]) == legal[0]
+    agent.reset()
+    with pytest.raises(ValueError):
+        MCTSAgent(max_rollout_moves=0)
+    # time-limited search runs and returns a legal move
+    timed = MCTSAgent(time_limit=0.2, seed=1, use_transposition_table=False)
+    assert timed.select_action(board, player, legal) in legal
+    assert timed.stats["iterations_run"] >= 64
+    # root-parallel trees: visits add up over trees
+    par = MCTSAgent(iterations=64, seed=2, num_trees=8, use_transposition_table=False)
+    r = par.search_root(board, player)
+    assert int(r["visits"].sum()) == 64 * 8
+
+
+def test_playout_segments_chain(golden_dir):
+    """A game played in segments through final_states equals the one-shot game (bk_playout first_turn)."""
+    n = 128
+    full = dev.playout(n, seed=9, game_offset=3, want_trace=True, want_final=True)
+    st, tr = None, None
+    cuts = [0, 7, 20, 45, 96]
+    out = {}
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        r = dev.playout(n, seed=9, game_offset=3, start_states=st, first_turn=a, max_turns=b, want_trace=True,
+                        want_final=True, out=out)
+        st = r["final_states"].clone()
+    assert torch.equal(r["trace"], full["trace"])
+    assert torch.equal(r["game_scores"], full["game_scores"])
+    assert torch.equal(st, full["final_states"])
