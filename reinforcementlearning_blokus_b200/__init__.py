@@ -32,4 +32,6 @@ def __getattr__(name):
     return getattr(importlib.import_module(f".{mod}", __name__), name)
 
 
+__all__ = sorted(_LAZY) + ["BOARD_SIZE", "NUM_ORIENTATIONS", "NUM_PIECES", "ORIENTATIONS", "PASS_ID", "decode_move",
+                           "encode_move", "STATE_BYTES", "STATE_DTYPE", "empty_states"]
 __version__ = "0.1.0"

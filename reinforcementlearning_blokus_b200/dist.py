@@ -1,0 +1,105 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL on GPUs, gloo in CPU tests).
+
+Two things shard:
+  * independent games -- rank r plays a contiguous block of GLOBAL game indices; the Philox stream of a game
+    depends on its global index only, so results do not depend on the number of ranks; no data-path
+    collective (scores can be gathered afterwards, 16 B per game);
+  * root-parallel MCTS -- every rank searches its own trees from the same root with rank-distinct tree
+    indices, then ONE all-reduce(sum) of the root visit / reward vectors (int64, <= 2048 entries each) and
+    every rank picks the same move.  The reference has no such step (it is single-process); the merge rule is
+    the standard root-parallel one: most summed visits, lowest move id on ties.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n_total: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """(first global index, count) of rank's contiguous block; blocks differ by at most one game."""
+    base, extra = divmod(int(n_total), int(world_size))
+    start = rank * base + min(rank, extra)
+    return start, base + (1 if rank < extra else 0)
+
+
+def sharded_playout(n_total: int, seed: int, game_offset: int = 0, gather_scores: bool = False, **kw) -> Dict[str, torch.Tensor]:
+    """Each rank plays its block of the n_total games [game_offset, game_offset+n_total).
+
+    Returns the local playout result plus ``first_game`` / ``count``; with gather_scores every rank also gets
+    ``all_game_scores`` int32[n_total, 4] in global game order (all_gather of equal-sized padded blocks)."""
+    from . import device as dev
+
+    rank, ws = world()
+    start, count = shard_range(n_total, rank, ws)
+    res = dev.playout(count, seed=seed, game_offset=game_offset + start, **kw)
+    res = dict(res)
+    res["first_game"], res["count"] = start, count
+    if gather_scores:
+        res["all_game_scores"] = gather_rows(res["game_scores"], n_total)
+    return res
+
+
+def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Concatenate per-rank row blocks (sizes from shard_range) in rank order on every rank."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    width = -(-int(n_total) // ws)
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(parts, pad, group=group)
+    out = []
+    for r in range(ws):
+        _, c = shard_range(n_total, r, ws)
+        out.append(parts[r][:c])
+    return torch.cat(out, dim=0)
+
+
+def merge_root_stats(visits: torch.Tensor, reward: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Sum root statistics over ranks: the single exchange step of a root-parallel search.
+
+    `visits` / `reward` are this rank's per-move sums (any integer dtype); both come back as int64 sums over all
+    ranks.  Integer sums make the result independent of reduction order and of the number of ranks."""
+    v = visits.to(torch.int64).clone()
+    w = reward.to(torch.int64).clone()
+    _, ws = world()
+    if ws > 1:
+        packed = torch.stack([v, w])            # one collective instead of two
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        v, w = packed[0], packed[1]
+    return v, w
+
+
+def pick_move(visits: torch.Tensor, n_root: int) -> int:
+    """Rank of the move with the most summed visits; lowest move id wins ties (same on every rank)."""
+    return int(torch.argmax(visits[:n_root]).item())     # argmax returns the first maximal index
+
+
+def root_parallel_search(root_state: torch.Tensor, sims_total: int, trees_per_rank: int, seed: int,
+                         max_rollout_moves: int = 50, exploration: float = 1.414, search_index: int = 0,
+                         group=None) -> Dict[str, object]:
+    """sims_total simulations split evenly over world_size * trees_per_rank trees; one all-reduce; every rank
+    returns the same {"rank_of_best", "visits", "reward", "n_root", "sims"}."""
+    from .mcts import DeviceUCT
+
+    rank, ws = world()
+    trees = ws * trees_per_rank
+    iters = max(1, int(sims_total) // trees)
+    # global tree index = search_index * trees + rank * trees_per_rank + k : disjoint Philox streams
+    eng = DeviceUCT(iters, n_trees=trees_per_rank, max_rollout_moves=max_rollout_moves, exploration=exploration,
+                    seed=seed, tree_offset=search_index * trees + rank * trees_per_rank)
+    res = eng.search(root_state, iters)
+    n_root = int(res["counts"][0].item())
+    v, w = merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0), group=group)
+    return {"rank_of_best": pick_move(v, n_root), "visits": v[:n_root], "reward": w[:n_root], "n_root": n_root,
+            "sims": iters * trees}

@@ -1,0 +1,90 @@
+"""Plugging the device path into a LIVE copy of the reference (when its ``engine`` package is importable).
+
+``install()`` replaces the reference's shared generator (``engine.move_generator._SHARED_GENERATOR``,
+engine/move_generator.py:1220-1233) by an adapter whose ``get_legal_moves`` / ``is_move_legal`` /
+``has_legal_moves`` read the reference's own ``Board`` object, run on the GPU and hand back the reference's own
+``Move`` objects -- so ``BlokusGame``, every agent constructor and ``MCTSNode`` (they all call
+``get_shared_generator()``) pick it up without further changes.  ``uninstall()`` restores the original.
+
+Nothing here is needed on a machine without the reference; see INTEGRATION.md for the maintainer-side stub.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+from . import pieces as P
+from . import single
+from .state import STATE_DTYPE
+
+_original = None
+
+
+def pack_reference_board(board) -> np.ndarray:
+    """reference ``engine.board.Board`` -> one packed ``bk_state`` (same recipe as engine-service/app.py:27-50)."""
+    from engine.board import Player  # the reference's enum
+
+    s = np.zeros((), dtype=STATE_DTYPE)
+    mask = 0
+    for k, p in enumerate(Player):
+        s["bits"][k] = np.frombuffer(int(board.player_bits[p]).to_bytes(56, "little"), dtype="<u8")
+        used = 0
+        for pid in board.player_pieces_used[p]:
+            if 1 <= pid <= 21:
+                used |= 1 << (pid - 1)
+        s["used"][k] = used
+        if board.player_first_move[p]:
+            mask |= 1 << k
+    s["first_mask"] = mask
+    s["to_move"] = board.current_player.value - 1
+    s["move_count"] = int(board.move_count) & 0xFFFF
+    return s
+
+
+def make_adapter():
+    """A subclass of the reference's LegalMoveGenerator whose three public queries run on the device."""
+    from engine.move_generator import LegalMoveGenerator as RefGenerator
+    from engine.move_generator import Move as RefMove
+
+    class B200LegalMoveGenerator(RefGenerator):
+        def get_legal_moves(self, board, player) -> List:
+            ids = single.legal_move_ids(pack_reference_board(board), player.value - 1)
+            return [RefMove(*P.decode_move(int(i))) for i in ids]
+
+        def is_move_legal(self, board, player, move) -> bool:
+            if move.piece_id in board.player_pieces_used[player]:
+                return False
+            per_piece = P.PIECE_ORIENTATIONS.get(move.piece_id)
+            if per_piece is None or not 0 <= move.orientation < len(per_piece):
+                return False
+            o = per_piece[move.orientation]
+            if not (0 <= move.anchor_row <= 20 - o.height and 0 <= move.anchor_col <= 20 - o.width):
+                return False
+            mid = o.gidx * 400 + move.anchor_row * 20 + move.anchor_col
+            return single.is_legal(pack_reference_board(board), player.value - 1, mid)
+
+        def has_legal_moves(self, board, player) -> bool:
+            return bool((single.has_moves_mask(pack_reference_board(board)) >> (player.value - 1)) & 1)
+
+    return B200LegalMoveGenerator()
+
+
+def install() -> Optional[object]:
+    """Swap the reference's shared generator for the device-backed adapter; returns the adapter."""
+    global _original
+    import engine.move_generator as mg
+
+    if _original is None:
+        _original = mg._SHARED_GENERATOR
+    mg._SHARED_GENERATOR = make_adapter()
+    return mg._SHARED_GENERATOR
+
+
+def uninstall() -> None:
+    global _original
+    import engine.move_generator as mg
+
+    mg._SHARED_GENERATOR = _original
+    _original = None
