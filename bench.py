@@ -64,7 +64,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -193,11 +193,17 @@ def run_cuda(args) -> None:
         # global game index = (k * world + rank) * n + i : disjoint Philox streams over steps and ranks
         dev.playout(n, seed=SEED, game_offset=(k * world + rank) * n, out=out, want_board_scores=False)
 
+    sampler = ClockSampler(local)
+    sampler.start()                                # nvidia-smi needs ~1 s to start: begin before the warm-up
     for w in range(args.warmup):
         step_device(1_000_000 + w)
+    # keep the GPU under the same load until the sampler delivers, so the clocks line covers the timed region
+    t_wait = time.perf_counter()
+    while len(sampler.lines) < 3 and time.perf_counter() - t_wait < 3.0:
+        step_device(1_500_000)
+        torch.cuda.synchronize()
+    sampler.lines.clear()
     launches0 = dev.launches()
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
@@ -384,7 +390,7 @@ def _cpu_baseline():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)

@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
         L.orc_tt_size.argtypes = [vp]
         L.orc_tt_size.restype = u64
         L.orc_mcts_search.argtypes = [vp, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, vp, vp]
+        L.orc_check_moves_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp]
         L.orc_init()
         _lib = L
     return _lib
@@ -284,3 +285,27 @@ def mcts_search(root: np.ndarray, iterations: int, seed: int, tree_id: int = 0, 
                               int(reward_mode), float(exploration), int(seed), int(tree_id), tt.h if tt else None, _ptr(zt),
                               int(max_root_moves), _ptr(vis), _ptr(rew), _ptr(mov))
     return {"n_root": int(n), "visits": vis, "reward": rew, "moves": mov}
+
+
+def check_moves_batch(states: np.ndarray, offsets: np.ndarray, ids: np.ndarray, naive: bool = False,
+                      threads: int = 0) -> Tuple[int, int]:
+    """Compare CSR move lists for the side to move of every state with the oracle's; (mismatches, first bad index)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    st = np.ascontiguousarray(states, dtype=STATE_DTYPE)
+    off = np.ascontiguousarray(offsets, dtype=np.uint32)
+    mv = np.ascontiguousarray(ids, dtype=np.uint16)
+    n = len(st)
+    threads = threads or min(32, os.cpu_count() or 1)
+    chunk = max(1, -(-n // (threads * 4)))
+
+    def work(lo):
+        fb = C.c_int(-1)
+        bad = lib().orc_check_moves_batch(_ptr(st), lo, min(n, lo + chunk), _ptr(off), _ptr(mv), int(naive), C.byref(fb))
+        return bad, fb.value
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(work, range(0, n, chunk)))
+    bad = sum(r[0] for r in res)
+    firsts = [r[1] for r in res if r[1] >= 0]
+    return bad, (min(firsts) if firsts else -1)

@@ -75,7 +75,7 @@ k_movegen_count(const bk_state* __restrict__ states, const uint8_t* __restrict__
         WarpState s; load_state(states + i, lane, s);
         const uint32_t p = players ? (players[i] & 3u) : s.to_move;
         uint32_t A, C; make_masks(s, p, lane, A, C);
-        CountSink sink; bk_gen_all(A, C, sel4(s.used, p), sink);
+        CountSink sink; bk_gen_all<CountSink, true>(A, C, sel4(s.used, p), sink);
         const uint32_t tot = __reduce_add_sync(BK_FULL, sink.acc);
         if (lane == 0) counts[i] = tot;
     }
@@ -92,6 +92,7 @@ k_movegen_count(const bk_state* __restrict__ states, const uint8_t* __restrict__
 static_assert(BK_EMIT_SMEM_BYTES == BK_WARPS * EMIT_SMEM_PER_WARP, "emit shared-memory size");
 
 struct SmemRowSink {
+    static constexpr bool kRows = true;
     uint32_t* rows; int lane;
     template <int O> __device__ __forceinline__ void put(uint32_t L) {
         if (lane < 20) rows[O * 20 + lane] = L;
@@ -382,33 +383,33 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& b
     const uint32_t res = warp_sums[w] + incl - v;
     return res;
 }
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_partial(const uint32_t* __restrict__ in, int n, uint32_t* __restrict__ out,
-                                                               uint32_t* __restrict__ block_sums) {
+// The first element of every 1024-block has within-block prefix 0, so its slot carries the block total
+// between the passes: no scratch buffer, no allocation.
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_partial(const uint32_t* __restrict__ in, int n, uint32_t* __restrict__ out) {
     __shared__ uint32_t total;
     const int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
     const uint32_t v = i < n ? in[i] : 0u;
     const uint32_t ex = block_exclusive_scan(v, total);
-    if (i < n) out[i] = ex;
     __syncthreads();
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+    if (i < n) out[i] = threadIdx.x == 0 ? total : ex;
 }
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_blocks(uint32_t* __restrict__ block_sums, int nb, uint32_t* __restrict__ grand) {
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_blocks(uint32_t* __restrict__ out, int nb, uint32_t* __restrict__ grand) {
     __shared__ uint32_t total;
     uint32_t carry = 0;
     for (int base = 0; base < nb; base += SCAN_BLOCK) {
         const int i = base + threadIdx.x;
-        const uint32_t v = i < nb ? block_sums[i] : 0u;
+        const uint32_t v = i < nb ? out[(size_t)i * SCAN_BLOCK] : 0u;
         const uint32_t ex = block_exclusive_scan(v, total);
-        if (i < nb) block_sums[i] = ex + carry;
+        if (i < nb) out[(size_t)i * SCAN_BLOCK] = ex + carry;
         __syncthreads();
         carry += total;
         __syncthreads();
     }
     if (threadIdx.x == 0) *grand = carry;
 }
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(uint32_t* __restrict__ out, int n, const uint32_t* __restrict__ block_sums) {
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(uint32_t* __restrict__ out, int n) {
     const int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
-    if (i < n) out[i] += block_sums[blockIdx.x];
+    if (i < n && threadIdx.x != 0) out[i] += out[(size_t)blockIdx.x * SCAN_BLOCK];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -665,14 +666,10 @@ extern "C" int bk_exclusive_scan_u32(const uint32_t* counts, int n, uint32_t* of
     cudaStream_t st = as_stream(stream);
     if (n == 0) { CUDA_TRY(cudaMemsetAsync(offsets, 0, sizeof(uint32_t), st)); return BK_OK; }
     const int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    uint32_t* block_sums = nullptr;
-    CUDA_TRY(cudaMallocAsync(&block_sums, (size_t)nb * sizeof(uint32_t), st));
-    k_scan_partial<<<nb, SCAN_BLOCK, 0, st>>>(counts, n, offsets, block_sums);
-    k_scan_blocks<<<1, SCAN_BLOCK, 0, st>>>(block_sums, nb, offsets + n);
-    k_scan_add<<<nb, SCAN_BLOCK, 0, st>>>(offsets, n, block_sums);
-    cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(block_sums, st);
-    if (e != cudaSuccess) return fail(BK_ERR_CUDA, "scan launch: %s", cudaGetErrorString(e));
+    k_scan_partial<<<nb, SCAN_BLOCK, 0, st>>>(counts, n, offsets);
+    k_scan_blocks<<<1, SCAN_BLOCK, 0, st>>>(offsets, nb, offsets + n);
+    k_scan_add<<<nb, SCAN_BLOCK, 0, st>>>(offsets, n);
+    LAUNCH_CHECK();
     return BK_OK;
 }
 

@@ -117,9 +117,21 @@ __device__ __forceinline__ void make_masks(const WarpState& s, uint32_t player, 
 }
 
 // Evaluate every orientation of every unspent piece; sink.put<O>(row_of_legal_anchors).
-template <class Sink>
-__device__ __forceinline__ void bk_gen_all(const uint32_t A, const uint32_t C, const uint32_t used, Sink& sink) {
+//
+// MIRROR = true runs the generated code on column-mirrored rows (bit j = column 19-j), which turns every
+// column shift into a LEFT shift; ptxas issues those as IMAD.SHL on the FMA pipe instead of SHF on the ALU pipe
+// that LOP3 already loads (profiles/r01a_playout_ncu.md: ALU 69 %, FMA 10 %).  Garbage above bit 19 cannot
+// survive: every orientation has a cell in column 0, so its AND contains an unshifted, clean factor.  Measured
+// on B200: +8 % for the count kernel, -4 % for the playout kernel (which is latency- rather than ALU-bound),
+// so only counting uses it.  Sinks that store rows (kRows) get them mirrored back with one BREV.
+template <class Sink, bool MIRROR = false>
+__device__ __forceinline__ void bk_gen_all(const uint32_t A_in, const uint32_t C_in, const uint32_t used, Sink& sink) {
+    const uint32_t A = MIRROR ? (__brev(A_in) >> 12) : A_in, C = MIRROR ? (__brev(C_in) >> 12) : C_in;
+#define BK_CS(x, c) (MIRROR ? ((x) << (c)) : ((x) >> (c)))
+#define BK_OUT(L) ((MIRROR && Sink::kRows) ? (__brev(L) >> 12) : (L))
 #include "orient_gen.cuh"
+#undef BK_CS
+#undef BK_OUT
 }
 
 // One orientation, table-driven (used after a move has been chosen, and by is_move_legal).
@@ -140,11 +152,13 @@ __device__ __forceinline__ uint32_t bk_gen_one(const uint32_t A, const uint32_t 
 
 // ---- sinks ------------------------------------------------------------------------------------
 struct CountSink {                 // per-lane move count
+    static constexpr bool kRows = false;
     uint32_t acc = 0;
     template <int O> __device__ __forceinline__ void put(uint32_t L) { acc += __popc(L); }
 };
 
 struct AnySink {                   // does any move exist
+    static constexpr bool kRows = false;
     uint32_t acc = 0;
     template <int O> __device__ __forceinline__ void put(uint32_t L) { acc |= L; }
 };
@@ -152,6 +166,7 @@ struct AnySink {                   // does any move exist
 // Per-lane counts of three orientations per register in 10-bit fields (a row holds <= 20 anchors, a
 // warp-wide field sum <= 400 < 1024), so one REDUX yields three per-orientation totals.
 struct PackSink {
+    static constexpr bool kRows = false;
     uint32_t pk[31];
     __device__ __forceinline__ PackSink() {
 #pragma unroll
@@ -163,32 +178,10 @@ struct PackSink {
 };
 
 struct BitmapSink {                // legal-anchor bitmap rows straight to memory
+    static constexpr bool kRows = true;
     uint32_t* out; int lane;
     template <int O> __device__ __forceinline__ void put(uint32_t L) {
         if (lane < 20) out[O * 20 + lane] = L;
-    }
-};
-
-struct EmitSink {                  // ascending move ids
-    uint16_t* out; uint32_t pos; int lane;
-    template <int O> __device__ __forceinline__ void put(uint32_t L) {
-        if (!__any_sync(BK_FULL, L != 0)) return;
-        const uint32_t c = __popc(L);
-        uint32_t incl = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t v = __shfl_up_sync(BK_FULL, incl, d);
-            if (lane >= d) incl += v;
-        }
-        uint32_t w = pos + incl - c;
-        uint32_t bits = L;
-        const uint32_t base = O * 400 + lane * 20;
-        while (bits) {
-            const int col = __ffs(bits) - 1;
-            bits &= bits - 1;
-            out[w++] = (uint16_t)(base + col);
-        }
-        pos += __shfl_sync(BK_FULL, incl, 31);
     }
 };
 

@@ -98,6 +98,16 @@ def movegen(states: torch.Tensor, players: Optional[torch.Tensor] = None) -> Tup
     return counts, offsets, ids[:total]
 
 
+def exclusive_scan(counts: torch.Tensor) -> torch.Tensor:
+    """int32[n] -> int32[n+1] exclusive prefix sums (last entry = total); three short kernels, no allocation."""
+    n = counts.numel()
+    lib = _lib_for(counts)
+    offsets = torch.empty(n + 1, dtype=torch.int32, device=counts.device)
+    check(lib.bk_exclusive_scan_u32(_ptr(counts), n, _ptr(offsets), _stream()))
+    _count(3)
+    return offsets
+
+
 def movegen_fixed(states: torch.Tensor, cap: int, players: Optional[torch.Tensor] = None,
                   out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """One-kernel generation into fixed slots: (counts int32[N], ids uint16[N, cap]); a list longer than

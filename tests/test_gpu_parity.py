@@ -292,3 +292,25 @@ def test_zobrist_and_tt(golden_dir, oracle_corpus):
     _, f3 = tt.get(k)
     assert not _np(f3).any() and tt.stats()["size"] == 0
     tt.close()
+
+
+def test_exclusive_scan_sizes():
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for n in (1, 2, 1023, 1024, 1025, 5000, (1 << 20) + 77, 3 * (1 << 20) + 5):
+        c = torch.randint(0, 900, (n,), generator=g, dtype=torch.int32)
+        got = dev.exclusive_scan(c.cuda()).cpu().numpy().astype(np.int64)
+        want = np.concatenate([[0], np.cumsum(c.numpy().astype(np.int64))])
+        assert np.array_equal(got, want), n
+
+
+def test_legality_sweep_small():
+    """A 30,000-state slice of the configs[2] sweep (tools/legality_sweep.py runs the 10^6 version)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "legality_sweep", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "legality_sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    res = mod.sweep(30000, seed=77)
+    assert res["states"] == 30000 and res["mismatches"] == 0 and res["naive_mismatches"] == 0
+    assert res["terminal_states"] > 0 and res["max_moves"] > 500
