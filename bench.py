@@ -250,6 +250,33 @@ def run_cuda(args) -> None:
     e2e_value = n * world * args.steps / (ms_e2e * 1e-3)
     mean_score = float(host_scores.float().mean())
 
+    # ---- root-parallel MCTS (the third part of BASELINE.json's metric): every rank searches its own trees from
+    # the empty board (50-ply rollouts), then ONE all-reduce of the root statistics (dist.merge_root_stats)
+    mcts = None
+    if not args.no_extras:
+        from reinforcementlearning_blokus_b200 import dist as bdist
+        from reinforcementlearning_blokus_b200.mcts import DeviceUCT
+
+        trees, iters = 1184, 256
+        root = dev.to_device(empty_states(1))
+        eng = DeviceUCT(iters, n_trees=trees, seed=SEED, tree_offset=rank * trees)
+        eng.search(root, iters)                       # warm-up
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(stream)
+        res = eng.search(root, iters)
+        v, w = bdist.merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0))
+        m1.record(stream)
+        barrier()
+        ms_m = m0.elapsed_time(m1)
+        if world > 1:
+            t = torch.tensor([ms_m], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_m = float(t.item())
+        mcts = {"mcts_sims_per_sec": world * trees * iters / (ms_m * 1e-3), "mcts_trees_per_gpu": trees,
+                "mcts_iterations_per_tree": iters, "mcts_rollout_plies": 50,
+                "mcts_root_visits_total": int(v.sum().item()), "mcts_collective": "1 all_reduce(int64[2,2048]) per search"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -279,8 +306,10 @@ def run_cuda(args) -> None:
         "int_roofline": int_roofline,
         "lib": _lib.load().bk_version().decode(),
     }
+    if not args.no_extras:
+        line["extras"] = dict(mcts or {})
     if world == 1 and not args.no_extras:
-        line["extras"] = _extras(dev, torch, n)
+        line["extras"].update(_extras(dev, torch, n))
         line["cpu_baseline"] = _cpu_baseline()
     print(json.dumps(line))
     if world > 1:
@@ -363,11 +392,6 @@ def _extras(dev, torch, n):
     ex["movegen_bitmap_gens_per_sec"] = m / ms * 1e3
     ms = timeit(lambda: dev.movegen(corpus))
     ex["movegen_csr_gens_per_sec"] = m / ms * 1e3
-    try:
-        from reinforcementlearning_blokus_b200 import mcts as _m
-        ex.update(_m.bench_extras())
-    except Exception:
-        pass
     return ex
 
 

@@ -132,7 +132,7 @@ int bk_scores(const bk_state* states, int n, int32_t* game_scores /*[n][4]*/,
 
 /* Game i (global index game_offset+i) starts from start_states[i] (NULL: the empty board) and plays
  * turns first_turn, first_turn+1, ... (passes count as turns): turn t of game g draws
- * r = philox4x32_10(key=seed, ctr=(g_lo,g_hi,t,0)).x and plays the ((uint64)r*n_legal)>>32-th move of the
+ * r = word t%4 of philox4x32_10(key=seed, ctr=(g_lo,g_hi,t/4,0)) and plays the ((uint64)r*n_legal)>>32-th move of the
  * ascending list; a player with no move passes; the game stops once no player can move or when
  * t reaches max_turns (0 = BK_MAX_TURNS).  A game played in segments [0,a), [a,b), ... through
  * final_states is the same game as one call.  Outputs (each may be NULL): game_scores/board_scores [n][4],

@@ -57,6 +57,7 @@ extern "C" int bk_init(int device) {
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_piece, BK_TBL_ORIENT_PIECE, sizeof(BK_TBL_ORIENT_PIECE)));
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_ncells, BK_TBL_ORIENT_NCELLS, sizeof(BK_TBL_ORIENT_NCELLS)));
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_cells, BK_TBL_ORIENT_CELLS, sizeof(BK_TBL_ORIENT_CELLS)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_group_first, BK_TBL_GROUP_FIRST, sizeof(BK_TBL_GROUP_FIRST)));
     CUDA_TRY(cudaFuncSetAttribute(k_movegen_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
     g_device = device;
     return BK_OK;
@@ -94,9 +95,10 @@ static_assert(BK_EMIT_SMEM_BYTES == BK_WARPS * EMIT_SMEM_PER_WARP, "emit shared-
 struct SmemRowSink {
     static constexpr bool kRows = true;
     uint32_t* rows; int lane;
-    template <int O> __device__ __forceinline__ void put(uint32_t L) {
+    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) {
         if (lane < 20) rows[O * 20 + lane] = L;
     }
+    template <int G> __device__ __forceinline__ void flush() {}
 };
 
 __global__ void __launch_bounds__(BK_THREADS)
@@ -297,10 +299,14 @@ k_scores(const bk_state* __restrict__ states, int n, int32_t* __restrict__ gs, i
 #ifndef BK_PLAYOUT_MIN_BLOCKS
 #define BK_PLAYOUT_MIN_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(BK_THREADS, BK_PLAYOUT_MIN_BLOCKS)
+#ifndef BK_PLAYOUT_THREADS
+#define BK_PLAYOUT_THREADS 256
+#endif
+__global__ void __launch_bounds__(BK_PLAYOUT_THREADS, BK_PLAYOUT_MIN_BLOCKS)
 k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int first_turn, int max_turns,
                   int32_t* __restrict__ gs, int32_t* __restrict__ bs, uint16_t* __restrict__ trace,
                   uint16_t* __restrict__ choice, bk_state* __restrict__ finals) {
+    __shared__ __align__(16) uint32_t s_slots[BK_PLAYOUT_THREADS / 32][BK_GROUP_SLOTS];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -328,7 +334,7 @@ k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint
             bool moved = false;
             if (!((dead >> p) & 1u)) {
                 uint32_t A, C; make_masks(s, p, lane, A, C);
-                PackSink sink; bk_gen_all(A, C, sel4(s.used, p), sink);
+                GroupSink sink; sink.begin(s_slots[threadIdx.x >> 5], lane); bk_gen_all(A, C, sel4(s.used, p), sink);
                 const Totals tot = reduce_totals(sink, lane);
                 if (tot.n == 0) {
                     dead |= 1u << p;      // a player without moves never regains any ("dead stay dead")
@@ -655,7 +661,9 @@ extern "C" int bk_playout(const bk_state* start_states, int n, uint64_t seed, ui
     if (n == 0) return BK_OK;
     if (max_turns == 0) max_turns = BK_MAX_TURNS;
     REQUIRE(first_turn >= 0 && first_turn <= max_turns, "bk_playout: first_turn out of range");
-    k_playout_uniform<<<grid_for(n, BK_PLAYOUT_MIN_BLOCKS), BK_THREADS, 0, as_stream(stream)>>>(
+    const int pw = BK_PLAYOUT_THREADS / 32;
+    long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)g_sms * BK_PLAYOUT_MIN_BLOCKS;
+    k_playout_uniform<<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, 0, as_stream(stream)>>>(
         start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     LAUNCH_CHECK();
     return BK_OK;

@@ -57,8 +57,8 @@ struct MctsTT {                // optional transposition table (mcts/zobrist.py:
     const uint64_t* zobrist;   // 2088-entry table, reference order
 };
 
-__device__ __noinline__ Totals gen_totals(uint32_t A, uint32_t C, uint32_t used, int lane) {
-    PackSink sink;
+__device__ __noinline__ Totals gen_totals(uint32_t A, uint32_t C, uint32_t used, int lane, uint32_t* slots) {
+    GroupSink sink; sink.begin(slots, lane);
     bk_gen_all(A, C, used, sink);
     return reduce_totals(sink, lane);
 }
@@ -75,6 +75,7 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
        unsigned char* __restrict__ workspace, int resume, int max_root_moves,
        int32_t* __restrict__ out_visits, long long* __restrict__ out_reward, uint32_t* __restrict__ out_counts,
        uint16_t* __restrict__ out_moves, uint32_t* __restrict__ out_status) {
+    __shared__ __align__(16) uint32_t s_slots[BK_GROUP_SLOTS];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -102,7 +103,7 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
         if (!resume) {
             load_state(roots + (tree % n_roots), lane, s);
             uint32_t A, C; make_masks(s, s.to_move, lane, A, C);
-            const Totals t0 = gen_totals(A, C, sel4(s.used, s.to_move), lane);
+            const Totals t0 = gen_totals(A, C, sel4(s.used, s.to_move), lane, s_slots);
             store_state(states + 0, lane, s);
             if (lane == 0) {
                 parent[0] = -1; visits[0] = 0; reward[0] = 0; child_base[0] = 0xFFFFFFFFu;
@@ -152,12 +153,12 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
                 if (ne < nl && (prm.max_depth <= 0 || (int)depth < prm.max_depth)) {
                     const uint32_t p = s.to_move;
                     uint32_t A, C; make_masks(s, p, lane, A, C);
-                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane);
+                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane, s_slots);
                     int o, row, col;
                     const uint32_t id = select_move(tot, nl - 1 - ne, A, C, lane, o, row, col);
                     place_move(s, p, o, row, col, lane);
                     uint32_t A2, C2; make_masks(s, s.to_move, lane, A2, C2);
-                    const Totals tc = gen_totals(A2, C2, sel4(s.used, s.to_move), lane);
+                    const Totals tc = gen_totals(A2, C2, sel4(s.used, s.to_move), lane, s_slots);
                     uint32_t cb = child_base[node];
                     if (cb == 0xFFFFFFFFu) {
                         const uint32_t remaining = (uint32_t)prm.iterations_total - iter_done;
@@ -199,7 +200,7 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
                 for (int ply = 0; ply < limit; ply++) {
                     const uint32_t p = s.to_move;
                     uint32_t A, C; make_masks(s, p, lane, A, C);
-                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane);
+                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane, s_slots);
                     if (tot.n == 0) break;                       // no passes inside a rollout (:488-489)
                     const uint32_t rnd = philox_draw(prm.seed, tree_id, draws++, 1);
                     int o, row, col;

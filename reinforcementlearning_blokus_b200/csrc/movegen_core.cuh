@@ -26,6 +26,7 @@
 __constant__ uint8_t c_orient_piece[BK_TBL_ORIENTS];
 __constant__ uint8_t c_orient_ncells[BK_TBL_ORIENTS];
 __constant__ uint8_t c_orient_cells[BK_TBL_ORIENTS * 5];
+__constant__ uint8_t c_group_first[BK_TBL_GROUPS + 1];
 
 // ---- per-warp game state in registers ----------------------------------------------------------
 struct WarpState {
@@ -125,7 +126,10 @@ __device__ __forceinline__ void make_masks(const WarpState& s, uint32_t player, 
 // on B200: +8 % for the count kernel, -4 % for the playout kernel (which is latency- rather than ALU-bound),
 // so only counting uses it.  Sinks that store rows (kRows) get them mirrored back with one BREV.
 template <class Sink, bool MIRROR = false>
-__device__ __forceinline__ void bk_gen_all(const uint32_t A_in, const uint32_t C_in, const uint32_t used, Sink& sink) {
+__device__ __forceinline__ void bk_gen_all(const uint32_t A_in, const uint32_t C_in, const uint32_t used_in, Sink& sink) {
+    // `used` is the same in every lane; routing it through REDUX puts it in a uniform register, so the 21 piece
+    // tests become uniform branches (no BSSY/BSYNC reconvergence pairs around every piece block)
+    const uint32_t used = __reduce_or_sync(BK_FULL, used_in);
     const uint32_t A = MIRROR ? (__brev(A_in) >> 12) : A_in, C = MIRROR ? (__brev(C_in) >> 12) : C_in;
 #define BK_CS(x, c) (MIRROR ? ((x) << (c)) : ((x) >> (c)))
 #define BK_OUT(L) ((MIRROR && Sink::kRows) ? (__brev(L) >> 12) : (L))
@@ -151,78 +155,98 @@ __device__ __forceinline__ uint32_t bk_gen_one(const uint32_t A, const uint32_t 
 }
 
 // ---- sinks ------------------------------------------------------------------------------------
+// put<O, SLOT>(L): this lane's row of legal anchors of orientation O (SLOT = index of O in its count group);
+// flush<G>(): end of count group G (emitted inside the piece's warp-uniform branch).
 struct CountSink {                 // per-lane move count
     static constexpr bool kRows = false;
     uint32_t acc = 0;
-    template <int O> __device__ __forceinline__ void put(uint32_t L) { acc += __popc(L); }
+    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) { acc += __popc(L); }
+    template <int G> __device__ __forceinline__ void flush() {}
 };
 
 struct AnySink {                   // does any move exist
     static constexpr bool kRows = false;
     uint32_t acc = 0;
-    template <int O> __device__ __forceinline__ void put(uint32_t L) { acc |= L; }
-};
-
-// Per-lane counts of three orientations per register in 10-bit fields (a row holds <= 20 anchors, a
-// warp-wide field sum <= 400 < 1024), so one REDUX yields three per-orientation totals.
-struct PackSink {
-    static constexpr bool kRows = false;
-    uint32_t pk[31];
-    __device__ __forceinline__ PackSink() {
-#pragma unroll
-        for (int i = 0; i < 31; i++) pk[i] = 0;
-    }
-    template <int O> __device__ __forceinline__ void put(uint32_t L) {
-        pk[O / 3] += (uint32_t)__popc(L) << (10 * (O % 3));
-    }
+    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) { acc |= L; }
+    template <int G> __device__ __forceinline__ void flush() {}
 };
 
 struct BitmapSink {                // legal-anchor bitmap rows straight to memory
     static constexpr bool kRows = true;
     uint32_t* out; int lane;
-    template <int O> __device__ __forceinline__ void put(uint32_t L) {
+    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) {
         if (lane < 20) out[O * 20 + lane] = L;
+    }
+    template <int G> __device__ __forceinline__ void flush() {}
+};
+
+// Per-orientation totals for choosing the idx-th move.  The counts of a group's <= 3 orientations sit in 10-bit
+// fields of ONE register (a row holds <= 20 anchors, a warp-wide field sum <= 400 < 1024); when the group ends a
+// single REDUX sums them over the warp (the result lands in a uniform register) and lane 0 parks it in the
+// warp's shared-memory slot G.  Only one accumulator is live at a time, and the bookkeeping costs no ALU-pipe
+// instruction (REDUX on the ADU, one predicated STS).
+#define BK_GROUP_SLOTS 44            /* 41 groups, padded to a multiple of 4 words */
+struct GroupSink {
+    static constexpr bool kRows = false;
+    uint32_t acc = 0;
+    uint32_t* slots;                 // this warp's BK_GROUP_SLOTS words of shared memory, zeroed by begin()
+    int lane;
+    __device__ __forceinline__ void begin(uint32_t* warp_slots, int lane_) {
+        slots = warp_slots; lane = lane_;
+        __syncwarp();
+        if (lane < BK_GROUP_SLOTS / 2) reinterpret_cast<uint2*>(slots)[lane] = make_uint2(0u, 0u);
+        __syncwarp();
+    }
+    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) {
+        acc += (uint32_t)__popc(L) << (10 * SLOT);
+    }
+    template <int G> __device__ __forceinline__ void flush() {
+        const uint32_t v = __reduce_add_sync(BK_FULL, acc);
+        if (lane == 0) slots[G] = v;
+        acc = 0;
     }
 };
 
 // ---- choosing the idx-th legal move in ascending id order ----------------------------------------
-// After PackSink: lane j (< 31) receives the warp totals of orientations 3j..3j+2.
 struct Totals {
-    uint32_t mine;    // packed totals owned by this lane (10-bit fields)
-    uint32_t incl;    // inclusive prefix of this lane's three totals over lanes
-    uint32_t n;       // total number of legal moves
+    uint32_t mine0, mine1;   // packed totals of groups 2*lane and 2*lane+1
+    uint32_t incl;           // inclusive prefix over lanes of this lane's move count
+    uint32_t n;              // total number of legal moves (uniform)
 };
 
-__device__ __forceinline__ Totals reduce_totals(const PackSink& s, int lane) {
-    Totals t; t.mine = 0;
-#pragma unroll
-    for (int j = 0; j < 31; j++) {
-        const uint32_t v = __reduce_add_sync(BK_FULL, s.pk[j]);
-        if (lane == j) t.mine = v;
-    }
-    uint32_t sum = (t.mine & 1023u) + ((t.mine >> 10) & 1023u) + ((t.mine >> 20) & 1023u);
-    uint32_t incl = sum;
+__device__ __forceinline__ uint32_t fields_sum(uint32_t m) { return (m & 1023u) + ((m >> 10) & 1023u) + ((m >> 20) & 1023u); }
+
+__device__ __forceinline__ Totals reduce_totals(const GroupSink& s, int lane) {
+    Totals t;
+    __syncwarp();
+    const uint2 m = (lane < BK_GROUP_SLOTS / 2) ? reinterpret_cast<const uint2*>(s.slots)[lane] : make_uint2(0u, 0u);
+    t.mine0 = m.x; t.mine1 = m.y;
+    const uint32_t mysum = fields_sum(m.x) + fields_sum(m.y);
+    uint32_t incl = mysum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         uint32_t v = __shfl_up_sync(BK_FULL, incl, d);
         if (lane >= d) incl += v;
     }
     t.incl = incl;
-    t.n = __shfl_sync(BK_FULL, incl, 31);
+    t.n = __reduce_add_sync(BK_FULL, mysum);   // uniform register: `n == 0` becomes a uniform branch
     return t;
 }
 
 // Locate move number idx (0-based, idx < t.n): returns the move id; A/C are the masks used for the count.
 __device__ __forceinline__ uint32_t select_move(const Totals& t, uint32_t idx, uint32_t A, uint32_t C, int lane,
                                                 int& o_out, int& row_out, int& col_out) {
-    // lane holding the orientation triple that contains idx
+    // lane holding the group pair that contains idx
     const uint32_t vote = __ballot_sync(BK_FULL, t.incl > idx);
     const int j = __ffs(vote) - 1;
-    const uint32_t mine = __shfl_sync(BK_FULL, t.mine, j);
+    const uint32_t m0 = __shfl_sync(BK_FULL, t.mine0, j), m1 = __shfl_sync(BK_FULL, t.mine1, j);
     const uint32_t incl = __shfl_sync(BK_FULL, t.incl, j);
-    const uint32_t f0 = mine & 1023u, f1 = (mine >> 10) & 1023u, f2 = (mine >> 20) & 1023u;
-    uint32_t rem = idx - (incl - f0 - f1 - f2);
-    int o = 3 * j;
+    const uint32_t s0 = fields_sum(m0), s1 = fields_sum(m1);
+    uint32_t rem = idx - (incl - s0 - s1);
+    int g = 2 * j; uint32_t m = m0;
+    if (rem >= s0) { rem -= s0; g++; m = m1; }
+    const uint32_t f0 = m & 1023u, f1 = (m >> 10) & 1023u;
+    int o = c_group_first[g];
     if (rem >= f0) { rem -= f0; o++; if (rem >= f1) { rem -= f1; o++; } }
     // rows of that orientation
     const uint32_t L = bk_gen_one(A, C, o);
@@ -287,8 +311,9 @@ __device__ __forceinline__ void scores_of(const WarpState& s, int lane, int32_t 
 }
 
 // ---- Philox4x32-10 (same stream as oracle/blokus_oracle.c:orc_philox4x32_10) -------------------------
+// Draw number t of (seed, g, stream): word t%4 of philox4x32_10(key = seed, ctr = (g_lo, g_hi, t/4, stream)).
 __device__ __forceinline__ uint32_t philox_draw(uint64_t seed, uint64_t g, uint32_t t, uint32_t stream) {
-    uint32_t c0 = (uint32_t)g, c1 = (uint32_t)(g >> 32), c2 = t, c3 = stream;
+    uint32_t c0 = (uint32_t)g, c1 = (uint32_t)(g >> 32), c2 = t >> 2, c3 = stream;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; r++) {
@@ -298,5 +323,6 @@ __device__ __forceinline__ uint32_t philox_draw(uint64_t seed, uint64_t g, uint3
         c0 = n0; c1 = l1; c2 = n2; c3 = l0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    return c0;
+    const uint32_t w = t & 3u;
+    return w == 0 ? c0 : w == 1 ? c1 : w == 2 ? c2 : c3;
 }

@@ -93,7 +93,8 @@ def philox4x32_10(ctr, key):
 
 
 def draw(seed: int, g: int, t: int, stream: int = 0) -> int:
-    return philox4x32_10([g & 0xFFFFFFFF, g >> 32, t, stream], [seed & 0xFFFFFFFF, seed >> 32])[0]
+    """Draw number t of (seed, g, stream): word t%4 of the Philox block with counter (g_lo, g_hi, t//4, stream)."""
+    return philox4x32_10([g & 0xFFFFFFFF, g >> 32, t >> 2, stream], [seed & 0xFFFFFFFF, seed >> 32])[t & 3]
 
 
 # ---------------------------------------------------------------------------------------------
