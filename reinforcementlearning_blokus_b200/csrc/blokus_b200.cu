@@ -302,6 +302,9 @@ k_scores(const bk_state* __restrict__ states, int n, int32_t* __restrict__ gs, i
 #ifndef BK_PLAYOUT_THREADS
 #define BK_PLAYOUT_THREADS 256
 #endif
+#ifndef BK_PLAYOUT_MIRROR
+#define BK_PLAYOUT_MIRROR true
+#endif
 __global__ void __launch_bounds__(BK_PLAYOUT_THREADS, BK_PLAYOUT_MIN_BLOCKS)
 k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int first_turn, int max_turns,
                   int32_t* __restrict__ gs, int32_t* __restrict__ bs, uint16_t* __restrict__ trace,
@@ -310,10 +313,12 @@ k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = warp; i < n; i += nwarps) {
+    for (int i0 = warp; i0 < n; i0 += nwarps) {
+        const int i = (int)uni((uint32_t)i0);              // warp-uniform game index
         WarpState s;
         if (start) load_state(start + i, lane, s); else init_empty(s);
         const uint64_t g = game_offset + (uint64_t)i;
+        PhiloxBlock rnd; rnd.w[0] = rnd.w[1] = rnd.w[2] = rnd.w[3] = 0;
         uint16_t* tr = trace ? trace + (size_t)i * BK_MAX_TURNS : nullptr;
         uint16_t* ch = choice ? choice + (size_t)i * BK_MAX_TURNS : nullptr;
         for (int k = first_turn + lane; k < BK_MAX_TURNS; k += 32) { if (tr) tr[k] = BK_PASS; if (ch) ch[k] = BK_PASS; }
@@ -330,11 +335,12 @@ k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint
         for (uint32_t t = (uint32_t)first_turn; dead != 0xFu; t++) {
             const bool probing = t >= (uint32_t)max_turns;
             if (t == (uint32_t)max_turns) cut_to_move = s.to_move;
+            if ((t & 3u) == 0u || t == (uint32_t)first_turn) rnd = philox_block(seed, g, t >> 2, 0);
             const uint32_t p = s.to_move;
             bool moved = false;
             if (!((dead >> p) & 1u)) {
                 uint32_t A, C; make_masks(s, p, lane, A, C);
-                GroupSink sink; sink.begin(s_slots[threadIdx.x >> 5], lane); bk_gen_all(A, C, sel4(s.used, p), sink);
+                GroupSink sink; sink.begin(s_slots[threadIdx.x >> 5], lane); bk_gen_all<GroupSink, BK_PLAYOUT_MIRROR>(A, C, sel4(s.used, p), sink);
                 const Totals tot = reduce_totals(sink, lane);
                 if (tot.n == 0) {
                     dead |= 1u << p;      // a player without moves never regains any ("dead stay dead")
@@ -342,8 +348,7 @@ k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint
                     still_alive = true;
                     break;
                 } else {
-                    const uint32_t r = philox_draw(seed, g, t, 0);
-                    const uint32_t idx = __umulhi(r, tot.n);
+                    const uint32_t idx = __umulhi(philox_word(rnd, t), tot.n);
                     int o, row, col;
                     const uint32_t id = select_move(tot, idx, A, C, lane, o, row, col);
                     place_move(s, p, o, row, col, lane);

@@ -41,6 +41,15 @@ __device__ __forceinline__ uint32_t sel4(const uint32_t (&v)[4], uint32_t i) {
     return (i & 2) ? b : a;
 }
 
+// The scalars of a state are equal in all lanes; passing them through REDUX once tells the compiler so (the
+// results live in uniform registers), and branches on them need no reconvergence bookkeeping.
+__device__ __forceinline__ uint32_t uni(uint32_t x) { return __reduce_max_sync(BK_FULL, x); }
+__device__ __forceinline__ void make_uniform(WarpState& s) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) s.used[q] = uni(s.used[q]);
+    s.to_move = uni(s.to_move); s.first_mask = uni(s.first_mask); s.move_count = uni(s.move_count);
+}
+
 __device__ __forceinline__ void init_empty(WarpState& s) {
 #pragma unroll
     for (int q = 0; q < 4; q++) { s.P[q] = 0; s.used[q] = 0; }
@@ -68,6 +77,7 @@ __device__ __forceinline__ void load_state(const bk_state* __restrict__ sp, int 
     s.to_move = (uint32_t)meta & 3u;
     s.first_mask = (uint32_t)(meta >> 8) & 0xFu;
     s.move_count = (uint32_t)(meta >> 16) & 0xFFFFu;
+    make_uniform(s);
 }
 
 // rows -> 256-byte packed state.  Lane i assembles 64-bit word i.
@@ -123,8 +133,8 @@ __device__ __forceinline__ void make_masks(const WarpState& s, uint32_t player, 
 // column shift into a LEFT shift; ptxas issues those as IMAD.SHL on the FMA pipe instead of SHF on the ALU pipe
 // that LOP3 already loads (profiles/r01a_playout_ncu.md: ALU 69 %, FMA 10 %).  Garbage above bit 19 cannot
 // survive: every orientation has a cell in column 0, so its AND contains an unshifted, clean factor.  Measured
-// on B200: +8 % for the count kernel, -4 % for the playout kernel (which is latency- rather than ALU-bound),
-// so only counting uses it.  Sinks that store rows (kRows) get them mirrored back with one BREV.
+// on B200: +8 % for the count kernel, +6 % for the playout kernel (14.6 -> 15.5 M playouts/s), so the counting
+// sinks use it.  Sinks that store rows (kRows) get them mirrored back with one BREV.
 template <class Sink, bool MIRROR = false>
 __device__ __forceinline__ void bk_gen_all(const uint32_t A_in, const uint32_t C_in, const uint32_t used_in, Sink& sink) {
     // `used` is the same in every lane; routing it through REDUX puts it in a uniform register, so the 21 piece
@@ -265,8 +275,9 @@ __device__ __forceinline__ uint32_t select_move(const Totals& t, uint32_t idx, u
     uint32_t bits = Lr;
     while (k--) bits &= bits - 1;
     const int col = __ffs(bits) - 1;
-    o_out = o; row_out = row; col_out = col;
-    return (uint32_t)(o * 400 + row * 20 + col);
+    const uint32_t id = uni((uint32_t)(o * 400 + row * 20 + col));    // same in all lanes -> uniform register
+    o_out = (int)(id / 400u); row_out = (int)((id % 400u) / 20u); col_out = (int)(id % 20u);
+    return id;
 }
 
 // Apply a placement for the side `player` -- engine/board.py:515-555 (cells, used, first-move flag,
@@ -312,6 +323,25 @@ __device__ __forceinline__ void scores_of(const WarpState& s, int lane, int32_t 
 
 // ---- Philox4x32-10 (same stream as oracle/blokus_oracle.c:orc_philox4x32_10) -------------------------
 // Draw number t of (seed, g, stream): word t%4 of philox4x32_10(key = seed, ctr = (g_lo, g_hi, t/4, stream)).
+struct PhiloxBlock { uint32_t w[4]; };
+__device__ __forceinline__ PhiloxBlock philox_block(uint64_t seed, uint64_t g, uint32_t block, uint32_t stream) {
+    uint32_t c0 = (uint32_t)g, c1 = (uint32_t)(g >> 32), c2 = block, c3 = stream;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    PhiloxBlock b; b.w[0] = c0; b.w[1] = c1; b.w[2] = c2; b.w[3] = c3;
+    return b;
+}
+__device__ __forceinline__ uint32_t philox_word(const PhiloxBlock& b, uint32_t t) {
+    const uint32_t w = t & 3u;
+    return w == 0 ? b.w[0] : w == 1 ? b.w[1] : w == 2 ? b.w[2] : b.w[3];
+}
 __device__ __forceinline__ uint32_t philox_draw(uint64_t seed, uint64_t g, uint32_t t, uint32_t stream) {
     uint32_t c0 = (uint32_t)g, c1 = (uint32_t)(g >> 32), c2 = t >> 2, c3 = stream;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
