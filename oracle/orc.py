@@ -78,7 +78,7 @@ def lib() -> C.CDLL:
         L.orc_philox4x32_10.argtypes = [vp, vp, vp]
         L.orc_heuristic_score.argtypes = [vp, i32, i32]
         L.orc_heuristic_score.restype = C.c_double
-        L.orc_playout.argtypes = [vp, u64, u64, i32, i32, i32, vp, vp, vp, vp, vp]
+        L.orc_playout.argtypes = [vp, u64, u64, i32, i32, i32, i32, vp, vp, vp, vp, vp]
         L.orc_zobrist_table.argtypes = [u32, vp]
         L.orc_zobrist_hash.argtypes = [vp, vp]
         L.orc_zobrist_hash.restype = u64
@@ -87,7 +87,7 @@ def lib() -> C.CDLL:
         L.orc_tt_destroy.argtypes = [vp]
         L.orc_tt_size.argtypes = [vp]
         L.orc_tt_size.restype = u64
-        L.orc_mcts_search.argtypes = [vp, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, vp, vp]
+        L.orc_mcts_search.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, vp, vp]
         L.orc_check_moves_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp]
         L.orc_init()
         _lib = L
@@ -238,6 +238,7 @@ def playout(
     max_turns: int = 0,
     fast: bool = True,
     first_turn: int = 0,
+    policy: int = 0,
     want_final: bool = False,
 ):
     """One Philox-driven random game; returns dict(game_scores, board_scores, trace, choice, turns)."""
@@ -249,7 +250,7 @@ def playout(
     st = None
     if start is not None:
         st = np.ascontiguousarray(np.atleast_1d(start), dtype=STATE_DTYPE)
-    turns = lib().orc_playout(_ptr(st), int(seed), int(game_index), int(first_turn), int(max_turns), int(fast),
+    turns = lib().orc_playout(_ptr(st), int(seed), int(game_index), int(policy), int(first_turn), int(max_turns), int(fast),
                               _ptr(gs), _ptr(bs), _ptr(tr), _ptr(ch), _ptr(fin))
     res = {"game_scores": gs, "board_scores": bs, "trace": tr, "choice": ch, "turns": int(turns)}
     if want_final:
@@ -273,7 +274,7 @@ class OracleTT:
 
 
 def mcts_search(root: np.ndarray, iterations: int, seed: int, tree_id: int = 0, max_rollout_moves: int = 50,
-                max_depth: int = 0, ucb_variant: int = 0, reward_mode: int = 0, exploration: float = 1.414, tt: Optional[OracleTT] = None,
+                max_depth: int = 0, ucb_variant: int = 0, reward_mode: int = 0, rollout_policy: int = 0, exploration: float = 1.414, tt: Optional[OracleTT] = None,
                 zobrist: Optional[np.ndarray] = None, max_root_moves: int = 2048):
     """Sequential UCT with canonical untried order and Philox rollouts; returns dict(n_root, visits, reward, moves)."""
     st = np.ascontiguousarray(np.atleast_1d(root), dtype=STATE_DTYPE)
@@ -282,7 +283,7 @@ def mcts_search(root: np.ndarray, iterations: int, seed: int, tree_id: int = 0, 
     mov = np.zeros(max_root_moves, dtype=np.uint16)
     zt = None if zobrist is None else np.ascontiguousarray(zobrist, dtype=np.uint64)
     n = lib().orc_mcts_search(_ptr(st), int(iterations), int(max_rollout_moves), int(max_depth), int(ucb_variant),
-                              int(reward_mode), float(exploration), int(seed), int(tree_id), tt.h if tt else None, _ptr(zt),
+                              int(reward_mode), int(rollout_policy), float(exploration), int(seed), int(tree_id), tt.h if tt else None, _ptr(zt),
                               int(max_root_moves), _ptr(vis), _ptr(rew), _ptr(mov))
     return {"n_root": int(n), "visits": vis, "reward": rew, "moves": mov}
 

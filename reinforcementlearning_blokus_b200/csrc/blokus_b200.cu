@@ -48,6 +48,9 @@ __global__ void k_movegen_emit(const bk_state* __restrict__, const uint8_t* __re
                                uint32_t, uint32_t* __restrict__, uint16_t* __restrict__);
 #define BK_EMIT_SMEM_BYTES (8 * (32 * 57 * 4 + 2048 * 2))
 
+static cudaError_t bk_init_policies_impl();
+static cudaError_t bk_init_policies() { return bk_init_policies_impl(); }
+
 extern "C" int bk_init(int device) {
     int count = 0;
     CUDA_TRY(cudaGetDeviceCount(&count));
@@ -59,6 +62,7 @@ extern "C" int bk_init(int device) {
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_cells, BK_TBL_ORIENT_CELLS, sizeof(BK_TBL_ORIENT_CELLS)));
     CUDA_TRY(cudaMemcpyToSymbol(c_group_first, BK_TBL_GROUP_FIRST, sizeof(BK_TBL_GROUP_FIRST)));
     CUDA_TRY(cudaFuncSetAttribute(k_movegen_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
+    CUDA_TRY(bk_init_policies());
     g_device = device;
     return BK_OK;
 }
@@ -293,8 +297,11 @@ k_scores(const bk_state* __restrict__ states, int n, int32_t* __restrict__ gs, i
     }
 }
 
+#include "heuristic.cuh"
+
 // ---------------------------------------------------------------------------------------------
-// K2: playouts (uniform policy).  One warp plays one whole game in registers.
+// K2: playouts.  One warp plays one whole game in registers.  POLICY 0 = uniform (agents/random_agent.py),
+// POLICY 1 = HeuristicAgent softmax (agents/heuristic_agent.py, heuristic.cuh).
 // ---------------------------------------------------------------------------------------------
 #ifndef BK_PLAYOUT_MIN_BLOCKS
 #define BK_PLAYOUT_MIN_BLOCKS 3
@@ -305,11 +312,15 @@ k_scores(const bk_state* __restrict__ states, int n, int32_t* __restrict__ gs, i
 #ifndef BK_PLAYOUT_MIRROR
 #define BK_PLAYOUT_MIRROR true
 #endif
-__global__ void __launch_bounds__(BK_PLAYOUT_THREADS, BK_PLAYOUT_MIN_BLOCKS)
-k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int first_turn, int max_turns,
+template <int POLICY>
+__global__ void __launch_bounds__(BK_PLAYOUT_THREADS, POLICY == 0 ? BK_PLAYOUT_MIN_BLOCKS : 2)
+k_playout(const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int first_turn, int max_turns,
                   int32_t* __restrict__ gs, int32_t* __restrict__ bs, uint16_t* __restrict__ trace,
                   uint16_t* __restrict__ choice, bk_state* __restrict__ finals) {
     __shared__ __align__(16) uint32_t s_slots[BK_PLAYOUT_THREADS / 32][BK_GROUP_SLOTS];
+    extern __shared__ __align__(16) unsigned char heur_smem[];
+    HeurScratch hs;
+    if (POLICY == 1) hs.bind(heur_smem + (size_t)(threadIdx.x >> 5) * HEUR_SMEM_PER_WARP);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -339,22 +350,40 @@ k_playout_uniform(const bk_state* __restrict__ start, int n, uint64_t seed, uint
             const uint32_t p = s.to_move;
             bool moved = false;
             if (!((dead >> p) & 1u)) {
-                uint32_t A, C; make_masks(s, p, lane, A, C);
-                GroupSink sink; sink.begin(s_slots[threadIdx.x >> 5], lane); bk_gen_all<GroupSink, BK_PLAYOUT_MIRROR>(A, C, sel4(s.used, p), sink);
-                const Totals tot = reduce_totals(sink, lane);
-                if (tot.n == 0) {
-                    dead |= 1u << p;      // a player without moves never regains any ("dead stay dead")
-                } else if (probing) {
-                    still_alive = true;
-                    break;
+                if (POLICY == 0) {
+                    uint32_t A, C; make_masks(s, p, lane, A, C);
+                    GroupSink sink; sink.begin(s_slots[threadIdx.x >> 5], lane);
+                    bk_gen_all<GroupSink, BK_PLAYOUT_MIRROR>(A, C, sel4(s.used, p), sink);
+                    const Totals tot = reduce_totals(sink, lane);
+                    if (tot.n == 0) {
+                        dead |= 1u << p;      // a player without moves never regains any ("dead stay dead")
+                    } else if (probing) {
+                        still_alive = true;
+                        break;
+                    } else {
+                        const uint32_t idx = __umulhi(philox_word(rnd, t), tot.n);
+                        int o, row, col;
+                        const uint32_t id = select_move(tot, idx, A, C, lane, o, row, col);
+                        place_move(s, p, o, row, col, lane);
+                        resume_to_move = s.to_move;
+                        if (lane == 0) { if (tr) tr[t] = (uint16_t)id; if (ch) ch[t] = (uint16_t)idx; }
+                        moved = true;
+                    }
                 } else {
-                    const uint32_t idx = __umulhi(philox_word(rnd, t), tot.n);
-                    int o, row, col;
-                    const uint32_t id = select_move(tot, idx, A, C, lane, o, row, col);
-                    place_move(s, p, o, row, col, lane);
-                    resume_to_move = s.to_move;
-                    if (lane == 0) { if (tr) tr[t] = (uint16_t)id; if (ch) ch[t] = (uint16_t)idx; }
-                    moved = true;
+                    uint32_t id = 0, idx = 0;
+                    const uint32_t nmoves = heuristic_pick(s, p, philox_word(rnd, t), hs, lane, id, idx);
+                    if (nmoves == 0) {
+                        dead |= 1u << p;
+                    } else if (probing) {
+                        still_alive = true;
+                        break;
+                    } else {
+                        const int o = (int)(id / 400u), row = (int)((id % 400u) / 20u), col = (int)(id % 20u);
+                        place_move(s, p, o, row, col, lane);
+                        resume_to_move = s.to_move;
+                        if (lane == 0) { if (tr) tr[t] = (uint16_t)id; if (ch) ch[t] = (uint16_t)idx; }
+                        moved = true;
+                    }
                 }
             }
             if (!moved) s.to_move = (p + 1) & 3u;   // pass: engine/board.py:557-560 via arena_runner.py:662-666
@@ -573,6 +602,18 @@ k_heuristic_scores(const bk_state* __restrict__ states, const uint8_t* __restric
 
 #include "mcts.cuh"
 
+#define BK_HEUR_PLAYOUT_SMEM ((BK_PLAYOUT_THREADS / 32) * HEUR_SMEM_PER_WARP)
+static cudaError_t bk_init_policies_impl() {
+    cudaError_t e = cudaFuncSetAttribute(k_playout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_HEUR_PLAYOUT_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_mcts, cudaFuncAttributeMaxDynamicSharedMemorySize, HEUR_SMEM_PER_WARP);
+    if (e != cudaSuccess) return e;
+    k_init_centre<<<2, 256>>>();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaDeviceSynchronize();
+}
+
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -662,14 +703,20 @@ extern "C" int bk_playout(const bk_state* start_states, int n, uint64_t seed, ui
                           uint16_t* choice, bk_state* final_states, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0, "bk_playout: negative n");
     REQUIRE(max_turns >= 0 && max_turns <= BK_MAX_TURNS, "bk_playout: max_turns out of range");
-    if (policy != BK_POLICY_UNIFORM) return fail(BK_ERR_ARG, "%s", "bk_playout: unknown policy");
+    if (policy != BK_POLICY_UNIFORM && policy != BK_POLICY_HEURISTIC) return fail(BK_ERR_ARG, "%s", "bk_playout: unknown policy");
     if (n == 0) return BK_OK;
     if (max_turns == 0) max_turns = BK_MAX_TURNS;
     REQUIRE(first_turn >= 0 && first_turn <= max_turns, "bk_playout: first_turn out of range");
     const int pw = BK_PLAYOUT_THREADS / 32;
     long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)g_sms * BK_PLAYOUT_MIN_BLOCKS;
-    k_playout_uniform<<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, 0, as_stream(stream)>>>(
-        start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+    if (policy == BK_POLICY_UNIFORM) {
+        k_playout<0><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, 0, as_stream(stream)>>>(
+            start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+    } else {
+        pcap = (long long)g_sms * 2;
+        k_playout<1><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, BK_HEUR_PLAYOUT_SMEM, as_stream(stream)>>>(
+            start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+    }
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -761,7 +808,8 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
     REQUIRE(roots && params && workspace && n_roots > 0 && n_trees > 0 && max_root_moves >= 0, "bk_mcts_search: bad argument");
     REQUIRE(params->iterations >= 0 && params->iterations_total > 0 && params->iterations_total <= 60000,
             "bk_mcts_search: iterations_total must be in [1, 60000]");
-    REQUIRE(params->rollout_policy == BK_POLICY_UNIFORM, "bk_mcts_search: unknown rollout policy");
+    REQUIRE(params->rollout_policy == BK_POLICY_UNIFORM || params->rollout_policy == BK_POLICY_HEURISTIC,
+            "bk_mcts_search: unknown rollout policy");
     REQUIRE(!tt || zobrist_table, "bk_mcts_search: a transposition table needs a Zobrist table");
     const MctsLayout L = mcts_layout(params->iterations_total);
     if ((int64_t)L.total * n_trees > workspace_bytes) return fail(BK_ERR_CAPACITY, "%s", "bk_mcts_search: workspace too small");
@@ -769,7 +817,8 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
     if (tt) { t.keys = tt->keys; t.rewards = tt->rewards; t.occupied = tt->occupied; t.log2_slots = tt->log2_slots; }
     const int cap = g_sms * 16;
     const int grid = n_trees < cap ? n_trees : cap;
-    k_mcts<<<grid, BK_MCTS_THREADS, 0, as_stream(stream)>>>(roots, n_roots, n_trees, *params, t,
+    const size_t mcts_smem = params->rollout_policy == BK_POLICY_HEURISTIC ? HEUR_SMEM_PER_WARP : 0;
+    k_mcts<<<grid, BK_MCTS_THREADS, mcts_smem, as_stream(stream)>>>(roots, n_roots, n_trees, *params, t,
         reinterpret_cast<unsigned char*>(workspace), params->resume, max_root_moves, root_visits,
         reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status);
     LAUNCH_CHECK();

@@ -1,0 +1,156 @@
+// heuristic.cuh -- HeuristicAgent as a device playout policy (agents/heuristic_agent.py:39-66, 222-244).
+//
+// select_action = softmax(T = 1) over the move scores, then one categorical draw.  On the device, per turn:
+//   1. rows of all legal anchors -> shared memory (same generator, SmemRowSink)
+//   2. ascending move list in shared memory (each lane owns 57 consecutive row words; one warp scan)
+//   3. per move: corner / edge features (1 byte), float64 score, warp max
+//   4. e_k = exp(score_k - max) summed per lane (lane L owns moves k = L, L+32, ...), Hillis-Steele scan over lanes
+//   5. target = total * r * 2^-32 with r the turn's Philox word; the lane whose inclusive sum first exceeds the
+//      target, then the first move inside that lane whose running sum exceeds it
+// Every floating-point operation has a fixed order, restated in oracle/blokus_oracle.c (heuristic_pick), so the
+// CPU oracle draws the same move.  The reference draws with numpy's RandomState.choice; as with the uniform
+// policy the random stream is Philox (DESIGN.md "Random streams"), the distribution is the reference's.
+#pragma once
+#include "movegen_core.cuh"
+
+#define HEUR_WORDS_PER_LANE 57
+#define HEUR_ROW_WORDS (32 * HEUR_WORDS_PER_LANE)       /* 1824 >= 91*20 */
+#define HEUR_MAX_MOVES 2048
+#define HEUR_SMEM_PER_WARP (HEUR_ROW_WORDS * 4 + HEUR_MAX_MOVES * 2 + HEUR_MAX_MOVES + 32 * 4)
+
+__device__ double g_centre[400];   // 1 - dist(anchor, centre)/max_dist, filled by k_init_centre (heuristic_agent.py:185-198)
+
+__global__ void k_init_centre() {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= 400) return;
+    const int ar = cell / 20, ac = cell - ar * 20;
+    const double dr = __dsub_rn((double)ar, 9.5), dc = __dsub_rn((double)ac, 9.5);
+    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc)));
+    const double maxd = __dsqrt_rn(__dmul_rn(2.0, __dmul_rn(9.5, 9.5)));
+    g_centre[cell] = __dsub_rn(1.0, __ddiv_rn(dist, maxd));
+}
+
+struct HeurScratch {
+    uint32_t* rows;    // HEUR_ROW_WORDS
+    uint16_t* ids;     // HEUR_MAX_MOVES
+    uint8_t* feat;     // HEUR_MAX_MOVES : corners | edge << 5
+    uint32_t* arows;   // 32
+    __device__ __forceinline__ void bind(unsigned char* base) {
+        rows = reinterpret_cast<uint32_t*>(base);
+        ids = reinterpret_cast<uint16_t*>(rows + HEUR_ROW_WORDS);
+        feat = reinterpret_cast<uint8_t*>(ids + HEUR_MAX_MOVES);
+        arows = reinterpret_cast<uint32_t*>(feat + HEUR_MAX_MOVES);
+    }
+};
+
+struct HeurRowSink {
+    static constexpr bool kRows = true;
+    uint32_t* rows; int lane;
+    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) { if (lane < 20) rows[O * 20 + lane] = L; }
+    template <int G> __device__ __forceinline__ void flush() {}
+};
+
+// corners (0..20) and edge cells (0..5) of a move, evaluated before the placement (heuristic_agent.py:105-176)
+__device__ __forceinline__ uint32_t heur_features(const uint32_t* __restrict__ arows, uint32_t id) {
+    const int o = id / 400, cell = id - o * 400, ar = cell / 20, ac = cell - ar * 20;
+    const int n = c_orient_ncells[o];
+    uint32_t corners = 0, edge = 0;
+    for (int i = 0; i < n; i++) {
+        const uint32_t rc = c_orient_cells[o * 5 + i];
+        const int r = ar + (int)(rc >> 4), c = ac + (int)(rc & 15);
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int nr = r + ((d & 2) ? 1 : -1), nc = c + ((d & 1) ? 1 : -1);
+            if (nr >= 0 && nr < 20 && nc >= 0 && nc < 20) corners += (arows[nr] >> nc) & 1u;
+        }
+        edge += (min(min(r, c), min(19 - r, 19 - c)) <= 2);
+    }
+    return corners | (edge << 5);
+}
+
+// the score of heuristic_score() (blokus_b200.cu) rebuilt from the stored features, same operation order
+__device__ __forceinline__ double heur_score_from(uint32_t feat, uint32_t id, uint32_t move_count) {
+    const int o = id / 400, cell = id - o * 400;
+    double score = __dadd_rn(0.0, __dmul_rn(1.0, (double)c_orient_ncells[o]));
+    score = __dadd_rn(score, __dmul_rn(2.0, (double)(feat & 31u)));
+    const double edge = (double)(feat >> 5);
+    const double progress = __ddiv_rn((double)move_count, 100.0);
+    const double edge_score = (progress < 0.3) ? edge : __dmul_rn(edge, 0.5);
+    score = __dadd_rn(score, __dmul_rn(-1.5, edge_score));
+    return __dadd_rn(score, __dmul_rn(0.5, g_centre[cell]));
+}
+
+// Returns the number of legal moves of `p`; when > 0 picks one by the Philox word r and returns it through
+// (id, idx = rank in the ascending list).  All lanes return the same values.
+__device__ __noinline__ uint32_t heuristic_pick(const WarpState& s, uint32_t p, uint32_t r, HeurScratch sc, int lane,
+                                                uint32_t& id_out, uint32_t& idx_out) {
+    uint32_t A, C; make_masks(s, p, lane, A, C);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < HEUR_WORDS_PER_LANE; k++) sc.rows[k * 32 + lane] = 0;
+    sc.arows[lane] = A;
+    __syncwarp();
+    HeurRowSink sink; sink.rows = sc.rows; sink.lane = lane;
+    bk_gen_all(A, C, sel4(s.used, p), sink);
+    __syncwarp();
+    // ---- ascending move list
+    const uint32_t* mine = sc.rows + lane * HEUR_WORDS_PER_LANE;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < HEUR_WORDS_PER_LANE; k++) cnt += __popc(mine[k]);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(BK_FULL, incl, d); if (lane >= d) incl += v; }
+    uint32_t n = __reduce_add_sync(BK_FULL, cnt);
+    if (n == 0) return 0;
+    if (n > HEUR_MAX_MOVES) n = HEUR_MAX_MOVES;            // never reached in play (largest list seen: 1003)
+    uint32_t pos = incl - cnt;
+    for (int k = 0; k < HEUR_WORDS_PER_LANE; k++) {
+        uint32_t bits = mine[k];
+        const uint32_t idb = (uint32_t)(lane * HEUR_WORDS_PER_LANE + k) * 20u;
+        while (bits) {
+            const int col = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (pos < HEUR_MAX_MOVES) sc.ids[pos] = (uint16_t)(idb + col);
+            pos++;
+        }
+    }
+    __syncwarp();
+    // ---- features, scores, max
+    const double NEG_INF = __longlong_as_double(0xFFF0000000000000ll);
+    double mx = NEG_INF;
+    for (uint32_t k = lane; k < n; k += 32) {
+        const uint32_t id = sc.ids[k];
+        const uint32_t f = heur_features(sc.arows, id);
+        sc.feat[k] = (uint8_t)f;
+        mx = fmax(mx, heur_score_from(f, id, s.move_count));
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(BK_FULL, mx, d));
+    __syncwarp();
+    // ---- per-lane sums of exp(score - max), scan over lanes
+    double sum = 0.0;
+    for (uint32_t k = lane; k < n; k += 32)
+        sum = __dadd_rn(sum, exp(__dsub_rn(heur_score_from(sc.feat[k], sc.ids[k], s.move_count), mx)));
+    double dincl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const double v = __shfl_up_sync(BK_FULL, dincl, d); if (lane >= d) dincl = __dadd_rn(dincl, v); }
+    const double total = __shfl_sync(BK_FULL, dincl, 31);
+    const double target = __dmul_rn(total, __dmul_rn((double)r, 2.3283064365386963e-10));   // r * 2^-32
+    const uint32_t vote = __ballot_sync(BK_FULL, dincl > target);
+    const int L = vote ? (__ffs(vote) - 1) : 31;
+    double acc = __shfl_up_sync(BK_FULL, dincl, 1);
+    if (lane == 0) acc = 0.0;
+    acc = __shfl_sync(BK_FULL, acc, L);
+    // walk lane L's moves (every lane does the same arithmetic, so the result is uniform without a broadcast)
+    uint32_t pick = (uint32_t)L;
+    for (uint32_t k = (uint32_t)L; k < n; k += 32) {
+        pick = k;
+        acc = __dadd_rn(acc, exp(__dsub_rn(heur_score_from(sc.feat[k], sc.ids[k], s.move_count), mx)));
+        if (acc > target) break;
+    }
+    if (pick >= n) pick = n - 1;     // only if lane L owns no move at all (cannot happen: its sum exceeded target)
+    idx_out = uni(pick);
+    id_out = uni((uint32_t)sc.ids[pick]);
+    return n;
+}

@@ -14,6 +14,7 @@
 // the row-sliced generator (count per orientation -> orientation -> row -> column).
 #pragma once
 #include "movegen_core.cuh"
+#include "heuristic.cuh"
 // (included by blokus_b200.cu after zobrist_of / tt_lookup / tt_insert are defined)
 
 struct MctsLayout {            // byte offsets inside one tree's workspace slice
@@ -76,6 +77,8 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
        int32_t* __restrict__ out_visits, long long* __restrict__ out_reward, uint32_t* __restrict__ out_counts,
        uint16_t* __restrict__ out_moves, uint32_t* __restrict__ out_status) {
     __shared__ __align__(16) uint32_t s_slots[BK_GROUP_SLOTS];
+    extern __shared__ __align__(16) unsigned char heur_smem[];    // HEUR_SMEM_PER_WARP bytes when rollout_policy == 1
+    HeurScratch hs; hs.bind(heur_smem);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -199,6 +202,13 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
                 const int limit = prm.max_rollout_moves > 0 ? prm.max_rollout_moves : 1 << 30;
                 for (int ply = 0; ply < limit; ply++) {
                     const uint32_t p = s.to_move;
+                    if (prm.rollout_policy == BK_POLICY_HEURISTIC) {      // HeuristicAgent, the reference's default (:275-276)
+                        uint32_t id = 0, idx = 0;
+                        if (heuristic_pick(s, p, philox_draw(prm.seed, tree_id, draws, 1), hs, lane, id, idx) == 0) break;
+                        draws++;
+                        place_move(s, p, (int)(id / 400u), (int)((id % 400u) / 20u), (int)(id % 20u), lane);
+                        continue;
+                    }
                     uint32_t A, C; make_masks(s, p, lane, A, C);
                     const Totals tot = gen_totals(A, C, sel4(s.used, p), lane, s_slots);
                     if (tot.n == 0) break;                       // no passes inside a rollout (:488-489)

@@ -111,13 +111,13 @@ class DeviceUCT:
 
     def __init__(self, iterations_total: int, n_trees: int = 1, max_rollout_moves: int = 50, max_depth: int = 0,
                  ucb_variant: int = 0, exploration: float = 1.414, seed: int = 0, tree_offset: int = 0,
-                 reward_mode: int = 0, tt: Optional[dev.DeviceTranspositionTable] = None, zobrist: Optional[ZobristHash] = None,
+                 reward_mode: int = 0, rollout_policy: int = 0, tt: Optional[dev.DeviceTranspositionTable] = None, zobrist: Optional[ZobristHash] = None,
                  max_root_moves: int = MAX_ROOT_MOVES):
         if not torch.cuda.is_available():
             raise _lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
         self.lib = _lib.init(torch.cuda.current_device())
         self.p = _lib.MctsParams(iterations=0, iterations_total=int(iterations_total),
-                                 max_rollout_moves=int(max_rollout_moves), rollout_policy=0, max_depth=int(max_depth),
+                                 max_rollout_moves=int(max_rollout_moves), rollout_policy=int(rollout_policy), max_depth=int(max_depth),
                                  ucb_variant=int(ucb_variant), resume=0, reward_mode=int(reward_mode), exploration=float(exploration),
                                  seed=int(seed) & (2**64 - 1), tree_offset=int(tree_offset))
         self.n_trees = int(n_trees)
@@ -186,9 +186,9 @@ def _best_by_visits_creation_order(visits: np.ndarray, n_root: int) -> int:
 class MCTSAgent:
     """UCT agent; every simulation (select/expand/rollout/backprop) runs in one device kernel.
 
-    Same constructor arguments as the reference.  Differences, all documented in DESIGN.md: rollouts draw
-    uniformly with Philox (``rollout_agent`` objects are accepted for interface compatibility but only their
-    kind matters); the learned-evaluator options (OUT OF SCOPE in SURVEY.md section 2) raise if enabled;
+    Same constructor arguments as the reference.  Differences, all documented in DESIGN.md: rollout moves are
+    drawn with Philox on the device (``rollout_agent`` objects are accepted for interface compatibility but only
+    their kind -- heuristic softmax, the default, or uniform random -- matters); the learned-evaluator options (OUT OF SCOPE in SURVEY.md section 2) raise if enabled;
     ``num_trees`` > 1 adds root-parallel trees whose root statistics are summed.
     """
 
@@ -214,7 +214,16 @@ class MCTSAgent:
         self.seed = 0 if seed is None else int(seed)
         self.move_generator = get_shared_generator()
         self.zobrist_hash = ZobristHash(seed=seed)
+        # rollout policy: HeuristicAgent by default, as in the reference (mcts_agent.py:275-276); an agent whose
+        # get_action_info() says "random" selects the uniform policy.  Either way the draw itself is Philox.
         self.rollout_agent = rollout_agent
+        kind = "heuristic"
+        if rollout_agent is not None:
+            try:
+                kind = rollout_agent.get_action_info().get("type", "heuristic")
+            except Exception:
+                kind = "heuristic"
+        self.rollout_policy = dev.POLICY_UNIFORM if kind == "random" else dev.POLICY_HEURISTIC
         self.transposition_table = TranspositionTable() if use_transposition_table else None
         self._searches = 0
         self.reset_stats()
@@ -230,7 +239,8 @@ class MCTSAgent:
         offset = self._searches * max(self.num_trees, 1)
         self._searches += 1
         return DeviceUCT(total, n_trees=self.num_trees, max_rollout_moves=self.max_rollout_moves,
-                         exploration=self.exploration_constant, seed=self.seed, tree_offset=offset, tt=tt,
+                         exploration=self.exploration_constant, seed=self.seed, tree_offset=offset,
+                         rollout_policy=self.rollout_policy, tt=tt,
                          zobrist=self.zobrist_hash if tt is not None else None)
 
     def search_root(self, board: Board, player: Player) -> Dict[str, np.ndarray]:

@@ -88,7 +88,7 @@ def test_mcts_agent_interface(golden_dir):
     # the move equals the oracle's best-by-visits with the reference's tie-break (first max in creation order)
     st = board.to_packed()
     ott = orc.OracleTT(18)
-    want = orc.mcts_search(st, 150, seed=4, tree_id=0, tt=ott, zobrist=orc.zobrist_table(4))
+    want = orc.mcts_search(st, 150, seed=4, tree_id=0, rollout_policy=1, tt=ott, zobrist=orc.zobrist_table(4))
     n = want["n_root"]
     best, best_v = -1, -1
     for rank in range(n - 1, -1, -1):
@@ -124,3 +124,26 @@ def test_playout_segments_chain(golden_dir):
     assert torch.equal(r["trace"], full["trace"])
     assert torch.equal(r["game_scores"], full["game_scores"])
     assert torch.equal(st, full["final_states"])
+
+
+def test_heuristic_policy_playouts_and_rollouts(golden_dir):
+    """N1: HeuristicAgent softmax as a device policy -- whole games and UCT rollouts equal the oracle's."""
+    n, seed = 96, 31
+    r = dev.playout(n, seed=seed, game_offset=500, policy=dev.POLICY_HEURISTIC, want_trace=True, want_choice=True,
+                    want_final=True)
+    tr, ch, gs = r["trace"].cpu().numpy(), r["choice"].cpu().numpy(), r["game_scores"].cpu().numpy()
+    for i in range(0, n, 6):
+        o = orc.playout(seed, 500 + i, policy=1, want_final=True)
+        assert np.array_equal(tr[i], o["trace"]), i
+        assert np.array_equal(ch[i], o["choice"]) and np.array_equal(gs[i], o["game_scores"])
+        assert r["final_states"][i].cpu().numpy().tobytes() == o["final"].tobytes()
+    # the heuristic prefers big pieces: it scores clearly higher than uniform play
+    uni = dev.playout(n, seed=seed, game_offset=500)["game_scores"].float().mean().item()
+    assert gs.mean() > uni + 3
+    # UCT with heuristic rollouts (the reference's default rollout policy)
+    root = _roots(golden_dir)[1]
+    want = orc.mcts_search(root, 80, seed=12, tree_id=3, rollout_policy=1)
+    res = DeviceUCT(80, n_trees=1, seed=12, tree_offset=3, rollout_policy=1).search(dev.to_device(np.atleast_1d(root)), 80)
+    nr = want["n_root"]
+    assert np.array_equal(res["visits"][0, :nr].cpu().numpy(), want["visits"][:nr])
+    assert np.array_equal(res["reward"][0, :nr].cpu().numpy(), want["reward"][:nr])
