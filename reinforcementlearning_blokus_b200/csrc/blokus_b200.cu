@@ -9,6 +9,9 @@
 #include "movegen_core.cuh"
 
 #define BK_THREADS 256
+#ifndef BK_COUNT_CTAS
+#define BK_COUNT_CTAS 4      /* k_movegen_count: 64 registers -> 4 CTAs (32 warps) per SM */
+#endif
 #define BK_WARPS (BK_THREADS / 32)
 
 // ---------------------------------------------------------------------------------------------
@@ -61,6 +64,7 @@ extern "C" int bk_init(int device) {
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_ncells, BK_TBL_ORIENT_NCELLS, sizeof(BK_TBL_ORIENT_NCELLS)));
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_cells, BK_TBL_ORIENT_CELLS, sizeof(BK_TBL_ORIENT_CELLS)));
     CUDA_TRY(cudaMemcpyToSymbol(c_group_first, BK_TBL_GROUP_FIRST, sizeof(BK_TBL_GROUP_FIRST)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_piece_first, BK_TBL_PIECE_FIRST, sizeof(BK_TBL_PIECE_FIRST)));
     CUDA_TRY(cudaFuncSetAttribute(k_movegen_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
     CUDA_TRY(bk_init_policies());
     g_device = device;
@@ -76,8 +80,11 @@ k_movegen_count(const bk_state* __restrict__ states, const uint8_t* __restrict__
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint64_t word = warp < n ? fetch_state_word(states + warp, lane) : 0ull;
     for (int i = warp; i < n; i += nwarps) {
-        WarpState s; load_state(states + i, lane, s);
+        const uint64_t next = (i + nwarps < n) ? fetch_state_word(states + i + nwarps, lane) : 0ull;   // prefetch
+        WarpState s; unpack_state(word, lane, s);
+        word = next;
         const uint32_t p = players ? (players[i] & 3u) : s.to_move;
         uint32_t A, C; make_masks(s, p, lane, A, C);
         CountSink sink; bk_gen_all<CountSink, true>(A, C, sel4(s.used, p), sink);
@@ -115,8 +122,11 @@ k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ 
     uint16_t* stage = reinterpret_cast<uint16_t*>(rows + EMIT_ROW_WORDS);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint64_t word = warp < n ? fetch_state_word(states + warp, lane) : 0ull;
     for (int i = warp; i < n; i += nwarps) {
-        WarpState s; load_state(states + i, lane, s);
+        const uint64_t next = (i + nwarps < n) ? fetch_state_word(states + i + nwarps, lane) : 0ull;   // prefetch
+        WarpState s; unpack_state(word, lane, s);
+        word = next;
         const uint32_t p = players ? (players[i] & 3u) : s.to_move;
         uint32_t A, C; make_masks(s, p, lane, A, C);
 #pragma unroll
@@ -166,12 +176,22 @@ k_movegen_bitmap(const bk_state* __restrict__ states, const uint8_t* __restrict_
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint64_t word = warp < n ? fetch_state_word(states + warp, lane) : 0ull;
     for (int i = warp; i < n; i += nwarps) {
-        WarpState s; load_state(states + i, lane, s);
+        const uint64_t next = (i + nwarps < n) ? fetch_state_word(states + i + nwarps, lane) : 0ull;   // prefetch
+        WarpState s; unpack_state(word, lane, s);
+        word = next;
         const uint32_t p = players ? (players[i] & 3u) : s.to_move;
         uint32_t A, C; make_masks(s, p, lane, A, C);
         BitmapSink sink; sink.out = bitmap + (size_t)i * BK_BITMAP_WORDS; sink.lane = lane;
-        bk_gen_all(A, C, sel4(s.used, p), sink);
+        const uint32_t used = sel4(s.used, p);
+        bk_gen_all(A, C, used, sink);
+        // rows of spent pieces are not visited by the generator: clear them here (no separate memset pass)
+        for (uint32_t rest = used & BK_ALL_PIECES; rest; rest &= rest - 1) {
+            const int pid = __ffs(rest);                         // 1..21
+            for (int o = c_piece_first[pid]; o < c_piece_first[pid + 1]; o++)
+                if (lane < 20) sink.out[o * 20 + lane] = 0u;
+        }
     }
 }
 
@@ -234,8 +254,11 @@ k_can_place_mask(const bk_state* __restrict__ states, const uint8_t* __restrict_
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint64_t word = warp < n ? fetch_state_word(states + warp, lane) : 0ull;
     for (int i = warp; i < n; i += nwarps) {
-        WarpState s; load_state(states + i, lane, s);
+        const uint64_t next = (i + nwarps < n) ? fetch_state_word(states + i + nwarps, lane) : 0ull;   // prefetch
+        WarpState s; unpack_state(word, lane, s);
+        word = next;
         const uint32_t p = players ? (players[i] & 3u) : s.to_move;
         uint32_t A, C; make_masks(s, p, lane, A, C);
         const uint64_t word = lane < BK_WORDS ? masks[(size_t)i * BK_WORDS + lane] : 0ull;
@@ -588,8 +611,11 @@ k_heuristic_scores(const bk_state* __restrict__ states, const uint8_t* __restric
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint64_t word = warp < n ? fetch_state_word(states + warp, lane) : 0ull;
     for (int i = warp; i < n; i += nwarps) {
-        WarpState s; load_state(states + i, lane, s);
+        const uint64_t next = (i + nwarps < n) ? fetch_state_word(states + i + nwarps, lane) : 0ull;   // prefetch
+        WarpState s; unpack_state(word, lane, s);
+        word = next;
         const uint32_t p = players ? (players[i] & 3u) : s.to_move;
         uint32_t A, C; make_masks(s, p, lane, A, C);
         __syncwarp();
@@ -622,7 +648,7 @@ static cudaError_t bk_init_policies_impl() {
 extern "C" int bk_movegen_count(const bk_state* states, const uint8_t* players, int n, uint32_t* counts, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && counts)), "bk_movegen_count: null buffer");
     if (n == 0) return BK_OK;
-    k_movegen_count<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, counts);
+    k_movegen_count<<<grid_for(n, BK_COUNT_CTAS), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, counts);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -648,8 +674,6 @@ extern "C" int bk_movegen_fixed(const bk_state* states, const uint8_t* players, 
 extern "C" int bk_movegen_bitmap(const bk_state* states, const uint8_t* players, int n, uint32_t* bitmap, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && bitmap)), "bk_movegen_bitmap: null buffer");
     if (n == 0) return BK_OK;
-    // rows of spent pieces are not visited by the generator: clear first
-    CUDA_TRY(cudaMemsetAsync(bitmap, 0, (size_t)n * BK_BITMAP_WORDS * sizeof(uint32_t), as_stream(stream)));
     k_movegen_bitmap<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, bitmap);
     LAUNCH_CHECK();
     return BK_OK;

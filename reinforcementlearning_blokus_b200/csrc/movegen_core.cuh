@@ -27,6 +27,7 @@ __constant__ uint8_t c_orient_piece[BK_TBL_ORIENTS];
 __constant__ uint8_t c_orient_ncells[BK_TBL_ORIENTS];
 __constant__ uint8_t c_orient_cells[BK_TBL_ORIENTS * 5];
 __constant__ uint8_t c_group_first[BK_TBL_GROUPS + 1];
+__constant__ uint8_t c_piece_first[BK_TBL_PIECES + 2];
 
 // ---- per-warp game state in registers ----------------------------------------------------------
 struct WarpState {
@@ -56,10 +57,13 @@ __device__ __forceinline__ void init_empty(WarpState& s) {
     s.to_move = 0; s.first_mask = 0xF; s.move_count = 0;
 }
 
-// 256-byte packed state -> rows.  Lane i reads 64-bit word i (two coalesced 128-byte lines per warp).
-__device__ __forceinline__ void load_state(const bk_state* __restrict__ sp, int lane, WarpState& s) {
-    const uint64_t* w = reinterpret_cast<const uint64_t*>(sp);
-    uint64_t word = __ldg(w + lane);
+// 256-byte packed state -> rows.  Lane i reads 64-bit word i (two coalesced 128-byte lines per warp).  The
+// fetch is separate from the unpacking so that streaming kernels can issue the next state's load before they
+// work on the current one (the count kernel was waiting on this load: long_scoreboard 1.6 per issue, r01d).
+__device__ __forceinline__ uint64_t fetch_state_word(const bk_state* __restrict__ sp, int lane) {
+    return __ldg(reinterpret_cast<const uint64_t*>(sp) + lane);
+}
+__device__ __forceinline__ void unpack_state(const uint64_t word, int lane, WarpState& s) {
     const int bitpos = lane * 20;
     const int wi = bitpos >> 6, off = bitpos & 63;
 #pragma unroll
@@ -78,6 +82,9 @@ __device__ __forceinline__ void load_state(const bk_state* __restrict__ sp, int 
     s.first_mask = (uint32_t)(meta >> 8) & 0xFu;
     s.move_count = (uint32_t)(meta >> 16) & 0xFFFFu;
     make_uniform(s);
+}
+__device__ __forceinline__ void load_state(const bk_state* __restrict__ sp, int lane, WarpState& s) {
+    unpack_state(fetch_state_word(sp, lane), lane, s);
 }
 
 // rows -> 256-byte packed state.  Lane i assembles 64-bit word i.
