@@ -257,7 +257,7 @@ def run_cuda(args) -> None:
         from reinforcementlearning_blokus_b200 import dist as bdist
         from reinforcementlearning_blokus_b200.mcts import DeviceUCT
 
-        trees, iters = 1184, 256
+        trees, iters = 2368, 256            # 16 one-warp trees per SM
         root = dev.to_device(empty_states(1))
         eng = DeviceUCT(iters, n_trees=trees, seed=SEED, tree_offset=rank * trees)
         eng.search(root, iters)                       # warm-up

@@ -632,7 +632,7 @@ k_heuristic_scores(const bk_state* __restrict__ states, const uint8_t* __restric
 static cudaError_t bk_init_policies_impl() {
     cudaError_t e = cudaFuncSetAttribute(k_playout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_HEUR_PLAYOUT_SMEM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_mcts, cudaFuncAttributeMaxDynamicSharedMemorySize, HEUR_SMEM_PER_WARP);
+    e = cudaFuncSetAttribute(k_mcts<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEUR_SMEM_PER_WARP);
     if (e != cudaSuccess) return e;
     k_init_centre<<<2, 256>>>();
     e = cudaGetLastError();
@@ -841,10 +841,14 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
     if (tt) { t.keys = tt->keys; t.rewards = tt->rewards; t.occupied = tt->occupied; t.log2_slots = tt->log2_slots; }
     const int cap = g_sms * 16;
     const int grid = n_trees < cap ? n_trees : cap;
-    const size_t mcts_smem = params->rollout_policy == BK_POLICY_HEURISTIC ? HEUR_SMEM_PER_WARP : 0;
-    k_mcts<<<grid, BK_MCTS_THREADS, mcts_smem, as_stream(stream)>>>(roots, n_roots, n_trees, *params, t,
-        reinterpret_cast<unsigned char*>(workspace), params->resume, max_root_moves, root_visits,
-        reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status);
+    if (params->rollout_policy == BK_POLICY_HEURISTIC)
+        k_mcts<1><<<grid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, as_stream(stream)>>>(roots, n_roots, n_trees, *params, t,
+            reinterpret_cast<unsigned char*>(workspace), params->resume, max_root_moves, root_visits,
+            reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status);
+    else
+        k_mcts<0><<<grid, BK_MCTS_THREADS, 0, as_stream(stream)>>>(roots, n_roots, n_trees, *params, t,
+            reinterpret_cast<unsigned char*>(workspace), params->resume, max_root_moves, root_visits,
+            reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status);
     LAUNCH_CHECK();
     return BK_OK;
 }

@@ -82,7 +82,7 @@ __device__ __forceinline__ double heur_score_from(uint32_t feat, uint32_t id, ui
 
 // Returns the number of legal moves of `p`; when > 0 picks one by the Philox word r and returns it through
 // (id, idx = rank in the ascending list).  All lanes return the same values.
-__device__ __noinline__ uint32_t heuristic_pick(const WarpState& s, uint32_t p, uint32_t r, HeurScratch sc, int lane,
+__device__ __noinline__ uint32_t heuristic_pick(const WarpState s, uint32_t p, uint32_t r, HeurScratch sc, int lane,
                                                 uint32_t& id_out, uint32_t& idx_out) {
     uint32_t A, C; make_masks(s, p, lane, A, C);
     __syncwarp();

@@ -71,6 +71,7 @@ __device__ __forceinline__ int32_t board_score_of(const WarpState& s, uint32_t q
 
 #define BK_MCTS_THREADS 32   /* one warp = one tree per CTA, so a handful of trees still spreads over the SMs */
 
+template <int POLICY>
 __global__ void __launch_bounds__(BK_MCTS_THREADS)
 k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_params prm, MctsTT tt,
        unsigned char* __restrict__ workspace, int resume, int max_root_moves,
@@ -78,7 +79,8 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
        uint16_t* __restrict__ out_moves, uint32_t* __restrict__ out_status) {
     __shared__ __align__(16) uint32_t s_slots[BK_GROUP_SLOTS];
     extern __shared__ __align__(16) unsigned char heur_smem[];    // HEUR_SMEM_PER_WARP bytes when rollout_policy == 1
-    HeurScratch hs; hs.bind(heur_smem);
+    HeurScratch hs;
+    if (POLICY == BK_POLICY_HEURISTIC) hs.bind(heur_smem);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -202,7 +204,7 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
                 const int limit = prm.max_rollout_moves > 0 ? prm.max_rollout_moves : 1 << 30;
                 for (int ply = 0; ply < limit; ply++) {
                     const uint32_t p = s.to_move;
-                    if (prm.rollout_policy == BK_POLICY_HEURISTIC) {      // HeuristicAgent, the reference's default (:275-276)
+                    if (POLICY == BK_POLICY_HEURISTIC) {                   // HeuristicAgent, the reference's default (:275-276)
                         uint32_t id = 0, idx = 0;
                         if (heuristic_pick(s, p, philox_draw(prm.seed, tree_id, draws, 1), hs, lane, id, idx) == 0) break;
                         draws++;
