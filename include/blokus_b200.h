@@ -142,6 +142,14 @@ int bk_playout(const bk_state* start_states, int n, uint64_t seed, uint64_t game
                int policy, int first_turn, int max_turns, int32_t* game_scores, int32_t* board_scores,
                uint16_t* trace, uint16_t* choice, bk_state* final_states, void* stream);
 
+/* Arena match-ups (analytics/tournament/arena_runner.py:578-760 with per-seat agents): as bk_playout, but the
+ * policy of player p in game i is byte p of seat_policies[i] (bk_policy values), so RandomAgent and
+ * HeuristicAgent seats can be mixed and rotated per game in one batch. */
+int bk_playout_seats(const bk_state* start_states, int n, uint64_t seed, uint64_t game_offset,
+                     const uint32_t* seat_policies, int first_turn, int max_turns, int32_t* game_scores,
+                     int32_t* board_scores, uint16_t* trace, uint16_t* choice, bk_state* final_states,
+                     void* stream);
+
 /* ---- K4: Zobrist keys and transposition table (mcts/zobrist.py:20-99, 155-220) ------------ */
 
 /* keys[i] = ZobristHash.hash_board(board_i)  (mcts/zobrist.py:70-99).  `table` is a DEVICE array of

@@ -23,12 +23,18 @@ _LAZY = {
 }
 
 
+_SUBMODULES = ("agents", "arena", "batched", "board", "device", "dist", "game", "integration", "mcts", "move_generator",
+               "service", "single")
+
+
 def __getattr__(name):
+    import importlib
+
+    if name in _SUBMODULES:
+        return importlib.import_module(f".{name}", __name__)
     mod = _LAZY.get(name)
     if mod is None:
         raise AttributeError(name)
-    import importlib
-
     return getattr(importlib.import_module(f".{mod}", __name__), name)
 
 

@@ -43,6 +43,7 @@ PROTOTYPES = {
     "bk_step": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bk_scores": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "bk_playout": (_i32, [_vp, _i32, _u64, _u64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bk_playout_seats": (_i32, [_vp, _i32, _u64, _u64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bk_zobrist_hash": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "bk_tt_create": (_i32, [C.POINTER(_vp), _u32]),
     "bk_tt_clear": (_i32, [_vp, _vp]),

@@ -335,9 +335,10 @@ k_scores(const bk_state* __restrict__ states, int n, int32_t* __restrict__ gs, i
 #ifndef BK_PLAYOUT_MIRROR
 #define BK_PLAYOUT_MIRROR true
 #endif
+// POLICY 2 = one policy per seat and game (arena match-ups): seat_policies[i] packs the policy of player p in byte p.
 template <int POLICY>
 __global__ void __launch_bounds__(BK_PLAYOUT_THREADS, POLICY == 0 ? BK_PLAYOUT_MIN_BLOCKS : 2)
-k_playout(const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int first_turn, int max_turns,
+k_playout(const uint32_t* __restrict__ seat_policies, const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int first_turn, int max_turns,
                   int32_t* __restrict__ gs, int32_t* __restrict__ bs, uint16_t* __restrict__ trace,
                   uint16_t* __restrict__ choice, bk_state* __restrict__ finals) {
     __shared__ __align__(16) uint32_t s_slots[BK_PLAYOUT_THREADS / 32][BK_GROUP_SLOTS];
@@ -352,6 +353,7 @@ k_playout(const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t gam
         WarpState s;
         if (start) load_state(start + i, lane, s); else init_empty(s);
         const uint64_t g = game_offset + (uint64_t)i;
+        const uint32_t seats = (POLICY == 2) ? uni(seat_policies[i]) : 0u;
         PhiloxBlock rnd; rnd.w[0] = rnd.w[1] = rnd.w[2] = rnd.w[3] = 0;
         uint16_t* tr = trace ? trace + (size_t)i * BK_MAX_TURNS : nullptr;
         uint16_t* ch = choice ? choice + (size_t)i * BK_MAX_TURNS : nullptr;
@@ -373,7 +375,7 @@ k_playout(const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t gam
             const uint32_t p = s.to_move;
             bool moved = false;
             if (!((dead >> p) & 1u)) {
-                if (POLICY == 0) {
+                if (POLICY == 0 || (POLICY == 2 && ((seats >> (8u * p)) & 0xFFu) == BK_POLICY_UNIFORM)) {
                     uint32_t A, C; make_masks(s, p, lane, A, C);
                     GroupSink sink; sink.begin(s_slots[threadIdx.x >> 5], lane);
                     bk_gen_all<GroupSink, BK_PLAYOUT_MIRROR>(A, C, sel4(s.used, p), sink);
@@ -632,6 +634,8 @@ k_heuristic_scores(const bk_state* __restrict__ states, const uint8_t* __restric
 static cudaError_t bk_init_policies_impl() {
     cudaError_t e = cudaFuncSetAttribute(k_playout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_HEUR_PLAYOUT_SMEM);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_playout<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_HEUR_PLAYOUT_SMEM);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_mcts<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEUR_SMEM_PER_WARP);
     if (e != cudaSuccess) return e;
     k_init_centre<<<2, 256>>>();
@@ -735,12 +739,30 @@ extern "C" int bk_playout(const bk_state* start_states, int n, uint64_t seed, ui
     long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)g_sms * BK_PLAYOUT_MIN_BLOCKS;
     if (policy == BK_POLICY_UNIFORM) {
         k_playout<0><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, 0, as_stream(stream)>>>(
-            start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+            nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     } else {
         pcap = (long long)g_sms * 2;
         k_playout<1><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, BK_HEUR_PLAYOUT_SMEM, as_stream(stream)>>>(
-            start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+            nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     }
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_playout_seats(const bk_state* start_states, int n, uint64_t seed, uint64_t game_offset,
+                                const uint32_t* seat_policies, int first_turn, int max_turns, int32_t* game_scores,
+                                int32_t* board_scores, uint16_t* trace, uint16_t* choice, bk_state* final_states,
+                                void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || seat_policies), "bk_playout_seats: null seat_policies");
+    REQUIRE(max_turns >= 0 && max_turns <= BK_MAX_TURNS, "bk_playout_seats: max_turns out of range");
+    if (n == 0) return BK_OK;
+    if (max_turns == 0) max_turns = BK_MAX_TURNS;
+    REQUIRE(first_turn >= 0 && first_turn <= max_turns, "bk_playout_seats: first_turn out of range");
+    const int pw = BK_PLAYOUT_THREADS / 32;
+    long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)g_sms * 2;
+    k_playout<2><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, BK_HEUR_PLAYOUT_SMEM, as_stream(stream)>>>(
+        seat_policies, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice,
+        final_states);
     LAUNCH_CHECK();
     return BK_OK;
 }

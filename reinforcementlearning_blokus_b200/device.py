@@ -200,12 +200,13 @@ def scores(states: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 # ---- K2 --------------------------------------------------------------------------------------
 def playout(n: int, seed: int, game_offset: int = 0, start_states: Optional[torch.Tensor] = None,
-            policy: int = POLICY_UNIFORM, max_turns: int = 0, first_turn: int = 0, want_trace: bool = False,
+            policy: int = POLICY_UNIFORM, seat_policies: Optional[torch.Tensor] = None, max_turns: int = 0, first_turn: int = 0, want_trace: bool = False,
             want_choice: bool = False, want_final: bool = False, want_board_scores: bool = True,
             out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     """Play n games to the end on the device.  Game i has global index game_offset+i (its Philox stream).
     Turns first_turn .. max_turns-1 are played (0 = to the end); segments chained through final_states give
-    the same game as one call.
+    the same game as one call.  `seat_policies` (int32[N], policy of player p in byte p) overrides `policy` per
+    seat and game (arena match-ups).
 
     `out` may carry preallocated tensors from a previous call (keys as returned) to avoid reallocation.
     """
@@ -230,8 +231,15 @@ def playout(n: int, seed: int, game_offset: int = 0, start_states: Optional[torc
     tr = buf("trace", (n, BK_MAX_TURNS), torch.uint16, want_trace)
     ch = buf("choice", (n, BK_MAX_TURNS), torch.uint16, want_choice)
     fin = buf("final_states", (n, STATE_BYTES), torch.uint8, want_final)
-    check(lib.bk_playout(_ptr(start_states), n, int(seed) & (2**64 - 1), int(game_offset), int(policy), int(first_turn), int(max_turns),
-                         _ptr(gs), _ptr(bs), _ptr(tr), _ptr(ch), _ptr(fin), _stream()))
+    if seat_policies is not None:
+        if not (seat_policies.is_cuda and seat_policies.dtype == torch.int32 and seat_policies.numel() == n):
+            raise ValueError("seat_policies must be a CUDA int32 tensor of length N (policy of player p in byte p)")
+        check(lib.bk_playout_seats(_ptr(start_states), n, int(seed) & (2**64 - 1), int(game_offset), _ptr(seat_policies),
+                                   int(first_turn), int(max_turns), _ptr(gs), _ptr(bs), _ptr(tr), _ptr(ch), _ptr(fin),
+                                   _stream()))
+    else:
+        check(lib.bk_playout(_ptr(start_states), n, int(seed) & (2**64 - 1), int(game_offset), int(policy),
+                             int(first_turn), int(max_turns), _ptr(gs), _ptr(bs), _ptr(tr), _ptr(ch), _ptr(fin), _stream()))
     _count()
     return res
 

@@ -1,0 +1,119 @@
+"""N2: the callers on top of the path -- arena match-ups (object loop and device batch) and the /think contract."""
+
+import json
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import orc  # noqa: E402
+from reinforcementlearning_blokus_b200 import (BlokusGame, FastMCTSAgent, HeuristicAgent, Player, RandomAgent,  # noqa: E402
+                                               arena, service)
+from reinforcementlearning_blokus_b200 import device as dev  # noqa: E402
+from reinforcementlearning_blokus_b200.batched import BatchedBlokus  # noqa: E402
+
+
+def _oracle_word(packed_i32):
+    """seat-policy word for orc.playout: same bytes with bit 31 set (as a C int)."""
+    return int(np.int32(packed_i32)) | -(1 << 31)
+
+
+def test_mixed_seat_policies_match_oracle():
+    n, seed = 64, 17
+    rng = np.random.RandomState(0)
+    seats = rng.randint(0, 2, size=(n, 4))
+    packed = (seats[:, 0] | (seats[:, 1] << 8) | (seats[:, 2] << 16) | (seats[:, 3] << 24)).astype(np.int32)
+    r = dev.playout(n, seed=seed, game_offset=9, seat_policies=torch.from_numpy(packed).cuda(), want_trace=True)
+    tr, gs = r["trace"].cpu().numpy(), r["game_scores"].cpu().numpy()
+    for i in range(0, n, 5):
+        o = orc.playout(seed, 9 + i, policy=_oracle_word(packed[i]))
+        assert np.array_equal(tr[i], o["trace"]), i
+        assert np.array_equal(gs[i], o["game_scores"])
+    # all-uniform and all-heuristic words reproduce the single-policy kernels
+    for pol in (0, 1):
+        word = torch.full((8,), pol * 0x01010101, dtype=torch.int32, device="cuda")
+        a = dev.playout(8, seed=3, seat_policies=word, want_trace=True)["trace"]
+        b = dev.playout(8, seed=3, policy=pol, want_trace=True)["trace"]
+        assert torch.equal(a, b)
+
+
+def test_seed_and_seat_utilities():
+    assert arena.stable_hash_int(42, 0, "game_seed") == arena.game_seed_from_run_seed(42, 0)
+    assert 0 <= arena.game_seed_from_run_seed(42, 7) < 2**31 - 1
+    names = ["a", "b", "c", "d"]
+    assert arena.seat_assignment_for_game(names, 1, 5, "round_robin") == {"1": "b", "2": "c", "3": "d", "4": "a"}
+    sa = arena.seat_assignment_for_game(names, 3, 1234, "randomized")
+    assert sorted(sa.values()) == names and sa == arena.seat_assignment_for_game(names, 3, 1234, "randomized")
+    assert arena.compute_ranks({"1": 50, "2": 70, "3": 70, "4": 10}) == {"1": 2, "2": 1, "3": 1, "4": 3}   # dense, as the reference
+
+
+def test_device_arena_heuristic_beats_random(tmp_path):
+    out = arena.run_device_arena({"h1": "heuristic", "r1": "random", "h2": "heuristic", "r2": "random"}, 2048,
+                                 run_seed=42, seat_policy="round_robin")
+    recs, summ = out["records"], out["summary"]
+    assert len(recs) == 2048 and sum(s["games"] for s in summ.values()) == 4 * 2048
+    assert abs(sum(s["wins"] for s in summ.values()) - 2048) < 1e-6
+    assert summ["h1"]["mean_score"] > summ["r1"]["mean_score"] + 3
+    assert summ["h1"]["win_rate"] + summ["h2"]["win_rate"] > 0.6
+    rec = recs[5]
+    for key in ("run_id", "game_id", "game_index", "game_seed", "seat_assignment", "seat_policy", "winner_ids",
+                "winner_agents", "is_tie", "final_scores", "final_ranks", "agent_scores", "agent_ranks", "winner_id",
+                "moves_made", "turn_count", "passes", "invalid_actions", "duration_sec", "truncated", "agent_move_stats",
+                "snapshot_checkpoints_hit", "error"):
+        assert key in rec
+    assert rec["game_seed"] == arena.game_seed_from_run_seed(42, 5)
+    assert rec["seat_assignment"] == arena.seat_assignment_for_game(["h1", "r1", "h2", "r2"], 5, rec["game_seed"], "round_robin")
+    # the record agrees with an oracle replay of the same game
+    o = orc.playout(42, 5, policy=_oracle_word(out["seat_policies"][5]))
+    assert rec["final_scores"] == {str(p + 1): int(o["game_scores"][p]) for p in range(4)}
+    assert rec["moves_made"] == int((o["trace"] != 0xFFFF).sum())
+    path = tmp_path / "games.jsonl"
+    arena.write_games_jsonl(str(path), recs[:10])
+    assert len([json.loads(line) for line in open(path)]) == 10
+
+
+def test_object_arena_game_and_think_contract():
+    agents = {"rand": RandomAgent(seed=1), "heur": HeuristicAgent(seed=2),
+              "fast": FastMCTSAgent(iterations=40, time_limit=5.0, seed=3), "rand2": RandomAgent(seed=4)}
+    seats = arena.seat_assignment_for_game(list(agents), 0, arena.game_seed_from_run_seed(1, 0), "round_robin")
+    rec = arena.run_single_game(run_id="t", game_index=0, game_seed=arena.game_seed_from_run_seed(1, 0),
+                                seat_assignment=seats, agents=agents, max_turns=12)
+    assert rec["error"] is None and rec["truncated"] and rec["turn_count"] == 12 and rec["moves_made"] == 12
+    assert rec["agent_move_stats"]["fast"]["moves"] == 3
+    # POST /think contract (engine-service/app.py:53-72)
+    game = BlokusGame()
+    for _ in range(6):
+        game.make_move(game.get_legal_moves()[0])
+    legal = game.get_legal_moves()
+    payload = {
+        "gameState": {"board": game.board.grid.tolist(),
+                      "pieces_used": {p.name: sorted(game.board.player_pieces_used[p]) for p in Player},
+                      "current_player": game.board.current_player.name, "move_count": game.board.move_count},
+        "legalMoves": [{"piece_id": m.piece_id, "orientation": m.orientation, "anchor_row": m.anchor_row,
+                        "anchor_col": m.anchor_col} for m in legal],
+        "timeBudgetMs": 300,
+    }
+    rebuilt = service.rebuild_board(payload["gameState"])
+    assert rebuilt.to_packed().tobytes() == game.board.to_packed().tobytes()
+    resp = service.think(payload, iterations=200)
+    assert resp["move"] in payload["legalMoves"]
+    assert {"timeBudgetMs", "timeSpentMs", "nodesEvaluated", "topMoves"} <= set(resp["stats"])
+    assert service.think({"gameState": payload["gameState"], "legalMoves": [], "timeBudgetMs": 10})["move"] is None
+
+
+def test_batched_blokus_api():
+    b = BatchedBlokus(512)
+    counts = b.legal_move_counts()
+    assert counts.tolist() == [58] * 512
+    _, offsets, ids = b.legal_moves()
+    first = ids[offsets[:-1].long()]                            # everybody plays its first legal move
+    ok, alive = b.step(first, want_alive=True)
+    assert ok.all() and (alive == 15).all() and (b.to_move() == 1).all()
+    gs, bs = b.scores()
+    assert (bs[:, 0] == 1).all() and (gs[:, 0] == 6).all()     # a monomino on the start corner: 1 cell + 5 corner bonus
+    moved = b.step_uniform_random(seed=5, turn=1)
+    assert (moved.cpu().numpy() != 0xFFFF).all() and (b.to_move() == 2).all()
+    fin = b.playout(seed=5, first_turn=2, want_final=True)
+    assert not dev.has_moves(fin["final_states"]).any()
