@@ -47,7 +47,9 @@ class BatchedBlokus:
     # ---- transitions ---------------------------------------------------------------------------------
     def step(self, move_ids: torch.Tensor, want_alive: bool = False):
         """make_move (or pass for 0xFFFF) for every game; returns (ok, alive) like device.step."""
-        return dev.step(self.states, move_ids.to(torch.uint16), want_alive=want_alive)
+        if move_ids.dtype == torch.int16:
+            move_ids = move_ids.view(torch.uint16)
+        return dev.step(self.states, move_ids.contiguous(), want_alive=want_alive)
 
     def step_uniform_random(self, seed: int, turn: int, game_offset: int = 0) -> torch.Tensor:
         """One turn of uniform-random play for every game (pass when no move): the single-turn slice of the

@@ -344,7 +344,7 @@ k_playout(const uint32_t* __restrict__ seat_policies, const bk_state* __restrict
     __shared__ __align__(16) uint32_t s_slots[BK_PLAYOUT_THREADS / 32][BK_GROUP_SLOTS];
     extern __shared__ __align__(16) unsigned char heur_smem[];
     HeurScratch hs;
-    if (POLICY == 1) hs.bind(heur_smem + (size_t)(threadIdx.x >> 5) * HEUR_SMEM_PER_WARP);
+    if (POLICY != 0) hs.bind(heur_smem + (size_t)(threadIdx.x >> 5) * HEUR_SMEM_PER_WARP);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;

@@ -108,7 +108,8 @@ def test_batched_blokus_api():
     counts = b.legal_move_counts()
     assert counts.tolist() == [58] * 512
     _, offsets, ids = b.legal_moves()
-    first = ids[offsets[:-1].long()]                            # everybody plays its first legal move
+    # everybody plays its first legal move (torch cannot index uint16 tensors: go through an int16 view)
+    first = ids.view(torch.int16)[offsets[:-1].long()].view(torch.uint16)
     ok, alive = b.step(first, want_alive=True)
     assert ok.all() and (alive == 15).all() and (b.to_move() == 1).all()
     gs, bs = b.scores()
