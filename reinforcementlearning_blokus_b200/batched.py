@@ -62,3 +62,18 @@ class BatchedBlokus:
     def playout(self, seed: int, game_offset: int = 0, **kw) -> Dict[str, torch.Tensor]:
         """Finish every game with uniform-random play from the current states (states are not modified)."""
         return dev.playout(self.n, seed=seed, game_offset=game_offset, start_states=self.states, **kw)
+
+
+def mobility_after_moves(state, player: int, mover: int, move_ids) -> "torch.Tensor":
+    """Next-turn mobility of `player` after each of `mover`'s candidate moves, as one batch (row N3 of SURVEY.md
+    section 8f): the inner loop of ``simulate_mobility_stability`` (engine/telemetry.py:17-77) -- copy the board, let
+    an opponent place one sampled move, count the player's legal moves -- for all samples at once:
+    one ``bk_step`` + one ``bk_movegen_count``.  Returns int32[len(move_ids)] (-1 where the move was illegal)."""
+    ids = torch.as_tensor(np.asarray(move_ids, dtype=np.int64).astype(np.uint16).view(np.int16)).view(torch.uint16).cuda()
+    k = ids.numel()
+    base = dev.to_device(np.atleast_1d(state))
+    states = base.repeat(k, 1).contiguous()
+    movers = torch.full((k,), int(mover), dtype=torch.uint8, device=states.device)
+    ok, _ = dev.step(states, ids, players=movers)
+    counts = dev.movegen_count(states, torch.full((k,), int(player), dtype=torch.uint8, device=states.device))
+    return torch.where(ok.bool(), counts, torch.full_like(counts, -1))

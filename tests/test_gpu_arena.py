@@ -118,3 +118,21 @@ def test_batched_blokus_api():
     assert (moved.cpu().numpy() != 0xFFFF).all() and (b.to_move() == 2).all()
     fin = b.playout(seed=5, first_turn=2, want_final=True)
     assert not dev.has_moves(fin["final_states"]).any()
+
+
+def test_mobility_after_moves_matches_oracle():
+    """N3: the movegen-bound inner loop of engine/telemetry.py:17-77 as one device batch."""
+    from reinforcementlearning_blokus_b200.batched import mobility_after_moves
+
+    o = orc.playout(5, 1, max_turns=14, want_final=True)
+    state = o["final"]
+    b = orc.OracleBoard.from_packed(state)
+    player, opp = 0, 2
+    legal = b.legal_moves(opp)
+    sample = legal[:: max(1, len(legal) // 12)][:12]
+    got = mobility_after_moves(state, player, opp, sample).cpu().numpy()
+    for mv, g in zip(sample, got):
+        c = b.copy()
+        assert c.place(opp, int(mv))
+        assert g == len(c.legal_moves(player))
+    assert mobility_after_moves(state, player, opp, [36399]).cpu().numpy()[0] == -1
