@@ -65,6 +65,8 @@ extern "C" int bk_init(int device) {
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_cells, BK_TBL_ORIENT_CELLS, sizeof(BK_TBL_ORIENT_CELLS)));
     CUDA_TRY(cudaMemcpyToSymbol(c_group_first, BK_TBL_GROUP_FIRST, sizeof(BK_TBL_GROUP_FIRST)));
     CUDA_TRY(cudaMemcpyToSymbol(c_piece_first, BK_TBL_PIECE_FIRST, sizeof(BK_TBL_PIECE_FIRST)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_orient_cells32, BK_TBL_ORIENT_CELLS32, sizeof(BK_TBL_ORIENT_CELLS32)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_orient_rowpat, BK_TBL_ORIENT_ROWPAT, sizeof(BK_TBL_ORIENT_ROWPAT)));
     CUDA_TRY(cudaFuncSetAttribute(k_movegen_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
     CUDA_TRY(bk_init_policies());
     g_device = device;

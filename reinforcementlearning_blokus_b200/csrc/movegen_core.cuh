@@ -27,6 +27,8 @@ __constant__ uint8_t c_orient_piece[BK_TBL_ORIENTS];
 __constant__ uint8_t c_orient_ncells[BK_TBL_ORIENTS];
 __constant__ uint8_t c_orient_cells[BK_TBL_ORIENTS * 5];
 __constant__ uint8_t c_group_first[BK_TBL_GROUPS + 1];
+__constant__ uint32_t c_orient_cells32[BK_TBL_ORIENTS];   // 5 x (row<<3|col), padded with repeats of cell 0
+__constant__ uint32_t c_orient_rowpat[BK_TBL_ORIENTS];    // 5 rows x 5 column bits
 __constant__ uint8_t c_piece_first[BK_TBL_PIECES + 2];
 
 // ---- per-warp game state in registers ----------------------------------------------------------
@@ -155,18 +157,16 @@ __device__ __forceinline__ void bk_gen_all(const uint32_t A_in, const uint32_t C
 #undef BK_OUT
 }
 
-// One orientation, table-driven (used after a move has been chosen, and by is_move_legal).
+// One orientation, table-driven (used after a move has been chosen, and by is_move_legal).  Short shapes are
+// padded by repeating their first cell (AND / OR are idempotent), so the loop has no shape-dependent branch.
 __device__ __forceinline__ uint32_t bk_gen_one(const uint32_t A, const uint32_t C, const int o) {
+    const uint32_t cells = c_orient_cells32[o];
     uint32_t fit = BK_ROWMASK, touch = 0;
-    const int n = c_orient_ncells[o];
 #pragma unroll
     for (int i = 0; i < 5; i++) {
-        if (i < n) {
-            const uint32_t rc = c_orient_cells[o * 5 + i];
-            const uint32_t a = __shfl_down_sync(BK_FULL, A, rc >> 4) >> (rc & 15);
-            const uint32_t c = __shfl_down_sync(BK_FULL, C, rc >> 4) >> (rc & 15);
-            fit &= a; touch |= c;
-        }
+        const uint32_t rc = (cells >> (6 * i)) & 63u;
+        fit &= __shfl_down_sync(BK_FULL, A, rc >> 3) >> (rc & 7u);
+        touch |= __shfl_down_sync(BK_FULL, C, rc >> 3) >> (rc & 7u);
     }
     return fit & touch;
 }
@@ -202,12 +202,13 @@ struct BitmapSink {                // legal-anchor bitmap rows straight to memor
 // single REDUX sums them over the warp (the result lands in a uniform register) and lane 0 parks it in the
 // warp's shared-memory slot G.  Only one accumulator is live at a time, and the bookkeeping costs no ALU-pipe
 // instruction (REDUX on the ADU, one predicated STS).
-#define BK_GROUP_SLOTS 44            /* 41 groups, padded to a multiple of 4 words */
+#define BK_GROUP_SLOTS 44            /* 41 groups, padded to a multiple of 4 words; the last slot is a dump */
 struct GroupSink {
     static constexpr bool kRows = false;
     uint32_t acc = 0;
     uint32_t* slots;                 // this warp's BK_GROUP_SLOTS words of shared memory, zeroed by begin()
     int lane;
+    uint32_t pend = 0, pend_g = BK_GROUP_SLOTS - 1;     // REDUX result of the previous group, stored one group late
     __device__ __forceinline__ void begin(uint32_t* warp_slots, int lane_) {
         slots = warp_slots; lane = lane_;
         __syncwarp();
@@ -217,10 +218,16 @@ struct GroupSink {
     template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) {
         acc += (uint32_t)__popc(L) << (10 * SLOT);
     }
+    // The store of a group's total is delayed until the next group ends, so no instruction waits on a REDUX
+    // that was issued just before it (REDUX latency showed up as 12 % of the stall samples, r01f).
     template <int G> __device__ __forceinline__ void flush() {
-        const uint32_t v = __reduce_add_sync(BK_FULL, acc);
-        if (lane == 0) slots[G] = v;
+        if (lane == 0) slots[pend_g] = pend;
+        pend = __reduce_add_sync(BK_FULL, acc);
+        pend_g = G;
         acc = 0;
+    }
+    __device__ __forceinline__ void finish() {
+        if (lane == 0) slots[pend_g] = pend;
     }
 };
 
@@ -233,8 +240,9 @@ struct Totals {
 
 __device__ __forceinline__ uint32_t fields_sum(uint32_t m) { return (m & 1023u) + ((m >> 10) & 1023u) + ((m >> 20) & 1023u); }
 
-__device__ __forceinline__ Totals reduce_totals(const GroupSink& s, int lane) {
+__device__ __forceinline__ Totals reduce_totals(GroupSink& s, int lane) {
     Totals t;
+    s.finish();
     __syncwarp();
     const uint2 m = (lane < BK_GROUP_SLOTS / 2) ? reinterpret_cast<const uint2*>(s.slots)[lane] : make_uint2(0u, 0u);
     t.mine0 = m.x; t.mine1 = m.y;
@@ -291,15 +299,9 @@ __device__ __forceinline__ uint32_t select_move(const Totals& t, uint32_t idx, u
 // move_count, next player).  The frontier sets of the reference are not state here: A and C are
 // recomputed from the cells each turn.
 __device__ __forceinline__ void place_move(WarpState& s, uint32_t player, int o, int row, int col, int lane) {
-    uint32_t add = 0;
-    const int n = c_orient_ncells[o];
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        if (i < n) {
-            const uint32_t rc = c_orient_cells[o * 5 + i];
-            if (lane == row + (int)(rc >> 4)) add |= 1u << (col + (rc & 15));
-        }
-    }
+    const uint32_t pat = c_orient_rowpat[o];                 // row k of the shape = bits 5k..5k+4
+    const uint32_t k = (uint32_t)(lane - row);
+    const uint32_t add = (k < 5u) ? (((pat >> (5u * k)) & 31u) << col) : 0u;
     const uint32_t pbit = 1u << (c_orient_piece[o] - 1);
 #pragma unroll
     for (int q = 0; q < 4; q++) {
