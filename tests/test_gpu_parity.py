@@ -314,3 +314,41 @@ def test_legality_sweep_small():
     res = mod.sweep(30000, seed=77)
     assert res["states"] == 30000 and res["mismatches"] == 0 and res["naive_mismatches"] == 0
     assert res["terminal_states"] > 0 and res["max_moves"] > 500
+
+
+def test_abi_error_codes_and_empty_batches():
+    """Never throws, never faults: bad arguments come back as negative codes with a message; n = 0 is a no-op."""
+    import ctypes as C
+
+    from reinforcementlearning_blokus_b200 import _lib
+
+    lib = _lib.init(torch.cuda.current_device())
+    st = _states_to_dev(empty_states(2))
+    counts = torch.zeros(2, dtype=torch.int32, device="cuda")
+    # n = 0 everywhere
+    assert lib.bk_movegen_count(None, None, 0, None, None) == 0
+    assert lib.bk_playout(None, 0, 1, 0, 0, 0, 0, None, None, None, None, None, None) == 0
+    assert lib.bk_scores(None, 0, None, None, None) == 0
+    e = dev.movegen(st[:0].contiguous())
+    assert e[0].numel() == 0 and e[1].tolist() == [0] and e[2].numel() == 0
+    # bad arguments
+    assert lib.bk_movegen_count(None, None, 2, counts.data_ptr(), None) == -2
+    assert b"null" in lib.bk_last_error()
+    assert lib.bk_playout(None, 4, 1, 0, 7, 0, 0, None, None, None, None, None, None) == -2          # unknown policy
+    assert lib.bk_playout(None, 4, 1, 0, 0, 0, 500, None, None, None, None, None, None) == -2        # max_turns > 96
+    assert lib.bk_playout(None, 4, 1, 0, 0, 50, 10, None, None, None, None, None, None) == -2        # first_turn > max_turns
+    h = C.c_void_p()
+    assert lib.bk_tt_create(C.byref(h), 2) == -2 and lib.bk_tt_create(C.byref(h), 40) == -2
+    p = _lib.MctsParams(iterations=1, iterations_total=8, max_rollout_moves=5, rollout_policy=0, max_depth=0, ucb_variant=0,
+                        resume=0, reward_mode=0, exploration=1.0, seed=1, tree_offset=0)
+    ws = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    assert lib.bk_mcts_search(st.data_ptr(), 1, 1, C.byref(p), None, None, ws.data_ptr(), 16, 8, None, None, None, None,
+                              None, None) == -4                                                       # workspace too small
+    assert lib.bk_init(99) == -2
+    # outputs a caller does not want may be NULL
+    assert lib.bk_playout(None, 4, 1, 0, 0, 0, 0, None, None, None, None, None, None) == 0
+    torch.cuda.synchronize()
+    # a game that is already over stays where it is
+    fin = dev.playout(8, seed=3, want_final=True)["final_states"]
+    again = dev.playout(8, seed=3, start_states=fin, want_final=True, want_trace=True)
+    assert torch.equal(again["final_states"], fin) and (again["trace"].cpu().numpy() == 0xFFFF).all()
