@@ -60,7 +60,7 @@ struct MctsTT {                // optional transposition table (mcts/zobrist.py:
 
 __device__ __noinline__ Totals gen_totals(uint32_t A, uint32_t C, uint32_t used, int lane, uint32_t* slots) {
     GroupSink sink; sink.begin(slots, lane);
-    bk_gen_all(A, C, used, sink);
+    bk_gen_all<GroupSink, true>(A, C, used, sink);
     return reduce_totals(sink, lane);
 }
 
