@@ -108,10 +108,10 @@ static_assert(BK_EMIT_SMEM_BYTES == BK_WARPS * EMIT_SMEM_PER_WARP, "emit shared-
 struct SmemRowSink {
     static constexpr bool kRows = true;
     uint32_t* rows; int lane;
-    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) {
+    template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) {
         if (lane < 20) rows[O * 20 + lane] = L;
     }
-    template <int G> __device__ __forceinline__ void flush() {}
+    template <int G0, int NG> __device__ __forceinline__ void flush() {}
 };
 
 __global__ void __launch_bounds__(BK_THREADS)

@@ -46,8 +46,8 @@ struct HeurScratch {
 struct HeurRowSink {
     static constexpr bool kRows = true;
     uint32_t* rows; int lane;
-    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) { if (lane < 20) rows[O * 20 + lane] = L; }
-    template <int G> __device__ __forceinline__ void flush() {}
+    template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) { if (lane < 20) rows[O * 20 + lane] = L; }
+    template <int G0, int NG> __device__ __forceinline__ void flush() {}
 };
 
 // corners (0..20) and edge cells (0..5) of a move, evaluated before the placement (heuristic_agent.py:105-176)

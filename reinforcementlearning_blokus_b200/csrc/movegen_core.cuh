@@ -177,24 +177,24 @@ __device__ __forceinline__ uint32_t bk_gen_one(const uint32_t A, const uint32_t 
 struct CountSink {                 // per-lane move count
     static constexpr bool kRows = false;
     uint32_t acc = 0;
-    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) { acc += __popc(L); }
-    template <int G> __device__ __forceinline__ void flush() {}
+    template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) { acc += __popc(L); }
+    template <int G0, int NG> __device__ __forceinline__ void flush() {}
 };
 
 struct AnySink {                   // does any move exist
     static constexpr bool kRows = false;
     uint32_t acc = 0;
-    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) { acc |= L; }
-    template <int G> __device__ __forceinline__ void flush() {}
+    template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) { acc |= L; }
+    template <int G0, int NG> __device__ __forceinline__ void flush() {}
 };
 
 struct BitmapSink {                // legal-anchor bitmap rows straight to memory
     static constexpr bool kRows = true;
     uint32_t* out; int lane;
-    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) {
+    template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) {
         if (lane < 20) out[O * 20 + lane] = L;
     }
-    template <int G> __device__ __forceinline__ void flush() {}
+    template <int G0, int NG> __device__ __forceinline__ void flush() {}
 };
 
 // Per-orientation totals for choosing the idx-th move.  The counts of a group's <= 3 orientations sit in 10-bit
@@ -205,30 +205,32 @@ struct BitmapSink {                // legal-anchor bitmap rows straight to memor
 #define BK_GROUP_SLOTS 44            /* 41 groups, padded to a multiple of 4 words; the last slot is a dump */
 struct GroupSink {
     static constexpr bool kRows = false;
-    uint32_t acc = 0;
-    uint32_t* slots;                 // this warp's BK_GROUP_SLOTS words of shared memory, zeroed by begin()
+    uint32_t acc0 = 0, acc1 = 0, acc2 = 0;   // the (up to three) groups of the piece being evaluated
+    uint32_t* slots;                          // this warp's BK_GROUP_SLOTS words of shared memory, zeroed by begin()
     int lane;
-    uint32_t pend = 0, pend_g = BK_GROUP_SLOTS - 1;     // REDUX result of the previous group, stored one group late
     __device__ __forceinline__ void begin(uint32_t* warp_slots, int lane_) {
         slots = warp_slots; lane = lane_;
         __syncwarp();
         if (lane < BK_GROUP_SLOTS / 2) reinterpret_cast<uint2*>(slots)[lane] = make_uint2(0u, 0u);
         __syncwarp();
     }
-    template <int O, int SLOT> __device__ __forceinline__ void put(uint32_t L) {
-        acc += (uint32_t)__popc(L) << (10 * SLOT);
+    template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) {
+        const uint32_t v = (uint32_t)__popc(L) << (10 * SLOT);
+        if (GI == 0) acc0 += v; else if (GI == 1) acc1 += v; else acc2 += v;
     }
-    // The store of a group's total is delayed until the next group ends, so no instruction waits on a REDUX
-    // that was issued just before it (REDUX latency showed up as 12 % of the stall samples, r01f).
-    template <int G> __device__ __forceinline__ void flush() {
-        if (lane == 0) slots[pend_g] = pend;
-        pend = __reduce_add_sync(BK_FULL, acc);
-        pend_g = G;
-        acc = 0;
+    // All REDUX of a piece are issued back to back (their latencies overlap) before the first result is stored.
+    template <int G0, int NG> __device__ __forceinline__ void flush() {
+        const uint32_t t0 = __reduce_add_sync(BK_FULL, acc0);
+        const uint32_t t1 = NG > 1 ? __reduce_add_sync(BK_FULL, acc1) : 0u;
+        const uint32_t t2 = NG > 2 ? __reduce_add_sync(BK_FULL, acc2) : 0u;
+        if (lane == 0) {
+            slots[G0] = t0;
+            if (NG > 1) slots[G0 + 1] = t1;
+            if (NG > 2) slots[G0 + 2] = t2;
+        }
+        acc0 = 0; if (NG > 1) acc1 = 0; if (NG > 2) acc2 = 0;
     }
-    __device__ __forceinline__ void finish() {
-        if (lane == 0) slots[pend_g] = pend;
-    }
+    __device__ __forceinline__ void finish() {}
 };
 
 // ---- choosing the idx-th legal move in ascending id order ----------------------------------------
