@@ -338,7 +338,7 @@ k_scores(const bk_state* __restrict__ states, int n, int32_t* __restrict__ gs, i
 #define BK_PLAYOUT_MIRROR true
 #endif
 // POLICY 2 = one policy per seat and game (arena match-ups): seat_policies[i] packs the policy of player p in byte p.
-template <int POLICY>
+template <int POLICY, bool TRACE = true>
 __global__ void __launch_bounds__(BK_PLAYOUT_THREADS, POLICY == 0 ? BK_PLAYOUT_MIN_BLOCKS : 2)
 k_playout(const uint32_t* __restrict__ seat_policies, const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int first_turn, int max_turns,
                   int32_t* __restrict__ gs, int32_t* __restrict__ bs, uint16_t* __restrict__ trace,
@@ -357,8 +357,8 @@ k_playout(const uint32_t* __restrict__ seat_policies, const bk_state* __restrict
         const uint64_t g = game_offset + (uint64_t)i;
         const uint32_t seats = (POLICY == 2) ? uni(seat_policies[i]) : 0u;
         PhiloxBlock rnd; rnd.w[0] = rnd.w[1] = rnd.w[2] = rnd.w[3] = 0;
-        uint16_t* tr = trace ? trace + (size_t)i * BK_MAX_TURNS : nullptr;
-        uint16_t* ch = choice ? choice + (size_t)i * BK_MAX_TURNS : nullptr;
+        uint16_t* tr = (TRACE && trace) ? trace + (size_t)i * BK_MAX_TURNS : nullptr;
+        uint16_t* ch = (TRACE && choice) ? choice + (size_t)i * BK_MAX_TURNS : nullptr;
         for (int k = first_turn + lane; k < BK_MAX_TURNS; k += 32) { if (tr) tr[k] = BK_PASS; if (ch) ch[k] = BK_PASS; }
         __syncwarp();
         uint32_t dead = 0;
@@ -393,7 +393,7 @@ k_playout(const uint32_t* __restrict__ seat_policies, const bk_state* __restrict
                         const uint32_t id = select_move(tot, idx, A, C, lane, o, row, col);
                         place_move(s, p, o, row, col, lane);
                         resume_to_move = s.to_move;
-                        if (lane == 0) { if (tr) tr[t] = (uint16_t)id; if (ch) ch[t] = (uint16_t)idx; }
+                        if (TRACE && lane == 0) { if (tr) tr[t] = (uint16_t)id; if (ch) ch[t] = (uint16_t)idx; }
                         moved = true;
                     }
                 } else {
@@ -739,7 +739,10 @@ extern "C" int bk_playout(const bk_state* start_states, int n, uint64_t seed, ui
     REQUIRE(first_turn >= 0 && first_turn <= max_turns, "bk_playout: first_turn out of range");
     const int pw = BK_PLAYOUT_THREADS / 32;
     long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)g_sms * BK_PLAYOUT_MIN_BLOCKS;
-    if (policy == BK_POLICY_UNIFORM) {
+    if (policy == BK_POLICY_UNIFORM && !trace && !choice) {     // scores only: no per-turn output code at all
+        k_playout<0, false><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, 0, as_stream(stream)>>>(
+            nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+    } else if (policy == BK_POLICY_UNIFORM) {
         k_playout<0><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, 0, as_stream(stream)>>>(
             nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     } else {
