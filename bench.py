@@ -392,6 +392,15 @@ def _extras(dev, torch, n):
     ex["movegen_bitmap_gens_per_sec"] = m / ms * 1e3
     ms = timeit(lambda: dev.movegen(corpus))
     ex["movegen_csr_gens_per_sec"] = m / ms * 1e3
+    # HBM view of the generators: algorithmic bytes = 256 B state in + output (4 B count | 7280 B bitmap | 2 B per id)
+    hbm, _, _ = _measured_peaks()
+    ex["movegen_bitmap_hbm_frac"] = ex["movegen_bitmap_gens_per_sec"] * (256 + 7280) / 1e9 / hbm
+    ex["movegen_count_hbm_frac"] = ex["movegen_count_gens_per_sec"] * (256 + 4) / 1e9 / hbm
+    # HeuristicAgent-policy playouts (row N1)
+    hout = {}
+    nh = n // 4
+    ms = timeit(lambda: dev.playout(nh, seed=SEED, policy=dev.POLICY_HEURISTIC, out=hout, want_board_scores=False), reps=3)
+    ex["heuristic_playouts_per_sec"] = nh / ms * 1e3
     return ex
 
 

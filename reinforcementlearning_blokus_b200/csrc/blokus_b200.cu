@@ -640,7 +640,7 @@ static cudaError_t bk_init_policies_impl() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_mcts<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEUR_SMEM_PER_WARP);
     if (e != cudaSuccess) return e;
-    k_init_centre<<<2, 256>>>();
+    k_init_heuristic_tables<<<(91 * 400 + 255) / 256, 256>>>();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return cudaDeviceSynchronize();

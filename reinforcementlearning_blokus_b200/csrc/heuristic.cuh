@@ -16,30 +16,47 @@
 #define HEUR_WORDS_PER_LANE 57
 #define HEUR_ROW_WORDS (32 * HEUR_WORDS_PER_LANE)       /* 1824 >= 91*20 */
 #define HEUR_MAX_MOVES 2048
-#define HEUR_SMEM_PER_WARP (HEUR_ROW_WORDS * 4 + HEUR_MAX_MOVES * 2 + HEUR_MAX_MOVES + 32 * 4)
+/* per warp: row words (bits | lane-local prefix << 20), ids, features, allowed rows, diagonal-count map, lane bases */
+#define HEUR_SMEM_PER_WARP (HEUR_ROW_WORDS * 4 + HEUR_MAX_MOVES * 2 + HEUR_MAX_MOVES + 32 * 4 + 400 + 32 * 4)
 
-__device__ double g_centre[400];   // 1 - dist(anchor, centre)/max_dist, filled by k_init_centre (heuristic_agent.py:185-198)
+__device__ double g_centre[400];      // 1 - dist(anchor, centre)/max_dist (heuristic_agent.py:185-198)
+__device__ uint8_t g_edge[91 * 400];  // cells of move (o,row,col) within 2 cells of the border (heuristic_agent.py:153-167)
 
-__global__ void k_init_centre() {
-    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= 400) return;
-    const int ar = cell / 20, ac = cell - ar * 20;
-    const double dr = __dsub_rn((double)ar, 9.5), dc = __dsub_rn((double)ac, 9.5);
-    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc)));
-    const double maxd = __dsqrt_rn(__dmul_rn(2.0, __dmul_rn(9.5, 9.5)));
-    g_centre[cell] = __dsub_rn(1.0, __ddiv_rn(dist, maxd));
+__global__ void k_init_heuristic_tables() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 400) {
+        const int ar = i / 20, ac = i - ar * 20;
+        const double dr = __dsub_rn((double)ar, 9.5), dc = __dsub_rn((double)ac, 9.5);
+        const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc)));
+        const double maxd = __dsqrt_rn(__dmul_rn(2.0, __dmul_rn(9.5, 9.5)));
+        g_centre[i] = __dsub_rn(1.0, __ddiv_rn(dist, maxd));
+    }
+    if (i < 91 * 400) {
+        const int o = i / 400, cell = i - o * 400, ar = cell / 20, ac = cell - ar * 20;
+        int edge = 0;
+        for (int k = 0; k < c_orient_ncells[o]; k++) {
+            const uint32_t rc = c_orient_cells[o * 5 + k];
+            const int r = ar + (int)(rc >> 4), c = ac + (int)(rc & 15);
+            edge += (min(min(r, c), min(19 - r, 19 - c)) <= 2);
+        }
+        g_edge[i] = (uint8_t)edge;
+    }
 }
 
 struct HeurScratch {
-    uint32_t* rows;    // HEUR_ROW_WORDS
-    uint16_t* ids;     // HEUR_MAX_MOVES
+    uint32_t* rows;    // HEUR_ROW_WORDS : bits 0..19 legal anchors of (orientation,row) word; bits 20..30 lane-local prefix
+    uint16_t* ids;     // HEUR_MAX_MOVES : ascending move ids
     uint8_t* feat;     // HEUR_MAX_MOVES : corners | edge << 5
-    uint32_t* arows;   // 32
-    __device__ __forceinline__ void bind(unsigned char* base) {
-        rows = reinterpret_cast<uint32_t*>(base);
+    uint32_t* arows;   // 32 : allowed rows A
+    uint8_t* dmap;     // 400 : number of diagonal neighbours of each cell that lie in A (0..4)
+    uint32_t* base;    // 32 : first list position owned by each lane's 57 row words
+    __device__ __forceinline__ void bind(unsigned char* p) {
+        rows = reinterpret_cast<uint32_t*>(p);
         ids = reinterpret_cast<uint16_t*>(rows + HEUR_ROW_WORDS);
         feat = reinterpret_cast<uint8_t*>(ids + HEUR_MAX_MOVES);
         arows = reinterpret_cast<uint32_t*>(feat + HEUR_MAX_MOVES);
+        dmap = reinterpret_cast<uint8_t*>(arows + 32);
+        base = reinterpret_cast<uint32_t*>(dmap + 400);
     }
 };
 
@@ -50,22 +67,19 @@ struct HeurRowSink {
     template <int G0, int NG> __device__ __forceinline__ void flush() {}
 };
 
-// corners (0..20) and edge cells (0..5) of a move, evaluated before the placement (heuristic_agent.py:105-176)
-__device__ __forceinline__ uint32_t heur_features(const uint32_t* __restrict__ arows, uint32_t id) {
-    const int o = id / 400, cell = id - o * 400, ar = cell / 20, ac = cell - ar * 20;
-    const int n = c_orient_ncells[o];
-    uint32_t corners = 0, edge = 0;
-    for (int i = 0; i < n; i++) {
-        const uint32_t rc = c_orient_cells[o * 5 + i];
-        const int r = ar + (int)(rc >> 4), c = ac + (int)(rc & 15);
+// corner_creation of a move = sum over its cells of the diagonal-neighbour count map; edge from the static table
+__device__ __forceinline__ uint32_t heur_features(const uint8_t* __restrict__ dmap, uint32_t id) {
+    const uint32_t o = id / 400u, cell = id - o * 400u;
+    const uint32_t cells = c_orient_cells32[o];          // 5 x (row<<3 | col), padded with repeats of cell 0
+    const uint32_t n = c_orient_ncells[o];
+    uint32_t corners = 0;
 #pragma unroll
-        for (int d = 0; d < 4; d++) {
-            const int nr = r + ((d & 2) ? 1 : -1), nc = c + ((d & 1) ? 1 : -1);
-            if (nr >= 0 && nr < 20 && nc >= 0 && nc < 20) corners += (arows[nr] >> nc) & 1u;
-        }
-        edge += (min(min(r, c), min(19 - r, 19 - c)) <= 2);
+    for (int i = 0; i < 5; i++) {
+        const uint32_t rc = (cells >> (6 * i)) & 63u;
+        const uint32_t d = dmap[cell + (rc >> 3) * 20u + (rc & 7u)];
+        corners += (i < (int)n) ? d : 0u;
     }
-    return corners | (edge << 5);
+    return corners | ((uint32_t)g_edge[id] << 5);
 }
 
 // the score of heuristic_score() (blokus_b200.cu) rebuilt from the stored features, same operation order
@@ -93,27 +107,56 @@ __device__ __noinline__ uint32_t heuristic_pick(const WarpState s, uint32_t p, u
     HeurRowSink sink; sink.rows = sc.rows; sink.lane = lane;
     bk_gen_all(A, C, sel4(s.used, p), sink);
     __syncwarp();
-    // ---- ascending move list
-    const uint32_t* mine = sc.rows + lane * HEUR_WORDS_PER_LANE;
+    // ---- diagonal-count map of A (this lane's row): D[r][c] = A[r-1][c-1] + A[r-1][c+1] + A[r+1][c-1] + A[r+1][c+1]
+    if (lane < 20) {
+        const uint32_t up = lane > 0 ? sc.arows[lane - 1] : 0u, dn = lane < 19 ? sc.arows[lane + 1] : 0u;
+        const uint32_t ul = up << 1, ur = up >> 1, dl = dn << 1, dr = dn >> 1;
+#pragma unroll
+        for (int c4 = 0; c4 < 5; c4++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = 4 * c4 + j;
+                w |= (((ul >> c) & 1u) + ((ur >> c) & 1u) + ((dl >> c) & 1u) + ((dr >> c) & 1u)) << (8 * j);
+            }
+            reinterpret_cast<uint32_t*>(sc.dmap)[lane * 5 + c4] = w;
+        }
+    }
+    // ---- ascending move list: lane L owns row words [57L, 57L+57); lane-local prefixes go into bits 20..30 of
+    // the words, lane bases into sc.base, and every list position k is then located by two binary searches, so
+    // all lanes extract the same number of moves (no divergent per-word bit loops)
+    uint32_t* mine = sc.rows + lane * HEUR_WORDS_PER_LANE;
     uint32_t cnt = 0;
 #pragma unroll
-    for (int k = 0; k < HEUR_WORDS_PER_LANE; k++) cnt += __popc(mine[k]);
+    for (int k = 0; k < HEUR_WORDS_PER_LANE; k++) {
+        const uint32_t bits = mine[k];
+        mine[k] = bits | (cnt << 20);
+        cnt += __popc(bits);
+    }
     uint32_t incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(BK_FULL, incl, d); if (lane >= d) incl += v; }
     uint32_t n = __reduce_add_sync(BK_FULL, cnt);
     if (n == 0) return 0;
     if (n > HEUR_MAX_MOVES) n = HEUR_MAX_MOVES;            // never reached in play (largest list seen: 1003)
-    uint32_t pos = incl - cnt;
-    for (int k = 0; k < HEUR_WORDS_PER_LANE; k++) {
-        uint32_t bits = mine[k];
-        const uint32_t idb = (uint32_t)(lane * HEUR_WORDS_PER_LANE + k) * 20u;
-        while (bits) {
-            const int col = __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (pos < HEUR_MAX_MOVES) sc.ids[pos] = (uint16_t)(idb + col);
-            pos++;
-        }
+    sc.base[lane] = incl - cnt;
+    __syncwarp();
+    for (uint32_t k = lane; k < n; k += 32) {
+        uint32_t L = 0;                                     // owner lane: the last one whose base is <= k
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) if (sc.base[L + step] <= k) L += step;
+        const uint32_t rem = k - sc.base[L];
+        const uint32_t* words = sc.rows + L * HEUR_WORDS_PER_LANE;
+        uint32_t w = 0;                                     // last word whose prefix is <= rem ...
+#pragma unroll
+        for (int step = 32; step >= 1; step >>= 1) if (w + step < HEUR_WORDS_PER_LANE && (words[w + step] >> 20) <= rem) w += step;
+        uint32_t word = words[w];
+        // ... and which actually holds the move: words with equal prefix before it are empty, so the LAST such word
+        // is the first non-empty one at that prefix only if no later word shares it -- the search lands on the last
+        // word with prefix <= rem, whose bit count covers rem by construction
+        uint32_t bits = word & BK_ROWMASK;
+        for (uint32_t skip = rem - (word >> 20); skip; skip--) bits &= bits - 1;
+        sc.ids[k] = (uint16_t)((L * HEUR_WORDS_PER_LANE + w) * 20u + (__ffs(bits) - 1));
     }
     __syncwarp();
     // ---- features, scores, max
@@ -121,7 +164,7 @@ __device__ __noinline__ uint32_t heuristic_pick(const WarpState s, uint32_t p, u
     double mx = NEG_INF;
     for (uint32_t k = lane; k < n; k += 32) {
         const uint32_t id = sc.ids[k];
-        const uint32_t f = heur_features(sc.arows, id);
+        const uint32_t f = heur_features(sc.dmap, id);
         sc.feat[k] = (uint8_t)f;
         mx = fmax(mx, heur_score_from(f, id, s.move_count));
     }
