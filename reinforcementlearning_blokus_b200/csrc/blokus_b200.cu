@@ -49,7 +49,7 @@ extern "C" const char* bk_version(void) { return "blokus_b200 r1 sm_100a (row-sl
 
 __global__ void k_movegen_emit(const bk_state* __restrict__, const uint8_t* __restrict__, int, const uint32_t* __restrict__,
                                uint32_t, uint32_t* __restrict__, uint16_t* __restrict__);
-#define BK_EMIT_SMEM_BYTES (8 * (32 * 57 * 4 + 2048 * 2))
+#define BK_EMIT_SMEM_BYTES (8 * (32 * 57 * 4 + 32 * 4))
 
 static cudaError_t bk_init_policies_impl();
 static cudaError_t bk_init_policies() { return bk_init_policies_impl(); }
@@ -96,13 +96,14 @@ k_movegen_count(const bk_state* __restrict__ states, const uint8_t* __restrict__
 }
 
 // Ascending move ids.  Phase 1 writes the legal-anchor rows of all 91 orientations to shared memory
-// (word w = o*20 + row, so a set bit `col` of word w is move id 20*w + col); phase 2 gives every lane a
-// contiguous slice of 57 words, so one warp scan orders the whole list; phase 3 stages the ids in shared
-// memory and copies them out with coalesced stores.
+// (word w = o*20 + row, so a set bit `col` of word w is move id 20*w + col).  Phase 2 gives every lane a
+// contiguous slice of 57 words: lane-local prefix counts go into bits 20..30 of the words and one warp scan
+// yields the lane bases.  Phase 3 locates list position k with two binary searches (owner lane, then word), so
+// lane L writes positions L, L+32, ...: every lane extracts the same number of moves and the global stores are
+// coalesced, with no staging buffer.
 #define EMIT_WORDS_PER_LANE 57            /* 32 * 57 = 1824 >= 1820 */
 #define EMIT_ROW_WORDS (32 * EMIT_WORDS_PER_LANE)
-#define EMIT_STAGE 2048                   /* ids staged per state; longer lists are written directly */
-#define EMIT_SMEM_PER_WARP (EMIT_ROW_WORDS * 4 + EMIT_STAGE * 2)
+#define EMIT_SMEM_PER_WARP (EMIT_ROW_WORDS * 4 + 32 * 4)
 static_assert(BK_EMIT_SMEM_BYTES == BK_WARPS * EMIT_SMEM_PER_WARP, "emit shared-memory size");
 
 struct SmemRowSink {
@@ -121,7 +122,7 @@ k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + (size_t)wib * EMIT_SMEM_PER_WARP);
-    uint16_t* stage = reinterpret_cast<uint16_t*>(rows + EMIT_ROW_WORDS);
+    uint32_t* lane_base = rows + EMIT_ROW_WORDS;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     uint64_t word = warp < n ? fetch_state_word(states + warp, lane) : 0ull;
@@ -137,36 +138,39 @@ k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ 
         SmemRowSink sink; sink.rows = rows; sink.lane = lane;
         bk_gen_all(A, C, sel4(s.used, p), sink);
         __syncwarp();
-        const uint32_t* mine = rows + lane * EMIT_WORDS_PER_LANE;
+        uint32_t* mine = rows + lane * EMIT_WORDS_PER_LANE;
         uint32_t cnt = 0;
 #pragma unroll
-        for (int k = 0; k < EMIT_WORDS_PER_LANE; k++) cnt += __popc(mine[k]);
+        for (int k = 0; k < EMIT_WORDS_PER_LANE; k++) {
+            const uint32_t bits = mine[k];
+            mine[k] = bits | (cnt << 20);
+            cnt += __popc(bits);
+        }
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(BK_FULL, incl, d); if (lane >= d) incl += v; }
-        const uint32_t total = __shfl_sync(BK_FULL, incl, 31);
-        uint32_t pos = incl - cnt;
+        const uint32_t total = __reduce_add_sync(BK_FULL, cnt);
+        lane_base[lane] = incl - cnt;
         // CSR mode: state i owns ids[offsets[i] .. offsets[i+1]);  fixed mode (offsets == NULL): state i owns
         // ids[i*cap .. (i+1)*cap) and a longer list is truncated (counts_out still reports the full length).
         const size_t base = offsets ? (size_t)offsets[i] : (size_t)i * cap;
-        const uint32_t limit = offsets ? 0xFFFFFFFFu : cap;
+        const uint32_t limit = offsets ? total : (total < cap ? total : cap);
         if (counts_out && lane == 0) counts_out[i] = total;
-        const bool staged = total <= EMIT_STAGE;
-        for (int k = 0; k < EMIT_WORDS_PER_LANE; k++) {
-            uint32_t bits = mine[k];
-            const uint32_t idb = (uint32_t)(lane * EMIT_WORDS_PER_LANE + k) * 20u;
-            while (bits) {
-                const int col = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (staged) stage[pos] = (uint16_t)(idb + col);
-                else if (pos < limit) ids[base + pos] = (uint16_t)(idb + col);
-                pos++;
-            }
-        }
         __syncwarp();
-        if (staged) {
-            const uint32_t m = total < limit ? total : limit;
-            for (uint32_t k = lane; k < m; k += 32) ids[base + k] = stage[k];
+        for (uint32_t k = lane; k < limit; k += 32) {
+            uint32_t L = 0;                                  // owner lane: the last one whose base is <= k
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) if (lane_base[L + step] <= k) L += step;
+            const uint32_t rem = k - lane_base[L];
+            const uint32_t* words = rows + L * EMIT_WORDS_PER_LANE;
+            uint32_t w = 0;                                  // last word whose prefix is <= rem: it holds the move
+#pragma unroll
+            for (int step = 32; step >= 1; step >>= 1)
+                if (w + step < EMIT_WORDS_PER_LANE && (words[w + step] >> 20) <= rem) w += step;
+            const uint32_t wd = words[w];
+            uint32_t bits = wd & BK_ROWMASK;
+            for (uint32_t skip = rem - (wd >> 20); skip; skip--) bits &= bits - 1;
+            ids[base + k] = (uint16_t)((L * EMIT_WORDS_PER_LANE + w) * 20u + (__ffs(bits) - 1));
         }
         __syncwarp();
     }
@@ -663,7 +667,7 @@ extern "C" int bk_movegen_emit(const bk_state* states, const uint8_t* players, i
                                uint16_t* move_ids, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids)), "bk_movegen_emit: null buffer");
     if (n == 0) return BK_OK;
-    k_movegen_emit<<<grid_for(n, 2), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, offsets, 0u, nullptr, move_ids);
+    k_movegen_emit<<<grid_for(n, 3), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, offsets, 0u, nullptr, move_ids);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -672,7 +676,7 @@ extern "C" int bk_movegen_fixed(const bk_state* states, const uint8_t* players, 
                                 uint16_t* move_ids, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && cap > 0 && (n == 0 || (states && counts && move_ids)), "bk_movegen_fixed: bad argument");
     if (n == 0) return BK_OK;
-    k_movegen_emit<<<grid_for(n, 2), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, nullptr, cap, counts, move_ids);
+    k_movegen_emit<<<grid_for(n, 3), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, nullptr, cap, counts, move_ids);
     LAUNCH_CHECK();
     return BK_OK;
 }
