@@ -260,7 +260,8 @@ def run_cuda(args) -> None:
         trees, iters = 2368, 256            # 16 one-warp trees per SM
         root = dev.to_device(empty_states(1))
         eng = DeviceUCT(iters, n_trees=trees, seed=SEED, tree_offset=rank * trees)
-        eng.search(root, iters)                       # warm-up
+        res = eng.search(root, iters)                 # warm-up (search and merge: the first reduction loads torch kernels)
+        bdist.merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0))
         barrier()
         m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         m0.record(stream)
