@@ -289,7 +289,7 @@ def run_cuda(args) -> None:
     hbm_achieved = ALG_BYTES_PER_PLAYOUT_DEVICE * n / per_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": hbm_achieved / hbm_peak, "traffic": _traffic_from_profiles(),
-                "peak_source": peak_src, "kernel": "k_playout_uniform",
+                "peak_source": peak_src, "kernel": "k_playout<0,false>",
                 "note": "integer-ALU bound by design: HBM fraction is expected to be tiny; see int_roofline"}
     int_roofline = _int_roofline(n, per_launch_s, clocks, sm_max)
 

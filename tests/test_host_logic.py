@@ -1,0 +1,111 @@
+"""Host-side logic that needs no GPU: board bookkeeping, packing, move ids, frontier view, arena utilities.
+
+Literal cases follow the reference's own unit tests (tests/test_bitboard_basic.py:21-40,137-153,
+tests/test_frontier_basic.py:107-164, tests/test_pieces_orientations.py, tests/test_engine.py:21-92)."""
+
+import numpy as np
+import pytest
+
+from reinforcementlearning_blokus_b200 import pieces as P
+from reinforcementlearning_blokus_b200.board import Board, Player, Position
+from reinforcementlearning_blokus_b200.move_generator import LegalMoveGenerator, Move
+from reinforcementlearning_blokus_b200.state import STATE_DTYPE, bits_to_int, empty_states, grid_of, int_to_bits
+
+
+def test_board_initial_state_and_cells():
+    b = Board()
+    assert b.grid.shape == (20, 20) and not b.grid.any()
+    assert b.current_player == Player.RED and b.move_count == 0 and not b.game_over
+    assert b.player_start_corners[Player.RED] == Position(0, 0)
+    assert b.player_start_corners[Player.BLUE] == Position(0, 19)
+    assert b.player_start_corners[Player.YELLOW] == Position(19, 19)
+    assert b.player_start_corners[Player.GREEN] == Position(19, 0)
+    assert b.is_valid_position(Position(19, 19)) and not b.is_valid_position(Position(20, 0))
+    assert b.is_empty(Position(5, 5)) and b.get_cell(Position(-1, 0)) == -1
+    b.set_cell(Position(5, 5), 2)
+    assert b.get_player_at(Position(5, 5)) == Player.BLUE and b.get_player_at(Position(0, 0)) is None
+    assert len(b.get_adjacent_positions(Position(0, 0))) == 3
+    assert len(b.get_edge_adjacent_positions(Position(10, 10))) == 4
+    assert len(b.get_corner_adjacent_positions(Position(0, 19))) == 1
+
+
+def test_bit_layout_literals():
+    """bit = row*20 + col (engine/bitboard.py:13-22); two dominoes give the reference's literal masks."""
+    b = Board()
+    b.place_piece([Position(0, 0), Position(0, 1)], Player.RED, 2, validate=False)
+    b.place_piece([Position(0, 19), Position(1, 19)], Player.BLUE, 2, validate=False)
+    assert b.player_bits[Player.RED] == (1 << 0) | (1 << 1)
+    assert b.player_bits[Player.BLUE] == (1 << 19) | (1 << 39)
+    assert b.occupied_bits == b.player_bits[Player.RED] | b.player_bits[Player.BLUE]
+    b.assert_bitboard_consistent()
+    s = b.to_packed()
+    assert int(s["bits"][0][0]) == 3 and int(s["bits"][1][0]) == (1 << 19) | (1 << 39)
+    assert int(s["used"][0]) == 2 and int(s["first_mask"]) == 0b1100 and int(s["to_move"]) == 2 and int(s["move_count"]) == 2
+    assert bits_to_int(int_to_bits(b.occupied_bits)) == b.occupied_bits
+    assert np.array_equal(grid_of(s), b.grid)
+
+
+def test_pack_roundtrip_and_copy():
+    rng = np.random.RandomState(0)
+    b = Board()
+    for k in range(12):
+        pl = b.current_player
+        cells = [Position(int(rng.randint(20)), int(rng.randint(20)))]
+        if b.grid[cells[0].row, cells[0].col] == 0:
+            b.place_piece(cells, pl, 1 + k, validate=False)
+        else:
+            b._update_current_player()
+    s = b.to_packed()
+    assert s.dtype == STATE_DTYPE and s.tobytes() == Board.from_packed(s).to_packed().tobytes()
+    c = b.copy()
+    c.place_piece([Position(10, 10)], c.current_player, 21, validate=False)
+    assert c.move_count == b.move_count + 1 and not np.array_equal(c.grid, b.grid)
+    assert b.to_packed().tobytes() == s.tobytes()          # the copy is deep
+    e = empty_states(1)[0]
+    assert Board().to_packed().tobytes() == e.tobytes()
+
+
+def test_frontier_literals():
+    """tests/test_frontier_basic.py:107-164 of the reference."""
+    b = Board()
+    for p in Player:
+        c = b.player_start_corners[p]
+        assert b.get_frontier(p) == {(c.row, c.col)}
+    b.place_piece([Position(0, 0)], Player.RED, 1, validate=False)
+    assert b.get_frontier(Player.RED) == {(1, 1)}
+    b2 = Board()
+    b2.place_piece([Position(0, 0), Position(0, 1)], Player.RED, 2, validate=False)
+    assert b2.get_frontier(Player.RED) == {(1, 2)}
+    # a cell taken by an opponent leaves the frontier (exact view)
+    b2.place_piece([Position(1, 2)], Player.BLUE, 1, validate=False)
+    assert b2.get_frontier(Player.RED) == set()
+    assert b2._compute_full_frontier(Player.BLUE) == {(0, 1), (0, 3), (2, 1), (2, 3)} - {(0, 1)}
+
+
+def test_move_ids_cover_every_orientation():
+    gen = LegalMoveGenerator()
+    assert len(gen.all_pieces) == 21 and sum(p.size for p in gen.all_pieces) == 88
+    seen = set()
+    for o in P.ORIENTATIONS:
+        m = Move(o.piece_id, o.index, 20 - o.height, 20 - o.width)
+        mid = m.to_id()
+        assert mid == P.encode_move(o.piece_id, o.index, 20 - o.height, 20 - o.width)
+        assert Move.from_id(mid) == m and mid not in seen
+        seen.add(mid)
+        assert Move(o.piece_id, o.index, 21 - o.height, 0).to_id() is None      # hangs over the bottom edge
+        cells = [(p.row, p.col) for p in m.get_positions(gen.piece_orientations_cache[o.piece_id])]
+        assert cells == [(20 - o.height + r, 20 - o.width + c) for r, c in o.cells]
+        assert gen.piece_position_cache[o.piece_id][o.index] == list(o.cells)
+    assert Move(1, 0, -1, -1).to_id() is None and Move(22, 0, 0, 0).to_id() is None and Move(1, 1, 0, 0).to_id() is None
+    assert max(seen) < P.MAX_MOVE_ID and P.decode_move(0) == (1, 0, 0, 0)
+
+
+def test_arena_utilities_without_gpu():
+    from reinforcementlearning_blokus_b200 import arena
+
+    assert arena.compute_ranks({"1": 10, "2": 10, "3": 3, "4": 7}) == {"1": 1, "2": 1, "3": 3, "4": 2}
+    sa = arena.seat_assignment_for_game(["a", "b", "c", "d"], 2, 0, "round_robin")
+    assert sa == {"1": "c", "2": "d", "3": "a", "4": "b"}
+    rec = arena._record("run", 3, 99, sa, "round_robin", {"1": 5, "2": 9, "3": 9, "4": 1}, 40, 50, 10, 0, 0.5, False, {}, None)
+    assert rec["winner_ids"] == [2, 3] and rec["is_tie"] and rec["winner_id"] is None
+    assert rec["winner_agents"] == ["d", "a"] and rec["agent_scores"]["c"] == 5 and rec["game_id"] == "run_g0003"
