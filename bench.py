@@ -380,11 +380,14 @@ def _extras(dev, torch, n):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    # mid-game corpus (BASELINE configs[0] flavour): random self-play stopped after k turns
+    # mid-game corpus: 2^20 states = random self-play stopped after k turns; 256 MiB of states,
+    # twice the L2, so every generation streams its state from HBM
     parts = []
-    for k in (8, 16, 24, 32, 40, 48):
-        parts.append(dev.playout(n // 4, seed=7, game_offset=k * 1_000_000, max_turns=k, want_final=True)["final_states"])
+    per = (1 << 20) // 8
+    for k in (6, 12, 18, 24, 30, 36, 42, 48):
+        parts.append(dev.playout(per, seed=7, game_offset=k * 1_000_000, max_turns=k, want_final=True)["final_states"].clone())
     corpus = torch.cat(parts).contiguous()
+    del parts
     m = corpus.shape[0]
     ex = {"movegen_states": m, "movegen_mean_legal_moves": float(dev.movegen_count(corpus).float().mean())}
     ms = timeit(lambda: dev.movegen_count(corpus))
