@@ -257,7 +257,7 @@ def run_cuda(args) -> None:
         from reinforcementlearning_blokus_b200 import dist as bdist
         from reinforcementlearning_blokus_b200.mcts import DeviceUCT
 
-        trees, iters = 2368, 256            # 16 one-warp trees per SM
+        trees, iters = 3552, 256            # 24 one-warp trees per SM
         root = dev.to_device(empty_states(1))
         eng = DeviceUCT(iters, n_trees=trees, seed=SEED, tree_offset=rank * trees)
         res = eng.search(root, iters)                 # warm-up (search and merge: the first reduction loads torch kernels)

@@ -70,9 +70,12 @@ __device__ __forceinline__ int32_t board_score_of(const WarpState& s, uint32_t q
 }
 
 #define BK_MCTS_THREADS 32   /* one warp = one tree per CTA, so a handful of trees still spreads over the SMs */
+#ifndef BK_MCTS_CTAS_PER_SM
+#define BK_MCTS_CTAS_PER_SM 24
+#endif
 
 template <int POLICY>
-__global__ void __launch_bounds__(BK_MCTS_THREADS)
+__global__ void __launch_bounds__(BK_MCTS_THREADS, POLICY == 0 ? BK_MCTS_CTAS_PER_SM : 8)
 k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_params prm, MctsTT tt,
        unsigned char* __restrict__ workspace, int resume, int max_root_moves,
        int32_t* __restrict__ out_visits, long long* __restrict__ out_reward, uint32_t* __restrict__ out_counts,
