@@ -221,25 +221,32 @@ def run_cuda(args) -> None:
     clocks = sampler.stop()
     value = n * world * args.steps / (ms * 1e-3)
 
-    # ---- e2e: host buffers through the public API; H2D of the start states and D2H of the scores inside
+    # ---- e2e: host buffers through the public API (device.PlayoutPipeline): every step uploads its start states
+    # from pinned host memory and downloads its scores to pinned host memory; the two pipeline slots overlap one
+    # step's copies with the other's kernel.  Timed with CUDA events on the main stream, whose end event waits for
+    # both pipeline streams; every step's H2D, kernel and D2H complete inside the timed region.
     host_states = torch.from_numpy(empty_states(n).view(np.uint8).reshape(n, 256).copy()).pin_memory()
-    host_scores = torch.empty((n, 4), dtype=torch.int32).pin_memory()
-    dstates = torch.empty((n, 256), dtype=torch.uint8, device="cuda")
-    out2 = {}
+    pipe = dev.PlayoutPipeline(n)
+    mean_score = 0.0
 
-    def step_e2e(k):
-        dstates.copy_(host_states, non_blocking=True)
-        r = dev.playout(n, seed=SEED, game_offset=(k * world + rank) * n, start_states=dstates, out=out2,
-                        want_board_scores=False)
-        host_scores.copy_(r["game_scores"], non_blocking=True)
+    def run_e2e(steps, base):
+        acc = 0.0
+        for k in range(steps):
+            pipe.submit(host_states, SEED, game_offset=((base + k) * world + rank) * n)
+            got = pipe.collect()
+            if got is not None:
+                acc += float(got[0, 0])          # touch the result on the host
+        for got in pipe.drain():
+            acc += float(got[0, 0])
+        return acc
 
-    for w in range(max(1, args.warmup // 2)):
-        step_e2e(2_000_000 + w)
+    run_e2e(max(2, args.warmup), 2_000_000)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for k in range(args.steps):
-        step_e2e(k)
+    run_e2e(args.steps, 0)
+    for slot in pipe.slots:                      # the end event waits for every pipeline stream
+        stream.wait_stream(slot["stream"])
     e1.record(stream)
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -248,7 +255,7 @@ def run_cuda(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e_value = n * world * args.steps / (ms_e2e * 1e-3)
-    mean_score = float(host_scores.float().mean())
+    mean_score = float(pipe.slots[0]["hscores"].float().mean())
 
     # ---- root-parallel MCTS (the third part of BASELINE.json's metric): every rank searches its own trees from
     # the empty board (50-ply rollouts), then ONE all-reduce of the root statistics (dist.merge_root_stats)

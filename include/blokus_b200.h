@@ -8,7 +8,8 @@
  *     `_host` or the comment says "host";
  *   - every function returns 0 on success or a negative bk_status; nothing throws;
  *     bk_last_error() returns a thread-local message for the last failure;
- *   - the caller owns every buffer; `stream` is a cudaStream_t passed as void* (NULL = the
+ *   - the caller owns every buffer (the library itself keeps only constant tables and a small pool of
+ *     per-launch work counters); `stream` is a cudaStream_t passed as void* (NULL = the
  *     legacy default stream); calls on distinct streams may run concurrently;
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
  *     BK_ERR_CUDA.

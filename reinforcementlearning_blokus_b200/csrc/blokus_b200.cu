@@ -18,6 +18,9 @@
 // error plumbing / lifecycle
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
+static unsigned int* g_tickets = nullptr;      // per-launch work counters of the playout kernels (device, BK_TICKETS of them)
+static unsigned int g_ticket_next = 0;
+#define BK_TICKETS 256
 static int g_device = -1;
 static int g_sms = 0;
 
@@ -36,6 +39,14 @@ static int fail(int code, const char* fmt, const char* detail) {
     do { if (!(cond)) return fail(BK_ERR_ARG, "%s", msg); } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// A zeroed work counter for one launch on `st` (round-robin over a small pool so that launches in flight on
+// different streams never share one).
+static unsigned int* fresh_ticket(cudaStream_t st) {
+    unsigned int* t = g_tickets + (__sync_fetch_and_add(&g_ticket_next, 1u) % BK_TICKETS);
+    cudaMemsetAsync(t, 0, sizeof(unsigned int), st);
+    return t;
+}
 
 static inline int grid_for(int n_items, int ctas_per_sm) {
     long long need = ((long long)n_items + BK_WARPS - 1) / BK_WARPS;
@@ -69,6 +80,7 @@ extern "C" int bk_init(int device) {
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_rowpat, BK_TBL_ORIENT_ROWPAT, sizeof(BK_TBL_ORIENT_ROWPAT)));
     CUDA_TRY(cudaFuncSetAttribute(k_movegen_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
     CUDA_TRY(bk_init_policies());
+    if (!g_tickets) CUDA_TRY(cudaMalloc(&g_tickets, BK_TICKETS * sizeof(unsigned int)));
     g_device = device;
     return BK_OK;
 }
@@ -344,7 +356,7 @@ k_scores(const bk_state* __restrict__ states, int n, int32_t* __restrict__ gs, i
 // POLICY 2 = one policy per seat and game (arena match-ups): seat_policies[i] packs the policy of player p in byte p.
 template <int POLICY, bool TRACE = true>
 __global__ void __launch_bounds__(BK_PLAYOUT_THREADS, POLICY == 0 ? BK_PLAYOUT_MIN_BLOCKS : 2)
-k_playout(const uint32_t* __restrict__ seat_policies, const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int first_turn, int max_turns,
+k_playout(unsigned int* __restrict__ ticket, const uint32_t* __restrict__ seat_policies, const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int first_turn, int max_turns,
                   int32_t* __restrict__ gs, int32_t* __restrict__ bs, uint16_t* __restrict__ trace,
                   uint16_t* __restrict__ choice, bk_state* __restrict__ finals) {
     __shared__ __align__(16) uint32_t s_slots[BK_PLAYOUT_THREADS / 32][BK_GROUP_SLOTS];
@@ -352,10 +364,14 @@ k_playout(const uint32_t* __restrict__ seat_policies, const bk_state* __restrict
     HeurScratch hs;
     if (POLICY != 0) hs.bind(heur_smem + (size_t)(threadIdx.x >> 5) * HEUR_SMEM_PER_WARP);
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int i0 = warp; i0 < n; i0 += nwarps) {
-        const int i = (int)uni((uint32_t)i0);              // warp-uniform game index
+    // Games differ in length (50..76 turns), so a fixed game->warp assignment leaves a tail of idle warps; every
+    // warp instead takes the next game from a per-launch ticket counter.  Results do not depend on the assignment:
+    // a game is a function of (seed, global game index) only.
+    for (;;) {
+        uint32_t i0 = 0;
+        if (lane == 0) i0 = atomicAdd(ticket, 1u);
+        const int i = (int)uni(i0);                        // warp-uniform game index (lanes != 0 contribute 0)
+        if (i >= n) break;
         WarpState s;
         if (start) load_state(start + i, lane, s); else init_empty(s);
         const uint64_t g = game_offset + (uint64_t)i;
@@ -745,14 +761,14 @@ extern "C" int bk_playout(const bk_state* start_states, int n, uint64_t seed, ui
     long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)g_sms * BK_PLAYOUT_MIN_BLOCKS;
     if (policy == BK_POLICY_UNIFORM && !trace && !choice) {     // scores only: no per-turn output code at all
         k_playout<0, false><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, 0, as_stream(stream)>>>(
-            nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+            fresh_ticket(as_stream(stream)), nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     } else if (policy == BK_POLICY_UNIFORM) {
         k_playout<0><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, 0, as_stream(stream)>>>(
-            nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+            fresh_ticket(as_stream(stream)), nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     } else {
         pcap = (long long)g_sms * 2;
         k_playout<1><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, BK_HEUR_PLAYOUT_SMEM, as_stream(stream)>>>(
-            nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+            fresh_ticket(as_stream(stream)), nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     }
     LAUNCH_CHECK();
     return BK_OK;
@@ -770,7 +786,7 @@ extern "C" int bk_playout_seats(const bk_state* start_states, int n, uint64_t se
     const int pw = BK_PLAYOUT_THREADS / 32;
     long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)g_sms * 2;
     k_playout<2><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, BK_HEUR_PLAYOUT_SMEM, as_stream(stream)>>>(
-        seat_policies, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice,
+        fresh_ticket(as_stream(stream)), seat_policies, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice,
         final_states);
     LAUNCH_CHECK();
     return BK_OK;

@@ -256,6 +256,68 @@ def heuristic_scores(states: torch.Tensor, offsets: torch.Tensor, move_ids: torc
     return out[:move_ids.numel()]
 
 
+class PlayoutPipeline:
+    """Host-to-host playouts with the copies overlapped with compute: start states arrive in pinned host memory,
+    final scores are wanted in pinned host memory.  Two slots, each with its own stream; while slot A's kernel runs,
+    slot B's states are uploading and the previous scores are downloading.
+
+        pipe = PlayoutPipeline(n)
+        for k, host_states in enumerate(batches):          # pinned uint8[n, 256]
+            pipe.submit(host_states, seed, game_offset=k * n)
+            scores = pipe.collect()                          # pinned int32[n, 4] of the OLDEST batch in flight, or None
+        scores = pipe.drain()                                # remaining batches, oldest first
+    """
+
+    def __init__(self, n: int, depth: int = 2, policy: int = POLICY_UNIFORM):
+        self.n, self.depth, self.policy = int(n), int(depth), int(policy)
+        d = torch.device("cuda", torch.cuda.current_device())
+        self.slots = []
+        for _ in range(self.depth):
+            self.slots.append({
+                "stream": torch.cuda.Stream(device=d),
+                "dstates": torch.empty((n, STATE_BYTES), dtype=torch.uint8, device=d),
+                "out": {},
+                "hscores": torch.empty((n, 4), dtype=torch.int32).pin_memory(),
+                "done": torch.cuda.Event(),
+                "busy": False,
+            })
+        self._head = 0      # next slot to fill
+        self._tail = 0      # oldest slot in flight
+        self._inflight = 0
+
+    def submit(self, host_states: torch.Tensor, seed: int, game_offset: int = 0) -> None:
+        if self._inflight == self.depth:
+            raise RuntimeError("pipeline full: collect() a result first")
+        slot = self.slots[self._head]
+        with torch.cuda.stream(slot["stream"]):
+            slot["dstates"].copy_(host_states, non_blocking=True)
+            r = playout(self.n, seed=seed, game_offset=game_offset, start_states=slot["dstates"], policy=self.policy,
+                        out=slot["out"], want_board_scores=False)
+            slot["hscores"].copy_(r["game_scores"], non_blocking=True)
+            slot["done"].record(slot["stream"])
+        slot["busy"] = True
+        self._head = (self._head + 1) % self.depth
+        self._inflight += 1
+
+    def collect(self, wait_if_full_only: bool = True):
+        """Scores of the oldest batch in flight.  With wait_if_full_only the call returns None while the pipeline
+        still has a free slot (so the caller keeps it full); otherwise it waits for the oldest batch."""
+        if self._inflight == 0 or (wait_if_full_only and self._inflight < self.depth):
+            return None
+        slot = self.slots[self._tail]
+        slot["done"].synchronize()
+        slot["busy"] = False
+        self._tail = (self._tail + 1) % self.depth
+        self._inflight -= 1
+        return slot["hscores"]
+
+    def drain(self):
+        out = []
+        while self._inflight:
+            out.append(self.collect(wait_if_full_only=False).clone())
+        return out
+
+
 # ---- K4 --------------------------------------------------------------------------------------
 def zobrist_hash(states: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     """uint64 keys (returned as int64 bit patterns) of ZobristHash.hash_board (mcts/zobrist.py:70)."""

@@ -136,3 +136,25 @@ def test_mobility_after_moves_matches_oracle():
         assert c.place(opp, int(mv))
         assert g == len(c.legal_moves(player))
     assert mobility_after_moves(state, player, opp, [36399]).cpu().numpy()[0] == -1
+
+
+def test_playout_pipeline_matches_direct_calls():
+    n = 2048
+    from reinforcementlearning_blokus_b200.state import empty_states
+
+    host = torch.from_numpy(empty_states(n).view(np.uint8).reshape(n, 256).copy()).pin_memory()
+    pipe = dev.PlayoutPipeline(n)
+    got = []
+    for k in range(5):
+        pipe.submit(host, 42, game_offset=k * n)
+        r = pipe.collect()
+        if r is not None:
+            got.append(r.clone())
+    got += pipe.drain()
+    assert len(got) == 5
+    for k in range(5):
+        want = dev.playout(n, seed=42, game_offset=k * n)["game_scores"].cpu()
+        assert torch.equal(got[k], want), k
+    with pytest.raises(RuntimeError):
+        pipe.submit(host, 1); pipe.submit(host, 1); pipe.submit(host, 1)
+    pipe.drain()
