@@ -101,6 +101,13 @@ int bk_movegen_fixed(const bk_state* states, const uint8_t* players, int n, uint
 int bk_movegen_bitmap(const bk_state* states, const uint8_t* players, int n,
                       uint32_t* bitmap, void* stream);
 
+/* Per-piece placement counts P_i of players[i] (NULL: side to move): piece_counts[i][pid-1] = number of legal moves
+ * that use piece pid -- the movegen-bound input of compute_player_mobility_metrics (engine/mobility_metrics.py:38-131,
+ * used by the snapshot features analytics/winprob/features.py:131-193).  anchor_max[i] (optional) = the largest
+ * number of legal moves that share one anchor cell (numerator of anchorTop1Share). */
+int bk_movegen_piece_counts(const bk_state* states, const uint8_t* players, int n, uint16_t* piece_counts /*[n][21]*/,
+                            uint16_t* anchor_max /*[n] or NULL*/, void* stream);
+
 /* has_legal_moves for all four players (engine/move_generator.py:961-1054): bit p of out[i]. */
 int bk_has_moves(const bk_state* states, int n, uint8_t* out_mask, void* stream);
 

@@ -124,7 +124,7 @@ struct SmemRowSink {
     template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) {
         if (lane < 20) rows[O * 20 + lane] = L;
     }
-    template <int G0, int NG> __device__ __forceinline__ void flush() {}
+    template <int G0, int NG, int PID> __device__ __forceinline__ void flush() {}
 };
 
 __global__ void __launch_bounds__(BK_THREADS)
@@ -210,6 +210,57 @@ k_movegen_bitmap(const bk_state* __restrict__ states, const uint8_t* __restrict_
             for (int o = c_piece_first[pid]; o < c_piece_first[pid + 1]; o++)
                 if (lane < 20) sink.out[o * 20 + lane] = 0u;
         }
+    }
+}
+
+// Per-piece placement counts P_i (the movegen-bound input of engine/mobility_metrics.py:38-131) and the largest
+// number of legal moves sharing one anchor cell (its anchorTop1Share numerator).  Anchor counts are kept
+// bit-sliced: plane k holds bit k of the count of every cell of this lane's row.
+struct PieceCountSink {
+    static constexpr bool kRows = false;            // counts per piece and per cell do not care about mirroring
+    uint32_t acc = 0;
+    uint32_t plane[7] = {0, 0, 0, 0, 0, 0, 0};      // <= 91 moves per anchor cell
+    uint16_t* out; int lane;
+    template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) {
+        acc += __popc(L);
+        uint32_t carry = L;
+#pragma unroll
+        for (int k = 0; k < 7; k++) { const uint32_t t = plane[k] & carry; plane[k] ^= carry; carry = t; }
+    }
+    template <int G0, int NG, int PID> __device__ __forceinline__ void flush() {
+        const uint32_t t = __reduce_add_sync(BK_FULL, acc);
+        if (lane == 0) out[PID - 1] = (uint16_t)t;
+        acc = 0;
+    }
+    __device__ __forceinline__ uint32_t anchor_max() const {
+        uint32_t best = 0;
+        for (int c = 0; c < 20; c++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 7; k++) v |= ((plane[k] >> c) & 1u) << k;
+            best = max(best, v);
+        }
+        return __reduce_max_sync(BK_FULL, best);
+    }
+};
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_piece_counts(const bk_state* __restrict__ states, const uint8_t* __restrict__ players, int n,
+               uint16_t* __restrict__ piece_counts, uint16_t* __restrict__ anchor_max) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        WarpState s; load_state(states + i, lane, s);
+        const uint32_t p = players ? (players[i] & 3u) : s.to_move;
+        uint32_t A, C; make_masks(s, p, lane, A, C);
+        uint16_t* out = piece_counts + (size_t)i * BK_PIECES;
+        if (lane < BK_PIECES) out[lane] = 0;            // spent pieces are never visited
+        __syncwarp();
+        PieceCountSink sink; sink.out = out; sink.lane = lane;
+        bk_gen_all<PieceCountSink, true>(A, C, sel4(s.used, p), sink);
+        const uint32_t amax = sink.anchor_max();
+        if (anchor_max && lane == 0) anchor_max[i] = (uint16_t)amax;
     }
 }
 
@@ -701,6 +752,15 @@ extern "C" int bk_movegen_bitmap(const bk_state* states, const uint8_t* players,
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && bitmap)), "bk_movegen_bitmap: null buffer");
     if (n == 0) return BK_OK;
     k_movegen_bitmap<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, bitmap);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_movegen_piece_counts(const bk_state* states, const uint8_t* players, int n, uint16_t* piece_counts,
+                                       uint16_t* anchor_max, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && piece_counts)), "bk_movegen_piece_counts: null buffer");
+    if (n == 0) return BK_OK;
+    k_piece_counts<<<grid_for(n, 3), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, piece_counts, anchor_max);
     LAUNCH_CHECK();
     return BK_OK;
 }

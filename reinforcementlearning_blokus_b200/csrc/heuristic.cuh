@@ -64,7 +64,7 @@ struct HeurRowSink {
     static constexpr bool kRows = true;
     uint32_t* rows; int lane;
     template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) { if (lane < 20) rows[O * 20 + lane] = L; }
-    template <int G0, int NG> __device__ __forceinline__ void flush() {}
+    template <int G0, int NG, int PID> __device__ __forceinline__ void flush() {}
 };
 
 // corner_creation of a move = sum over its cells of the diagonal-neighbour count map; edge from the static table

@@ -178,14 +178,14 @@ struct CountSink {                 // per-lane move count
     static constexpr bool kRows = false;
     uint32_t acc = 0;
     template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) { acc += __popc(L); }
-    template <int G0, int NG> __device__ __forceinline__ void flush() {}
+    template <int G0, int NG, int PID> __device__ __forceinline__ void flush() {}
 };
 
 struct AnySink {                   // does any move exist
     static constexpr bool kRows = false;
     uint32_t acc = 0;
     template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) { acc |= L; }
-    template <int G0, int NG> __device__ __forceinline__ void flush() {}
+    template <int G0, int NG, int PID> __device__ __forceinline__ void flush() {}
 };
 
 struct BitmapSink {                // legal-anchor bitmap rows straight to memory
@@ -194,7 +194,7 @@ struct BitmapSink {                // legal-anchor bitmap rows straight to memor
     template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) {
         if (lane < 20) out[O * 20 + lane] = L;
     }
-    template <int G0, int NG> __device__ __forceinline__ void flush() {}
+    template <int G0, int NG, int PID> __device__ __forceinline__ void flush() {}
 };
 
 // Per-orientation totals for choosing the idx-th move.  The counts of a group's <= 3 orientations sit in 10-bit
@@ -219,7 +219,7 @@ struct GroupSink {
         if (GI == 0) acc0 += v; else if (GI == 1) acc1 += v; else acc2 += v;
     }
     // All REDUX of a piece are issued back to back (their latencies overlap) before the first result is stored.
-    template <int G0, int NG> __device__ __forceinline__ void flush() {
+    template <int G0, int NG, int PID> __device__ __forceinline__ void flush() {
         const uint32_t t0 = __reduce_add_sync(BK_FULL, acc0);
         const uint32_t t1 = NG > 1 ? __reduce_add_sync(BK_FULL, acc1) : 0u;
         const uint32_t t2 = NG > 2 ? __reduce_add_sync(BK_FULL, acc2) : 0u;

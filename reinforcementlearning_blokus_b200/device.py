@@ -150,6 +150,19 @@ def movegen_bitmap(states: torch.Tensor, players: Optional[torch.Tensor] = None)
     return bitmap
 
 
+def piece_counts(states: torch.Tensor, players: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(P int16[N, 21], anchor_max int16[N]): legal placements per piece and the most moves sharing one anchor cell
+    (inputs of engine/mobility_metrics.py:38-131)."""
+    n = _check_states(states)
+    _check_players(players, n)
+    lib = _lib_for(states)
+    pc = torch.empty((n, 21), dtype=torch.int16, device=states.device)
+    am = torch.empty(n, dtype=torch.int16, device=states.device)
+    check(lib.bk_movegen_piece_counts(_ptr(states), _ptr(players), n, _ptr(pc), _ptr(am), _stream()))
+    _count()
+    return pc, am
+
+
 def has_moves(states: torch.Tensor) -> torch.Tensor:
     """uint8[N]: bit p set iff player p has a legal move (engine/move_generator.py:961)."""
     n = _check_states(states)

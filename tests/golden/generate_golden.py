@@ -315,8 +315,57 @@ def gen_heuristic():
     print("heuristic", offs[-1], "scored moves")
 
 
+def gen_mobility():
+    """engine/mobility_metrics.py compute_player_mobility_metrics on the random-state corpus (row N4)."""
+    from engine.mobility_metrics import compute_player_mobility_metrics
+
+    z = np.load(os.path.join(HERE, "random_states.npz"))
+    states = z["states"].view(STATE_DTYPE).reshape(-1)
+    n = len(states)
+    P = np.zeros((n, 4, 21), dtype=np.int32)
+    M = np.zeros((n, 4, 12), dtype=np.float64)
+    for i in range(n):
+        board = random_state_from_packed(states[i])
+        for p in range(4):
+            pl = Player(p + 1)
+            moves = GEN.get_legal_moves(board, pl)
+            for m in moves:
+                P[i, p, m.piece_id - 1] += 1
+            mm = compute_player_mobility_metrics(moves, sorted(board.player_pieces_used[pl]))
+            M[i, p] = [mm.totalPlacements, mm.totalOrientationNormalized, mm.totalCellWeighted, mm.buckets[1],
+                       mm.buckets[2], mm.buckets[3], mm.buckets[4], mm.buckets[5], mm.mobilityEntropy,
+                       mm.pieceTop1Share, mm.anchorTop1Share, 0.0]
+    np.savez_compressed(os.path.join(HERE, "mobility.npz"), piece_counts=P, metrics=M)
+    print("mobility", n, "states")
+
+
+def random_state_from_packed(s) -> Board:
+    """Rebuild a reference Board from a packed state (the recipe of engine-service/app.py:27-50)."""
+    board = Board()
+    for p in range(4):
+        pl = Player(p + 1)
+        m = int.from_bytes(np.ascontiguousarray(s["bits"][p], dtype="<u8").tobytes(), "little")
+        board.player_bits[pl] = m
+        board.occupied_bits |= m
+        for i in range(400):
+            if (m >> i) & 1:
+                board.grid[i // 20, i % 20] = pl.value
+        used = int(s["used"][p])
+        board.player_pieces_used[pl] = {pid for pid in range(1, 22) if (used >> (pid - 1)) & 1}
+        board.player_first_move[pl] = bool((int(s["first_mask"]) >> p) & 1)
+    for pl in Player:
+        if board.player_pieces_used[pl]:
+            board.player_frontiers[pl] = board._compute_full_frontier(pl)
+        else:
+            c = board.player_start_corners[pl]
+            board.player_frontiers[pl] = {(c.row, c.col)}
+    board.current_player = Player(int(s["to_move"]) + 1)
+    board.move_count = int(s["move_count"])
+    return board
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic"]
+    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility"]
     for w in which:
         {"tables": gen_tables, "kat1": gen_kat1, "kat2": gen_kat2, "random": gen_random_states,
-         "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic}[w]()
+         "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic, "mobility": gen_mobility}[w]()
