@@ -29,8 +29,10 @@ __host__ __device__ inline MctsLayout mcts_layout(int iterations_total) {
     MctsLayout L;
     const size_t T = (size_t)(iterations_total > 0 ? iterations_total : 1);
     L.max_nodes = (uint32_t)(T + 1);
-    // a node first expanded at iteration t can still gain at most T - t children
-    const size_t pool = T * (T + 1) / 2 + 1;
+    // a node first expanded at iteration t can still gain at most T - t children, and never more than its number
+    // of legal moves (largest list seen in 10^6 states: 1003); a tree that outgrows the pool reports status 1
+    size_t pool = T * (T + 1) / 2 + 1;
+    if (pool > T * 2048) pool = T * 2048;
     L.pool_slots = (uint32_t)(pool > 0xFFFFFF00ull ? 0xFFFFFF00ull : pool);
     size_t o = 0;
     L.off_states = o;      o += (size_t)L.max_nodes * sizeof(bk_state);

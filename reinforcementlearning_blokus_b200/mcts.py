@@ -248,7 +248,9 @@ class MCTSAgent:
         start = time.time()
         root = _root_state(board, player)
         if self.time_limit:
-            chunk, cap = 64, 60000
+            # capacity for the time budget: one warp runs about 12-15 k simulations/s (profiles/r01_agent_latency.json)
+            chunk = 64
+            cap = min(60000, max(4 * chunk, int(self.time_limit * 30000)))
             eng = self._engine(cap)
             done = 0
             res = eng.search(root, chunk)
