@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
         L.orc_tt_size.restype = u64
         L.orc_mcts_search.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, vp, vp]
         L.orc_check_moves_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp]
+        L.orc_check_playouts.argtypes = [u64, u64, i32, i32, i32, vp, vp, vp]
         L.orc_init()
         _lib = L
     return _lib
@@ -310,3 +311,26 @@ def check_moves_batch(states: np.ndarray, offsets: np.ndarray, ids: np.ndarray, 
     bad = sum(r[0] for r in res)
     firsts = [r[1] for r in res if r[1] >= 0]
     return bad, (min(firsts) if firsts else -1)
+
+
+def check_playouts(seed: int, first_game: int, traces: np.ndarray, game_scores: np.ndarray, policy: int = 0,
+                   threads: int = 0) -> Tuple[int, int]:
+    """Replay every game with the oracle and compare trace + final scores; (mismatches, first bad index)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    tr = np.ascontiguousarray(traces, dtype=np.uint16)
+    gs = np.ascontiguousarray(game_scores, dtype=np.int32)
+    n = len(tr)
+    threads = threads or min(32, os.cpu_count() or 1)
+    chunk = max(1, -(-n // (threads * 8)))
+
+    def work(lo):
+        fb = C.c_int(-1)
+        bad = lib().orc_check_playouts(int(seed), int(first_game), lo, min(n, lo + chunk), int(policy), _ptr(tr), _ptr(gs),
+                                       C.byref(fb))
+        return bad, fb.value
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(work, range(0, n, chunk)))
+    firsts = [r[1] for r in res if r[1] >= 0]
+    return sum(r[0] for r in res), (min(firsts) if firsts else -1)

@@ -352,3 +352,18 @@ def test_abi_error_codes_and_empty_batches():
     fin = dev.playout(8, seed=3, want_final=True)["final_states"]
     again = dev.playout(8, seed=3, start_states=fin, want_final=True, want_trace=True)
     assert torch.equal(again["final_states"], fin) and (again["trace"].cpu().numpy() == 0xFFFF).all()
+
+
+def test_playout_replay_sweep_small():
+    """tools/playout_sweep.py at test size: every move of 3,000 uniform and 400 heuristic games equals the oracle's
+    (profiles/r01_playout_replay_sweep.json holds the 50,000 + 5,000 game run)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "playout_sweep", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "playout_sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    u = mod.sweep(3000, seed=7, policy=0, first_game=123456)
+    h = mod.sweep(400, seed=7, policy=1, first_game=654321)
+    assert u["mismatches"] == 0 and h["mismatches"] == 0
+    assert h["mean_score"] > u["mean_score"]
