@@ -23,7 +23,7 @@ import json
 import random
 import time
 import traceback
-from typing import Any, Dict, List, Mapping, Optional, Sequence, Tuple
+from typing import Any, Dict, Mapping, Optional, Sequence, Tuple
 
 import numpy as np
 

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BK_BITMAP_WORDS, BK_MAX_TURNS, BK_PASS, STATE_BYTES, check
+from ._lib import BK_BITMAP_WORDS, BK_MAX_TURNS, STATE_BYTES, check
 
 POLICY_UNIFORM = 0
 POLICY_HEURISTIC = 1

@@ -19,7 +19,6 @@ from . import _lib
 from . import device as dev
 from .board import Board, Player
 from .move_generator import Move, get_shared_generator
-from .state import STATE_BYTES
 
 MAX_ROOT_MOVES = 2048
 

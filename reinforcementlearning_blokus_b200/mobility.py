@@ -14,8 +14,6 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Sequence
 
-import numpy as np
-
 from . import pieces as P
 
 ORIENTATION_COUNTS = {pid: len(P.PIECE_ORIENTATIONS[pid]) for pid in range(1, 22)}

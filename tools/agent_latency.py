@@ -1,6 +1,5 @@
 """Latency of the object-API agents on one board (BASELINE config 4: 1,000 simulations per move)."""
 import sys, time, json
-import torch
 sys.path.insert(0, ".")
 from reinforcementlearning_blokus_b200 import BlokusGame, FastMCTSAgent, MCTSAgent, RandomAgent, get_shared_generator
 

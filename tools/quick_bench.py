@@ -1,6 +1,5 @@
 """Quick device timing of the hot kernels (development aid; bench.py is the contract)."""
-import sys, time
-import numpy as np
+import sys
 import torch
 sys.path.insert(0, ".")
 from reinforcementlearning_blokus_b200 import device as dev

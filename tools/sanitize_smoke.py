@@ -1,6 +1,5 @@
 """Small end-to-end pass over every kernel for compute-sanitizer (memcheck / racecheck) runs."""
 import sys
-import numpy as np
 import torch
 sys.path.insert(0, ".")
 from reinforcementlearning_blokus_b200 import device as dev
