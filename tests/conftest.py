@@ -14,6 +14,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """Build the CUDA library (and the oracle) if this tree has not been built yet -- nvcc cross-compiles without a
+    GPU, so this works on both boxes.  Building is not a fallback: without the library every product call raises."""
+    try:
+        from reinforcementlearning_blokus_b200 import build
+
+        if build.needs_build():
+            build.build()
+    except Exception as exc:  # report, and let the tests that need the library fail loudly
+        sys.stderr.write(f"[conftest] could not build libblokus_b200.so: {exc}\n")
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
