@@ -1,8 +1,9 @@
 // blokus_b200.cu -- kernels and the C ABI of libblokus_b200.so (sm_100a only).
 //
-// One warp owns one game state (see movegen_core.cuh).  All kernels are warp-per-item grid-stride
-// loops launched with a grid that fills the 148 SMs; nothing here uses tensor cores (no dense
-// contraction on this path) and nothing falls back to the CPU.
+// One warp owns one game state (see movegen_core.cuh).  The streaming kernels are warp-per-item grid-stride
+// loops, the playout kernels hand out games through a per-launch ticket counter; grids are sized to fill the
+// 148 SMs at the kernel's occupancy.  Nothing here uses tensor cores (no dense contraction on this path) and
+// nothing falls back to the CPU.  One process drives one GPU (bk_init(device) binds the library to it).
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -70,6 +71,7 @@ extern "C" int bk_init(int device) {
     CUDA_TRY(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail(BK_ERR_ARG, "%s", "bk_init: no such CUDA device");
     CUDA_TRY(cudaSetDevice(device));
+    if (g_device >= 0 && g_device != device) g_tickets = nullptr;      // re-bound to another GPU: its own counters
     CUDA_TRY(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_piece, BK_TBL_ORIENT_PIECE, sizeof(BK_TBL_ORIENT_PIECE)));
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_ncells, BK_TBL_ORIENT_NCELLS, sizeof(BK_TBL_ORIENT_NCELLS)));
