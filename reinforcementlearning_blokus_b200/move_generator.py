@@ -68,6 +68,10 @@ class Move:
     __repr__ = __str__
 
 
+_ORIENT_PIECE = np.array([o.piece_id for o in P.ORIENTATIONS], dtype=np.int64)
+_ORIENT_INDEX = np.array([o.index for o in P.ORIENTATIONS], dtype=np.int64)
+
+
 class Piece:
     """id / name / shape / size record (engine/pieces.py:13-27)."""
 
@@ -94,7 +98,11 @@ class LegalMoveGenerator:
         return single.legal_move_ids(board.to_packed(), player.value - 1)
 
     def get_legal_moves(self, board: Board, player: Player) -> List[Move]:
-        return [Move.from_id(i) for i in self.get_legal_move_ids(board, player)]
+        ids = self.get_legal_move_ids(board, player).astype(np.int64)
+        g, cell = np.divmod(ids, P.NUM_CELLS)
+        pid, ori = _ORIENT_PIECE[g].tolist(), _ORIENT_INDEX[g].tolist()
+        row, col = np.divmod(cell, P.BOARD_SIZE)
+        return [Move(a, b, c, d) for a, b, c, d in zip(pid, ori, row.tolist(), col.tolist())]
 
     # the reference exposes its variants under these names; tests and benchmarks call them directly
     _get_legal_moves_naive = get_legal_moves
