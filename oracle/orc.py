@@ -90,6 +90,10 @@ def lib() -> C.CDLL:
         L.orc_mcts_search.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, vp, vp]
         L.orc_check_moves_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp]
         L.orc_check_playouts.argtypes = [u64, u64, i32, i32, i32, vp, vp, vp]
+        L.orc_num_snapshot_features.restype = i32
+        L.orc_snapshot_features.argtypes = [vp, i32, i32, vp]
+        L.orc_snapshot_features_packed.argtypes = [vp, vp, i32, i32, vp]
+        L.orc_replay_snapshots.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]
         L.orc_init()
         _lib = L
     return _lib
@@ -257,6 +261,36 @@ def playout(
     if want_final:
         res["final"] = fin[0]
     return res
+
+
+NUM_SNAPSHOT_FEATURES = 34
+
+
+def snapshot_features(state: np.ndarray, turn_index: Optional[int] = None, max_turns: int = 2500,
+                      frontiers: Optional[np.ndarray] = None) -> np.ndarray:
+    """float64[4, 34] feature rows of one packed state (analytics/winprob/features.py).  frontiers = uint8[4, 400]
+    incremental frontier sets, or None for the sets rebuilt from the cells; turn_index None = move_count."""
+    st = np.ascontiguousarray(np.atleast_1d(state), dtype=STATE_DTYPE)
+    out = np.zeros((4, NUM_SNAPSHOT_FEATURES), dtype=np.float64)
+    fr = None if frontiers is None else np.ascontiguousarray(frontiers, dtype=np.uint8)
+    ti = int(st[0]["move_count"]) if turn_index is None else int(turn_index)
+    lib().orc_snapshot_features_packed(_ptr(st), _ptr(fr), ti, int(max_turns), _ptr(out))
+    return out
+
+
+def replay_snapshots(trace: np.ndarray, checkpoints: Sequence[int], max_turns: int = 2500, start: Optional[np.ndarray] = None):
+    """Replay one recorded game and capture the feature rows at the checkpoint plies (arena_runner.py:625-650,698).
+    Returns dict(features float64[k,4,34], turn_index int32[k] (-1 = never reached), states, frontiers uint8[k,4,400])."""
+    tr = np.ascontiguousarray(trace, dtype=np.uint16)
+    ck = np.ascontiguousarray(checkpoints, dtype=np.int32)
+    k = len(ck)
+    feats = np.zeros((k, 4, NUM_SNAPSHOT_FEATURES), dtype=np.float64)
+    ti = np.zeros(k, dtype=np.int32)
+    states = np.zeros(k, dtype=STATE_DTYPE)
+    fr = np.zeros((k, 4, 400), dtype=np.uint8)
+    st = None if start is None else np.ascontiguousarray(np.atleast_1d(start), dtype=STATE_DTYPE)
+    lib().orc_replay_snapshots(_ptr(st), _ptr(tr), len(tr), _ptr(ck), k, int(max_turns), _ptr(feats), _ptr(ti), _ptr(states), _ptr(fr))
+    return {"features": feats, "turn_index": ti, "states": states, "frontiers": fr}
 
 
 class OracleTT:

@@ -339,6 +339,86 @@ def gen_mobility():
     print("mobility", n, "states")
 
 
+SNAPSHOT_CHECKPOINTS = [0, 8, 16, 24, 32, 40, 48, 56, 64]   # ply 0 + arena_runner.py:44 DEFAULT_SNAPSHOT_PLYS
+
+
+def _snapshot_matrix(board: Board, turn_index: int, max_turns: int) -> np.ndarray:
+    """float64[4, 34]: the feature columns of analytics/winprob/features.py for the four players, computed exactly as
+    analytics/tournament/arena_runner.py:522-575 and mcts/learned_evaluator.py:79-95 do."""
+    from analytics.winprob.features import (SNAPSHOT_FEATURE_COLUMNS, build_snapshot_runtime_context,
+                                            coerce_feature_dict, extract_player_snapshot_features)
+
+    ctx = build_snapshot_runtime_context(board, turn_index=turn_index, max_turns=max_turns)
+    out = np.zeros((4, len(SNAPSHOT_FEATURE_COLUMNS)), dtype=np.float64)
+    for p in range(4):
+        f = coerce_feature_dict(extract_player_snapshot_features(board, player=Player(p + 1), context=ctx, move_generator=GEN))
+        out[p] = [f[c] for c in SNAPSHOT_FEATURE_COLUMNS]
+    return out
+
+
+def _frontier_bytes(board: Board) -> np.ndarray:
+    fr = np.zeros((4, 400), dtype=np.uint8)
+    for p in range(4):
+        for (r, c) in board.get_frontier(Player(p + 1)):
+            fr[p, r * 20 + c] = 1
+    return fr
+
+
+def gen_snapshots(max_turns=2500):
+    """Row N4: snapshot feature rows.  (a) the golden games of games.npz replayed through BlokusGame with the
+    arena loop, features captured at the checkpoints exactly where arena_runner.py:625-650,698 captures them
+    (incremental frontier sets, turn_index = loop turn count); (b) the random-state corpus evaluated the way
+    mcts/learned_evaluator.py does (turn_index = move_count)."""
+    from analytics.winprob.features import SNAPSHOT_FEATURE_COLUMNS
+
+    z = np.load(os.path.join(HERE, "games.npz"))
+    traces = z["traces"]
+    ng, nk, nf = traces.shape[0], len(SNAPSHOT_CHECKPOINTS), len(SNAPSHOT_FEATURE_COLUMNS)
+    feats = np.zeros((ng, nk, 4, nf), dtype=np.float64)
+    turn_idx = np.full((ng, nk), -1, dtype=np.int32)
+    fronts = np.zeros((ng, nk, 4, 400), dtype=np.uint8)
+    snaps = np.zeros((ng, nk), dtype=STATE_DTYPE)
+    for gi in range(ng):
+        game = BlokusGame(enable_telemetry=False)
+        hits = set()
+        turn_count = 0
+
+        def capture():
+            ply = int(game.board.move_count)
+            if ply in SNAPSHOT_CHECKPOINTS and ply not in hits:
+                k = SNAPSHOT_CHECKPOINTS.index(ply)
+                feats[gi, k] = _snapshot_matrix(game.board, turn_count, max_turns)
+                turn_idx[gi, k] = turn_count
+                fronts[gi, k] = _frontier_bytes(game.board)
+                snaps[gi, k] = pack(game.board)
+                hits.add(ply)
+
+        capture()
+        for t in range(int(z["turns"][gi])):
+            pl = game.get_current_player()
+            turn_count += 1
+            if traces[gi, t] == 0xFFFF:
+                game.board._update_current_player()
+                game._check_game_over()
+                continue
+            assert game.make_move(id_to_move(traces[gi, t]), pl)
+            capture()
+        print("snapshots game", gi, "hit", sorted(hits))
+    zs = np.load(os.path.join(HERE, "random_states.npz"))
+    states = zs["states"].view(STATE_DTYPE).reshape(-1)
+    sfe = np.zeros((len(states), 4, nf), dtype=np.float64)
+    for i in range(len(states)):
+        b = random_state_from_packed(states[i])
+        sfe[i] = _snapshot_matrix(b, int(b.move_count), max_turns)
+    np.savez_compressed(os.path.join(HERE, "snapshots.npz"), checkpoints=np.array(SNAPSHOT_CHECKPOINTS, dtype=np.int32),
+                        max_turns=np.array([max_turns], dtype=np.int32), features=feats, turn_index=turn_idx,
+                        frontiers=np.packbits(fronts, axis=-1, bitorder="little"),
+                        snap_states=snaps.view(np.uint8).reshape(ng, nk, 256), state_features=sfe)
+    with open(os.path.join(HERE, "snapshot_columns.json"), "w") as f:
+        json.dump(SNAPSHOT_FEATURE_COLUMNS, f)
+    print("snapshots", ng, "games,", len(states), "states")
+
+
 def random_state_from_packed(s) -> Board:
     """Rebuild a reference Board from a packed state (the recipe of engine-service/app.py:27-50)."""
     board = Board()
@@ -365,7 +445,8 @@ def random_state_from_packed(s) -> Board:
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility"]
+    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots"]
     for w in which:
         {"tables": gen_tables, "kat1": gen_kat1, "kat2": gen_kat2, "random": gen_random_states,
-         "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic, "mobility": gen_mobility}[w]()
+         "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic, "mobility": gen_mobility,
+         "snapshots": gen_snapshots}[w]()

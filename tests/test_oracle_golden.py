@@ -169,3 +169,28 @@ def test_heuristic_scores_match_reference(golden_dir):
         got = np.array([b.heuristic_score(p, m) for m in ids])
         # same float64 operations in the same order -> bit-identical
         assert np.array_equal(got, z["scores"][offs[i]:offs[i + 1]])
+
+
+# ---- snapshot feature rows -------------------------------------------------------------
+def test_snapshot_features_of_replayed_games_match_reference(golden_dir):
+    """features.py rows captured by the reference at the arena checkpoints of the 16 golden games: every float equal."""
+    z = np.load(os.path.join(golden_dir, "snapshots.npz"))
+    g = np.load(os.path.join(golden_dir, "games.npz"))
+    ck, mt = z["checkpoints"], int(z["max_turns"][0])
+    fronts = np.unpackbits(z["frontiers"], axis=-1, bitorder="little")[..., :400]
+    for gi in range(g["traces"].shape[0]):
+        r = orc.replay_snapshots(g["traces"][gi], ck, mt)
+        assert (r["turn_index"] == z["turn_index"][gi]).all()
+        hit = r["turn_index"] >= 0
+        assert hit.sum() >= 8
+        assert (r["frontiers"][hit] == fronts[gi][hit]).all()            # incremental (stale cells included) sets
+        assert (r["states"].view(np.uint8).reshape(len(ck), 256)[hit] == z["snap_states"][gi][hit]).all()
+        assert (r["features"][hit] == z["features"][gi][hit]).all()
+
+
+def test_snapshot_features_of_state_corpus_match_reference(golden_dir):
+    """The learned-evaluator call (turn_index = move_count, rebuilt frontier sets) on the 240-state corpus."""
+    z = np.load(os.path.join(golden_dir, "snapshots.npz"))
+    states = np.load(os.path.join(golden_dir, "random_states.npz"))["states"].view(orc.STATE_DTYPE).reshape(-1)
+    for i in range(len(states)):
+        assert (orc.snapshot_features(states[i]) == z["state_features"][i]).all(), i
