@@ -108,6 +108,27 @@ int bk_movegen_bitmap(const bk_state* states, const uint8_t* players, int n,
 int bk_movegen_piece_counts(const bk_state* states, const uint8_t* players, int n, uint16_t* piece_counts /*[n][21]*/,
                             uint16_t* anchor_max /*[n] or NULL*/, void* stream);
 
+/* Win-probability snapshot feature rows: features[i][p][0..33] = the 34 columns of SNAPSHOT_FEATURE_COLUMNS
+ * (analytics/winprob/features.py:23-58) for player p of states[i], as build_snapshot_runtime_context (:103-128) +
+ * extract_player_snapshot_features (:131-193) compute them -- the input of the arena's snapshot dataset
+ * (analytics/tournament/arena_runner.py:522-575) and of LearnedWinProbabilityEvaluator (mcts/learned_evaluator.py:79-95).
+ * frontiers: uint64[n][4][7] bitboards of the reference's incrementally maintained frontier sets (Board.get_frontier,
+ * engine/board.py:247-259), or NULL to use the sets a freshly restored board has (_compute_full_frontier, :261-313,
+ * plus the start corner before the first move).  turn_index: int32[n] or NULL (= move_count, as the evaluator passes). */
+#define BK_SNAPSHOT_FEATURES 34
+int bk_snapshot_features(const bk_state* states, const uint64_t* frontiers, const int32_t* turn_index, int n,
+                         int max_turns, double* features /*[n][4][34]*/, void* stream);
+
+/* Replay n recorded games (traces[g][t] = move id of turn t, BK_PASS = pass; start = NULL for the empty board) and
+ * capture the feature rows where analytics/tournament/arena_runner.py:625-650,698 captures them: before the first turn
+ * and after each placement whose move_count equals a checkpoint ply, with turn_index = turns played so far (passes
+ * included) and the frontier sets maintained by the rule of engine/board.py:315-367.  checkpoints_host: HOST array of
+ * 1..32 distinct plies.  features[g][k][p][34], turn_index[g][k] (-1: game g never reached checkpoint k); optional
+ * snap_states[g][k] and snap_frontiers[g][k][4][7] receive the captured boards. */
+int bk_replay_snapshots(const bk_state* start, const uint16_t* traces, int n, int n_turns,
+                        const int32_t* checkpoints_host, int n_checkpoints, int max_turns, double* features,
+                        int32_t* turn_index, bk_state* snap_states, uint64_t* snap_frontiers, void* stream);
+
 /* has_legal_moves for all four players (engine/move_generator.py:961-1054): bit p of out[i]. */
 int bk_has_moves(const bk_state* states, int n, uint8_t* out_mask, void* stream);
 

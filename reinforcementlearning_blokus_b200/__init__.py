@@ -19,12 +19,12 @@ _LAZY = {
     "BlokusGame": "game", "GameResult": "game",
     "RandomAgent": "agents", "HeuristicAgent": "agents", "FastMCTSAgent": "agents", "GameplayFastMCTSAgent": "agents",
     "MCTSAgent": "mcts", "ZobristHash": "mcts", "TranspositionTable": "mcts", "DeviceUCT": "mcts",
-    "BatchedBlokus": "batched",
+    "BatchedBlokus": "batched", "LearnedWinProbabilityEvaluator": "winprob",
 }
 
 
 _SUBMODULES = ("agents", "arena", "batched", "board", "device", "dist", "game", "integration", "mcts", "move_generator",
-               "service", "single")
+               "mobility", "service", "single", "winprob")
 
 
 def __getattr__(name):

@@ -40,6 +40,8 @@ PROTOTYPES = {
     "bk_movegen_bitmap": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "bk_movegen_piece_counts": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "bk_has_moves": (_i32, [_vp, _i32, _vp, _vp]),
+    "bk_snapshot_features": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "bk_replay_snapshots": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "bk_is_move_legal": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "bk_step": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bk_scores": (_i32, [_vp, _i32, _vp, _vp, _vp]),

@@ -158,12 +158,18 @@ def run_single_game(*, run_id: str, game_index: int, game_seed: int, seat_assign
 
 # ---- device-batched match-ups between the built-in policies ----------------------------------------------
 def run_device_arena(agent_policies: Mapping[str, str], num_games: int, run_seed: int = 42,
-                     seat_policy: str = "round_robin", run_id: str = "device_arena") -> Dict[str, Any]:
+                     seat_policy: str = "round_robin", run_id: str = "device_arena",
+                     snapshots: Optional[Sequence[int]] = None, max_turns: int = 2500) -> Dict[str, Any]:
     """agent_policies: four agent names -> "random" | "heuristic".  All num_games games run in one launch.
 
     Returns {"records": [...], "summary": {agent: {"games", "wins", "win_rate", "mean_score", "mean_rank"}}}.
     Seat assignment and the recorded game_seed follow the reference; the moves of game i come from the Philox
     stream (key = run_seed, game index = i).
+
+    snapshots: checkpoint plies (e.g. winprob.DEFAULT_SNAPSHOT_PLYS).  When given, the recorded games are replayed on
+    the device and the win-probability feature rows are captured where arena_runner.py:625-650,698 captures them;
+    "snapshot_rows" holds the rows of snapshots.csv (arena_runner.py:522-575 + the end-of-game labels, :722-731), with
+    phase_progress_* computed against `max_turns` (RunConfig.max_turns).
     """
     import torch
 
@@ -208,7 +214,17 @@ def run_device_arena(agent_policies: Mapping[str, str], num_games: int, run_seed
     summary = {n: {"games": a["games"], "wins": a["wins"], "win_rate": a["wins"] / max(a["games"], 1),
                    "mean_score": a["score_sum"] / max(a["games"], 1), "mean_rank": a["rank_sum"] / max(a["games"], 1)}
                for n, a in agg.items()}
-    return {"records": records, "summary": summary, "seat_policies": packed}
+    out = {"records": records, "summary": summary, "seat_policies": packed}
+    if snapshots:
+        from . import winprob
+
+        replay = dev.replay_snapshots(r["trace"], snapshots, max_turns=max_turns)
+        hit = (replay["turn_index"] >= 0).cpu().numpy()
+        for i, rec in enumerate(records):
+            rec["snapshot_checkpoints_hit"] = [int(c) for c, h in zip(replay["checkpoints"], hit[i]) if h]
+        out["snapshot_rows"] = winprob.snapshot_rows_from_replay(replay, records)
+        out["snapshot_features"] = replay
+    return out
 
 
 def write_games_jsonl(path: str, records: Sequence[Mapping[str, Any]]) -> None:

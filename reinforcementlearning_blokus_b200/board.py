@@ -6,10 +6,11 @@ game-over detection -- runs on the GPU.  Interface followed: ``engine/board.py:1
 ``:29-40`` (Position), ``:43-78`` (state), ``:136-220`` (placement rules), ``:515-560`` (place / turn),
 ``:562-591`` (score / winner), ``:643-660`` (copy).
 
-Deliberate differences from the reference, all outside the rules:
-  * ``get_frontier`` returns the exact frontier recomputed from the masks, not the incrementally
-    maintained superset that can keep cells later taken by opponents (SURVEY.md Q8);
-  * the debug helpers tied to the incremental frontier bookkeeping are not provided.
+``get_frontier`` follows the reference's bookkeeping (``engine/board.py:315-406``): each player's set is updated
+only by that player's own placements, so it can keep cells an opponent has taken since.  The sets
+are 400-bit masks here; they feed the snapshot features (``winprob.py``), not the rules -- legality on the device is
+computed from the cells.  ``_compute_full_frontier`` is the exact view.  A board restored from a packed state starts
+from the exact sets (plus the start corner before the first move), like a board rebuilt from the wire.
 """
 
 from __future__ import annotations
@@ -89,6 +90,9 @@ class Board:
         self.move_count = 0
         self.occupied_bits = 0
         self.player_bits: Dict[Player, int] = {p: 0 for p in Player}
+        # engine/board.py:369-406: every frontier starts as the player's start corner
+        self.player_frontier_bits: Dict[Player, int] = {
+            p: 1 << (c.row * SIZE + c.col) for p, c in self.player_start_corners.items()}
 
     # ---- packed state --------------------------------------------------------------------------
     def to_packed(self) -> np.ndarray:
@@ -125,7 +129,19 @@ class Board:
             b.player_first_move[p] = bool((int(state["first_mask"]) >> k) & 1)
         b.current_player = _PLAYERS[int(state["to_move"]) & 3]
         b.move_count = int(state["move_count"])
+        b.rebuild_frontiers()
         return b
+
+    def rebuild_frontiers(self) -> None:
+        """Frontier sets of a board restored from its cells (engine-service/app.py:37): the exact set for a player who
+        has moved, the start corner for one who has not."""
+        for p in _PLAYERS:
+            orth, diag = _neighbours(self.player_bits[p])
+            m = diag & ~orth & ~self.occupied_bits & _FULL
+            c = self.player_start_corners[p]
+            if self.player_first_move[p] and self.grid[c.row, c.col] == 0:
+                m |= 1 << (c.row * SIZE + c.col)
+            self.player_frontier_bits[p] = m
 
     # ---- cell helpers (engine/board.py:80-134) ---------------------------------------------------
     def is_valid_position(self, pos: Position) -> bool:
@@ -190,6 +206,12 @@ class Board:
         self.player_bits[player] |= m
         self.player_pieces_used[player].add(piece_id)
         self.player_first_move[player] = False
+        # engine/board.py:315-367: the placed cells and their edge neighbours leave the mover's set; empty corner
+        # neighbours that touch no own cell by an edge join it
+        gone_orth, join_diag = _neighbours(m)
+        own_orth, _ = _neighbours(self.player_bits[player])
+        self.player_frontier_bits[player] = ((self.player_frontier_bits[player] & ~(m | gone_orth))
+                                             | (join_diag & ~self.occupied_bits & ~own_orth)) & _FULL
         self.move_count += 1
         self._update_current_player()
         return True
@@ -197,18 +219,18 @@ class Board:
     def _update_current_player(self) -> None:
         self.current_player = _PLAYERS[(_PLAYERS.index(self.current_player) + 1) % len(_PLAYERS)]
 
-    # ---- frontier (exact) ---------------------------------------------------------------------------
+    # ---- frontier -----------------------------------------------------------------------------------
     def get_frontier(self, player: Player) -> Set[Tuple[int, int]]:
-        """Empty cells diagonal to an own cell and not edge-adjacent to one; the start corner before the
-        first move (engine/board.py:248-313, :369-406)."""
-        own = self.player_bits[player]
-        orth, diag = _neighbours(own)
-        m = diag & ~orth & ~self.occupied_bits & _FULL
-        if self.player_first_move[player]:
-            c = self.player_start_corners[player]
-            if self.grid[c.row, c.col] == 0:
-                m |= 1 << (c.row * SIZE + c.col)
+        """The incrementally maintained set of engine/board.py:247-259 (see the module docstring)."""
+        m = self.player_frontier_bits[player]
         return {(i // SIZE, i % SIZE) for i in range(SIZE * SIZE) if (m >> i) & 1}
+
+    def frontier_words(self) -> np.ndarray:
+        """int64[4, 7]: the four frontier sets as bitboards, the `frontiers` argument of bk_snapshot_features."""
+        out = np.zeros((4, 7), dtype="<i8")
+        for k, p in enumerate(_PLAYERS):
+            out[k] = np.frombuffer(int(self.player_frontier_bits[p]).to_bytes(56, "little"), dtype="<i8")
+        return out
 
     def _compute_full_frontier(self, player: Player) -> Set[Tuple[int, int]]:
         own = self.player_bits[player]
@@ -257,6 +279,7 @@ class Board:
         b.move_count = self.move_count
         b.occupied_bits = self.occupied_bits
         b.player_bits = dict(self.player_bits)
+        b.player_frontier_bits = dict(self.player_frontier_bits)
         return b
 
     def __str__(self) -> str:

@@ -704,6 +704,7 @@ k_heuristic_scores(const bk_state* __restrict__ states, const uint8_t* __restric
 }
 
 #include "mcts.cuh"
+#include "snapshot.cuh"
 
 #define BK_HEUR_PLAYOUT_SMEM ((BK_PLAYOUT_THREADS / 32) * HEUR_SMEM_PER_WARP)
 static cudaError_t bk_init_policies_impl() {
@@ -763,6 +764,34 @@ extern "C" int bk_movegen_piece_counts(const bk_state* states, const uint8_t* pl
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && piece_counts)), "bk_movegen_piece_counts: null buffer");
     if (n == 0) return BK_OK;
     k_piece_counts<<<grid_for(n, 3), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, piece_counts, anchor_max);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_snapshot_features(const bk_state* states, const uint64_t* frontiers, const int32_t* turn_index, int n,
+                                    int max_turns, double* features, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && features)), "bk_snapshot_features: null buffer");
+    if (n == 0) return BK_OK;
+    k_snapshot_features<<<grid_for(n, 3), BK_THREADS, BK_WARPS * BK_SNAP_SMEM_PER_WARP, as_stream(stream)>>>(
+        states, frontiers, turn_index, n, max_turns, features);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_replay_snapshots(const bk_state* start, const uint16_t* traces, int n, int n_turns,
+                                   const int32_t* checkpoints_host, int n_checkpoints, int max_turns, double* features,
+                                   int32_t* turn_index, bk_state* snap_states, uint64_t* snap_frontiers, void* stream) {
+    REQUIRE_INIT();
+    REQUIRE(n >= 0 && n_turns >= 0 && (n == 0 || (traces && features && turn_index)), "bk_replay_snapshots: null buffer");
+    REQUIRE(n_checkpoints >= 1 && n_checkpoints <= BK_MAX_CHECKPOINTS && checkpoints_host,
+            "bk_replay_snapshots: 1..32 checkpoint plies required");
+    bk_checkpoints ck; ck.n = n_checkpoints;
+    for (int k = 0; k < BK_MAX_CHECKPOINTS; k++) ck.ply[k] = k < n_checkpoints ? checkpoints_host[k] : -1;
+    for (int k = 0; k < n_checkpoints; k++)
+        for (int j = 0; j < k; j++) REQUIRE(ck.ply[j] != ck.ply[k], "bk_replay_snapshots: duplicate checkpoint ply");
+    if (n == 0) return BK_OK;
+    k_replay_snapshots<<<grid_for(n, 3), BK_THREADS, BK_WARPS * BK_SNAP_SMEM_PER_WARP, as_stream(stream)>>>(
+        start, traces, n, n_turns, ck, max_turns, features, turn_index, snap_states, snap_frontiers);
     LAUNCH_CHECK();
     return BK_OK;
 }

@@ -163,6 +163,57 @@ def piece_counts(states: torch.Tensor, players: Optional[torch.Tensor] = None) -
     return pc, am
 
 
+NUM_SNAPSHOT_FEATURES = 34
+
+
+def snapshot_features(states: torch.Tensor, frontiers: Optional[torch.Tensor] = None,
+                      turn_index: Optional[torch.Tensor] = None, max_turns: int = 2500) -> torch.Tensor:
+    """float64[N, 4, 34]: the SNAPSHOT_FEATURE_COLUMNS rows of all four players of every state
+    (analytics/winprob/features.py:103-193).  frontiers: int64[N, 4, 7] bitboards of the reference's incremental
+    frontier sets, or None for the sets of a freshly restored board; turn_index: int32[N] or None (= move_count)."""
+    n = _check_states(states)
+    if frontiers is not None and not (frontiers.is_cuda and frontiers.dtype == torch.int64 and frontiers.is_contiguous()
+                                      and tuple(frontiers.shape) == (n, 4, 7)):
+        raise ValueError("frontiers must be a contiguous CUDA int64 tensor of shape [N, 4, 7]")
+    if turn_index is not None and not (turn_index.is_cuda and turn_index.dtype == torch.int32 and turn_index.is_contiguous()
+                                       and turn_index.numel() == n):
+        raise ValueError("turn_index must be a contiguous CUDA int32 tensor of length N")
+    lib = _lib_for(states)
+    out = torch.empty((n, 4, NUM_SNAPSHOT_FEATURES), dtype=torch.float64, device=states.device)
+    check(lib.bk_snapshot_features(_ptr(states), _ptr(frontiers), _ptr(turn_index), n, int(max_turns), _ptr(out), _stream()))
+    _count()
+    return out
+
+
+def replay_snapshots(traces: torch.Tensor, checkpoints, max_turns: int = 2500, start: Optional[torch.Tensor] = None,
+                     want_states: bool = False) -> dict:
+    """Replay recorded games (uint16[N, T] move ids, 0xFFFF = pass) and capture the feature rows at the checkpoint
+    plies, where analytics/tournament/arena_runner.py:625-650,698 captures them.  Returns features float64[N, K, 4, 34]
+    (zero where not captured), turn_index int32[N, K] (-1 = game never reached that ply) and, with want_states, the
+    captured boards (states uint8[N, K, 256], frontiers int64[N, K, 4, 7])."""
+    if not (traces.is_cuda and traces.dtype == torch.uint16 and traces.dim() == 2 and traces.is_contiguous()):
+        raise ValueError("traces must be a contiguous CUDA uint16 tensor of shape [N, T]")
+    n, n_turns = traces.shape
+    ck = np.ascontiguousarray(sorted({int(c) for c in checkpoints}), dtype=np.int32)
+    if not 1 <= len(ck) <= 32 or ck.min() < 0:
+        raise ValueError("1..32 distinct non-negative checkpoint plies required")
+    if start is not None and _check_states(start) != n:
+        raise ValueError("start must hold one state per trace")
+    lib = _lib_for(traces)
+    k = len(ck)
+    feats = torch.zeros((n, k, 4, NUM_SNAPSHOT_FEATURES), dtype=torch.float64, device=traces.device)
+    ti = torch.empty((n, k), dtype=torch.int32, device=traces.device)
+    st = torch.zeros((n, k, STATE_BYTES), dtype=torch.uint8, device=traces.device) if want_states else None
+    fr = torch.zeros((n, k, 4, 7), dtype=torch.int64, device=traces.device) if want_states else None
+    check(lib.bk_replay_snapshots(_ptr(start), _ptr(traces), n, n_turns, ck.ctypes.data, k, int(max_turns), _ptr(feats),
+                                  _ptr(ti), _ptr(st), _ptr(fr), _stream()))
+    _count()
+    res = {"features": feats, "turn_index": ti, "checkpoints": ck}
+    if want_states:
+        res["states"], res["frontiers"] = st, fr
+    return res
+
+
 def has_moves(states: torch.Tensor) -> torch.Tensor:
     """uint8[N]: bit p set iff player p has a legal move (engine/move_generator.py:961)."""
     n = _check_states(states)

@@ -45,6 +45,7 @@ def rebuild_board(game_state: Dict[str, Any]) -> Board:
                 bit = 1 << (r * 20 + c)
                 board.occupied_bits |= bit
                 board.player_bits[Player(v)] |= bit
+    board.rebuild_frontiers()
     return board
 
 

@@ -1,0 +1,200 @@
+"""Win-probability snapshot features and the learned leaf evaluator.
+
+Mirrors ``analytics/winprob/features.py`` (``SNAPSHOT_FEATURE_COLUMNS``, ``build_snapshot_runtime_context``,
+``extract_player_snapshot_features``, ``coerce_feature_dict``), the snapshot rows of
+``analytics/tournament/arena_runner.py:522-575,722-731,815-858`` and ``mcts/learned_evaluator.py``.  All 34 columns of all
+four players of a board come from ONE device call (``bk_snapshot_features``: four piece-count move generations, a flood
+fill for the dead zones, popcounts for the rest); whole datasets come from ``bk_replay_snapshots``, which replays
+recorded games on the device and captures the rows at the checkpoint plies.  Values are bit-identical to the
+reference's (``tests/golden/snapshots.npz``).
+"""
+
+from __future__ import annotations
+
+import json
+import math
+from collections.abc import Mapping
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .board import Board, Player
+
+SNAPSHOT_FEATURE_COLUMNS: List[str] = [          # analytics/winprob/features.py:23-58, in the order of the device row
+    "frontier_size", "corner_differential", "center_proximity", "opponent_adjacency", "deadzone_count",
+    "deadzone_fraction", "mobility_total_placements", "mobility_total_orientation_normalized",
+    "mobility_total_cell_weighted", "mobility_bucket_1", "mobility_bucket_2", "mobility_bucket_3", "mobility_bucket_4",
+    "mobility_bucket_5", "blocking_exposure_legal_moves_opp_sum", "utility_frontier_plus_mobility", "pieces_used_count",
+    "pieces_remaining_count", "remaining_squares", "remaining_size_1_count", "remaining_size_2_count",
+    "remaining_size_3_count", "remaining_size_4_count", "remaining_size_5_count", "remaining_key_piece_17",
+    "remaining_key_piece_19", "remaining_key_piece_20", "phase_ply", "phase_turn_index", "phase_board_occupancy",
+    "phase_piece_usage_ratio", "phase_progress_turn_ratio", "phase_progress_placement_ratio", "player_board_occupancy",
+]
+DEFAULT_SNAPSHOT_PLYS = [8, 16, 24, 32, 40, 48, 56, 64]          # arena_runner.py:44
+
+
+def board_feature_block(board: Board, turn_index: Optional[int] = None, max_turns: int = 2500) -> np.ndarray:
+    """float64[4, 34]: the feature rows of the four players of one board (one upload, one kernel, one download)."""
+    import torch
+
+    from . import device as dev
+
+    st = dev.to_device(np.atleast_1d(board.to_packed()))
+    fr = torch.from_numpy(board.frontier_words()[None].copy()).to(st.device)
+    ti = torch.tensor([board.move_count if turn_index is None else int(turn_index)], dtype=torch.int32, device=st.device)
+    return dev.snapshot_features(st, fr, ti, max_turns)[0].cpu().numpy()
+
+
+@dataclass(frozen=True)
+class SnapshotRuntimeContext:
+    """features.py:61-71, plus the device block shared by the four per-player extractions of one snapshot."""
+
+    ply: int
+    turn_index: int
+    board_occupancy: float
+    deadzone_count: int
+    deadzone_fraction: float
+    progress_turn_ratio: float
+    progress_placement_ratio: float
+    block: Any = None
+
+
+def build_snapshot_runtime_context(board: Board, *, turn_index: int, max_turns: int) -> SnapshotRuntimeContext:
+    blk = board_feature_block(board, turn_index, max_turns)
+    col = SNAPSHOT_FEATURE_COLUMNS.index
+    return SnapshotRuntimeContext(
+        ply=int(board.move_count), turn_index=int(turn_index), board_occupancy=float(blk[0, col("phase_board_occupancy")]),
+        deadzone_count=int(blk[0, col("deadzone_count")]), deadzone_fraction=float(blk[0, col("deadzone_fraction")]),
+        progress_turn_ratio=float(blk[0, col("phase_progress_turn_ratio")]),
+        progress_placement_ratio=float(blk[0, col("phase_progress_placement_ratio")]), block=blk)
+
+
+def extract_player_snapshot_features(board: Board, *, player: Player, context: SnapshotRuntimeContext,
+                                     move_generator=None) -> Dict[str, float]:
+    """features.py:131-193; `move_generator` is accepted for signature compatibility (the device generates)."""
+    blk = context.block if context.block is not None else board_feature_block(board, context.turn_index, 2500)
+    row = blk[player.value - 1]
+    return {name: float(row[i]) for i, name in enumerate(SNAPSHOT_FEATURE_COLUMNS)}
+
+
+def coerce_feature_dict(features: Mapping[str, Any]) -> Dict[str, float]:
+    return {c: float(features.get(c, 0.0)) for c in SNAPSHOT_FEATURE_COLUMNS}
+
+
+# ---- dataset rows (arena_runner.py:522-575, 722-731) ---------------------------------------------------------
+def snapshot_rows_from_replay(replay: Mapping[str, Any], records: Sequence[Mapping[str, Any]]) -> List[Dict[str, Any]]:
+    """Rows of snapshots.csv / snapshots.parquet for a batch of replayed games.
+
+    replay: the dict of ``device.replay_snapshots`` (features [N,K,4,34], turn_index [N,K], checkpoints [K]);
+    records: the N game records of ``arena.run_device_arena`` (run_id, game_id, seeds, seats, final scores / ranks).
+    Row keys and order follow ``_build_snapshot_rows_for_checkpoint`` plus the labels filled in at the end of the game."""
+    feats = replay["features"].cpu().numpy()
+    turns = replay["turn_index"].cpu().numpy()
+    cks = [int(c) for c in replay["checkpoints"]]
+    rows: List[Dict[str, Any]] = []
+    for g, rec in enumerate(records):
+        scores = rec["final_scores"]
+        winner_ids = list(rec["winner_ids"])
+        for k, ply in enumerate(cks):
+            if turns[g, k] < 0:
+                continue
+            # the side to move after `ply` placements and the passes in between: turn_index turns from RED
+            current = int(turns[g, k]) % 4 + 1
+            for p in Player:
+                pid = int(p.value)
+                row: Dict[str, Any] = {
+                    "run_id": rec["run_id"], "game_id": rec["game_id"], "game_index": int(rec["game_index"]),
+                    "game_seed": int(rec["game_seed"]), "checkpoint_index": k, "checkpoint_ply": ply, "ply": ply,
+                    "turn_index": int(turns[g, k]), "current_player_id": current, "player_id": pid, "player_name": p.name,
+                    "agent_name": rec["seat_assignment"][str(pid)], "seat_index": pid - 1,
+                    "winner_id": rec["winner_id"], "winner_ids_json": json.dumps(winner_ids, sort_keys=True),
+                    "label_is_winner": int(pid in winner_ids), "final_score": int(scores[str(pid)]),
+                    "final_rank": int(rec["final_ranks"][str(pid)]),
+                    "final_scores_json": json.dumps(scores, sort_keys=True), "is_tie": bool(rec["is_tie"]),
+                }
+                row.update({c: float(feats[g, k, pid - 1, i]) for i, c in enumerate(SNAPSHOT_FEATURE_COLUMNS)})
+                rows.append(row)
+    return rows
+
+
+def write_snapshots_dataset(run_dir: str, snapshot_rows: Sequence[Mapping[str, Any]]) -> Dict[str, Any]:
+    """arena_runner.py:815-858: snapshots.csv always, snapshots.parquet when a parquet engine is present."""
+    import os
+
+    if not snapshot_rows:
+        return {"enabled": False, "rows": 0, "path_parquet": None, "path_csv": None, "parquet_written": False,
+                "parquet_error": None}
+    import pandas as pd
+
+    frame = pd.DataFrame(list(snapshot_rows))
+    csv_path = os.path.join(run_dir, "snapshots.csv")
+    frame.to_csv(csv_path, index=False)
+    parquet_path, written, err = os.path.join(run_dir, "snapshots.parquet"), False, None
+    try:
+        frame.to_parquet(parquet_path, index=False)
+        written = True
+    except Exception as exc:                                  # depends on the parquet engine, as in the reference
+        err = str(exc)
+    return {"enabled": True, "rows": int(len(frame)), "path_parquet": parquet_path if written else None,
+            "path_csv": csv_path, "parquet_written": written, "parquet_error": err}
+
+
+# ---- learned leaf evaluator (mcts/learned_evaluator.py) ----------------------------------------------------------
+def _phase_bucket_from_occupancy(board_occupancy: float, *, early_max: float = 0.33, mid_max: float = 0.66) -> str:
+    return "early" if board_occupancy < early_max else ("mid" if board_occupancy < mid_max else "late")
+
+
+class LearnedWinProbabilityEvaluator:
+    """Same constructor, artifact format and methods as mcts/learned_evaluator.py:36-152.  The feature rows come from
+    the device; the pairwise model (a scikit-learn pipeline or per-phase gradient-boosted models stored with joblib) is
+    evaluated by scikit-learn on the host, for all three opponents in one ``predict_proba`` call."""
+
+    def __init__(self, artifact_path: str, *, max_turns: int = 2500, potential_mode: str = "prob") -> None:
+        self.artifact_path = str(artifact_path)
+        self.max_turns = int(max_turns)
+        self.potential_mode = potential_mode
+        self._is_dummy = self.artifact_path.endswith("dummy_model.json")
+        if self._is_dummy:
+            self.model_type, self.feature_columns = "dummy", []
+            return
+        import joblib
+
+        self.artifact: Dict[str, Any] = joblib.load(self.artifact_path)
+        self.model_type = str(self.artifact.get("model_type", ""))
+        self.feature_columns = list(self.artifact.get("feature_columns", SNAPSHOT_FEATURE_COLUMNS))
+        if self.model_type not in {"pairwise_logreg", "pairwise_gbt_phase"}:
+            raise ValueError(f"Unsupported learned evaluator model_type '{self.model_type}' in {self.artifact_path}.")
+        self._cols = [SNAPSHOT_FEATURE_COLUMNS.index(c) for c in self.feature_columns]
+
+    def _extract_features_for_all_players(self, board: Board) -> Dict[int, Dict[str, float]]:
+        blk = board_feature_block(board, int(board.move_count), self.max_turns)
+        return {p + 1: {c: float(blk[p, i]) for i, c in enumerate(SNAPSHOT_FEATURE_COLUMNS)} for p in range(4)}
+
+    def _pairwise_matrix(self, blk: np.ndarray, x: np.ndarray, i: int, others: Sequence[int]) -> np.ndarray:
+        if self.model_type == "pairwise_logreg":
+            return self.artifact["pipeline"].predict_proba(x)[:, 1]
+        occ_col = SNAPSHOT_FEATURE_COLUMNS.index("phase_board_occupancy")
+        out = np.zeros(len(others))
+        for n, j in enumerate(others):
+            phase = _phase_bucket_from_occupancy(float((blk[i, occ_col] + blk[j, occ_col]) / 2.0))
+            model = self.artifact.get("phase_models", {}).get(phase) or self.artifact.get("fallback_model")
+            if model is None:
+                raise RuntimeError("GBT evaluator artifact missing both phase model and fallback model.")
+            out[n] = model.predict_proba(x[n:n + 1])[:, 1][0]
+        return out
+
+    def predict_player_win_probability(self, board: Board, player: Player) -> float:
+        if self._is_dummy:
+            return 0.5
+        blk = board_feature_block(board, int(board.move_count), self.max_turns)
+        i = player.value - 1
+        others = [j for j in range(4) if j != i]
+        x = np.array([[float(blk[i, c]) - float(blk[j, c]) for c in self._cols] for j in others], dtype=float)
+        return float(np.mean(self._pairwise_matrix(blk, x, i, others)))
+
+    def potential(self, board: Board, player: Player) -> float:
+        probability = min(max(self.predict_player_win_probability(board, player), 1e-6), 1 - 1e-6)
+        if self.potential_mode == "logit":
+            return float(math.log(probability / (1.0 - probability)))
+        return float(probability)

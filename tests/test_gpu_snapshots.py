@@ -1,0 +1,123 @@
+"""Win-probability snapshot features on the device: bit-exact against the reference fixtures and
+the CPU oracle, through the C ABI."""
+
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from reinforcementlearning_blokus_b200 import device
+
+    return device
+
+
+def _golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "snapshots.npz"))
+    g = np.load(os.path.join(golden_dir, "games.npz"))
+    return z, g
+
+
+def test_replayed_games_match_reference_rows(dev, golden_dir):
+    """The 16 golden games replayed on the device: capture points, boards, incremental frontier sets and all
+    34 x 4 floats of every captured row equal what the unmodified reference produced."""
+    z, g = _golden(golden_dir)
+    ck = z["checkpoints"]
+    r = dev.replay_snapshots(torch.from_numpy(g["traces"].copy()).cuda(), ck, int(z["max_turns"][0]), want_states=True)
+    ti = r["turn_index"].cpu().numpy()
+    assert (ti == z["turn_index"]).all()
+    hit = ti >= 0
+    assert (r["states"].cpu().numpy()[hit] == z["snap_states"][hit]).all()
+    want_fr = np.unpackbits(z["frontiers"], axis=-1, bitorder="little")[..., :400]
+    got_fr = np.unpackbits(r["frontiers"].cpu().numpy().view(np.uint8).reshape(*ti.shape, 4, 56), axis=-1, bitorder="little")[..., :400]
+    assert (got_fr[hit] == want_fr[hit]).all()
+    got = r["features"].cpu().numpy()
+    assert (got[hit] == z["features"][hit]).all()
+    assert (got[~hit] == 0).all()
+
+
+def test_state_corpus_matches_reference_rows(dev, golden_dir):
+    """The learned-evaluator call (rebuilt frontier sets, turn_index = move_count) on the 240-state corpus."""
+    z, _ = _golden(golden_dir)
+    states = np.load(os.path.join(golden_dir, "random_states.npz"))["states"]
+    got = dev.snapshot_features(dev.to_device(states)).cpu().numpy()
+    assert (got == z["state_features"]).all()
+
+
+def test_explicit_frontiers_and_turn_index(dev, golden_dir):
+    """Boards captured mid-game with their (stale-cell carrying) frontier sets and loop turn counts as inputs."""
+    z, _ = _golden(golden_dir)
+    hit = z["turn_index"] >= 0
+    states = z["snap_states"][hit]
+    fr_bits = np.unpackbits(z["frontiers"], axis=-1, bitorder="little")[hit]            # [M, 4, 400]
+    fr_words = np.packbits(np.pad(fr_bits, ((0, 0), (0, 0), (0, 48))), axis=-1, bitorder="little").view("<i8").reshape(-1, 4, 7)
+    got = dev.snapshot_features(dev.to_device(states), torch.from_numpy(fr_words.copy()).cuda(),
+                                torch.from_numpy(z["turn_index"][hit].astype(np.int32)).cuda(),
+                                int(z["max_turns"][0])).cpu().numpy()
+    assert (got == z["features"][hit]).all()
+
+
+def test_random_playouts_against_oracle(dev):
+    """2,000 device playouts replayed on the device and on the CPU oracle: same capture points, same rows."""
+    from oracle import orc
+
+    n, ck = 2000, [0, 5, 8, 16, 24, 31, 32, 40, 48, 56, 64, 70]
+    r = dev.playout(n, seed=2024, want_trace=True)
+    rep = dev.replay_snapshots(r["trace"], ck, max_turns=300)
+    traces = r["trace"].cpu().numpy()
+    feats, ti = rep["features"].cpu().numpy(), rep["turn_index"].cpu().numpy()
+    for gi in range(0, n, 40):                                    # 50 games on the CPU
+        o = orc.replay_snapshots(traces[gi], ck, max_turns=300)
+        assert (o["turn_index"] == ti[gi]).all()
+        hit = ti[gi] >= 0
+        assert (o["features"][hit] == feats[gi][hit]).all(), gi
+    # size-independent properties over all games
+    hit = ti >= 0
+    col = {c: i for i, c in enumerate(__import__("reinforcementlearning_blokus_b200.winprob", fromlist=["x"]).SNAPSHOT_FEATURE_COLUMNS)}
+    f = feats[hit]                                                 # [M, 4, 34]
+    assert (f[..., col["phase_ply"]] == np.broadcast_to(np.array(ck)[None, :], ti.shape)[hit][:, None]).all()
+    assert (f[..., col["pieces_used_count"]].sum(axis=1) == f[:, 0, col["phase_ply"]]).all()      # one piece per ply
+    assert (f[..., col["pieces_used_count"]] + f[..., col["pieces_remaining_count"]] == 21).all()
+    assert np.allclose(f[..., col["player_board_occupancy"]].sum(axis=1), f[:, 0, col["phase_board_occupancy"]])
+    total = f[..., col["mobility_total_placements"]]
+    assert (f[..., col["blocking_exposure_legal_moves_opp_sum"]] == total.sum(axis=1, keepdims=True) - total).all()
+    assert (f[..., col["corner_differential"]] == 2 * f[..., col["frontier_size"]] - f[..., col["frontier_size"]].sum(axis=1, keepdims=True)).all()
+
+
+def test_object_api_and_dataset_rows(dev, golden_dir, tmp_path):
+    """winprob.extract_player_snapshot_features on a live BlokusGame (incremental frontier kept by the host Board) and
+    the snapshots.csv rows of a device arena."""
+    from reinforcementlearning_blokus_b200 import BlokusGame, Player, arena, winprob
+    from reinforcementlearning_blokus_b200.move_generator import Move
+
+    z, g = _golden(golden_dir)
+    game = BlokusGame(enable_telemetry=False)
+    turn = 0
+    for t in range(int(g["turns"][0])):
+        turn += 1
+        if g["traces"][0, t] == 0xFFFF:
+            game.board._update_current_player(); game._check_game_over()
+            continue
+        assert game.make_move(Move.from_id(int(g["traces"][0, t])), game.get_current_player())
+        if game.board.move_count in (8, 32, 56):
+            k = list(z["checkpoints"]).index(game.board.move_count)
+            ctx = winprob.build_snapshot_runtime_context(game.board, turn_index=turn, max_turns=int(z["max_turns"][0]))
+            for p in Player:
+                f = winprob.coerce_feature_dict(winprob.extract_player_snapshot_features(game.board, player=p, context=ctx))
+                assert [f[c] for c in winprob.SNAPSHOT_FEATURE_COLUMNS] == z["features"][0, k, p.value - 1].tolist()
+    out = arena.run_device_arena({"a": "random", "b": "heuristic", "c": "random", "d": "heuristic"}, 24, run_seed=7,
+                                 snapshots=winprob.DEFAULT_SNAPSHOT_PLYS)
+    rows = out["snapshot_rows"]
+    assert len(rows) == 4 * sum(len(r["snapshot_checkpoints_hit"]) for r in out["records"]) and len(rows) >= 24 * 4 * 6
+    first = rows[0]
+    assert list(first)[:7] == ["run_id", "game_id", "game_index", "game_seed", "checkpoint_index", "checkpoint_ply", "ply"]
+    assert all(r["label_is_winner"] == int(r["player_id"] in out["records"][r["game_index"]]["winner_ids"]) for r in rows)
+    meta = winprob.write_snapshots_dataset(str(tmp_path), rows)
+    assert meta["enabled"] and meta["rows"] == len(rows) and os.path.exists(meta["path_csv"])
+    assert winprob.LearnedWinProbabilityEvaluator("x/dummy_model.json").predict_player_win_probability(game.board, Player.RED) == 0.5
