@@ -412,6 +412,14 @@ def _extras(dev, torch, n):
     nh = n // 4
     ms = timeit(lambda: dev.playout(nh, seed=SEED, policy=dev.POLICY_HEURISTIC, out=hout, want_board_scores=False), reps=3)
     ex["heuristic_playouts_per_sec"] = nh / ms * 1e3
+    # win-probability snapshot rows (row N4): 4 x 34 float64 per board = four piece-count generations + a flood fill;
+    # and a whole dataset pass: replay recorded games, capture 8 checkpoints each
+    sub = corpus[: 1 << 18]
+    ms = timeit(lambda: dev.snapshot_features(sub), reps=3)
+    ex["snapshot_boards_per_sec"] = sub.shape[0] / ms * 1e3
+    tr = dev.playout(n, seed=SEED, want_trace=True)["trace"]
+    ms = timeit(lambda: dev.replay_snapshots(tr, (8, 16, 24, 32, 40, 48, 56, 64)), reps=3)
+    ex["snapshot_replay_games_per_sec"] = n / ms * 1e3
     return ex
 
 
