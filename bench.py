@@ -434,9 +434,26 @@ def _cpu_baseline():
         orc.playout(SEED, g)
         g += 1
     dt = time.perf_counter() - t0
-    return {"value": g / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{g} games of the same workload in {dt:.1f} s (oracle/blokus_oracle.c, default "
-                      "frontier+bitboard generator, game-over check after every move as engine/game.py:182)"}
+    out = {"value": g / dt, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"{g} games of the same workload in {dt:.1f} s (oracle/blokus_oracle.c, default "
+                     "frontier+bitboard generator, game-over check after every move as engine/game.py:182)"}
+    # the other two parts of the metric on the same core: legal-move generations/s on mid-game states and UCT
+    # simulations/s with the bench's search settings (uniform 50-ply rollouts, transposition table off)
+    mids = [orc.playout(SEED, k, max_turns=6 * (1 + k % 8), want_final=True)["final"] for k in range(64)]
+    boards = [orc.OracleBoard.from_packed(m) for m in mids]
+    t0 = time.perf_counter(); gens = 0
+    while time.perf_counter() - t0 < 2.0:
+        for b in boards:
+            b.legal_moves(b.current_player)
+        gens += len(boards)
+    out["movegen_gens_per_sec"] = gens / (time.perf_counter() - t0)
+    root = np.zeros(1, dtype=orc.STATE_DTYPE); root["first_mask"] = 0xF
+    t0 = time.perf_counter(); sims = 0
+    while time.perf_counter() - t0 < 3.0:
+        orc.mcts_search(root, 256, SEED, tree_id=sims // 256, rollout_policy=0)
+        sims += 256
+    out["mcts_sims_per_sec"] = sims / (time.perf_counter() - t0)
+    return out
 
 
 def main():

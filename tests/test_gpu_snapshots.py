@@ -121,3 +121,41 @@ def test_object_api_and_dataset_rows(dev, golden_dir, tmp_path):
     meta = winprob.write_snapshots_dataset(str(tmp_path), rows)
     assert meta["enabled"] and meta["rows"] == len(rows) and os.path.exists(meta["path_csv"])
     assert winprob.LearnedWinProbabilityEvaluator("x/dummy_model.json").predict_player_win_probability(game.board, Player.RED) == 0.5
+
+
+def test_learned_evaluator_with_sklearn_artifacts(dev, golden_dir, tmp_path):
+    """mcts/learned_evaluator.py:97-152 with real joblib artifacts of both supported model types: the probability is
+    the mean over the three opponents of predict_proba(feature_i - feature_j), features taken from the reference rows."""
+    joblib = pytest.importorskip("joblib")
+    from sklearn.ensemble import GradientBoostingClassifier
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+
+    from reinforcementlearning_blokus_b200 import Board, Player, winprob
+
+    z, _ = _golden(golden_dir)
+    states = np.load(os.path.join(golden_dir, "random_states.npz"))["states"].view(winprob.np.uint8).reshape(-1, 256)
+    rows = z["state_features"]                                             # reference rows of those boards [240, 4, 34]
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rows[:, 0] - rows[:, 1], rows[:, 2] - rows[:, 3]])
+    y = rng.integers(0, 2, len(x))
+    cols = winprob.SNAPSHOT_FEATURE_COLUMNS
+    logreg = Pipeline([("scale", StandardScaler()), ("clf", LogisticRegression(max_iter=200))]).fit(x, y)
+    gbt = GradientBoostingClassifier(n_estimators=5, random_state=0).fit(x, y)
+    p1, p2 = str(tmp_path / "logreg.joblib"), str(tmp_path / "gbt.joblib")
+    joblib.dump({"model_type": "pairwise_logreg", "feature_columns": cols, "pipeline": logreg}, p1)
+    joblib.dump({"model_type": "pairwise_gbt_phase", "feature_columns": cols, "phase_models": {"mid": gbt}, "fallback_model": gbt}, p2)
+    from reinforcementlearning_blokus_b200.state import STATE_DTYPE
+    for path, model in ((p1, logreg), (p2, gbt)):
+        ev = winprob.LearnedWinProbabilityEvaluator(path)
+        for i in (3, 77, 200):
+            board = Board.from_packed(states[i].view(STATE_DTYPE)[0])
+            for pl in (Player.RED, Player.GREEN):
+                a = pl.value - 1
+                want = float(np.mean([model.predict_proba((rows[i, a] - rows[i, b])[None])[:, 1][0] for b in range(4) if b != a]))
+                assert ev.predict_player_win_probability(board, pl) == pytest.approx(want, abs=1e-15)
+        assert 0.0 < ev.potential(board, Player.BLUE) < 1.0
+    with pytest.raises(ValueError):
+        joblib.dump({"model_type": "other"}, str(tmp_path / "bad.joblib"))
+        winprob.LearnedWinProbabilityEvaluator(str(tmp_path / "bad.joblib"))
