@@ -3,8 +3,12 @@
 // select_action = softmax(T = 1) over the move scores, then one categorical draw.  On the device, per turn:
 //   1. rows of all legal anchors -> shared memory (same generator, SmemRowSink)
 //   2. ascending move list in shared memory (each lane owns 57 consecutive row words; one warp scan)
-//   3. per move: corner / edge features (1 byte), float64 score, warp max
-//   4. e_k = exp(score_k - max) summed per lane (lane L owns moves k = L, L+32, ...), Hillis-Steele scan over lanes
+//   3. per move: corner / edge features (1 byte) and the softmax weight e_k = exp(s1_k) * exp(s2_k), where the score
+//      is split as score = s1 + s2: s1 = size + 2*corners - 1.5*edge_score is a multiple of 0.25 with 1260 possible
+//      values (table g_e2, indexed by the feature byte, the size and the game phase) and s2 = 0.5*centre(anchor)
+//      depends on the anchor cell only (table g_e1).  exp(score - max)/sum of the reference equals e_k/sum e_k up to
+//      rounding; no max pass, no exp and no float64 score in the loop (r01p profile: they were 26 % of the kernel)
+//   4. e_k summed per lane (lane L owns moves k = L, L+32, ...), Hillis-Steele scan over lanes
 //   5. target = total * r * 2^-32 with r the turn's Philox word; the lane whose inclusive sum first exceeds the
 //      target, then the first move inside that lane whose running sum exceeds it
 // Every floating-point operation has a fixed order, restated in oracle/blokus_oracle.c (heuristic_pick), so the
@@ -21,6 +25,9 @@
 
 __device__ double g_centre[400];      // 1 - dist(anchor, centre)/max_dist (heuristic_agent.py:185-198)
 __device__ uint8_t g_edge[91 * 400];  // cells of move (o,row,col) within 2 cells of the border (heuristic_agent.py:153-167)
+#define HEUR_E2_SIZE (2 * 6 * 21 * 5)
+__device__ double g_e1[400];          // exp(0.5 * g_centre[anchor])
+__device__ double g_e2[HEUR_E2_SIZE]; // exp(size + 2*corners - 1.5*edge_score), index ((late*6 + edge)*21 + corners)*5 + size-1
 
 __global__ void k_init_heuristic_tables() {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -30,6 +37,14 @@ __global__ void k_init_heuristic_tables() {
         const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc)));
         const double maxd = __dsqrt_rn(__dmul_rn(2.0, __dmul_rn(9.5, 9.5)));
         g_centre[i] = __dsub_rn(1.0, __ddiv_rn(dist, maxd));
+        g_e1[i] = exp(__dmul_rn(0.5, g_centre[i]));
+    }
+    if (i < HEUR_E2_SIZE) {
+        const int size = i % 5 + 1, corners = (i / 5) % 21, edge = (i / 105) % 6, late = i / 630;
+        double s1 = __dadd_rn(0.0, __dmul_rn(1.0, (double)size));
+        s1 = __dadd_rn(s1, __dmul_rn(2.0, (double)corners));
+        const double edge_score = late ? __dmul_rn((double)edge, 0.5) : (double)edge;
+        g_e2[i] = exp(__dadd_rn(s1, __dmul_rn(-1.5, edge_score)));
     }
     if (i < 91 * 400) {
         const int o = i / 400, cell = i - o * 400, ar = cell / 20, ac = cell - ar * 20;
@@ -82,16 +97,11 @@ __device__ __forceinline__ uint32_t heur_features(const uint8_t* __restrict__ dm
     return corners | ((uint32_t)g_edge[id] << 5);
 }
 
-// the score of heuristic_score() (blokus_b200.cu) rebuilt from the stored features, same operation order
-__device__ __forceinline__ double heur_score_from(uint32_t feat, uint32_t id, uint32_t move_count) {
-    const int o = id / 400, cell = id - o * 400;
-    double score = __dadd_rn(0.0, __dmul_rn(1.0, (double)c_orient_ncells[o]));
-    score = __dadd_rn(score, __dmul_rn(2.0, (double)(feat & 31u)));
-    const double edge = (double)(feat >> 5);
-    const double progress = __ddiv_rn((double)move_count, 100.0);
-    const double edge_score = (progress < 0.3) ? edge : __dmul_rn(edge, 0.5);
-    score = __dadd_rn(score, __dmul_rn(-1.5, edge_score));
-    return __dadd_rn(score, __dmul_rn(0.5, g_centre[cell]));
+// softmax weight of a move from its stored feature byte (corners | edge << 5): two table loads and one product
+__device__ __forceinline__ double heur_weight(uint32_t feat, uint32_t id, uint32_t late) {
+    const uint32_t o = id / 400u, cell = id - o * 400u;
+    const uint32_t idx = ((late * 6u + (feat >> 5)) * 21u + (feat & 31u)) * 5u + (c_orient_ncells[o] - 1u);
+    return __dmul_rn(__ldg(g_e2 + idx), __ldg(g_e1 + cell));
 }
 
 // Returns the number of legal moves of `p`; when > 0 picks one by the Philox word r and returns it through
@@ -159,22 +169,16 @@ __device__ __noinline__ uint32_t heuristic_pick(const WarpState s, uint32_t p, u
         sc.ids[k] = (uint16_t)((L * HEUR_WORDS_PER_LANE + w) * 20u + (__ffs(bits) - 1));
     }
     __syncwarp();
-    // ---- features, scores, max
-    const double NEG_INF = __longlong_as_double(0xFFF0000000000000ll);
-    double mx = NEG_INF;
+    // ---- features and per-lane sums of the weights
+    const uint32_t late = (__ddiv_rn((double)s.move_count, 100.0) < 0.3) ? 0u : 1u;      // heuristic_agent.py:169-172
+    double sum = 0.0;
     for (uint32_t k = lane; k < n; k += 32) {
         const uint32_t id = sc.ids[k];
         const uint32_t f = heur_features(sc.dmap, id);
         sc.feat[k] = (uint8_t)f;
-        mx = fmax(mx, heur_score_from(f, id, s.move_count));
+        sum = __dadd_rn(sum, heur_weight(f, id, late));
     }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(BK_FULL, mx, d));
     __syncwarp();
-    // ---- per-lane sums of exp(score - max), scan over lanes
-    double sum = 0.0;
-    for (uint32_t k = lane; k < n; k += 32)
-        sum = __dadd_rn(sum, exp(__dsub_rn(heur_score_from(sc.feat[k], sc.ids[k], s.move_count), mx)));
     double dincl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const double v = __shfl_up_sync(BK_FULL, dincl, d); if (lane >= d) dincl = __dadd_rn(dincl, v); }
@@ -189,7 +193,7 @@ __device__ __noinline__ uint32_t heuristic_pick(const WarpState s, uint32_t p, u
     uint32_t pick = (uint32_t)L;
     for (uint32_t k = (uint32_t)L; k < n; k += 32) {
         pick = k;
-        acc = __dadd_rn(acc, exp(__dsub_rn(heur_score_from(sc.feat[k], sc.ids[k], s.move_count), mx)));
+        acc = __dadd_rn(acc, heur_weight(sc.feat[k], sc.ids[k], late));
         if (acc > target) break;
     }
     if (pick >= n) pick = n - 1;     // only if lane L owns no move at all (cannot happen: its sum exceeded target)

@@ -127,6 +127,14 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
             draws = hdr->draws; overflow = hdr->overflow; root_player = hdr->root_player; root_score = hdr->root_score;
         }
 
+        // rollout draws: 4 per Philox block (draw t = word t%4 of block t/4 of stream 1); the block is kept in
+        // registers and recomputed when the draw counter enters the next one
+        PhiloxBlock blk = philox_block(prm.seed, tree_id, draws >> 2, 1);
+        uint32_t blk_of = draws >> 2;
+        auto next_draw = [&]() -> uint32_t {
+            if ((draws >> 2) != blk_of) { blk_of = draws >> 2; blk = philox_block(prm.seed, tree_id, blk_of, 1); }
+            return philox_word(blk, draws++);
+        };
         for (int it = 0; it < prm.iterations && !overflow; it++, iter_done++) {
             // ---- selection (mcts_agent.py:384-406)
             uint32_t node = 0, depth = 0;
@@ -211,15 +219,17 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
                     const uint32_t p = s.to_move;
                     if (POLICY == BK_POLICY_HEURISTIC) {                   // HeuristicAgent, the reference's default (:275-276)
                         uint32_t id = 0, idx = 0;
-                        if (heuristic_pick(s, p, philox_draw(prm.seed, tree_id, draws, 1), hs, lane, id, idx) == 0) break;
-                        draws++;
+                        // a turn without a move consumes no draw: peek, then commit
+                        const uint32_t before_draws = draws;
+                        const uint32_t rnd = next_draw();
+                        if (heuristic_pick(s, p, rnd, hs, lane, id, idx) == 0) { draws = before_draws; break; }
                         place_move(s, p, (int)(id / 400u), (int)((id % 400u) / 20u), (int)(id % 20u), lane);
                         continue;
                     }
                     uint32_t A, C; make_masks(s, p, lane, A, C);
                     const Totals tot = gen_totals(A, C, sel4(s.used, p), lane, s_slots);
                     if (tot.n == 0) break;                       // no passes inside a rollout (:488-489)
-                    const uint32_t rnd = philox_draw(prm.seed, tree_id, draws++, 1);
+                    const uint32_t rnd = next_draw();
                     int o, row, col;
                     select_move(tot, __umulhi(rnd, tot.n), A, C, lane, o, row, col);
                     place_move(s, p, o, row, col, lane);
