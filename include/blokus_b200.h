@@ -215,7 +215,10 @@ typedef struct bk_mcts_params {
     int32_t  ucb_variant;       /* 0: c*sqrt(ln N/n) (mcts_agent.py:86); 1: c*sqrt(2 ln N/n) (fast_mcts_agent.py:52) */
     int32_t  resume;            /* 0: build a fresh tree from the root; 1: continue the trees in `workspace` */
     int32_t  reward_mode;       /* 0: gain of the player to move at the leaf, from the leaf (mcts_agent.py:470-521);
-                                   1: gain of the ROOT player measured from the root position (flat bandit) */
+                                   1: gain of the ROOT player measured from the root position (flat bandit);
+                                   2: no rollout, every leaf is worth the constant 0.5 of the reference's dummy learned
+                                      evaluator (mcts_agent.py:427-451, learned_evaluator.py:51-55); rewards are then
+                                      counted in halves (root_reward = number of halves) */
     double   exploration;       /* 1.414 */
     uint64_t seed;
     uint64_t tree_offset;       /* global index of tree 0 (root-parallel sharding across GPUs) */

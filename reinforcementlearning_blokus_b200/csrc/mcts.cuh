@@ -143,6 +143,8 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
                 const bool may_expand = ne < nl && (prm.max_depth <= 0 || (int)depth < prm.max_depth);
                 if (may_expand || ne == 0) break;
                 const double logN = log((double)visits[node]) * (prm.ucb_variant ? 2.0 : 1.0);
+                // reward_mode 2 counts rewards in halves (the constant 0.5 of the reference's dummy evaluator); x1.0 is exact
+                const double unit = prm.reward_mode == 2 ? 0.5 : 1.0;
                 const uint32_t cb = child_base[node];
                 double best = -1.0; uint32_t best_k = 0xFFFFFFFFu; bool have = false;
                 for (uint32_t k = lane; k < ne; k += 32) {
@@ -150,7 +152,7 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
                     const double v = (double)visits[ch];
                     double u;
                     if (visits[ch] == 0) u = __longlong_as_double(0x7FF0000000000000ll);
-                    else u = __dadd_rn(__ddiv_rn((double)reward[ch], v), __dmul_rn(prm.exploration, sqrt(__ddiv_rn(logN, v))));
+                    else u = __dadd_rn(__ddiv_rn(__dmul_rn((double)reward[ch], unit), v), __dmul_rn(prm.exploration, sqrt(__ddiv_rn(logN, v))));
                     if (!have || u > best) { best = u; best_k = k; have = true; }
                 }
                 // warp argmax, ties -> smallest k (Python's max keeps the first maximal child)
@@ -211,7 +213,12 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
                 double rv = 0.0;
                 if (tt_lookup(tt.keys, tt.rewards, tt.log2_slots, key, rv)) { r = (long long)rv; cached = true; }
             }
-            if (!cached) {
+            if (!cached && prm.reward_mode == 2) {
+                // learned leaf evaluation in place of the rollout (mcts_agent.py:427-451) with the reference's dummy
+                // artifact (learned_evaluator.py:51-55,129-131): every leaf is worth 0.5, counted here as one half
+                r = 1;
+                if (tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, (double)r);
+            } else if (!cached) {
                 const uint32_t me = prm.reward_mode ? root_player : s.to_move;      // node.player (mcts_agent.py:483)
                 const int32_t before = prm.reward_mode ? root_score : board_score_of(s, me);
                 const int limit = prm.max_rollout_moves > 0 ? prm.max_rollout_moves : 1 << 30;

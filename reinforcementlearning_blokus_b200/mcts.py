@@ -187,8 +187,15 @@ class MCTSAgent:
 
     Same constructor arguments as the reference.  Differences, all documented in DESIGN.md: rollout moves are
     drawn with Philox on the device (``rollout_agent`` objects are accepted for interface compatibility but only
-    their kind -- heuristic softmax, the default, or uniform random -- matters); the learned-evaluator options (OUT OF SCOPE in SURVEY.md section 2) raise if enabled;
-    ``num_trees`` > 1 adds root-parallel trees whose root statistics are summed.
+    their kind -- heuristic softmax, the default, or uniform random -- matters); ``num_trees`` > 1 adds root-parallel
+    trees whose root statistics are summed.
+
+    Learned-evaluator options (mcts_agent.py:427-466, 486-551): with the reference's ``dummy_model.json`` artifact --
+    the only one its recorded arena runs use -- every probability is 0.5, so leaf evaluation is the kernel's constant
+    leaf value (reward_mode 2), the progressive bias term is exactly 0 and the shaping term is exactly 0 for gamma = 1
+    or potential_mode "logit"; those combinations run on the device.  A fitted artifact is served out of tree by
+    ``winprob.LearnedWinProbabilityEvaluator`` (device features, scikit-learn model); using it INSIDE the tree would
+    need the estimator on the device and raises NotImplementedError.
     """
 
     def __init__(self, iterations: int = 1000, time_limit: Optional[float] = None, exploration_constant: float = 1.414,
@@ -202,8 +209,31 @@ class MCTSAgent:
             raise ValueError("potential_mode must be either 'prob' or 'logit'.")
         if int(max_rollout_moves) <= 0:
             raise ValueError("max_rollout_moves must be > 0.")
-        if leaf_evaluation_enabled or progressive_bias_enabled or potential_shaping_enabled or learned_model_path:
-            raise NotImplementedError("learned evaluator options are outside the B200 hot path (SURVEY.md section 2)")
+        self.leaf_evaluation_enabled = bool(leaf_evaluation_enabled)
+        self.progressive_bias_enabled = bool(progressive_bias_enabled)
+        self.progressive_bias_weight = float(progressive_bias_weight)
+        self.potential_shaping_enabled = bool(potential_shaping_enabled)
+        self.potential_shaping_gamma = float(potential_shaping_gamma)
+        self.potential_shaping_weight = float(potential_shaping_weight)
+        self.potential_mode = potential_mode
+        self.learned_model_path = learned_model_path
+        self._requires_learned_evaluator = (self.leaf_evaluation_enabled or self.progressive_bias_enabled
+                                            or self.potential_shaping_enabled)
+        if self._requires_learned_evaluator and not learned_model_path:
+            raise ValueError("learned_model_path is required when learned evaluation, progressive bias, "
+                             "or potential shaping is enabled.")
+        self.learned_evaluator = None
+        if learned_model_path:
+            from .winprob import LearnedWinProbabilityEvaluator
+
+            self.learned_evaluator = LearnedWinProbabilityEvaluator(learned_model_path, potential_mode=potential_mode)
+            if self._requires_learned_evaluator and not self.learned_evaluator._is_dummy:
+                raise NotImplementedError("a fitted win-probability model inside the tree is not on the device path; "
+                                          "use winprob.LearnedWinProbabilityEvaluator for out-of-tree evaluation")
+            if (self.potential_shaping_enabled and potential_mode == "prob" and self.potential_shaping_gamma != 1.0
+                    and self.potential_shaping_weight != 0.0):
+                raise NotImplementedError("potential shaping with gamma != 1 adds a non-zero constant to truncated "
+                                          "rollouts; only the zero-term configurations run on the device")
         self.iterations = iterations
         self.time_limit = time_limit
         self.exploration_constant = exploration_constant
@@ -239,6 +269,7 @@ class MCTSAgent:
         self._searches += 1
         return DeviceUCT(total, n_trees=self.num_trees, max_rollout_moves=self.max_rollout_moves,
                          exploration=self.exploration_constant, seed=self.seed, tree_offset=offset,
+                         reward_mode=2 if self.leaf_evaluation_enabled else 0,
                          rollout_policy=self.rollout_policy, tt=tt,
                          zobrist=self.zobrist_hash if tt is not None else None)
 
@@ -270,6 +301,11 @@ class MCTSAgent:
         reward = res["reward"][:, :n_root].sum(dim=0).cpu().numpy()
         self.stats["iterations_run"] = done
         self.stats["time_elapsed"] = time.time() - start
+        if self.leaf_evaluation_enabled:
+            reward = reward * 0.5                            # halves -> the evaluator's probabilities
+            self.stats["leaf_eval_calls"] = done
+        if self.progressive_bias_enabled:
+            self.stats["progressive_bias_updates"] = done    # one (zero-valued) prior per expansion
         return {"visits": visits, "reward": reward, "n_root": n_root}
 
     def select_action(self, board: Board, player: Player, legal_moves: List[Move]) -> Optional[Move]:

@@ -147,3 +147,42 @@ def test_heuristic_policy_playouts_and_rollouts(golden_dir):
     nr = want["n_root"]
     assert np.array_equal(res["visits"][0, :nr].cpu().numpy(), want["visits"][:nr])
     assert np.array_equal(res["reward"][0, :nr].cpu().numpy(), want["reward"][:nr])
+
+
+def test_learned_evaluator_options_with_dummy_artifact(golden_dir):
+    """mcts_agent.py:427-466 with the reference's dummy artifact (every probability 0.5): leaf evaluation replaces the
+    rollout by a constant, progressive bias and (gamma = 1) shaping terms vanish.  Kernel == oracle, with and without
+    the transposition table; the agent accepts the reference's constructor arguments."""
+    iters = 200
+    for root_np in _roots(golden_dir)[:2]:
+        root = dev.to_device(np.atleast_1d(root_np))
+        want = orc.mcts_search(root_np, iters, seed=11, tree_id=3, reward_mode=2)
+        res = DeviceUCT(iters, n_trees=1, seed=11, tree_offset=3, reward_mode=2).search(root, iters)
+        n = want["n_root"]
+        assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n])
+        assert np.array_equal(res["reward"][0, :n].cpu().numpy(), want["reward"][:n])
+        assert np.array_equal(res["reward"][0, :n].cpu().numpy(), want["visits"][:n])          # one half per visit
+        zob, tt, ott = ZobristHash(seed=42), TranspositionTable(max_size=1 << 16), orc.OracleTT(18)
+        want = orc.mcts_search(root_np, iters, seed=11, tree_id=3, reward_mode=2, tt=ott, zobrist=zob.table)
+        res = DeviceUCT(iters, n_trees=1, seed=11, tree_offset=3, reward_mode=2, tt=tt.device, zobrist=zob).search(root, iters)
+        assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n])
+        ott.close()
+    board = Board.from_packed(_roots(golden_dir)[1])
+    player = board.current_player
+    legal = get_shared_generator().get_legal_moves(board, player)
+    agent = MCTSAgent(iterations=120, seed=4, learned_model_path="models/dummy_model.json", leaf_evaluation_enabled=True,
+                      progressive_bias_enabled=True, potential_shaping_enabled=True, use_transposition_table=False)
+    r = agent.search_root(board, player)
+    assert int(r["visits"].sum()) == 120 and np.array_equal(r["reward"], r["visits"] * 0.5)
+    assert agent.stats["leaf_eval_calls"] == 120 and agent.stats["progressive_bias_updates"] == 120
+    assert agent.select_action(board, player, legal) in legal
+    # bias / shaping only: rollouts as usual, same tree as the plain agent
+    plain = MCTSAgent(iterations=120, seed=4, use_transposition_table=False).search_root(board, player)
+    shaped = MCTSAgent(iterations=120, seed=4, use_transposition_table=False, learned_model_path="x/dummy_model.json",
+                       progressive_bias_enabled=True, potential_shaping_enabled=True, potential_mode="logit",
+                       potential_shaping_gamma=0.9).search_root(board, player)
+    assert np.array_equal(plain["visits"], shaped["visits"]) and np.array_equal(plain["reward"], shaped["reward"])
+    with pytest.raises(ValueError):
+        MCTSAgent(leaf_evaluation_enabled=True)
+    with pytest.raises(NotImplementedError):
+        MCTSAgent(learned_model_path="x/dummy_model.json", potential_shaping_enabled=True, potential_shaping_gamma=0.9)
