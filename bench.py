@@ -264,7 +264,7 @@ def run_cuda(args) -> None:
         from reinforcementlearning_blokus_b200 import dist as bdist
         from reinforcementlearning_blokus_b200.mcts import DeviceUCT
 
-        trees, iters = 3552, 256            # 24 one-warp trees per SM
+        trees, iters = 4 * 3552, 256        # four waves of 24 one-warp trees per SM, handed out by a ticket counter
         root = dev.to_device(empty_states(1))
         eng = DeviceUCT(iters, n_trees=trees, seed=SEED, tree_offset=rank * trees)
         res = eng.search(root, iters)                 # warm-up (search and merge: the first reduction loads torch kernels)
@@ -284,6 +284,18 @@ def run_cuda(args) -> None:
         mcts = {"mcts_sims_per_sec": world * trees * iters / (ms_m * 1e-3), "mcts_trees_per_gpu": trees,
                 "mcts_iterations_per_tree": iters, "mcts_rollout_plies": 50,
                 "mcts_root_visits_total": int(v.sum().item()), "mcts_collective": "1 all_reduce(int64[2,2048]) per search"}
+        # the reference's default rollout policy (HeuristicAgent softmax, mcts_agent.py:275-276), no collective
+        del eng
+        ht = 2 * 2072                       # two waves of 14 one-warp trees per SM
+        heng = DeviceUCT(iters, n_trees=ht, seed=SEED, tree_offset=rank * ht, rollout_policy=dev.POLICY_HEURISTIC)
+        heng.search(root, iters)
+        torch.cuda.synchronize()
+        m0.record(stream)
+        heng.search(root, iters)
+        m1.record(stream)
+        torch.cuda.synchronize()
+        mcts["mcts_heuristic_rollout_sims_per_sec_per_gpu"] = ht * iters / (m0.elapsed_time(m1) * 1e-3)
+        del heng
 
     if rank != 0:
         if world > 1:

@@ -977,14 +977,14 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
     if ((int64_t)L.total * n_trees > workspace_bytes) return fail(BK_ERR_CAPACITY, "%s", "bk_mcts_search: workspace too small");
     MctsTT t; t.keys = nullptr; t.rewards = nullptr; t.occupied = nullptr; t.log2_slots = 0; t.zobrist = zobrist_table;
     if (tt) { t.keys = tt->keys; t.rewards = tt->rewards; t.occupied = tt->occupied; t.log2_slots = tt->log2_slots; }
-    const int cap = g_sms * (params->rollout_policy == BK_POLICY_HEURISTIC ? 8 : BK_MCTS_CTAS_PER_SM);
+    const int cap = g_sms * (params->rollout_policy == BK_POLICY_HEURISTIC ? BK_MCTS_HEUR_CTAS_PER_SM : BK_MCTS_CTAS_PER_SM);
     const int grid = n_trees < cap ? n_trees : cap;
     if (params->rollout_policy == BK_POLICY_HEURISTIC)
-        k_mcts<1><<<grid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, as_stream(stream)>>>(roots, n_roots, n_trees, *params, t,
+        k_mcts<1><<<grid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, as_stream(stream)>>>(fresh_ticket(as_stream(stream)), roots, n_roots, n_trees, *params, t,
             reinterpret_cast<unsigned char*>(workspace), params->resume, max_root_moves, root_visits,
             reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status);
     else
-        k_mcts<0><<<grid, BK_MCTS_THREADS, 0, as_stream(stream)>>>(roots, n_roots, n_trees, *params, t,
+        k_mcts<0><<<grid, BK_MCTS_THREADS, 0, as_stream(stream)>>>(fresh_ticket(as_stream(stream)), roots, n_roots, n_trees, *params, t,
             reinterpret_cast<unsigned char*>(workspace), params->resume, max_root_moves, root_visits,
             reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status);
     LAUNCH_CHECK();

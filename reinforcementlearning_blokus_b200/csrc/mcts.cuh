@@ -75,10 +75,15 @@ __device__ __forceinline__ int32_t board_score_of(const WarpState& s, uint32_t q
 #ifndef BK_MCTS_CTAS_PER_SM
 #define BK_MCTS_CTAS_PER_SM 24
 #endif
+// heuristic rollouts: 14 KB of list scratch per warp allows 14 one-warp CTAs per SM (16 KB each with the static part
+// and the per-CTA reservation, 228 KB per SM); the register cap that goes with it is 146
+#ifndef BK_MCTS_HEUR_CTAS_PER_SM
+#define BK_MCTS_HEUR_CTAS_PER_SM 14
+#endif
 
 template <int POLICY>
-__global__ void __launch_bounds__(BK_MCTS_THREADS, POLICY == 0 ? BK_MCTS_CTAS_PER_SM : 8)
-k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_params prm, MctsTT tt,
+__global__ void __launch_bounds__(BK_MCTS_THREADS, POLICY == 0 ? BK_MCTS_CTAS_PER_SM : BK_MCTS_HEUR_CTAS_PER_SM)
+k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_params prm, MctsTT tt,
        unsigned char* __restrict__ workspace, int resume, int max_root_moves,
        int32_t* __restrict__ out_visits, long long* __restrict__ out_reward, uint32_t* __restrict__ out_counts,
        uint16_t* __restrict__ out_moves, uint32_t* __restrict__ out_status) {
@@ -87,10 +92,14 @@ k_mcts(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_par
     HeurScratch hs;
     if (POLICY == BK_POLICY_HEURISTIC) hs.bind(heur_smem);
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const MctsLayout L = mcts_layout(prm.iterations_total);
-    for (int tree = warp; tree < n_trees; tree += nwarps) {
+    // trees differ in cost (rollout lengths, tree depth): warps take the next tree from a per-launch ticket counter so
+    // that a batch larger than the resident warps has no idle tail; a tree's result depends on (seed, tree id) only
+    for (;;) {
+        uint32_t t0 = 0;
+        if (lane == 0) t0 = atomicAdd(ticket, 1u);
+        const int tree = (int)uni(t0);
+        if (tree >= n_trees) break;
         unsigned char* base = workspace + (size_t)tree * L.total;
         bk_state* states = reinterpret_cast<bk_state*>(base + L.off_states);
         long long* reward = reinterpret_cast<long long*>(base + L.off_reward);
