@@ -1,0 +1,30 @@
+"""ncu driver for the final build: one launch of every kernel family after the 8 corpus-building playout launches.
+
+  ncu --set full --clock-control none --import-source on --launch-skip 8 \
+      -k regex:"k_playout|k_movegen|k_snapshot|k_replay|k_mcts" -o gpurun_out/<name> python tools/profile_all.py
+"""
+import sys
+import torch
+sys.path.insert(0, ".")
+from reinforcementlearning_blokus_b200 import device as dev
+from reinforcementlearning_blokus_b200.mcts import DeviceUCT
+from reinforcementlearning_blokus_b200.state import empty_states
+
+n = 1 << 18
+parts = [dev.playout(n // 8, seed=7, game_offset=k * 1_000_000, max_turns=k, want_final=True)["final_states"].clone()
+         for k in (6, 12, 18, 24, 30, 36, 42, 48)]                       # 8 skipped launches
+corpus = torch.cat(parts).contiguous()
+out = {}
+dev.playout(65536, seed=42, out=out, want_board_scores=False)             # k_playout<0,false>: the headline launch
+tr = dev.playout(65536, seed=42, want_trace=True)["trace"].clone()        # k_playout<0,true>
+dev.playout(16384, seed=42, policy=dev.POLICY_HEURISTIC, out={}, want_board_scores=False)   # k_playout<1,...>
+dev.movegen_count(corpus)
+dev.movegen(corpus)                                                       # count + scan + emit
+dev.movegen_bitmap(corpus)
+dev.snapshot_features(corpus)
+dev.replay_snapshots(tr, (8, 16, 24, 32, 40, 48, 56, 64))
+roots = dev.to_device(empty_states(1))
+DeviceUCT(256, n_trees=3552, seed=42).search(roots, 256)
+DeviceUCT(256, n_trees=2072, seed=42, rollout_policy=dev.POLICY_HEURISTIC).search(roots, 256)
+torch.cuda.synchronize()
+print("ok")
