@@ -414,8 +414,7 @@ k_playout(unsigned int* __restrict__ ticket, const uint32_t* __restrict__ seat_p
                   uint16_t* __restrict__ choice, bk_state* __restrict__ finals) {
     __shared__ __align__(16) uint32_t s_slots[BK_PLAYOUT_THREADS / 32][BK_GROUP_SLOTS];
     extern __shared__ __align__(16) unsigned char heur_smem[];
-    HeurScratch hs;
-    if (POLICY != 0) hs.bind(heur_smem + (size_t)(threadIdx.x >> 5) * HEUR_SMEM_PER_WARP);
+    const uint32_t hs = (uint32_t)(threadIdx.x >> 5) * HEUR_SMEM_PER_WARP;     // this warp's heuristic scratch
     const int lane = threadIdx.x & 31;
     // Games differ in length (50..76 turns), so a fixed game->warp assignment leaves a tail of idle warps; every
     // warp instead takes the next game from a per-launch ticket counter.  Results do not depend on the assignment:

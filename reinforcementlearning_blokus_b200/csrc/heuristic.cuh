@@ -106,8 +106,14 @@ __device__ __forceinline__ double heur_weight(uint32_t feat, uint32_t id, uint32
 
 // Returns the number of legal moves of `p`; when > 0 picks one by the Philox word r and returns it through
 // (id, idx = rank in the ascending list).  All lanes return the same values.
-__device__ __noinline__ uint32_t heuristic_pick(const WarpState s, uint32_t p, uint32_t r, HeurScratch sc, int lane,
+// `scratch_off` = byte offset of this warp's HEUR_SMEM_PER_WARP scratch inside the kernel's dynamic shared memory.  The
+// pointers are rebuilt from the extern array HERE so that the compiler knows their address space: handed over as plain
+// pointers they compiled to generic LD.E / ST.E with 64-bit address arithmetic, and those loads were the kernel's
+// long-scoreboard stalls (profiles/r01r_all_kernels_ncu.md: 51 % issue-active, 1.8 long-scoreboard stalls per issue).
+__device__ __noinline__ uint32_t heuristic_pick(const WarpState s, uint32_t p, uint32_t r, uint32_t scratch_off, int lane,
                                                 uint32_t& id_out, uint32_t& idx_out) {
+    extern __shared__ __align__(16) unsigned char heur_dyn_smem[];
+    HeurScratch sc; sc.bind(heur_dyn_smem + scratch_off);
     uint32_t A, C; make_masks(s, p, lane, A, C);
     __syncwarp();
 #pragma unroll

@@ -60,7 +60,10 @@ struct MctsTT {                // optional transposition table (mcts/zobrist.py:
     const uint64_t* zobrist;   // 2088-entry table, reference order
 };
 
-__device__ __noinline__ Totals gen_totals(uint32_t A, uint32_t C, uint32_t used, int lane, uint32_t* slots) {
+// One-warp CTAs: the group slots are this function's own static shared array (a pointer parameter would hide the
+// address space and turn the sink's STS into generic stores).
+__device__ __noinline__ Totals gen_totals(uint32_t A, uint32_t C, uint32_t used, int lane) {
+    __shared__ __align__(16) uint32_t slots[BK_GROUP_SLOTS];
     GroupSink sink; sink.begin(slots, lane);
     bk_gen_all<GroupSink, true>(A, C, used, sink);
     return reduce_totals(sink, lane);
@@ -87,10 +90,8 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
        unsigned char* __restrict__ workspace, int resume, int max_root_moves,
        int32_t* __restrict__ out_visits, long long* __restrict__ out_reward, uint32_t* __restrict__ out_counts,
        uint16_t* __restrict__ out_moves, uint32_t* __restrict__ out_status) {
-    __shared__ __align__(16) uint32_t s_slots[BK_GROUP_SLOTS];
     extern __shared__ __align__(16) unsigned char heur_smem[];    // HEUR_SMEM_PER_WARP bytes when rollout_policy == 1
-    HeurScratch hs;
-    if (POLICY == BK_POLICY_HEURISTIC) hs.bind(heur_smem);
+    const uint32_t hs = 0;                                        // one warp per CTA: its heuristic scratch starts at 0
     const int lane = threadIdx.x & 31;
     const MctsLayout L = mcts_layout(prm.iterations_total);
     // trees differ in cost (rollout lengths, tree depth): warps take the next tree from a per-launch ticket counter so
@@ -122,7 +123,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
         if (!resume) {
             load_state(roots + (tree % n_roots), lane, s);
             uint32_t A, C; make_masks(s, s.to_move, lane, A, C);
-            const Totals t0 = gen_totals(A, C, sel4(s.used, s.to_move), lane, s_slots);
+            const Totals t0 = gen_totals(A, C, sel4(s.used, s.to_move), lane);
             store_state(states + 0, lane, s);
             if (lane == 0) {
                 parent[0] = -1; visits[0] = 0; reward[0] = 0; child_base[0] = 0xFFFFFFFFu;
@@ -182,12 +183,12 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                 if (ne < nl && (prm.max_depth <= 0 || (int)depth < prm.max_depth)) {
                     const uint32_t p = s.to_move;
                     uint32_t A, C; make_masks(s, p, lane, A, C);
-                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane, s_slots);
+                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane);
                     int o, row, col;
                     const uint32_t id = select_move(tot, nl - 1 - ne, A, C, lane, o, row, col);
                     place_move(s, p, o, row, col, lane);
                     uint32_t A2, C2; make_masks(s, s.to_move, lane, A2, C2);
-                    const Totals tc = gen_totals(A2, C2, sel4(s.used, s.to_move), lane, s_slots);
+                    const Totals tc = gen_totals(A2, C2, sel4(s.used, s.to_move), lane);
                     uint32_t cb = child_base[node];
                     if (cb == 0xFFFFFFFFu) {
                         const uint32_t remaining = (uint32_t)prm.iterations_total - iter_done;
@@ -243,7 +244,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                         continue;
                     }
                     uint32_t A, C; make_masks(s, p, lane, A, C);
-                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane, s_slots);
+                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane);
                     if (tot.n == 0) break;                       // no passes inside a rollout (:488-489)
                     const uint32_t rnd = next_draw();
                     int o, row, col;
