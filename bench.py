@@ -157,7 +157,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -331,7 +331,7 @@ def run_cuda(args) -> None:
     if world == 1 and not args.no_extras:
         line["extras"].update(_extras(dev, torch, n))
         line["cpu_baseline"] = _cpu_baseline()
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -468,7 +468,20 @@ def _cpu_baseline():
     return out
 
 
+def _emit(line: dict) -> None:
+    """The ONE line of stdout: everything else that libraries print (e.g. NCCL's version banner when NCCL_DEBUG is
+    set) was sent to stderr by main()."""
+    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+
+
+_STDOUT_FD = 1
+
+
 def main():
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)          # keep the real stdout for the JSON line ...
+    os.dup2(2, 1)                   # ... and route everything else written to fd 1 (C libraries included) to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
