@@ -12,7 +12,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libblokus_b200.so")
 SOURCES = ["blokus_b200.cu"]
 DEPS = ["blokus_b200.cu", "movegen_core.cuh", "orient_gen.cuh", "tables_gen.h", "mcts.cuh", "heuristic.cuh",
-        os.path.join("..", "..", "include", "blokus_b200.h")]
+        "snapshot.cuh", "probe.cu", os.path.join("..", "..", "include", "blokus_b200.h")]
+PROBE_LIB = os.path.join(HERE, "libbk_probe.so")
+STAMP = LIB + ".srchash"          # hash of the sources the library was built from (mtimes do not survive a copy)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -28,35 +30,39 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libblokus_b200.so")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
+def _source_hash() -> str:
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     for d in DEPS:
-        p = os.path.join(CSRC, d)
-        if os.path.exists(p) and os.path.getmtime(p) > t:
-            return True
-    return False
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 
-PROBE_LIB = os.path.join(HERE, "libbk_probe.so")
+def needs_build() -> bool:
+    """True when the library is missing or was built from other sources (content hash, not mtimes: the tree is
+    copied to the GPU box and a copy does not keep modification times in order)."""
+    if not (os.path.exists(LIB) and os.path.exists(PROBE_LIB) and os.path.exists(STAMP)):
+        return True
+    with open(STAMP) as f:
+        return f.read().strip() != _source_hash()
+
+
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile libblokus_b200.so (and the bench-only pipe-throughput probe) if stale."""
+    """Compile libblokus_b200.so and the bench-only pipe-throughput probe if missing or stale."""
     if force or needs_build():
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-        proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-        if proc.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
-        if verbose:
-            sys.stderr.write(proc.stderr)
-    probe_src = os.path.join(CSRC, "probe.cu")
-    if force or not os.path.exists(PROBE_LIB) or os.path.getmtime(PROBE_LIB) < os.path.getmtime(probe_src):
-        proc = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-o", PROBE_LIB, "probe.cu"], cwd=CSRC,
-                              capture_output=True, text=True)
-        if proc.returncode != 0:
-            raise RuntimeError("nvcc failed (probe):\n" + proc.stdout + proc.stderr)
+        for out, srcs in ((LIB, SOURCES), (PROBE_LIB, ["probe.cu"])):
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
+            proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+            if proc.returncode != 0:
+                raise RuntimeError(f"nvcc failed ({srcs[0]}):\n" + proc.stdout + proc.stderr)
+            if verbose:
+                sys.stderr.write(proc.stderr)
+        with open(STAMP, "w") as f:
+            f.write(_source_hash() + "\n")
     return LIB
 
 
