@@ -367,3 +367,34 @@ def test_playout_replay_sweep_small():
     h = mod.sweep(400, seed=7, policy=1, first_game=654321)
     assert u["mismatches"] == 0 and h["mismatches"] == 0
     assert h["mean_score"] > u["mean_score"]
+
+
+def test_policy_distributions_are_the_references(golden_dir):
+    """Not only deterministic parity with the oracle: the SAMPLED distribution of the device policies is the
+    reference's.  One mid-game state, 400,000 independent draws of its next move (one per game index): the uniform
+    policy hits every legal move equally often, the heuristic policy follows softmax(T=1) of the reference's move
+    scores (agents/heuristic_agent.py:222-244; scores are the bit-exact ones of bk_heuristic_scores)."""
+    z = np.load(os.path.join(golden_dir, "random_states.npz"))
+    states = z["states"].view(STATE_DTYPE).reshape(-1)
+    st = next(s for s in states if 12 <= int(s["move_count"]) <= 20)
+    n = 400_000
+    start = dev.to_device(np.repeat(np.atleast_1d(st), n))
+    t0 = int(st["move_count"])                                  # any first_turn works: it only names the Philox word
+    counts, offsets, ids = dev.movegen(start[:1].contiguous())
+    legal = ids.cpu().numpy().astype(np.int64)
+    m = len(legal)
+    assert m > 50
+    scores = dev.heuristic_scores(start[:1].contiguous(), offsets, ids).cpu().numpy()
+    p_heur = np.exp(scores - scores.max()); p_heur /= p_heur.sum()
+    for policy, p in ((dev.POLICY_UNIFORM, np.full(m, 1.0 / m)), (dev.POLICY_HEURISTIC, p_heur)):
+        r = dev.playout(n, seed=123, start_states=start, policy=policy, first_turn=t0, max_turns=t0 + 1, want_trace=True)
+        picked = r["trace"][:, t0].cpu().numpy().astype(np.int64)
+        pos = np.searchsorted(legal, picked)
+        assert (legal[pos] == picked).all()                     # every draw is a legal move
+        freq = np.bincount(pos, minlength=m).astype(np.float64)
+        expect = n * p
+        big = expect >= 20                                      # chi-square over the well-populated cells
+        chi2 = float((((freq - expect) ** 2) / expect)[big].sum())
+        dof = int(big.sum()) - 1
+        assert abs(chi2 - dof) < 6.0 * np.sqrt(2.0 * dof), (policy, chi2, dof)
+        assert abs(freq[~big].sum() - expect[~big].sum()) < 6.0 * np.sqrt(expect[~big].sum() + 1.0)
