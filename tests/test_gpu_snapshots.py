@@ -164,3 +164,40 @@ def test_learned_evaluator_with_sklearn_artifacts(dev, golden_dir, tmp_path):
     with pytest.raises(ValueError):
         joblib.dump({"model_type": "other"}, str(tmp_path / "bad.joblib"))
         winprob.LearnedWinProbabilityEvaluator(str(tmp_path / "bad.joblib"))
+
+
+def test_replay_edge_cases(dev):
+    """Illegal or out-of-range ids stop the replay of that game only; replay from given start states; empty batch."""
+    from oracle import orc
+
+    r = dev.playout(64, seed=5, want_trace=True)
+    tr = r["trace"].cpu().numpy().copy()
+    ck = [0, 8, 16, 24, 32]
+    first = np.array([np.nonzero(t != 0xFFFF)[0][20] for t in tr])          # turn of the 21st placement
+    tr[0, first[0]] = 40000                                                  # out of range
+    tr[1, first[1]] = tr[1, np.nonzero(tr[1] != 0xFFFF)[0][0]]               # the game's first move again: illegal now
+    rep = dev.replay_snapshots(torch.from_numpy(tr).cuda(), ck, max_turns=100)
+    ti = rep["turn_index"].cpu().numpy()
+    assert (ti[:2, :3] >= 0).all() and (ti[:2, 3:] == -1).all()              # plies 0, 8, 16 captured, 24 and 32 not
+    assert (ti[2:] >= 0).all()
+    for gi in (0, 1, 2):
+        o = orc.replay_snapshots(tr[gi], ck, max_turns=100)
+        assert (o["turn_index"] == ti[gi]).all()
+        assert (o["features"][ti[gi] >= 0] == rep["features"][gi].cpu().numpy()[ti[gi] >= 0]).all()
+    # continue games from mid-game boards: turns and plies count from the given start state
+    seg = dev.playout(32, seed=9, max_turns=20, want_final=True, want_trace=True)
+    rest = dev.playout(32, seed=9, start_states=seg["final_states"], first_turn=20, want_trace=True)
+    tail = rest["trace"][:, 20:].contiguous()
+    mc = seg["final_states"].cpu().numpy().view(orc.STATE_DTYPE).reshape(-1)
+    ck2 = sorted({int(mc["move_count"].min()), int(mc["move_count"].max()), 30, 40})
+    rep = dev.replay_snapshots(tail, ck2, max_turns=76, start=seg["final_states"])
+    ti = rep["turn_index"].cpu().numpy()
+    for gi in range(0, 32, 5):
+        o = orc.replay_snapshots(tail[gi].cpu().numpy(), ck2, max_turns=76, start=mc[gi])
+        assert (o["turn_index"] == ti[gi]).all()
+        hit = ti[gi] >= 0
+        assert hit.any() and (o["features"][hit] == rep["features"][gi].cpu().numpy()[hit]).all()
+    empty = dev.snapshot_features(torch.empty((0, 256), dtype=torch.uint8, device="cuda"))
+    assert tuple(empty.shape) == (0, 4, 34)
+    with pytest.raises(ValueError):
+        dev.replay_snapshots(tail, [])
