@@ -424,6 +424,28 @@ def _extras(dev, torch, n):
     nh = n // 4
     ms = timeit(lambda: dev.playout(nh, seed=SEED, policy=dev.POLICY_HEURISTIC, out=hout, want_board_scores=False), reps=3)
     ex["heuristic_playouts_per_sec"] = nh / ms * 1e3
+    # BASELINE config 0: the reference's micro-benchmark protocol (benchmarks/benchmark_move_generation.py:136-224) --
+    # its five seeded states, side to move, mean milliseconds of single-board get_legal_moves calls through the
+    # drop-in object API (one upload, one kernel, one download, Python Move objects); reference: 2.36-8.01 ms
+    try:
+        import json as _json
+
+        from reinforcementlearning_blokus_b200 import Board, LegalMoveGenerator
+        from reinforcementlearning_blokus_b200.state import STATE_DTYPE
+
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "kat1_states.json")) as f:
+            kat = _json.load(f)
+        gen, per_state = LegalMoveGenerator(), []
+        for k in kat:
+            board = Board.from_packed(np.frombuffer(bytes.fromhex(k["packed_hex"]), dtype=STATE_DTYPE)[0])
+            gen.get_legal_moves(board, board.current_player)
+            t0 = time.perf_counter()
+            for _ in range(50):
+                gen.get_legal_moves(board, board.current_player)
+            per_state.append(round((time.perf_counter() - t0) / 50 * 1e3, 4))
+        ex["movegen_single_board_ms_kat1"] = per_state
+    except FileNotFoundError:
+        pass
     # win-probability snapshot rows (row N4): 4 x 34 float64 per board = four piece-count generations + a flood fill;
     # and a whole dataset pass: replay recorded games, capture 8 checkpoints each
     sub = corpus[: 1 << 18]
