@@ -32,20 +32,30 @@ class _Ctx:
         self.d_state = torch.empty((1, STATE_BYTES), dtype=torch.uint8, device=d)
         self.d_player = torch.empty(1, dtype=torch.uint8, device=d)
         self.h_player = torch.empty(1, dtype=torch.uint8).pin_memory()
-        self.d_counts = torch.empty(1, dtype=torch.int32, device=d)
-        self.d_ids = torch.empty((1, MAX_MOVES), dtype=torch.uint16, device=d)
-        self.h_counts = torch.empty(1, dtype=torch.int32).pin_memory()
-        self.h_ids = torch.empty((1, MAX_MOVES), dtype=torch.uint16).pin_memory()
+        # move list and its length in ONE device buffer (ids, then the int32 count) so that one copy brings both back
+        self.d_list = torch.empty(MAX_MOVES * 2 + 8, dtype=torch.uint8, device=d)
+        self.h_list = torch.empty(MAX_MOVES * 2 + 8, dtype=torch.uint8).pin_memory()
+        self.d_ids = self.d_list[: MAX_MOVES * 2].view(torch.uint16).view(1, MAX_MOVES)
+        self.d_counts = self.d_list[MAX_MOVES * 2: MAX_MOVES * 2 + 4].view(torch.int32)
+        self.h_ids_np = self.h_list.numpy()[: MAX_MOVES * 2].view(np.uint16)
+        self.h_count_np = self.h_list.numpy()[MAX_MOVES * 2: MAX_MOVES * 2 + 4].view(np.int32)
+        self.h_state_np = self.h_state.numpy()
         self.h_mask = torch.empty((1, 7), dtype=torch.int64).pin_memory()
         self.d_mask = torch.empty((1, 7), dtype=torch.int64, device=d)
         self.h_move = torch.empty(1, dtype=torch.uint16).pin_memory()
         self.d_move = torch.empty(1, dtype=torch.uint16, device=d)
 
     def upload(self, state_np, player: int) -> None:
-        self.h_state.numpy()[0] = np.frombuffer(np.asarray(state_np).tobytes(), dtype=np.uint8)
+        self.h_state_np[0] = np.frombuffer(np.asarray(state_np).tobytes(), dtype=np.uint8)
         self.h_player[0] = player
         self.d_state.copy_(self.h_state, non_blocking=True)
         self.d_player.copy_(self.h_player, non_blocking=True)
+
+    def upload_as_mover(self, state_np, player: int) -> None:
+        """One copy: the player rides in the state's side-to-move byte (the kernels default to it)."""
+        self.h_state_np[0] = np.frombuffer(np.asarray(state_np).tobytes(), dtype=np.uint8)
+        self.h_state_np[0, 240] = player
+        self.d_state.copy_(self.h_state, non_blocking=True)
 
 
 def _get() -> _Ctx:
@@ -59,15 +69,14 @@ def legal_move_ids(state_np, player: int) -> np.ndarray:
     """Ascending move ids of one packed state for `player` (0..3): one upload, one kernel, one download."""
     with _lock:
         c = _get()
-        c.upload(state_np, player)
-        dev.movegen_fixed(c.d_state, MAX_MOVES, c.d_player, out=(c.d_counts, c.d_ids))
-        c.h_counts.copy_(c.d_counts, non_blocking=True)
-        c.h_ids.copy_(c.d_ids, non_blocking=True)        # 8 KB: cheaper than a second round trip for the exact length
+        c.upload_as_mover(state_np, player)
+        dev.movegen_fixed(c.d_state, MAX_MOVES, None, out=(c.d_counts, c.d_ids))
+        c.h_list.copy_(c.d_list, non_blocking=True)       # 8 KB: cheaper than a second round trip for the exact length
         torch.cuda.current_stream().synchronize()
-        n = int(c.h_counts[0])
+        n = int(c.h_count_np[0])
         if n > MAX_MOVES:
             raise dev._lib.BlokusB200Error(f"{n} legal moves exceed the single-state buffer ({MAX_MOVES})")
-        return c.h_ids.numpy()[0, :n].copy()
+        return c.h_ids_np[:n].copy()
 
 
 def count_moves(state_np, player: int) -> int:
