@@ -42,7 +42,12 @@ class BlokusGame:
         """False for an illegal move (board untouched), True after applying a legal one."""
         if player is None:
             player = self.board.current_player
-        if not self.move_generator.is_move_legal(self.board, player, move):
+        # one device launch: legality of the move and, after it, who can still move (engine/game.py:79-90, 182-214)
+        move_id = move.to_id()            # None for bad piece / orientation indices and off-board anchors
+        if move_id is None or move.piece_id in self.board.player_pieces_used[player]:
+            return False
+        ok, alive = single.step_check(self.board.to_packed(), player.value - 1, move_id)
+        if not ok:
             return False
         cells = self.move_generator.piece_position_cache[move.piece_id][move.orientation]
         positions = [Position(move.anchor_row + r, move.anchor_col + c) for r, c in cells]
@@ -56,15 +61,19 @@ class BlokusGame:
                        "anchor_row": move.anchor_row, "anchor_col": move.anchor_col},
             "board_state": self.board.grid.tolist(),
         })
-        self._check_game_over()
+        if alive == 0:
+            self._set_game_over()
         return True
 
     def _check_game_over(self) -> None:
         """Game over iff no player has a legal move: one has-moves launch for all four players."""
         if single.has_moves_mask(self.board.to_packed()) == 0:
-            self.board.game_over = True
-            result = self.get_game_result()
-            self.winner = None if result.is_tie else Player(result.winner_ids[0])
+            self._set_game_over()
+
+    def _set_game_over(self) -> None:
+        self.board.game_over = True
+        result = self.get_game_result()
+        self.winner = None if result.is_tie else Player(result.winner_ids[0])
 
     # ---- results ------------------------------------------------------------------------------------------
     def _scores(self) -> List[int]:

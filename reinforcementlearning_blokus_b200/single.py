@@ -105,6 +105,21 @@ def is_legal(state_np, player: int, move_id: int) -> bool:
         return bool(dev.is_move_legal(c.d_state, c.d_move, c.d_player).item())
 
 
+def step_check(state_np, player: int, move_id: int) -> Tuple[bool, int]:
+    """BlokusGame.make_move's device work in ONE launch (bk_step): is the move legal for `player`, and -- after placing
+    it -- which players still have a move (bit p; 0 = game over, engine/game.py:182-214).  (False, 0) for ids out of range."""
+    if not 0 <= int(move_id) < 0xFFFF:
+        return False, 0
+    with _lock:
+        c = _get()
+        c.upload_as_mover(state_np, player)
+        c.h_move[0] = int(move_id)
+        c.d_move.copy_(c.h_move, non_blocking=True)
+        ok, alive = dev.step(c.d_state, c.d_move, None, want_alive=True)
+        both = torch.stack([ok[0], alive[0]]).cpu()
+        return bool(both[0]), int(both[1])
+
+
 def can_place(state_np, player: int, cell_mask: int) -> bool:
     with _lock:
         c = _get()
