@@ -15,6 +15,7 @@ from the exact sets (plus the start corner before the first move), like a board 
 
 from __future__ import annotations
 
+import struct
 from dataclasses import dataclass
 from enum import Enum
 from typing import Dict, Iterable, List, Optional, Set, Tuple
@@ -24,6 +25,8 @@ import numpy as np
 from .state import STATE_DTYPE
 
 SIZE = 20
+_META = struct.Struct("<4IBBH")        # used[4], to_move, first_mask, move_count of bk_state
+_PAD = bytes(12)
 _FULL = (1 << 400) - 1
 _COL0 = sum(1 << (r * SIZE) for r in range(SIZE))
 _COL19 = _COL0 << (SIZE - 1)
@@ -96,22 +99,21 @@ class Board:
 
     # ---- packed state --------------------------------------------------------------------------
     def to_packed(self) -> np.ndarray:
-        """This board as one ``bk_state`` record (numpy scalar of STATE_DTYPE)."""
-        s = np.zeros((), dtype=STATE_DTYPE)
-        mask = 0
+        """This board as one ``bk_state`` record (numpy scalar of STATE_DTYPE), assembled as raw bytes."""
+        used, mask = [0, 0, 0, 0], 0
         for k, p in enumerate(_PLAYERS):
-            s["bits"][k] = np.frombuffer(int(self.player_bits[p]).to_bytes(56, "little"), dtype="<u8")
-            used = 0
+            u = 0
             for pid in self.player_pieces_used[p]:
                 if 1 <= pid <= 21:
-                    used |= 1 << (pid - 1)
-            s["used"][k] = used
+                    u |= 1 << (pid - 1)
+            used[k] = u
             if self.player_first_move[p]:
                 mask |= 1 << k
-        s["first_mask"] = mask
-        s["to_move"] = self.current_player.value - 1
-        s["move_count"] = self.move_count & 0xFFFF
-        return s
+        bits = self.player_bits
+        buf = bytearray(b"".join(int(bits[p]).to_bytes(56, "little") for p in _PLAYERS))
+        buf += _META.pack(used[0], used[1], used[2], used[3], self.current_player.value - 1, mask, self.move_count & 0xFFFF)
+        buf += _PAD
+        return np.frombuffer(buf, dtype=STATE_DTYPE)[0]
 
     @classmethod
     def from_packed(cls, state) -> "Board":
