@@ -219,6 +219,12 @@ typedef struct bk_mcts_params {
                                    2: no rollout, every leaf is worth the constant 0.5 of the reference's dummy learned
                                       evaluator (mcts_agent.py:427-451, learned_evaluator.py:51-55); rewards are then
                                       counted in halves (root_reward = number of halves) */
+    int32_t  leaf_batch;        /* 1 (or 0): one rollout per iteration, one warp per tree -- the reference's search.
+                                   2..16: leaf-batched rollouts -- a CTA of that many warps owns the tree; after each
+                                   selection/expansion every warp rolls out from the new leaf with its own random stream
+                                   and the rewards are backed up together (visits += leaf_batch).  Not combinable with a
+                                   transposition table. */
+    int32_t  reserved0;
     double   exploration;       /* 1.414 */
     uint64_t seed;
     uint64_t tree_offset;       /* global index of tree 0 (root-parallel sharding across GPUs) */

@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
         L.orc_tt_size.argtypes = [vp]
         L.orc_tt_size.restype = u64
         L.orc_mcts_search.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, vp, vp]
+        L.orc_mcts_search_batched.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, i32, vp, vp, vp]
         L.orc_check_moves_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp]
         L.orc_check_playouts.argtypes = [u64, u64, i32, i32, i32, vp, vp, vp]
         L.orc_num_snapshot_features.restype = i32
@@ -310,16 +311,16 @@ class OracleTT:
 
 def mcts_search(root: np.ndarray, iterations: int, seed: int, tree_id: int = 0, max_rollout_moves: int = 50,
                 max_depth: int = 0, ucb_variant: int = 0, reward_mode: int = 0, rollout_policy: int = 0, exploration: float = 1.414, tt: Optional[OracleTT] = None,
-                zobrist: Optional[np.ndarray] = None, max_root_moves: int = 2048):
+                zobrist: Optional[np.ndarray] = None, max_root_moves: int = 2048, leaf_batch: int = 1):
     """Sequential UCT with canonical untried order and Philox rollouts; returns dict(n_root, visits, reward, moves)."""
     st = np.ascontiguousarray(np.atleast_1d(root), dtype=STATE_DTYPE)
     vis = np.zeros(max_root_moves, dtype=np.int32)
     rew = np.zeros(max_root_moves, dtype=np.int64)
     mov = np.zeros(max_root_moves, dtype=np.uint16)
     zt = None if zobrist is None else np.ascontiguousarray(zobrist, dtype=np.uint64)
-    n = lib().orc_mcts_search(_ptr(st), int(iterations), int(max_rollout_moves), int(max_depth), int(ucb_variant),
-                              int(reward_mode), int(rollout_policy), float(exploration), int(seed), int(tree_id), tt.h if tt else None, _ptr(zt),
-                              int(max_root_moves), _ptr(vis), _ptr(rew), _ptr(mov))
+    n = lib().orc_mcts_search_batched(_ptr(st), int(iterations), int(max_rollout_moves), int(max_depth), int(ucb_variant),
+                                      int(reward_mode), int(rollout_policy), float(exploration), int(seed), int(tree_id),
+                                      tt.h if tt else None, _ptr(zt), int(max_root_moves), int(leaf_batch), _ptr(vis), _ptr(rew), _ptr(mov))
     return {"n_root": int(n), "visits": vis, "reward": rew, "moves": mov}
 
 

@@ -66,7 +66,8 @@ class MctsParams(C.Structure):
     _fields_ = [
         ("iterations", C.c_int32), ("iterations_total", C.c_int32), ("max_rollout_moves", C.c_int32),
         ("rollout_policy", C.c_int32), ("max_depth", C.c_int32), ("ucb_variant", C.c_int32),
-        ("resume", C.c_int32), ("reward_mode", C.c_int32), ("exploration", C.c_double),
+        ("resume", C.c_int32), ("reward_mode", C.c_int32), ("leaf_batch", C.c_int32), ("reserved0", C.c_int32),
+        ("exploration", C.c_double),
         ("seed", C.c_uint64), ("tree_offset", C.c_uint64),
     ]
 

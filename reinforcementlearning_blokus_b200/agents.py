@@ -135,7 +135,7 @@ class FastMCTSAgent:
 
     def __init__(self, iterations: int = 30, time_limit: float = 0.5, exploration_constant: float = 1.414,
                  seed: Optional[int] = None, enable_diagnostics: bool = False, diagnostics_sample_interval: int = 100,
-                 rollout_plies: int = 50):
+                 rollout_plies: int = 50, leaf_batch: int = 1):
         self.iterations = iterations
         self.time_limit = time_limit
         self.exploration_constant = exploration_constant
@@ -144,6 +144,9 @@ class FastMCTSAgent:
         self.enable_diagnostics = enable_diagnostics
         self.diagnostics_sample_interval = max(1, int(diagnostics_sample_interval))
         self.rollout_plies = int(rollout_plies)
+        # GPU-batched leaf rollouts: `leaf_batch` warps roll out from every selected child at once (1 = the reference's
+        # one simulation per iteration); `iterations` stays the budget in SIMULATIONS
+        self.leaf_batch = max(1, min(16, int(leaf_batch)))
         self._thinks = 0
 
     def select_action(self, board: Board, player: Player, legal_moves: List[Move]) -> Optional[Move]:
@@ -167,17 +170,19 @@ class FastMCTSAgent:
                                          "nodesEvaluated": 1, "maxDepthReached": 1,
                                          "topMoves": [dict(self._move_dict(m, 1, 0.0), q_value=0.0)]}}
         ordered = sorted(legal_moves, key=lambda m: m.to_id())      # rank <-> move (ascending id)
-        total = max(1, int(self.iterations))
+        W = self.leaf_batch
+        total = max(1, -(-int(self.iterations) // W))            # device iterations of W simulations each
         eng = DeviceUCT(total, n_trees=1, max_rollout_moves=self.rollout_plies, max_depth=1, ucb_variant=1,
                         exploration=self.exploration_constant, seed=self.seed, tree_offset=self._thinks,
-                        reward_mode=1)
+                        reward_mode=1, leaf_batch=W)
         self._thinks += 1
         root = _root_state(board, player)
         n_root = len(ordered)
         done = 0
         trace: List[Dict[str, Any]] = []
         res = None
-        next_sample = self.diagnostics_sample_interval
+        interval = max(1, self.diagnostics_sample_interval // W)    # in device iterations
+        next_sample = interval
         while done < total and (done == 0 or time.perf_counter() - start < budget_s):
             n = min(self.CHUNK, total - done)
             if self.enable_diagnostics:
@@ -186,13 +191,13 @@ class FastMCTSAgent:
             done += n
             torch.cuda.current_stream().synchronize()
             if self.enable_diagnostics and done == next_sample:
-                next_sample += self.diagnostics_sample_interval
+                next_sample += interval
                 if done < total:
                     v = res["visits"][0, :n_root].cpu().numpy()
                     w = res["reward"][0, :n_root].cpu().numpy()
                     b = int(np.argmax(v))
                     bm = ordered[b]
-                    trace.append({"sim": done,
+                    trace.append({"sim": done * W,
                                   "bestActionId": f"{bm.piece_id}-{bm.orientation}-{bm.anchor_row}-{bm.anchor_col}",
                                   "bestQMean": float(w[b] / v[b]) if v[b] > 0 else 0.0,
                                   "entropy": float(compute_policy_entropy([int(x) for x in v if x > 0]))})
@@ -206,6 +211,7 @@ class FastMCTSAgent:
         cand.sort(key=lambda x: x["visits"], reverse=True)
         top_moves = cand[:10]
         spent_ms = int((time.perf_counter() - start) * 1000)
+        done *= W                                                  # from here on: simulations
         if done < 5:        # fast_mcts_agent.py:179-191: too few simulations -> quick heuristic pick
             pick = sorted(sorted(legal_moves, key=lambda m: m.piece_id, reverse=True)[:3],
                           key=lambda m: abs(m.anchor_row - 9.5) + abs(m.anchor_col - 9.5))[0]

@@ -711,6 +711,8 @@ static cudaError_t bk_init_policies_impl() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_playout<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_HEUR_PLAYOUT_SMEM);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_mcts<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MCTS_MAX_WARPS * HEUR_SMEM_PER_WARP);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_mcts<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEUR_SMEM_PER_WARP);
     if (e != cudaSuccess) return e;
     k_init_heuristic_tables<<<(91 * 400 + 255) / 256, 256>>>();
@@ -976,16 +978,32 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
     if ((int64_t)L.total * n_trees > workspace_bytes) return fail(BK_ERR_CAPACITY, "%s", "bk_mcts_search: workspace too small");
     MctsTT t; t.keys = nullptr; t.rewards = nullptr; t.occupied = nullptr; t.log2_slots = 0; t.zobrist = zobrist_table;
     if (tt) { t.keys = tt->keys; t.rewards = tt->rewards; t.occupied = tt->occupied; t.log2_slots = tt->log2_slots; }
-    const int cap = g_sms * (params->rollout_policy == BK_POLICY_HEURISTIC ? BK_MCTS_HEUR_CTAS_PER_SM : BK_MCTS_CTAS_PER_SM);
-    const int grid = n_trees < cap ? n_trees : cap;
-    if (params->rollout_policy == BK_POLICY_HEURISTIC)
-        k_mcts<1><<<grid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, as_stream(stream)>>>(fresh_ticket(as_stream(stream)), roots, n_roots, n_trees, *params, t,
-            reinterpret_cast<unsigned char*>(workspace), params->resume, max_root_moves, root_visits,
-            reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status);
-    else
-        k_mcts<0><<<grid, BK_MCTS_THREADS, 0, as_stream(stream)>>>(fresh_ticket(as_stream(stream)), roots, n_roots, n_trees, *params, t,
-            reinterpret_cast<unsigned char*>(workspace), params->resume, max_root_moves, root_visits,
-            reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status);
+    const bool heur = params->rollout_policy == BK_POLICY_HEURISTIC;
+    const int W = params->leaf_batch > 1 ? params->leaf_batch : 1;
+    REQUIRE(W <= BK_MCTS_MAX_WARPS, "bk_mcts_search: leaf_batch must be in [0, 16]");
+    REQUIRE(W == 1 || !tt, "bk_mcts_search: leaf-batched rollouts cannot use a transposition table");
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    long long* rr = reinterpret_cast<long long*>(root_reward);
+    cudaStream_t st = as_stream(stream);
+    if (W == 1) {
+        const int cap = g_sms * (heur ? BK_MCTS_HEUR_CTAS_PER_SM : BK_MCTS_CTAS_PER_SM);
+        const int grid = n_trees < cap ? n_trees : cap;
+        if (heur)
+            k_mcts<1, false><<<grid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+                ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
+        else
+            k_mcts<0, false><<<grid, BK_MCTS_THREADS, 0, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+                ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
+    } else {
+        const int cap = g_sms * ((heur ? 16 : 24) / W);                       // CTAs of W warps: 16-24 warps per SM
+        const int grid = n_trees < cap ? n_trees : cap;
+        if (heur)
+            k_mcts<1, true><<<grid, 32 * W, W * HEUR_SMEM_PER_WARP, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+                ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
+        else
+            k_mcts<0, true><<<grid, 32 * W, 0, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+                ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
+    }
     LAUNCH_CHECK();
     return BK_OK;
 }

@@ -45,26 +45,31 @@ __host__ __device__ inline MctsLayout mcts_layout(int iterations_total) {
     L.off_n_expanded = o;  o += (size_t)L.max_nodes * 2;
     L.off_move = o;        o += (size_t)L.max_nodes * 2;
     o = bk_align_up(o, 8);
-    L.off_header = o;      o += 64;
+    L.off_header = o;      o += 128;
     L.total = bk_align_up(o, 256);
     return L;
 }
 
-struct MctsHeader {            // persistent between launches of the same search (resume)
+#define BK_MCTS_MAX_WARPS 16     /* leaf-batched rollouts: warps per tree */
+struct MctsHeader {            // persistent between launches of the same search (resume); 92 of the slot's 128 bytes
     uint32_t n_nodes, pool_used, iterations_done, draws, overflow, root_children, root_player;
     int32_t root_score;
+    uint32_t draws_x[BK_MCTS_MAX_WARPS - 1];   // draw counters of warps 1..15 (leaf-batched rollouts)
 };
+
+static_assert(sizeof(MctsHeader) <= 128, "MctsHeader must fit its workspace slot");
 
 struct MctsTT {                // optional transposition table (mcts/zobrist.py:155-220); keys == nullptr: off
     unsigned long long* keys; double* rewards; unsigned long long* occupied; uint32_t log2_slots;
     const uint64_t* zobrist;   // 2088-entry table, reference order
 };
 
-// One-warp CTAs: the group slots are this function's own static shared array (a pointer parameter would hide the
+// The group slots (one row per warp of the CTA) are this function's own static shared array (a pointer parameter would hide the
 // address space and turn the sink's STS into generic stores).
+template <int NW>
 __device__ __noinline__ Totals gen_totals(uint32_t A, uint32_t C, uint32_t used, int lane) {
-    __shared__ __align__(16) uint32_t slots[BK_GROUP_SLOTS];
-    GroupSink sink; sink.begin(slots, lane);
+    __shared__ __align__(16) uint32_t slots[NW][BK_GROUP_SLOTS];
+    GroupSink sink; sink.begin(slots[threadIdx.x >> 5], lane);
     bk_gen_all<GroupSink, true>(A, C, used, sink);
     return reduce_totals(sink, lane);
 }
@@ -84,22 +89,44 @@ __device__ __forceinline__ int32_t board_score_of(const WarpState& s, uint32_t q
 #define BK_MCTS_HEUR_CTAS_PER_SM 14
 #endif
 
-template <int POLICY>
-__global__ void __launch_bounds__(BK_MCTS_THREADS, POLICY == 0 ? BK_MCTS_CTAS_PER_SM : BK_MCTS_HEUR_CTAS_PER_SM)
+// BATCH = false: one warp per tree (CTA of 32 threads), the reference's one-rollout-per-iteration search.
+// BATCH = true : "leaf-batched rollouts" -- a CTA of W <= 16 warps owns the tree; warp 0 selects and expands exactly as
+// before, then ALL W warps roll out from the new leaf with their own Philox streams (stream 1 + w of the tree) and the
+// W rewards are backed up together (visits += W).  One tree then advances ~W simulations per iteration latency, which
+// is what a single agent move needs (BASELINE config 4); W = 1 is bit-identical to BATCH = false.
+template <int POLICY, bool BATCH = false>
+__global__ void __launch_bounds__(BATCH ? 32 * BK_MCTS_MAX_WARPS : BK_MCTS_THREADS,
+                                  BATCH ? 1 : (POLICY == 0 ? BK_MCTS_CTAS_PER_SM : BK_MCTS_HEUR_CTAS_PER_SM))
 k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_params prm, MctsTT tt,
        unsigned char* __restrict__ workspace, int resume, int max_root_moves,
        int32_t* __restrict__ out_visits, long long* __restrict__ out_reward, uint32_t* __restrict__ out_counts,
        uint16_t* __restrict__ out_moves, uint32_t* __restrict__ out_status) {
-    extern __shared__ __align__(16) unsigned char heur_smem[];    // HEUR_SMEM_PER_WARP bytes when rollout_policy == 1
-    const uint32_t hs = 0;                                        // one warp per CTA: its heuristic scratch starts at 0
+    extern __shared__ __align__(16) unsigned char heur_smem[];    // HEUR_SMEM_PER_WARP bytes per warp when rollout_policy == 1
+    __shared__ int sh_tree;
+    __shared__ uint32_t sh_node, sh_stop, sh_root_player;
+    __shared__ int32_t sh_root_score;
+    __shared__ long long sh_r[BK_MCTS_MAX_WARPS];
     const int lane = threadIdx.x & 31;
+    const int wib = BATCH ? (int)(threadIdx.x >> 5) : 0;          // warp in block; warp 0 leads the tree
+    const int W = BATCH ? (int)(blockDim.x >> 5) : 1;
+    const bool lead = wib == 0;
+    const uint32_t hs = (uint32_t)wib * HEUR_SMEM_PER_WARP;       // this warp's heuristic scratch
     const MctsLayout L = mcts_layout(prm.iterations_total);
-    // trees differ in cost (rollout lengths, tree depth): warps take the next tree from a per-launch ticket counter so
-    // that a batch larger than the resident warps has no idle tail; a tree's result depends on (seed, tree id) only
+    // trees differ in cost (rollout lengths, tree depth): the next tree comes from a per-launch ticket counter so that
+    // a batch larger than the resident CTAs has no idle tail; a tree's result depends on (seed, tree id) only
     for (;;) {
-        uint32_t t0 = 0;
-        if (lane == 0) t0 = atomicAdd(ticket, 1u);
-        const int tree = (int)uni(t0);
+        int tree;
+        {
+            uint32_t t0 = 0;
+            if (lead && lane == 0) t0 = atomicAdd(ticket, 1u);
+            tree = (int)uni(t0);
+            if (BATCH) {
+                if (lead && lane == 0) sh_tree = tree;
+                __syncthreads();
+                tree = sh_tree;
+                __syncthreads();
+            }
+        }
         if (tree >= n_trees) break;
         unsigned char* base = workspace + (size_t)tree * L.total;
         bk_state* states = reinterpret_cast<bk_state*>(base + L.off_states);
@@ -117,37 +144,48 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
         // result of a tree depends on (seed, tree id) only
         const uint64_t salt = tree_id * 0xD6E8FEB86659FD93ull;
 
-        uint32_t n_nodes, pool_used, iter_done, draws, overflow = 0, root_player;
-        int32_t root_score;
+        uint32_t n_nodes = 0, pool_used = 0, iter_done = 0, draws = 0, overflow = 0, root_player = 0;
+        int32_t root_score = 0;
         WarpState s;
-        if (!resume) {
-            load_state(roots + (tree % n_roots), lane, s);
-            uint32_t A, C; make_masks(s, s.to_move, lane, A, C);
-            const Totals t0 = gen_totals(A, C, sel4(s.used, s.to_move), lane);
-            store_state(states + 0, lane, s);
-            if (lane == 0) {
-                parent[0] = -1; visits[0] = 0; reward[0] = 0; child_base[0] = 0xFFFFFFFFu;
-                n_legal[0] = (uint16_t)t0.n; n_expanded[0] = 0; move_of[0] = 0xFFFF;
+        if (lead) {
+            if (!resume) {
+                load_state(roots + (tree % n_roots), lane, s);
+                uint32_t A, C; make_masks(s, s.to_move, lane, A, C);
+                const Totals t0 = gen_totals<BATCH ? BK_MCTS_MAX_WARPS : 1>(A, C, sel4(s.used, s.to_move), lane);
+                store_state(states + 0, lane, s);
+                if (lane == 0) {
+                    parent[0] = -1; visits[0] = 0; reward[0] = 0; child_base[0] = 0xFFFFFFFFu;
+                    n_legal[0] = (uint16_t)t0.n; n_expanded[0] = 0; move_of[0] = 0xFFFF;
+                }
+                n_nodes = 1; pool_used = 0; iter_done = 0; draws = 0;
+                root_player = s.to_move; root_score = board_score_of(s, s.to_move);
+                __syncwarp();
+            } else {
+                n_nodes = hdr->n_nodes; pool_used = hdr->pool_used; iter_done = hdr->iterations_done;
+                draws = hdr->draws; overflow = hdr->overflow; root_player = hdr->root_player; root_score = hdr->root_score;
             }
-            n_nodes = 1; pool_used = 0; iter_done = 0; draws = 0;
-            root_player = s.to_move; root_score = board_score_of(s, s.to_move);
-            __syncwarp();
-        } else {
-            n_nodes = hdr->n_nodes; pool_used = hdr->pool_used; iter_done = hdr->iterations_done;
-            draws = hdr->draws; overflow = hdr->overflow; root_player = hdr->root_player; root_score = hdr->root_score;
+            if (BATCH && lane == 0) { sh_root_player = root_player; sh_root_score = root_score; }
+        } else if (resume) {
+            draws = hdr->draws_x[wib - 1];
+        }
+        if (BATCH) {
+            __syncthreads();
+            root_player = sh_root_player; root_score = sh_root_score;
         }
 
-        // rollout draws: 4 per Philox block (draw t = word t%4 of block t/4 of stream 1); the block is kept in
-        // registers and recomputed when the draw counter enters the next one
-        PhiloxBlock blk = philox_block(prm.seed, tree_id, draws >> 2, 1);
+        // rollout draws: 4 per Philox block (draw t = word t%4 of block t/4 of this warp's stream 1 + w); the block is
+        // kept in registers and recomputed when the draw counter enters the next one
+        const uint32_t stream = 1u + (uint32_t)wib;
+        PhiloxBlock blk = philox_block(prm.seed, tree_id, draws >> 2, stream);
         uint32_t blk_of = draws >> 2;
         auto next_draw = [&]() -> uint32_t {
-            if ((draws >> 2) != blk_of) { blk_of = draws >> 2; blk = philox_block(prm.seed, tree_id, blk_of, 1); }
+            if ((draws >> 2) != blk_of) { blk_of = draws >> 2; blk = philox_block(prm.seed, tree_id, blk_of, stream); }
             return philox_word(blk, draws++);
         };
-        for (int it = 0; it < prm.iterations && !overflow; it++, iter_done++) {
-            // ---- selection (mcts_agent.py:384-406)
+        for (int it = 0; it < prm.iterations; it++) {
             uint32_t node = 0, depth = 0;
+            if (lead && !overflow) {
+            // ---- selection (mcts_agent.py:384-406)
             while (true) {
                 const uint32_t nl = n_legal[node], ne = n_expanded[node];
                 const bool may_expand = ne < nl && (prm.max_depth <= 0 || (int)depth < prm.max_depth);
@@ -183,12 +221,12 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                 if (ne < nl && (prm.max_depth <= 0 || (int)depth < prm.max_depth)) {
                     const uint32_t p = s.to_move;
                     uint32_t A, C; make_masks(s, p, lane, A, C);
-                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane);
+                    const Totals tot = gen_totals<BATCH ? BK_MCTS_MAX_WARPS : 1>(A, C, sel4(s.used, p), lane);
                     int o, row, col;
                     const uint32_t id = select_move(tot, nl - 1 - ne, A, C, lane, o, row, col);
                     place_move(s, p, o, row, col, lane);
                     uint32_t A2, C2; make_masks(s, s.to_move, lane, A2, C2);
-                    const Totals tc = gen_totals(A2, C2, sel4(s.used, s.to_move), lane);
+                    const Totals tc = gen_totals<BATCH ? BK_MCTS_MAX_WARPS : 1>(A2, C2, sel4(s.used, s.to_move), lane);
                     uint32_t cb = child_base[node];
                     if (cb == 0xFFFFFFFFu) {
                         const uint32_t remaining = (uint32_t)prm.iterations_total - iter_done;
@@ -198,27 +236,36 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                         pool_used += want;
                     }
                     if (n_nodes >= L.max_nodes) overflow = 1;
-                    if (overflow) break;
-                    const uint32_t child = n_nodes++;
-                    store_state(states + child, lane, s);
-                    if (lane == 0) {
-                        child_base[node] = cb;
-                        pool[cb + ne] = child;
-                        n_expanded[node] = (uint16_t)(ne + 1);
-                        parent[child] = (int32_t)node; visits[child] = 0; reward[child] = 0;
-                        child_base[child] = 0xFFFFFFFFu; n_legal[child] = (uint16_t)tc.n; n_expanded[child] = 0;
-                        move_of[child] = (uint16_t)id;
+                    if (!overflow) {
+                        const uint32_t child = n_nodes++;
+                        store_state(states + child, lane, s);
+                        if (lane == 0) {
+                            child_base[node] = cb;
+                            pool[cb + ne] = child;
+                            n_expanded[node] = (uint16_t)(ne + 1);
+                            parent[child] = (int32_t)node; visits[child] = 0; reward[child] = 0;
+                            child_base[child] = 0xFFFFFFFFu; n_legal[child] = (uint16_t)tc.n; n_expanded[child] = 0;
+                            move_of[child] = (uint16_t)id;
+                        }
+                        node = child;
+                        depth++;
+                        __syncwarp();
                     }
-                    node = child;
-                    depth++;
-                    __syncwarp();
                 }
             }
+            }   // lead && !overflow
+            if (BATCH) {
+                if (lead && lane == 0) { sh_node = node; sh_stop = overflow; }
+                __syncthreads();                    // the leaf's state (global) and its index are visible to all warps
+                overflow = sh_stop; node = sh_node;
+                if (!lead && !overflow) load_state(states + node, lane, s);
+            }
+            if (overflow) break;
             // ---- simulation (mcts_agent.py:408-437); `s` holds the state of `node`
             long long r = 0;
             bool cached = false;
             uint64_t key = 0;
-            if (tt.keys) {
+            if (!BATCH && tt.keys) {
                 key = zobrist_of(s, tt.zobrist, lane) ^ salt;
                 double rv = 0.0;
                 if (tt_lookup(tt.keys, tt.rewards, tt.log2_slots, key, rv)) { r = (long long)rv; cached = true; }
@@ -227,7 +274,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                 // learned leaf evaluation in place of the rollout (mcts_agent.py:427-451) with the reference's dummy
                 // artifact (learned_evaluator.py:51-55,129-131): every leaf is worth 0.5, counted here as one half
                 r = 1;
-                if (tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, (double)r);
+                if (!BATCH && tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, (double)r);
             } else if (!cached) {
                 const uint32_t me = prm.reward_mode ? root_player : s.to_move;      // node.player (mcts_agent.py:483)
                 const int32_t before = prm.reward_mode ? root_score : board_score_of(s, me);
@@ -244,7 +291,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                         continue;
                     }
                     uint32_t A, C; make_masks(s, p, lane, A, C);
-                    const Totals tot = gen_totals(A, C, sel4(s.used, p), lane);
+                    const Totals tot = gen_totals<BATCH ? BK_MCTS_MAX_WARPS : 1>(A, C, sel4(s.used, p), lane);
                     if (tot.n == 0) break;                       // no passes inside a rollout (:488-489)
                     const uint32_t rnd = next_draw();
                     int o, row, col;
@@ -252,16 +299,23 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                     place_move(s, p, o, row, col, lane);
                 }
                 r = (long long)(board_score_of(s, me) - before);
-                if (tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, (double)r);
+                if (!BATCH && tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, (double)r);
             }
-            // ---- back-propagation (mcts_agent.py:572-582)
-            if (lane == 0) {
-                for (int32_t v = (int32_t)node; v >= 0; v = parent[v]) { visits[v] += 1; reward[v] += r; }
+            if (BATCH) {
+                if (lane == 0) sh_r[wib] = r;
+                __syncthreads();
+                if (lead) { r = 0; for (int w = 0; w < W; w++) r += sh_r[w]; }
             }
+            // ---- back-propagation (mcts_agent.py:572-582): W simulations at once in batch mode
+            if (lead && lane == 0) {
+                for (int32_t v = (int32_t)node; v >= 0; v = parent[v]) { visits[v] += W; reward[v] += r; }
+            }
+            if (lead) iter_done++;
             __syncwarp();
         }
 
-        if (lane == 0) {
+        if (!lead && lane == 0) hdr->draws_x[wib - 1] = draws;
+        if (lead && lane == 0) {
             hdr->n_nodes = n_nodes; hdr->pool_used = pool_used; hdr->iterations_done = iter_done;
             hdr->draws = draws; hdr->overflow = overflow; hdr->root_children = n_expanded[0];
             hdr->root_player = root_player; hdr->root_score = root_score;
@@ -270,17 +324,20 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
         }
         __syncwarp();
         // ---- root statistics by ascending legal-move rank (child k of the root is rank n_legal-1-k)
-        const uint32_t nl0 = n_legal[0], ne0 = n_expanded[0], cb0 = child_base[0];
-        for (uint32_t rank = lane; rank < (uint32_t)max_root_moves; rank += 32) {
-            int32_t v = 0; long long w = 0; uint16_t m = 0xFFFF;
-            if (rank < nl0) {
-                const uint32_t k = nl0 - 1 - rank;
-                if (k < ne0) { const uint32_t ch = pool[cb0 + k]; v = visits[ch]; w = reward[ch]; m = move_of[ch]; }
+        if (lead) {
+            const uint32_t nl0 = n_legal[0], ne0 = n_expanded[0], cb0 = child_base[0];
+            for (uint32_t rank = lane; rank < (uint32_t)max_root_moves; rank += 32) {
+                int32_t v = 0; long long w = 0; uint16_t m = 0xFFFF;
+                if (rank < nl0) {
+                    const uint32_t k = nl0 - 1 - rank;
+                    if (k < ne0) { const uint32_t ch = pool[cb0 + k]; v = visits[ch]; w = reward[ch]; m = move_of[ch]; }
+                }
+                const size_t oi = (size_t)tree * max_root_moves + rank;
+                if (out_visits) out_visits[oi] = v;
+                if (out_reward) out_reward[oi] = w;
+                if (out_moves) out_moves[oi] = m;
             }
-            const size_t oi = (size_t)tree * max_root_moves + rank;
-            if (out_visits) out_visits[oi] = v;
-            if (out_reward) out_reward[oi] = w;
-            if (out_moves) out_moves[oi] = m;
         }
+        if (BATCH) __syncthreads();
     }
 }

@@ -111,15 +111,21 @@ class DeviceUCT:
     def __init__(self, iterations_total: int, n_trees: int = 1, max_rollout_moves: int = 50, max_depth: int = 0,
                  ucb_variant: int = 0, exploration: float = 1.414, seed: int = 0, tree_offset: int = 0,
                  reward_mode: int = 0, rollout_policy: int = 0, tt: Optional[dev.DeviceTranspositionTable] = None, zobrist: Optional[ZobristHash] = None,
-                 max_root_moves: int = MAX_ROOT_MOVES):
+                 max_root_moves: int = MAX_ROOT_MOVES, leaf_batch: int = 1):
         if not torch.cuda.is_available():
             raise _lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
         self.lib = _lib.init(torch.cuda.current_device())
         self.p = _lib.MctsParams(iterations=0, iterations_total=int(iterations_total),
                                  max_rollout_moves=int(max_rollout_moves), rollout_policy=int(rollout_policy), max_depth=int(max_depth),
-                                 ucb_variant=int(ucb_variant), resume=0, reward_mode=int(reward_mode), exploration=float(exploration),
+                                 ucb_variant=int(ucb_variant), resume=0, reward_mode=int(reward_mode), leaf_batch=int(leaf_batch),
+                                 reserved0=0, exploration=float(exploration),
                                  seed=int(seed) & (2**64 - 1), tree_offset=int(tree_offset))
         self.n_trees = int(n_trees)
+        self.leaf_batch = max(1, int(leaf_batch))       # simulations per iteration (warps per tree)
+        if self.leaf_batch > 16:
+            raise ValueError("leaf_batch must be in [1, 16]")
+        if self.leaf_batch > 1 and tt is not None:
+            raise ValueError("leaf-batched rollouts cannot use a transposition table")
         self.max_root_moves = int(max_root_moves)
         self.tt, self.zobrist = tt, zobrist
         if tt is not None and zobrist is None:
@@ -204,7 +210,7 @@ class MCTSAgent:
                  progressive_bias_enabled: bool = False, progressive_bias_weight: float = 0.25,
                  potential_shaping_enabled: bool = False, potential_shaping_gamma: float = 1.0,
                  potential_shaping_weight: float = 1.0, potential_mode: str = "prob", max_rollout_moves: int = 50,
-                 num_trees: int = 1):
+                 num_trees: int = 1, leaf_batch: int = 1):
         if potential_mode not in {"prob", "logit"}:
             raise ValueError("potential_mode must be either 'prob' or 'logit'.")
         if int(max_rollout_moves) <= 0:
@@ -240,6 +246,11 @@ class MCTSAgent:
         self.use_transposition_table = use_transposition_table
         self.max_rollout_moves = int(max_rollout_moves)
         self.num_trees = int(num_trees)
+        # leaf-batched rollouts: every iteration rolls out `leaf_batch` times from the new leaf (1 = the reference)
+        self.leaf_batch = max(1, int(leaf_batch))
+        if self.leaf_batch > 1 and use_transposition_table:
+            raise ValueError("leaf_batch > 1 needs use_transposition_table=False (a batch of rollouts has no single "
+                             "reward to cache)")
         self.seed = 0 if seed is None else int(seed)
         self.move_generator = get_shared_generator()
         self.zobrist_hash = ZobristHash(seed=seed)
@@ -269,7 +280,7 @@ class MCTSAgent:
         self._searches += 1
         return DeviceUCT(total, n_trees=self.num_trees, max_rollout_moves=self.max_rollout_moves,
                          exploration=self.exploration_constant, seed=self.seed, tree_offset=offset,
-                         reward_mode=2 if self.leaf_evaluation_enabled else 0,
+                         reward_mode=2 if self.leaf_evaluation_enabled else 0, leaf_batch=self.leaf_batch,
                          rollout_policy=self.rollout_policy, tt=tt,
                          zobrist=self.zobrist_hash if tt is not None else None)
 

@@ -186,3 +186,42 @@ def test_learned_evaluator_options_with_dummy_artifact(golden_dir):
         MCTSAgent(leaf_evaluation_enabled=True)
     with pytest.raises(NotImplementedError):
         MCTSAgent(learned_model_path="x/dummy_model.json", potential_shaping_enabled=True, potential_shaping_gamma=0.9)
+
+
+def test_leaf_batched_rollouts_match_oracle(golden_dir):
+    """BASELINE config 4 "GPU-batched leaf rollouts": a CTA of W warps owns the tree, every iteration rolls out W times
+    from the new leaf (streams 1..W of the tree) and backs the rewards up together.  Kernel == sequential oracle for
+    W = 2, 4, 8, 16 (UCT, flat bandit, heuristic rollouts, constant leaf); W = 1 is the unbatched search; resume works."""
+    iters = 96
+    roots = _roots(golden_dir)
+    for W, kw in ((2, dict()), (4, dict(max_depth=1, ucb_variant=1, reward_mode=1)), (8, dict()), (16, dict()),
+                  (4, dict(rollout_policy=1)), (16, dict(rollout_policy=1)), (8, dict(reward_mode=2))):
+        for ri in (0, 2):
+            root = dev.to_device(np.atleast_1d(roots[ri]))
+            want = orc.mcts_search(roots[ri], iters, seed=21, tree_id=ri, leaf_batch=W, **kw)
+            res = DeviceUCT(iters, n_trees=1, seed=21, tree_offset=ri, leaf_batch=W, **kw).search(root, iters)
+            n = want["n_root"]
+            assert int(res["counts"][0]) == n and int(res["status"][0]) == 0
+            assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n]), (W, kw, ri)
+            assert np.array_equal(res["reward"][0, :n].cpu().numpy(), want["reward"][:n]), (W, kw, ri)
+            assert np.array_equal(res["moves"][0, :n].cpu().numpy(), want["moves"][:n])
+            assert int(res["visits"][0, :n].sum()) == iters * W
+    root = dev.to_device(np.atleast_1d(roots[1]))
+    plain = DeviceUCT(iters, n_trees=3, seed=5).search(root, iters)
+    one = DeviceUCT(iters, n_trees=3, seed=5, leaf_batch=1).search(root, iters)
+    assert torch.equal(plain["visits"], one["visits"]) and torch.equal(plain["reward"], one["reward"])
+    full = DeviceUCT(iters, n_trees=5, seed=6, leaf_batch=4).search(root, iters)
+    v, w = full["visits"].clone(), full["reward"].clone()
+    eng = DeviceUCT(iters, n_trees=5, seed=6, leaf_batch=4)
+    eng.search(root, 32); eng.search(None, 40, resume=True)
+    res = eng.search(None, 24, resume=True)
+    assert torch.equal(res["visits"], v) and torch.equal(res["reward"], w)
+    with pytest.raises(ValueError):
+        DeviceUCT(8, leaf_batch=4, tt=TranspositionTable(max_size=1 << 10).device, zobrist=ZobristHash(seed=1))
+    # the agent: same budget in simulations, spent 8 at a time
+    from reinforcementlearning_blokus_b200 import FastMCTSAgent
+    board = Board.from_packed(roots[1])
+    legal = get_shared_generator().get_legal_moves(board, board.current_player)
+    out = FastMCTSAgent(iterations=800, time_limit=5.0, seed=3, leaf_batch=8).think(board, board.current_player, legal, 5000)
+    assert out["move"] in legal and out["stats"]["nodesEvaluated"] == 800
+    assert sum(m["visits"] for m in out["stats"]["topMoves"]) <= 800
