@@ -446,6 +446,19 @@ def _extras(dev, torch, n):
         ex["movegen_single_board_ms_kat1"] = per_state
     except FileNotFoundError:
         pass
+    # BASELINE config 4: one agent move of ~1,000 simulations on a mid-game root (flat UCB bandit of FastMCTSAgent, 50-ply
+    # rollouts): one warp per tree vs 16-way leaf-batched rollouts (63 iterations x 16 = 1,008 simulations)
+    try:
+        from reinforcementlearning_blokus_b200.mcts import DeviceUCT
+
+        root = corpus[3 * per + 17: 3 * per + 18].contiguous()              # a 24-turn position
+        for tag, iters, wb in (("mcts_move_1000_sims_ms_one_warp", 1000, 1), ("mcts_move_1008_sims_ms_leaf_batch16", 63, 16)):
+            eng = DeviceUCT(iters, n_trees=1, max_depth=1, ucb_variant=1, reward_mode=1, seed=SEED, leaf_batch=wb)
+            eng.search(root, iters)
+            torch.cuda.synchronize()
+            ex[tag] = round(timeit(lambda: eng.search(root, iters), reps=3), 3)
+    except Exception as exc:                                                # extras never break the headline line
+        ex["mcts_move_error"] = str(exc)[:200]
     # win-probability snapshot rows (row N4): 4 x 34 float64 per board = four piece-count generations + a flood fill;
     # and a whole dataset pass: replay recorded games, capture 8 checkpoints each
     sub = corpus[: 1 << 18]
