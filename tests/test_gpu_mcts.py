@@ -225,3 +225,16 @@ def test_leaf_batched_rollouts_match_oracle(golden_dir):
     out = FastMCTSAgent(iterations=800, time_limit=5.0, seed=3, leaf_batch=8).think(board, board.current_player, legal, 5000)
     assert out["move"] in legal and out["stats"]["nodesEvaluated"] == 800
     assert sum(m["visits"] for m in out["stats"]["topMoves"]) <= 800
+
+
+def test_leaf_batched_many_trees_per_cta(golden_dir):
+    """More leaf-batched trees than resident CTAs: every CTA takes several trees from the ticket counter, and tree k of
+    the batch still equals a lone tree with tree_offset k."""
+    root = dev.to_device(np.atleast_1d(_roots(golden_dir)[2]))
+    n_trees, iters, W = 400, 12, 16
+    res = DeviceUCT(iters, n_trees=n_trees, seed=31, leaf_batch=W).search(root, iters)
+    assert int(res["status"].max()) == 0
+    assert (res["visits"].sum(dim=1) == iters * W).all()
+    for k in (0, 147, 148, 399):
+        solo = DeviceUCT(iters, n_trees=1, seed=31, tree_offset=k, leaf_batch=W).search(root, iters)
+        assert torch.equal(solo["visits"][0], res["visits"][k]) and torch.equal(solo["reward"][0], res["reward"][k])
