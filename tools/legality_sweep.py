@@ -52,4 +52,23 @@ def sweep(n_total: int, seed: int = 0xB10C05) -> dict:
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-    print(json.dumps(sweep(n)))
+    chunks = int(sys.argv[2]) if len(sys.argv) > 2 else 1          # chunks of n states, each with its own seed
+    if chunks == 1:
+        print(json.dumps(sweep(n)))
+    else:
+        tot = None
+        for c in range(chunks):
+            r = sweep(n, seed=0xB10C05 + 7919 * c)
+            torch.cuda.empty_cache()
+            if tot is None:
+                tot = dict(r, chunks=1)
+            else:
+                for k in ("states", "total_moves", "mismatches", "naive_subsample", "naive_mismatches", "terminal_states"):
+                    tot[k] += r[k]
+                tot["max_moves"] = max(tot["max_moves"], r["max_moves"])
+                tot["gpu_seconds"] = round(tot["gpu_seconds"] + r["gpu_seconds"], 3)
+                tot["oracle_seconds"] = round(tot["oracle_seconds"] + r["oracle_seconds"], 1)
+                tot["chunks"] += 1
+                if tot["first_bad"] < 0 and r["first_bad"] >= 0:
+                    tot["first_bad"] = r["first_bad"]
+        print(json.dumps(tot))
