@@ -500,6 +500,11 @@ def _cpu_baseline():
         orc.mcts_search(root, 256, SEED, tree_id=sims // 256, rollout_policy=0)
         sims += 256
     out["mcts_sims_per_sec"] = sims / (time.perf_counter() - t0)
+    t0 = time.perf_counter(); sims = 0
+    while time.perf_counter() - t0 < 3.0:                       # the reference's default: HeuristicAgent rollouts
+        orc.mcts_search(root, 64, SEED, tree_id=sims // 64, rollout_policy=1)
+        sims += 64
+    out["mcts_heuristic_rollout_sims_per_sec"] = sims / (time.perf_counter() - t0)
     return out
 
 
