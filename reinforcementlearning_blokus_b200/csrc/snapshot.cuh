@@ -232,7 +232,7 @@ __device__ __forceinline__ void snapshot_features(const WarpState& s, const uint
 
 // Feature rows of n boards.  frontiers: uint64[n][28] bitboards (or NULL: rebuilt from the cells); turn_index: int32[n]
 // (or NULL: the board's move_count, as mcts/learned_evaluator.py:79-84 passes it).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_snapshot_features(const bk_state* __restrict__ states, const uint64_t* __restrict__ frontiers,
                     const int32_t* __restrict__ turn_index, int n, int max_turns, double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char snap_smem[];
@@ -258,7 +258,7 @@ struct bk_checkpoints { int32_t n; int32_t ply[BK_MAX_CHECKPOINTS]; };
 // placement whose move_count is a checkpoint, with turn_index = the number of turns (passes included) played so far --
 // the capture points of analytics/tournament/arena_runner.py:625-650,698.  A move that is not legal stops the replay of
 // that game (its remaining checkpoints stay at turn_index -1).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_replay_snapshots(const bk_state* __restrict__ start, const uint16_t* __restrict__ traces, int n, int n_turns,
                    const bk_checkpoints ck, int max_turns, double* __restrict__ features, int32_t* __restrict__ turn_index,
                    bk_state* __restrict__ snap_states, uint64_t* __restrict__ snap_frontiers) {
