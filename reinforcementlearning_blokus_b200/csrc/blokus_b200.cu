@@ -800,7 +800,7 @@ extern "C" int bk_replay_snapshots(const bk_state* start, const uint16_t* traces
 extern "C" int bk_has_moves(const bk_state* states, int n, uint8_t* out_mask, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && out_mask)), "bk_has_moves: null buffer");
     if (n == 0) return BK_OK;
-    k_has_moves<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, n, out_mask);
+    k_has_moves<<<grid_for(n, 3), BK_THREADS, 0, as_stream(stream)>>>(states, n, out_mask);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -809,7 +809,7 @@ extern "C" int bk_is_move_legal(const bk_state* states, const uint8_t* players, 
                                 uint8_t* out, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && move_ids && out)), "bk_is_move_legal: null buffer");
     if (n == 0) return BK_OK;
-    k_is_move_legal<<<grid_for(n, 4), BK_THREADS, 0, as_stream(stream)>>>(states, players, move_ids, n, out);
+    k_is_move_legal<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, move_ids, n, out);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -818,7 +818,7 @@ extern "C" int bk_can_place_mask(const bk_state* states, const uint8_t* players,
                                  uint8_t* out, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && cell_masks && out)), "bk_can_place_mask: null buffer");
     if (n == 0) return BK_OK;
-    k_can_place_mask<<<grid_for(n, 4), BK_THREADS, 0, as_stream(stream)>>>(states, players, cell_masks, n, out);
+    k_can_place_mask<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, cell_masks, n, out);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -827,7 +827,7 @@ extern "C" int bk_step(bk_state* states, const uint8_t* players, const uint16_t*
                        uint8_t* alive, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && move_ids)), "bk_step: null buffer");
     if (n == 0) return BK_OK;
-    k_step<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, players, move_ids, n, ok, alive);
+    k_step<<<grid_for(n, 3), BK_THREADS, 0, as_stream(stream)>>>(states, players, move_ids, n, ok, alive);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -835,7 +835,7 @@ extern "C" int bk_step(bk_state* states, const uint8_t* players, const uint16_t*
 extern "C" int bk_scores(const bk_state* states, int n, int32_t* game_scores, int32_t* board_scores, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || states), "bk_scores: null buffer");
     if (n == 0) return BK_OK;
-    k_scores<<<grid_for(n, 4), BK_THREADS, 0, as_stream(stream)>>>(states, n, game_scores, board_scores);
+    k_scores<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, n, game_scores, board_scores);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -899,7 +899,7 @@ extern "C" int bk_exclusive_scan_u32(const uint32_t* counts, int n, uint32_t* of
 extern "C" int bk_zobrist_hash(const bk_state* states, int n, const uint64_t* table, uint64_t* keys, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && table && (n == 0 || (states && keys)), "bk_zobrist_hash: null buffer");
     if (n == 0) return BK_OK;
-    k_zobrist<<<grid_for(n, 4), BK_THREADS, 0, as_stream(stream)>>>(states, n, table, keys);
+    k_zobrist<<<grid_for(n, 8), BK_THREADS, 0, as_stream(stream)>>>(states, n, table, keys);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -1012,7 +1012,7 @@ extern "C" int bk_heuristic_scores(const bk_state* states, const uint8_t* player
                                    const uint16_t* move_ids, int n, double* scores, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids && scores)), "bk_heuristic_scores: null buffer");
     if (n == 0) return BK_OK;
-    k_heuristic_scores<<<grid_for(n, 4), BK_THREADS, 0, as_stream(stream)>>>(states, players, offsets, move_ids, n, scores);
+    k_heuristic_scores<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, offsets, move_ids, n, scores);
     LAUNCH_CHECK();
     return BK_OK;
 }
