@@ -97,7 +97,8 @@ int bk_movegen_emit(const bk_state* states, const uint8_t* players, int n,
 int bk_movegen_fixed(const bk_state* states, const uint8_t* players, int n, uint32_t cap,
                      uint32_t* counts, uint16_t* move_ids, void* stream);
 
-/* Legal-anchor bitmap: bitmap[i][o*20+row] has bit col set iff move (o,row,col) is legal. */
+/* Legal-anchor bitmap: bitmap[i][o*20+row] has bit col set iff move (o,row,col) is legal.  `bitmap` must be 16-byte
+ * aligned (each state's 7 280 bytes leave as 16-byte stores). */
 int bk_movegen_bitmap(const bk_state* states, const uint8_t* players, int n,
                       uint32_t* bitmap, void* stream);
 

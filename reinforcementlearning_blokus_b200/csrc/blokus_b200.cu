@@ -61,6 +61,7 @@ extern "C" const char* bk_version(void) { return "blokus_b200 r1 sm_100a (row-sl
 
 __global__ void k_movegen_emit(const bk_state* __restrict__, const uint8_t* __restrict__, int, const uint32_t* __restrict__,
                                uint32_t, uint32_t* __restrict__, uint16_t* __restrict__);
+__global__ void k_movegen_bitmap(const bk_state* __restrict__, const uint8_t* __restrict__, int, uint32_t* __restrict__);
 #define BK_EMIT_SMEM_BYTES (8 * (32 * 57 * 4 + 32 * 4))
 
 static cudaError_t bk_init_policies_impl();
@@ -81,6 +82,7 @@ extern "C" int bk_init(int device) {
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_cells32, BK_TBL_ORIENT_CELLS32, sizeof(BK_TBL_ORIENT_CELLS32)));
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_rowpat, BK_TBL_ORIENT_ROWPAT, sizeof(BK_TBL_ORIENT_ROWPAT)));
     CUDA_TRY(cudaFuncSetAttribute(k_movegen_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_movegen_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
     CUDA_TRY(bk_init_policies());
     if (!g_tickets) CUDA_TRY(cudaMalloc(&g_tickets, BK_TICKETS * sizeof(unsigned int)));
     g_device = device;
@@ -190,10 +192,15 @@ k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ 
     }
 }
 
+// The 1 820 row words of a state are staged in shared memory and leave as 455 full 16-byte stores per warp (7 280 B,
+// 16-byte aligned per state); writing each orientation's 20 words straight from the sink made 91 partial-sector stores.
+#define BITMAP_SMEM_PER_WARP (EMIT_ROW_WORDS * 4)
 __global__ void __launch_bounds__(BK_THREADS)
 k_movegen_bitmap(const bk_state* __restrict__ states, const uint8_t* __restrict__ players, int n,
                  uint32_t* __restrict__ bitmap) {
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + (size_t)wib * BITMAP_SMEM_PER_WARP);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     uint64_t word = warp < n ? fetch_state_word(states + warp, lane) : 0ull;
@@ -203,15 +210,16 @@ k_movegen_bitmap(const bk_state* __restrict__ states, const uint8_t* __restrict_
         word = next;
         const uint32_t p = players ? (players[i] & 3u) : s.to_move;
         uint32_t A, C; make_masks(s, p, lane, A, C);
-        BitmapSink sink; sink.out = bitmap + (size_t)i * BK_BITMAP_WORDS; sink.lane = lane;
-        const uint32_t used = sel4(s.used, p);
-        bk_gen_all(A, C, used, sink);
-        // rows of spent pieces are not visited by the generator: clear them here (no separate memset pass)
-        for (uint32_t rest = used & BK_ALL_PIECES; rest; rest &= rest - 1) {
-            const int pid = __ffs(rest);                         // 1..21
-            for (int o = c_piece_first[pid]; o < c_piece_first[pid + 1]; o++)
-                if (lane < 20) sink.out[o * 20 + lane] = 0u;
-        }
+#pragma unroll
+        for (int k = 0; k < EMIT_WORDS_PER_LANE; k++) rows[k * 32 + lane] = 0;   // rows of spent pieces stay zero
+        __syncwarp();
+        SmemRowSink sink; sink.rows = rows; sink.lane = lane;
+        bk_gen_all(A, C, sel4(s.used, p), sink);
+        __syncwarp();
+        uint4* dst = reinterpret_cast<uint4*>(bitmap + (size_t)i * BK_BITMAP_WORDS);
+        const uint4* src = reinterpret_cast<const uint4*>(rows);
+        for (int k = lane; k < BK_BITMAP_WORDS / 4; k += 32) __stcs(dst + k, src[k]);   // written once, never re-read here
+        __syncwarp();
     }
 }
 
@@ -754,8 +762,9 @@ extern "C" int bk_movegen_fixed(const bk_state* states, const uint8_t* players, 
 
 extern "C" int bk_movegen_bitmap(const bk_state* states, const uint8_t* players, int n, uint32_t* bitmap, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && bitmap)), "bk_movegen_bitmap: null buffer");
+    REQUIRE(reinterpret_cast<uintptr_t>(bitmap) % 16 == 0, "bk_movegen_bitmap: bitmap must be 16-byte aligned");
     if (n == 0) return BK_OK;
-    k_movegen_bitmap<<<grid_for(n, 2), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, bitmap);
+    k_movegen_bitmap<<<grid_for(n, 3), BK_THREADS, BK_WARPS * BITMAP_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, bitmap);
     LAUNCH_CHECK();
     return BK_OK;
 }
