@@ -281,7 +281,7 @@ __device__ __forceinline__ uint32_t alive_mask(const WarpState& s, int lane) {
         uint32_t A, C; make_masks(s, p, lane, A, C);
         // no corner cell at all -> no move (cheap early out, warp-uniform)
         if (!__any_sync(BK_FULL, C != 0)) continue;
-        AnySink sink; bk_gen_all(A, C, sel4(s.used, p), sink);
+        AnySink sink; bk_gen_all<AnySink, true>(A, C, sel4(s.used, p), sink);
         if (__any_sync(BK_FULL, sink.acc != 0)) mask |= 1u << p;
     }
     return mask;
