@@ -234,8 +234,8 @@ typedef struct bk_mcts_params {
 /* Bytes of device workspace per tree for a search of params->iterations_total iterations (host call). */
 int64_t bk_mcts_workspace_bytes(const bk_mcts_params* params);
 
-/* Run n_trees independent UCT searches, one warp each; tree k searches roots[k % n_roots] (side to move =
- * the root player) with random stream (seed, tree_offset+k).  `tt` (may be NULL) caches rollout rewards by
+/* Run n_trees independent UCT searches, one warp each (a CTA of params->leaf_batch warps each when leaf_batch > 1);
+ * tree k searches roots[k % n_roots] (side to move = the root player) with random stream (seed, tree_offset+k).  `tt` (may be NULL) caches rollout rewards by
  * Zobrist key of `zobrist_table` (device, BK_ZOBRIST_ENTRIES; required when tt != NULL).  Outputs per tree,
  * indexed by the rank of the move in the root's ascending legal-move list:
  *   root_visits [n_trees][max_root_moves] int32, root_reward [n_trees][max_root_moves] int64 (rollout

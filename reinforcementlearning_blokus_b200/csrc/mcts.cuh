@@ -1,4 +1,5 @@
-// mcts.cuh -- K5: UCT search with device rollouts, one warp per tree (root-parallel across warps/GPUs).
+// mcts.cuh -- K5: UCT search with device rollouts: one warp per tree (root-parallel across warps/GPUs), or a CTA of up
+// to 16 warps per tree that batches the rollouts of every new leaf (leaf_batch, see k_mcts).
 //
 // Mirrors MCTSAgent of the reference (mcts/mcts_agent.py):
 //   iteration (:360-382)  select -> expand one child -> simulate -> back-propagate the same reward to the root
