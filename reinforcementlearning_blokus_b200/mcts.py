@@ -57,6 +57,16 @@ class ZobristHash:
     def hash_states(self, states: torch.Tensor) -> torch.Tensor:
         return dev.zobrist_hash(states, self.device_table())
 
+    def hash_move(self, board: Board, move_hash: int, player: Player, piece_id: int) -> int:
+        """Turn and spent-piece part of an incremental update (mcts/zobrist.py:101-128): plain table arithmetic."""
+        cur = board.current_player.value - 1
+        h = int(move_hash) ^ int(self.player_turn_hashes[cur]) ^ int(self.player_turn_hashes[(cur + 1) % self.num_players])
+        return h ^ int(self.piece_used_hashes[player.value - 1, piece_id - 1])
+
+    def hash_position_placement(self, row: int, col: int, player: Player) -> int:
+        """mcts/zobrist.py:130-142."""
+        return int(self.position_player_hashes[row, col, player.value])
+
     def get_hash_info(self) -> Dict[str, Any]:
         return {"board_size": self.board_size, "num_players": self.num_players, "hash_bits": 64,
                 "total_positions": self.board_size * self.board_size, "total_pieces": 21}
