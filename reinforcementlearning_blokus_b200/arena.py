@@ -100,8 +100,11 @@ def _choose(agent, board, player, legal_moves, thinking_time_ms) -> Tuple[Option
 
 
 def run_single_game(*, run_id: str, game_index: int, game_seed: int, seat_assignment: Mapping[str, str],
-                    agents: Mapping[str, Any], max_turns: int = 2500, thinking_time_ms: Optional[int] = None,
-                    seat_policy: str = "round_robin") -> Dict[str, Any]:
+                    agents: Mapping[str, Any], max_turns: int = 2500, thinking_time_ms: Any = None,
+                    seat_policy: str = "round_robin", record_trace: bool = False) -> Dict[str, Any]:
+    """thinking_time_ms: one budget for every agent or a mapping agent name -> budget (AgentConfig.thinking_time_ms).
+    record_trace adds "move_trace" (move id per turn, 0xFFFF = pass) to the record, the input of
+    device.replay_snapshots."""
     random.seed(game_seed)
     np.random.seed(game_seed)
     start = time.perf_counter()
@@ -110,19 +113,22 @@ def run_single_game(*, run_id: str, game_index: int, game_seed: int, seat_assign
     game = BlokusGame(enable_telemetry=False)
     passes = invalid = turns = 0
     error = None
+    trace = []
     try:
         while not game.is_game_over() and turns < max_turns:
             player = game.get_current_player()
             name = seat_assignment[str(player.value)]
             legal = game.get_legal_moves(player)
             turns += 1
+            trace.append(0xFFFF)
             if not legal:
                 passes += 1
                 game.board._update_current_player()
                 game._check_game_over()
                 continue
             t0 = time.perf_counter()
-            move, raw = _choose(agents[name], game.board, player, legal, thinking_time_ms)
+            budget = thinking_time_ms.get(name) if isinstance(thinking_time_ms, Mapping) else thinking_time_ms
+            move, raw = _choose(agents[name], game.board, player, legal, budget)
             elapsed = float(raw.get("timeSpentMs", (time.perf_counter() - t0) * 1000.0))
             sims = raw.get("nodesEvaluated", raw.get("iterations_run"))
             st = stats[name]
@@ -137,6 +143,8 @@ def run_single_game(*, run_id: str, game_index: int, game_seed: int, seat_assign
                 passes += 1
                 game.board._update_current_player()
                 game._check_game_over()
+            else:
+                trace[-1] = move.to_id()
     except Exception:
         error = traceback.format_exc()
     truncated = turns >= max_turns and not game.is_game_over()
@@ -152,8 +160,11 @@ def run_single_game(*, run_id: str, game_index: int, game_seed: int, seat_assign
             st["avg_simulations_per_move"] = st["simulations_per_second"] = st["total_simulations"] = None
     result = game.get_game_result()
     scores = {str(pid): int(s) for pid, s in result.scores.items()}
-    return _record(run_id, game_index, game_seed, seat_assignment, seat_policy, scores, game.board.move_count, turns,
-                   passes, invalid, time.perf_counter() - start, truncated, stats, error)
+    rec = _record(run_id, game_index, game_seed, seat_assignment, seat_policy, scores, game.board.move_count, turns,
+                  passes, invalid, time.perf_counter() - start, truncated, stats, error)
+    if record_trace:
+        rec["move_trace"] = trace
+    return rec
 
 
 # ---- device-batched match-ups between the built-in policies ----------------------------------------------
@@ -231,3 +242,291 @@ def write_games_jsonl(path: str, records: Sequence[Mapping[str, Any]]) -> None:
     with open(path, "w", encoding="utf-8") as f:
         for rec in records:
             f.write(json.dumps(rec, sort_keys=True) + "\n")
+
+
+# ---- experiment configuration and driver (arena_runner.py:41-236, 308-492, 914-1000) -------------------------------
+DEFAULT_OUTPUT_ROOT = "arena_runs"
+DEFAULT_MAX_TURNS = 2500
+SUPPORTED_SEAT_POLICIES = {"randomized", "round_robin"}
+DEFAULT_SNAPSHOT_PLYS = [8, 16, 24, 32, 40, 48, 56, 64]
+
+
+class AgentConfig:
+    """One arena agent: the reference's JSON shape {"name", "type", "thinking_time_ms", "params"} (arena_runner.py:52-87);
+    keys outside these four are folded into params."""
+
+    def __init__(self, name: str, type: str, thinking_time_ms: Optional[int] = None, params: Optional[Dict[str, Any]] = None):
+        self.name, self.type = str(name), str(type)
+        self.thinking_time_ms = int(thinking_time_ms) if thinking_time_ms is not None else None
+        self.params = dict(params or {})
+
+    @classmethod
+    def from_dict(cls, item: Mapping[str, Any]) -> "AgentConfig":
+        if "name" not in item:
+            raise ValueError("Agent entries must include 'name'")
+        if "type" not in item:
+            raise ValueError(f"Agent '{item['name']}' is missing required field 'type'")
+        params = dict(item.get("params") or {})
+        params.update({k: v for k, v in item.items() if k not in {"name", "type", "thinking_time_ms", "params"}})
+        return cls(item["name"], item["type"], item.get("thinking_time_ms"), params)
+
+    def to_dict(self) -> Dict[str, Any]:
+        return {"name": self.name, "type": self.type, "thinking_time_ms": self.thinking_time_ms, "params": dict(self.params)}
+
+
+class SnapshotConfig:
+    """arena_runner.py:90-121."""
+
+    def __init__(self, enabled: bool = False, strategy: str = "fixed_ply", checkpoints: Optional[Sequence[int]] = None):
+        self.enabled, self.strategy = bool(enabled), str(strategy)
+        self.checkpoints = sorted({int(v) for v in (DEFAULT_SNAPSHOT_PLYS if checkpoints is None else checkpoints) if int(v) >= 0})
+
+    @classmethod
+    def from_dict(cls, item: Mapping[str, Any]) -> "SnapshotConfig":
+        cps = item.get("checkpoints", list(DEFAULT_SNAPSHOT_PLYS))
+        if not isinstance(cps, list):
+            raise ValueError("snapshots.checkpoints must be a list of integers")
+        return cls(item.get("enabled", False), item.get("strategy", "fixed_ply"), cps)
+
+    def validate(self) -> None:
+        if self.strategy != "fixed_ply":
+            raise ValueError(f"Unsupported snapshot strategy '{self.strategy}'. Supported values: ['fixed_ply'].")
+
+    def to_dict(self) -> Dict[str, Any]:
+        return {"enabled": self.enabled, "strategy": self.strategy, "checkpoints": list(self.checkpoints)}
+
+
+class RunConfig:
+    """Top-level experiment configuration with the reference's keys, defaults and validation (arena_runner.py:124-236),
+    including the legacy {name: {type, ...}} shape of scripts/arena_config.json."""
+
+    def __init__(self, agents: Sequence[AgentConfig], num_games: int, seed: int, seat_policy: str = "randomized",
+                 output_root: str = DEFAULT_OUTPUT_ROOT, max_turns: int = DEFAULT_MAX_TURNS, notes: str = "",
+                 snapshots: Optional[SnapshotConfig] = None):
+        self.agents, self.num_games, self.seed = list(agents), int(num_games), int(seed)
+        self.seat_policy, self.output_root, self.max_turns, self.notes = str(seat_policy), str(output_root), int(max_turns), str(notes)
+        self.snapshots = snapshots or SnapshotConfig()
+
+    @classmethod
+    def from_dict(cls, config: Mapping[str, Any]) -> "RunConfig":
+        raw = config.get("agents")
+        if raw is None:                                          # legacy shape
+            raw = []
+            for name, item in config.items():
+                if not isinstance(item, Mapping) or "type" not in item:
+                    continue
+                ttm = item.get("thinking_time_ms")
+                if ttm is None and item.get("time_limit") is not None:
+                    ttm = int(float(item["time_limit"]) * 1000)
+                raw.append({"name": str(name), "type": str(item["type"]), "thinking_time_ms": ttm,
+                            "params": {k: v for k, v in item.items() if k not in {"type", "thinking_time_ms"}}})
+            if not raw:
+                raise ValueError("Invalid run config: missing 'agents' list and no legacy agent entries were found.")
+        if not isinstance(raw, list):
+            raise ValueError("RunConfig 'agents' must be a list.")
+        snaps = config.get("snapshots") or {}
+        if not isinstance(snaps, Mapping):
+            raise ValueError("RunConfig 'snapshots' must be an object when provided.")
+        cfg = cls([AgentConfig.from_dict(a) for a in raw], config.get("num_games", 100), config.get("seed", 0),
+                  config.get("seat_policy", "randomized"), config.get("output_root", DEFAULT_OUTPUT_ROOT),
+                  config.get("max_turns", DEFAULT_MAX_TURNS), config.get("notes", ""), SnapshotConfig.from_dict(snaps))
+        cfg.validate()
+        return cfg
+
+    def validate(self) -> None:
+        if self.num_games <= 0:
+            raise ValueError("num_games must be > 0.")
+        if len(self.agents) != 4:
+            raise ValueError(f"Arena expects exactly 4 agents; received {len(self.agents)}.")
+        if len({a.name for a in self.agents}) != len(self.agents):
+            raise ValueError("Agent names must be unique.")
+        if self.seat_policy not in SUPPORTED_SEAT_POLICIES:
+            raise ValueError(f"Unsupported seat_policy '{self.seat_policy}'. Expected one of {sorted(SUPPORTED_SEAT_POLICIES)}.")
+        if self.max_turns <= 0:
+            raise ValueError("max_turns must be > 0.")
+        self.snapshots.validate()
+
+    def to_dict(self) -> Dict[str, Any]:
+        return {"agents": [a.to_dict() for a in self.agents], "num_games": self.num_games, "seed": self.seed,
+                "seat_policy": self.seat_policy, "output_root": self.output_root, "max_turns": self.max_turns,
+                "notes": self.notes, "snapshots": self.snapshots.to_dict()}
+
+    @property
+    def agent_names(self):
+        return [a.name for a in self.agents]
+
+
+def load_run_config(config_path: str) -> RunConfig:
+    with open(config_path, "r", encoding="utf-8") as f:
+        payload = json.load(f)
+    if not isinstance(payload, Mapping):
+        raise ValueError("Run config must be a JSON object.")
+    return RunConfig.from_dict(payload)
+
+
+class _BudgetedAgent:
+    """choose_move wrapper for the think-style agents with the reference's deterministic budget rule
+    (arena_runner.py:334-412): iteration cap = round(iterations_per_ms * thinking_time_ms), wall clock not limiting."""
+
+    def __init__(self, agent, deterministic: bool, iterations_per_ms: float):
+        self.agent, self.deterministic, self.iterations_per_ms = agent, deterministic, iterations_per_ms
+
+    def choose_move(self, board, player, legal_moves, thinking_time_ms):
+        inner = getattr(self.agent, "_agent", self.agent)                    # GameplayFastMCTSAgent wraps a FastMCTSAgent
+        budget = int(thinking_time_ms or max(int(getattr(inner, "time_limit", 0.001) * 1000), 1))
+        if not self.deterministic:
+            res = inner.think(board, player, legal_moves, budget)
+            return res.get("move"), dict(res.get("stats") or {})
+        cap, keep = max(1, int(round(self.iterations_per_ms * budget))), inner.iterations
+        inner.iterations = cap
+        try:
+            res = inner.think(board, player, legal_moves, max(10_000_000, budget))
+        finally:
+            inner.iterations = keep
+        stats = dict(res.get("stats") or {})
+        stats["timeBudgetMs"], stats["iterationCap"] = budget, cap
+        return res.get("move"), stats
+
+
+def build_agent(config: AgentConfig, seed: int):
+    """The reference's agent factory (arena_runner.py:415-492) over this package's agents; same type names, parameter
+    names and defaults.  `leaf_batch` (params) is the one extra knob: warps per tree for the MCTS types."""
+    from .agents import FastMCTSAgent, GameplayFastMCTSAgent, HeuristicAgent, RandomAgent
+    from .mcts import MCTSAgent
+
+    kind, p = config.type.lower(), dict(config.params)
+    if kind == "random":
+        return RandomAgent(seed=seed)
+    if kind == "heuristic":
+        agent = HeuristicAgent(seed=seed)
+        if isinstance(p.get("weights"), Mapping):
+            agent.set_weights(dict(p["weights"]))
+        return agent
+    if kind == "mcts":
+        det, ipm = bool(p.get("deterministic_time_budget", True)), float(p.get("iterations_per_ms", 10.0))
+        iterations, time_limit = int(p.get("iterations", 1000)), p.get("time_limit")
+        if det and config.thinking_time_ms is not None:
+            iterations, time_limit = max(1, int(round(ipm * config.thinking_time_ms))), None
+        elif time_limit is None and config.thinking_time_ms is not None:
+            time_limit = float(config.thinking_time_ms) / 1000.0
+        leaf_batch = int(p.get("leaf_batch", 1))
+        return MCTSAgent(
+            iterations=iterations, time_limit=float(time_limit) if time_limit is not None else None,
+            exploration_constant=float(p.get("exploration_constant", 1.414)),
+            use_transposition_table=bool(p.get("use_transposition_table", leaf_batch <= 1)), seed=seed,
+            learned_model_path=p.get("learned_model_path"), leaf_evaluation_enabled=bool(p.get("leaf_evaluation_enabled", False)),
+            progressive_bias_enabled=bool(p.get("progressive_bias_enabled", False)),
+            progressive_bias_weight=float(p.get("progressive_bias_weight", 0.25)),
+            potential_shaping_enabled=bool(p.get("potential_shaping_enabled", False)),
+            potential_shaping_gamma=float(p.get("potential_shaping_gamma", 1.0)),
+            potential_shaping_weight=float(p.get("potential_shaping_weight", 1.0)),
+            potential_mode=str(p.get("potential_mode", "prob")), max_rollout_moves=int(p.get("max_rollout_moves", 50)),
+            leaf_batch=leaf_batch)
+    if kind == "fast_mcts":
+        default_time = float(config.thinking_time_ms) / 1000.0 if config.thinking_time_ms is not None else float(p.get("time_limit", 0.1))
+        agent = FastMCTSAgent(iterations=int(p.get("iterations", 5000)), time_limit=default_time,
+                              exploration_constant=float(p.get("exploration_constant", 1.414)), seed=seed,
+                              leaf_batch=int(p.get("leaf_batch", 1)))
+        return _BudgetedAgent(agent, bool(p.get("deterministic_time_budget", True)), float(p.get("iterations_per_ms", 20.0)))
+    if kind in {"gameplay_fast_mcts", "gameplay_mcts"}:
+        agent = GameplayFastMCTSAgent(iterations=int(p.get("iterations", 5000)),
+                                      exploration_constant=float(p.get("exploration_constant", 1.414)), seed=seed)
+        return _BudgetedAgent(agent, bool(p.get("deterministic_time_budget", True)), float(p.get("iterations_per_ms", 20.0)))
+    raise ValueError(f"Unsupported agent type: {config.type}")
+
+
+def summarize(records: Sequence[Mapping[str, Any]], agent_names: Sequence[str]) -> Dict[str, Any]:
+    """Per-agent games / wins (ties split) / win rate / mean score / mean rank.  The reference's full statistics module
+    (pairwise tables, Elo, confidence intervals: analytics/tournament/arena_stats.py) is outside the hot path."""
+    agg = {n: {"games": 0, "wins": 0.0, "score_sum": 0, "rank_sum": 0} for n in agent_names}
+    done = 0
+    for rec in records:
+        if rec.get("error"):
+            continue
+        done += 1
+        for name, score in rec["agent_scores"].items():
+            a = agg[name]
+            a["games"] += 1
+            a["score_sum"] += score
+            a["rank_sum"] += rec["agent_ranks"][name]
+            if name in rec["winner_agents"]:
+                a["wins"] += 1.0 / len(rec["winner_agents"])
+    return {"completed_games": done, "error_games": len(records) - done,
+            "agents": {n: {"games": a["games"], "wins": a["wins"], "win_rate": a["wins"] / max(a["games"], 1),
+                           "mean_score": a["score_sum"] / max(a["games"], 1), "mean_rank": a["rank_sum"] / max(a["games"], 1)}
+                       for n, a in agg.items()}}
+
+
+def run_experiment(run_config: RunConfig, *, verbose: bool = False, device_batch: bool = True) -> Dict[str, Any]:
+    """arena_runner.py:914-1000: run all games of a RunConfig and write run_config.json, games.jsonl, snapshots.csv
+    (+ .parquet) and summary.json under <output_root>/<run_id>/.
+
+    When every agent is of a built-in policy type ("random" / "heuristic", default weights) and `device_batch` is set,
+    the whole experiment is ONE device batch (run_device_arena): same seeds, seat assignments, record keys and
+    snapshot rows, moves drawn with Philox.  Any other agent mix runs the reference's per-game loop over agent objects
+    (a fresh agent per game and name, seeded with the reference's agent_seed)."""
+    import os
+    from datetime import datetime
+
+    from . import winprob
+
+    stamp = datetime.now()
+    digest = hashlib.sha256(json.dumps(run_config.to_dict(), sort_keys=True).encode("utf-8")).hexdigest()[:8]
+    base_id = f"{stamp.strftime('%Y%m%d_%H%M%S')}_{digest}"
+    os.makedirs(run_config.output_root, exist_ok=True)
+    run_id, attempt = base_id, 1
+    while os.path.exists(os.path.join(run_config.output_root, run_id)):
+        run_id, attempt = f"{base_id}_{attempt:02d}", attempt + 1
+    run_dir = os.path.join(run_config.output_root, run_id)
+    os.makedirs(run_dir)
+    payload = dict(run_config.to_dict(), run_id=run_id, created_at=stamp.isoformat(timespec="seconds"))
+    with open(os.path.join(run_dir, "run_config.json"), "w", encoding="utf-8") as f:
+        json.dump(payload, f, indent=2, sort_keys=True)
+        f.write("\n")
+    builtin = all(a.type.lower() in POLICY_OF and not a.params.get("weights") for a in run_config.agents)
+    snaps = run_config.snapshots.checkpoints if run_config.snapshots.enabled else None
+    if builtin and device_batch:
+        out = run_device_arena({a.name: a.type.lower() for a in run_config.agents}, run_config.num_games,
+                               run_seed=run_config.seed, seat_policy=run_config.seat_policy, run_id=run_id,
+                               snapshots=snaps, max_turns=run_config.max_turns)
+        records, rows = out["records"], out.get("snapshot_rows", [])
+    else:
+        records, rows = [], []
+        cfg_of = {a.name: a for a in run_config.agents}
+        for gi in range(run_config.num_games):
+            gs = game_seed_from_run_seed(run_config.seed, gi)
+            seats = seat_assignment_for_game(run_config.agent_names, gi, gs, run_config.seat_policy)
+            agents = {n: build_agent(cfg_of[n], agent_seed(run_config.seed, gi, n)) for n in set(seats.values())}
+            think_ms = {n: cfg_of[n].thinking_time_ms for n in agents}
+            rec = run_single_game(run_id=run_id, game_index=gi, game_seed=gs, seat_assignment=seats, agents=agents,
+                                  max_turns=run_config.max_turns, thinking_time_ms=think_ms,
+                                  seat_policy=run_config.seat_policy, record_trace=bool(snaps))
+            records.append(rec)
+            if verbose:
+                print(f"[{gi + 1}/{run_config.num_games}] seed={gs} winners={','.join(rec['winner_agents'])} scores={rec['agent_scores']}")
+        if snaps:                                     # replay the recorded moves on the device, capture the feature rows
+            import torch
+
+            from . import device as dev
+
+            traces = [rec.pop("move_trace") for rec in records]
+            width = max(96, max(len(t) for t in traces))
+            mat = np.full((len(traces), width), 0xFFFF, dtype=np.uint16)
+            for i, t in enumerate(traces):
+                mat[i, :len(t)] = t
+            replay = dev.replay_snapshots(torch.from_numpy(mat).cuda(), snaps, max_turns=run_config.max_turns)
+            hit = (replay["turn_index"] >= 0).cpu().numpy()
+            for i, rec in enumerate(records):
+                rec["snapshot_checkpoints_hit"] = [int(c) for c, h in zip(replay["checkpoints"], hit[i]) if h]
+            rows = winprob.snapshot_rows_from_replay(replay, records)
+    write_games_jsonl(os.path.join(run_dir, "games.jsonl"), records)
+    summary = dict(summarize(records, run_config.agent_names), run_id=run_id, run_seed=run_config.seed,
+                   seat_policy=run_config.seat_policy, run_config=payload,
+                   thinking_time_ms_by_agent={a.name: a.thinking_time_ms for a in run_config.agents})
+    meta = winprob.write_snapshots_dataset(run_dir, rows)
+    if meta["enabled"]:
+        summary["snapshots"] = dict(meta, expected_rows_max=run_config.num_games * len(run_config.snapshots.checkpoints) * 4)
+    with open(os.path.join(run_dir, "summary.json"), "w", encoding="utf-8") as f:
+        json.dump(summary, f, indent=2, sort_keys=True)
+        f.write("\n")
+    return {"run_id": run_id, "run_dir": run_dir, "summary": summary, "snapshot_rows": len(rows)}

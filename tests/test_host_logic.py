@@ -112,3 +112,33 @@ def test_arena_utilities_without_gpu():
     rec = arena._record("run", 3, 99, sa, "round_robin", {"1": 5, "2": 9, "3": 9, "4": 1}, 40, 50, 10, 0, 0.5, False, {}, None)
     assert rec["winner_ids"] == [2, 3] and rec["is_tie"] and rec["winner_id"] is None
     assert rec["winner_agents"] == ["d", "a"] and rec["agent_scores"]["c"] == 5 and rec["game_id"] == "run_g0003"
+
+
+def test_arena_run_config_parsing():
+    """RunConfig / AgentConfig / SnapshotConfig: the reference's keys, defaults, legacy shape and validation errors
+    (analytics/tournament/arena_runner.py:52-236); the literal below is what the reference's own parser returns."""
+    import pytest
+
+    from reinforcementlearning_blokus_b200 import arena
+
+    cfg = {"agents": [{"name": "a", "type": "random"}, {"name": "b", "type": "heuristic", "thinking_time_ms": 50},
+                      {"name": "c", "type": "fast_mcts", "iterations": 200}, {"name": "d", "type": "mcts", "params": {"iterations": 64}}],
+           "num_games": 3, "seed": 11, "seat_policy": "round_robin", "snapshots": {"enabled": True, "checkpoints": [16, 8, 8]}}
+    got = arena.RunConfig.from_dict(cfg).to_dict()
+    assert got == {
+        "agents": [{"name": "a", "type": "random", "thinking_time_ms": None, "params": {}},
+                   {"name": "b", "type": "heuristic", "thinking_time_ms": 50, "params": {}},
+                   {"name": "c", "type": "fast_mcts", "thinking_time_ms": None, "params": {"iterations": 200}},
+                   {"name": "d", "type": "mcts", "thinking_time_ms": None, "params": {"iterations": 64}}],
+        "num_games": 3, "seed": 11, "seat_policy": "round_robin", "output_root": "arena_runs", "max_turns": 2500, "notes": "",
+        "snapshots": {"enabled": True, "strategy": "fixed_ply", "checkpoints": [8, 16]}}
+    legacy = {"x": {"type": "random"}, "y": {"type": "heuristic", "time_limit": 0.2}, "z": {"type": "random"},
+              "w": {"type": "random"}, "num_games": 2, "seed": 1}
+    lg = arena.RunConfig.from_dict(legacy)
+    assert lg.seat_policy == "randomized" and lg.agents[1].thinking_time_ms == 200 and lg.agents[1].params == {"time_limit": 0.2}
+    for bad in ({**cfg, "num_games": 0}, {**cfg, "agents": cfg["agents"][:3]}, {**cfg, "seat_policy": "fixed"},
+                {**cfg, "agents": [dict(a, name="same") for a in cfg["agents"]]}, {**cfg, "snapshots": {"strategy": "x"}}):
+        with pytest.raises(ValueError):
+            arena.RunConfig.from_dict(bad)
+    with pytest.raises(ValueError):
+        arena.build_agent(arena.AgentConfig("q", "alphazero"), seed=1)
