@@ -198,3 +198,117 @@ class LearnedWinProbabilityEvaluator:
         if self.potential_mode == "logit":
             return float(math.log(probability / (1.0 - probability)))
         return float(probability)
+
+
+# ---- pairwise training set (analytics/winprob/dataset.py) ------------------------------------------------------------
+def resolve_snapshot_path(path: str) -> str:
+    """A snapshots file, or the snapshots.parquet / snapshots.csv of a run directory (dataset.py:15-30)."""
+    import os
+
+    if os.path.isfile(path):
+        return path
+    if os.path.isdir(path):
+        for name in ("snapshots.parquet", "snapshots.csv"):
+            cand = os.path.join(path, name)
+            if os.path.exists(cand):
+                return cand
+    raise FileNotFoundError(f"Could not resolve snapshots dataset from '{path}'. Expected snapshots.parquet or snapshots.csv.")
+
+
+def load_snapshots_dataframe(path: str):
+    import pandas as pd
+
+    resolved = resolve_snapshot_path(path)
+    if resolved.lower().endswith(".parquet"):
+        return pd.read_parquet(resolved)
+    if resolved.lower().endswith(".csv"):
+        return pd.read_csv(resolved)
+    raise ValueError(f"Unsupported snapshot dataset extension: {resolved}")
+
+
+phase_bucket_from_occupancy = _phase_bucket_from_occupancy
+
+
+def build_pairwise_dataset(snapshots_df, *, feature_columns: Sequence[str] = SNAPSHOT_FEATURE_COLUMNS, tie_policy: str = "drop"):
+    """dataset.py:57-148: for every (run, game, checkpoint) and every pair of players i < j with different final
+    scores, the rows (f_i - f_j, label = score_i > score_j) and the reciprocal (f_j - f_i, 1 - label); tied pairs are
+    dropped.  Same rows, order and columns as the reference; the differences are computed per group as one matrix."""
+    import pandas as pd
+
+    missing = [c for c in feature_columns if c not in snapshots_df.columns]
+    if missing:
+        raise ValueError(f"Snapshot dataset missing feature columns: {missing}")
+    required = ["run_id", "game_id", "checkpoint_index", "player_id", "agent_name", "final_score", "phase_board_occupancy"]
+    missing_required = [c for c in required if c not in snapshots_df.columns]
+    if missing_required:
+        raise ValueError(f"Snapshot dataset missing required columns: {missing_required}")
+    if tie_policy != "drop":
+        raise ValueError(f"Unsupported tie_policy '{tie_policy}'. Expected 'drop'.")
+    feats = list(feature_columns)
+    rows: List[Dict[str, Any]] = []
+    ties = 0
+    for (run_id, game_id, ck), group in snapshots_df.groupby(["run_id", "game_id", "checkpoint_index"], sort=True):
+        players = group.sort_values("player_id")
+        if len(players) < 2:
+            continue
+        occ = float(players["phase_board_occupancy"].mean())
+        bucket = _phase_bucket_from_occupancy(occ)
+        vals = players[feats].astype(float).to_numpy(dtype=float)
+        pids = players["player_id"].astype(int).to_numpy()
+        names = players["agent_name"].astype(str).to_numpy()
+        scores = players["final_score"].astype(float).to_numpy()
+        ii, jj = np.triu_indices(len(players), k=1)                 # pairs in (i, j) lexicographic order
+        keep = scores[ii] != scores[jj]
+        ties += int((~keep).sum())
+        ii, jj = ii[keep], jj[keep]
+        diff = vals[ii] - vals[jj]
+        label = (scores[ii] > scores[jj]).astype(int)
+        for n in range(len(ii)):
+            for a, b, d, y in ((ii[n], jj[n], diff[n], label[n]), (jj[n], ii[n], -diff[n], 1 - label[n])):
+                row = {"run_id": run_id, "game_id": game_id, "checkpoint_index": int(ck), "phase_board_occupancy": occ,
+                       "phase_bucket": bucket, "player_i_id": int(pids[a]), "player_j_id": int(pids[b]),
+                       "agent_i": names[a], "agent_j": names[b]}
+                row.update(zip(feats, d.tolist()))
+                row["label"] = int(y)
+                rows.append(row)
+    frame = pd.DataFrame(rows)
+    meta = {"rows": int(len(frame)), "games": int(frame["game_id"].nunique()) if not frame.empty else 0,
+            "checkpoints": int(frame["checkpoint_index"].nunique()) if not frame.empty else 0,
+            "ties_dropped": int(ties), "tie_policy": tie_policy}
+    return frame, meta
+
+
+def split_pairwise_by_game(pairwise_df, *, test_size: float, seed: int):
+    """dataset.py:151-180: shuffle the sorted game ids with RandomState(seed), first round(n * (1 - test_size)) train."""
+    if pairwise_df.empty:
+        raise ValueError("Pairwise dataset is empty.")
+    games = sorted(pairwise_df["game_id"].unique().tolist())
+    np.random.RandomState(seed).shuffle(games)
+    cut = max(1, min(int(round(len(games) * (1.0 - test_size))), len(games) - 1))
+    train, test = set(games[:cut]), set(games[cut:])
+    train_df = pairwise_df[pairwise_df["game_id"].isin(train)].copy()
+    test_df = pairwise_df[pairwise_df["game_id"].isin(test)].copy()
+    return train_df, test_df, {"train_games": len(train), "test_games": len(test), "train_rows": len(train_df),
+                               "test_rows": len(test_df)}
+
+
+def pairwise_tensors(replay: Mapping[str, Any], game_scores):
+    """The same training set straight from device tensors, without a data frame: for replay features [N, K, 4, 34],
+    capture mask turn_index >= 0 and final scores [N, 4] (torch tensors on one device) returns (X float64[M, 34],
+    y int64[M], game int64[M], checkpoint int64[M]) over all captured snapshots, ordered like build_pairwise_dataset
+    (pairs i < j, each followed by its reciprocal; tied pairs dropped)."""
+    import torch
+
+    f, ti = replay["features"], replay["turn_index"]
+    n, k = ti.shape
+    sc = game_scores.to(f.device).to(torch.float64)
+    i_idx = torch.tensor([0, 1, 0, 2, 0, 3, 1, 2, 1, 3, 2, 3], device=f.device).view(6, 2)
+    a = torch.stack([i_idx[:, 0], i_idx[:, 1]], dim=1).reshape(-1)             # i, j, i, j ... -> rows ij then ji
+    b = torch.stack([i_idx[:, 1], i_idx[:, 0]], dim=1).reshape(-1)
+    x = f[:, :, a, :] - f[:, :, b, :]                                          # [N, K, 12, 34]
+    sa, sb = sc[:, a], sc[:, b]                                                # [N, 12]
+    y = (sa > sb).to(torch.int64)[:, None, :].expand(n, k, 12)
+    keep = (ti >= 0)[:, :, None] & (sa != sb)[:, None, :]
+    g = torch.arange(n, device=f.device)[:, None, None].expand(n, k, 12)
+    c = torch.arange(k, device=f.device)[None, :, None].expand(n, k, 12)
+    return x[keep], y[keep], g[keep], c[keep]

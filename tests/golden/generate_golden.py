@@ -419,6 +419,47 @@ def gen_snapshots(max_turns=2500):
     print("snapshots", ng, "games,", len(states), "states")
 
 
+def pairwise_input_frame():
+    """A small snapshots frame for the pairwise-dataset fixture: reference feature rows of four golden games at three
+    checkpoints, made-up final scores (one tie), rows shuffled.  Shared by the generator and tests/test_host_logic.py."""
+    import pandas as pd
+
+    z = np.load(os.path.join(HERE, "snapshots.npz"))
+    with open(os.path.join(HERE, "snapshot_columns.json")) as f:
+        cols = json.load(f)
+    rng = np.random.RandomState(0)
+    rows = []
+    for g in range(4):
+        scores = [int(v) for v in rng.randint(40, 90, 4)]
+        if g == 1:
+            scores[2] = scores[0]
+        for k in (1, 3, 5):
+            for p in range(4):
+                r = {"run_id": "r", "game_id": f"r_g{g:04d}", "checkpoint_index": k, "player_id": p + 1,
+                     "agent_name": f"ag{(p + g) % 4}", "final_score": scores[p]}
+                r.update({c: float(z["features"][g, k, p, i]) for i, c in enumerate(cols)})
+                rows.append(r)
+    return pd.DataFrame(rows).sample(frac=1.0, random_state=1), cols
+
+
+def gen_pairwise():
+    """analytics/winprob/dataset.py build_pairwise_dataset / split_pairwise_by_game on pairwise_input_frame()."""
+    from analytics.winprob.dataset import build_pairwise_dataset, split_pairwise_by_game
+
+    df, cols = pairwise_input_frame()
+    out, meta = build_pairwise_dataset(df)
+    train, test, split = split_pairwise_by_game(out, test_size=0.25, seed=3)
+    np.savez_compressed(
+        os.path.join(HERE, "pairwise.npz"), X=out[cols].to_numpy(dtype=np.float64), label=out["label"].to_numpy(np.int64),
+        player_i=out["player_i_id"].to_numpy(np.int64), player_j=out["player_j_id"].to_numpy(np.int64),
+        checkpoint=out["checkpoint_index"].to_numpy(np.int64), occupancy=out["phase_board_occupancy"].to_numpy(np.float64),
+        game=np.array(out["game_id"].tolist()), agent_i=np.array(out["agent_i"].tolist()), agent_j=np.array(out["agent_j"].tolist()),
+        bucket=np.array(out["phase_bucket"].tolist()), columns=np.array(list(out.columns)),
+        meta=np.array([json.dumps(meta), json.dumps(split)]), train_index=train.index.to_numpy(np.int64),
+        test_index=test.index.to_numpy(np.int64))
+    print("pairwise", meta, split)
+
+
 def random_state_from_packed(s) -> Board:
     """Rebuild a reference Board from a packed state (the recipe of engine-service/app.py:27-50)."""
     board = Board()
@@ -445,8 +486,8 @@ def random_state_from_packed(s) -> Board:
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots"]
+    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise"]
     for w in which:
         {"tables": gen_tables, "kat1": gen_kat1, "kat2": gen_kat2, "random": gen_random_states,
          "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic, "mobility": gen_mobility,
-         "snapshots": gen_snapshots}[w]()
+         "snapshots": gen_snapshots, "pairwise": gen_pairwise}[w]()

@@ -201,3 +201,21 @@ def test_replay_edge_cases(dev):
     assert tuple(empty.shape) == (0, 4, 34)
     with pytest.raises(ValueError):
         dev.replay_snapshots(tail, [])
+
+
+def test_pairwise_tensors_equal_dataframe_path(dev):
+    """The training set straight from device tensors equals the data-frame route of analytics/winprob/dataset.py."""
+    import pandas as pd
+
+    from reinforcementlearning_blokus_b200 import arena, winprob
+
+    out = arena.run_device_arena({"a": "random", "b": "heuristic", "c": "random", "d": "random"}, 40, run_seed=3,
+                                 snapshots=[8, 24, 48, 64])
+    frame, meta = winprob.build_pairwise_dataset(pd.DataFrame(out["snapshot_rows"]))
+    scores = torch.tensor([[r["final_scores"][str(p)] for p in (1, 2, 3, 4)] for r in out["records"]])
+    x, y, g, c = winprob.pairwise_tensors(out["snapshot_features"], scores)
+    assert x.shape[0] == meta["rows"] > 0
+    assert np.array_equal(x.cpu().numpy(), frame[winprob.SNAPSHOT_FEATURE_COLUMNS].to_numpy(dtype=np.float64))
+    assert np.array_equal(y.cpu().numpy(), frame["label"].to_numpy())
+    assert np.array_equal(c.cpu().numpy(), frame["checkpoint_index"].to_numpy())
+    assert [f"device_arena_g{i:04d}" for i in g.cpu().tolist()] == frame["game_id"].tolist()

@@ -142,3 +142,32 @@ def test_arena_run_config_parsing():
             arena.RunConfig.from_dict(bad)
     with pytest.raises(ValueError):
         arena.build_agent(arena.AgentConfig("q", "alphazero"), seed=1)
+
+
+def test_pairwise_dataset_matches_reference(golden_dir):
+    """winprob.build_pairwise_dataset / split_pairwise_by_game against the reference's output on the same frame
+    (tests/golden/pairwise.npz, written by generate_golden.py pairwise): same rows, order, columns and floats."""
+    import importlib.util
+    import json
+    import os
+
+    from reinforcementlearning_blokus_b200 import winprob
+
+    spec = importlib.util.spec_from_file_location("generate_golden_input", os.path.join(golden_dir, "generate_golden.py"))
+    z = np.load(os.path.join(golden_dir, "pairwise.npz"))
+    # rebuild the input frame with the generator's recipe without importing the reference
+    src = open(spec.origin).read()
+    start = src.index("def pairwise_input_frame():")
+    ns = {"np": np, "os": os, "json": json, "HERE": golden_dir}
+    exec(src[start:src.index("def gen_pairwise():")], ns)
+    df, cols = ns["pairwise_input_frame"]()
+    out, meta = winprob.build_pairwise_dataset(df)
+    assert list(out.columns) == z["columns"].tolist() and meta == json.loads(str(z["meta"][0]))
+    assert np.array_equal(out[cols].to_numpy(dtype=np.float64), z["X"]) and np.array_equal(out["label"].to_numpy(), z["label"])
+    assert np.array_equal(out["player_i_id"].to_numpy(), z["player_i"]) and np.array_equal(out["player_j_id"].to_numpy(), z["player_j"])
+    assert out["game_id"].tolist() == z["game"].tolist() and out["agent_i"].tolist() == z["agent_i"].tolist()
+    assert out["agent_j"].tolist() == z["agent_j"].tolist() and out["phase_bucket"].tolist() == z["bucket"].tolist()
+    assert np.array_equal(out["phase_board_occupancy"].to_numpy(), z["occupancy"])
+    train, test, split = winprob.split_pairwise_by_game(out, test_size=0.25, seed=3)
+    assert split == json.loads(str(z["meta"][1]))
+    assert np.array_equal(train.index.to_numpy(), z["train_index"]) and np.array_equal(test.index.to_numpy(), z["test_index"])
