@@ -77,3 +77,54 @@ def mobility_after_moves(state, player: int, mover: int, move_ids) -> "torch.Ten
     ok, _ = dev.step(states, ids, players=movers)
     counts = dev.movegen_count(states, torch.full((k,), int(player), dtype=torch.uint8, device=states.device))
     return torch.where(ok.bool(), counts, torch.full_like(counts, -1))
+
+
+def selfplay_mcts(n_games: int, iterations: int, *, seed: int = 0, trees_per_game: int = 1, leaf_batch: int = 1,
+                  rollout_policy: int = dev.POLICY_UNIFORM, max_rollout_moves: int = 50, exploration: float = 1.414,
+                  game_offset: int = 0, max_turns: int = 96, want_policy: bool = False) -> Dict[str, torch.Tensor]:
+    """Self-play where EVERY move of every game is chosen by UCT search -- the league's data generator
+    (configs/stage3_selfplay_gpu.yaml feeds such games to training) as device batches: per turn one launch searches the
+    current position of all n_games games (tree k searches game k % n_games; `trees_per_game` root-parallel trees per
+    game, their root statistics summed), the most visited move is played (ties: the reference's rule for one tree,
+    first child in creation order = highest rank), and games whose mover has no move pass
+    (analytics/tournament/arena_runner.py:653-695).
+
+    Returns trace uint16[N, T] (0xFFFF = pass), game_scores / board_scores int32[N, 4], turns int32[N] and, with
+    want_policy, a list of (visits int32[N, M], move_ids uint16[N, M]) per turn -- visit-count policy targets."""
+    from .mcts import MAX_ROOT_MOVES, DeviceUCT
+
+    games = BatchedBlokus(n_games)
+    n_trees = n_games * int(trees_per_game)
+    eng = DeviceUCT(iterations, n_trees=n_trees, max_rollout_moves=max_rollout_moves, exploration=exploration, seed=seed,
+                    rollout_policy=rollout_policy, leaf_batch=leaf_batch)
+    trace = torch.full((n_games, max_turns), PASS, dtype=torch.int32, device=games.states.device)
+    turns = torch.zeros(n_games, dtype=torch.int32, device=games.states.device)
+    policy = []
+    rank_weight = torch.arange(MAX_ROOT_MOVES, device=games.states.device, dtype=torch.int64)
+    for t in range(max_turns):
+        alive = games.alive_mask()
+        running = alive != 0
+        if not bool(running.any()):
+            break
+        # every (game, turn) pair gets its own block of Philox streams
+        eng.p.tree_offset = (int(game_offset) + t * (1 << 24)) * int(trees_per_game)
+        res = eng.search(games.states, iterations)
+        visits = res["visits"].view(trees_per_game, n_games, -1).sum(dim=0)
+        # most visited root move, ties to the highest rank; unexpanded ranks have 0 visits
+        key = visits.to(torch.int64) * MAX_ROOT_MOVES + rank_weight[None, : visits.shape[1]]
+        best = key.argmax(dim=1)
+        ids = res["moves"][:n_games].view(torch.int16).gather(1, best[:, None]).view(torch.uint16)[:, 0]
+        has_move = (res["counts"][:n_games] > 0) & running
+        move = torch.where(has_move, ids.to(torch.int32), torch.full_like(ids, PASS, dtype=torch.int32))
+        move16 = move.to(torch.int16).view(torch.uint16).contiguous()      # 0..36399 and 0xFFFF survive the round trip
+        ok, _ = games.step(move16)
+        trace[:, t] = torch.where(running, move, trace[:, t])
+        turns += running.to(torch.int32)
+        if want_policy:
+            policy.append((visits.clone(), res["moves"][:n_games].clone()))
+    gs, bs = games.scores()
+    out = {"trace": trace.to(torch.int16).view(torch.uint16), "game_scores": gs, "board_scores": bs, "turns": turns,
+           "final_states": games.states}
+    if want_policy:
+        out["policy"] = policy
+    return out

@@ -48,6 +48,21 @@ def sharded_playout(n_total: int, seed: int, game_offset: int = 0, gather_scores
     return res
 
 
+def sharded_selfplay_mcts(n_total: int, iterations: int, seed: int = 0, game_offset: int = 0, gather_scores: bool = False,
+                          **kw) -> Dict[str, torch.Tensor]:
+    """MCTS self-play (batched.selfplay_mcts) with the n_total games sharded over the ranks; game g keeps its random
+    streams whatever the world size.  No collective on the data path; gather_scores adds all_game_scores on every rank."""
+    from . import batched
+
+    rank, ws = world()
+    start, count = shard_range(n_total, rank, ws)
+    res = dict(batched.selfplay_mcts(count, iterations, seed=seed, game_offset=game_offset + start, **kw))
+    res["first_game"], res["count"] = start, count
+    if gather_scores:
+        res["all_game_scores"] = gather_rows(res["game_scores"], n_total)
+    return res
+
+
 def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     """Concatenate per-rank row blocks (sizes from shard_range) in rank order on every rank."""
     rank, ws = world()

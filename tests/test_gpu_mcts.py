@@ -238,3 +238,34 @@ def test_leaf_batched_many_trees_per_cta(golden_dir):
     for k in (0, 147, 148, 399):
         solo = DeviceUCT(iters, n_trees=1, seed=31, tree_offset=k, leaf_batch=W).search(root, iters)
         assert torch.equal(solo["visits"][0], res["visits"][k]) and torch.equal(solo["reward"][0], res["reward"][k])
+
+
+def test_batched_mcts_selfplay():
+    """batched.selfplay_mcts: every move of every game chosen by device UCT.  Games are legal and complete (the oracle
+    replays the traces to the same scores), deterministic in the seed, and the first move of each game is the oracle
+    search's most visited move under the reference's tie rule."""
+    from reinforcementlearning_blokus_b200 import batched
+
+    n, iters = 12, 48
+    a = batched.selfplay_mcts(n, iters, seed=13)
+    b = batched.selfplay_mcts(n, iters, seed=13)
+    assert torch.equal(a["trace"], b["trace"]) and torch.equal(a["game_scores"], b["game_scores"])
+    tr, gs, turns = a["trace"].cpu().numpy(), a["game_scores"].cpu().numpy(), a["turns"].cpu().numpy()
+    assert int(dev.has_moves(a["final_states"]).max()) == 0                       # all games finished
+    for g in range(n):
+        board = orc.OracleBoard()
+        for t in range(int(turns[g])):
+            if tr[g, t] == 0xFFFF:
+                assert not board.has_legal_moves(board.current_player)            # passes only when forced
+                board.pass_turn()
+            else:
+                assert board.make_move(board.current_player, int(tr[g, t]))
+        assert [board.game_score(p) for p in range(4)] == gs[g].tolist()
+        want = orc.mcts_search(empty_states(1)[0], iters, seed=13, tree_id=g)
+        m = want["n_root"]
+        best = max(range(m - 1, -1, -1), key=lambda r: want["visits"][r])          # highest rank among the most visited
+        assert int(tr[g, 0]) == int(want["moves"][best])
+    # root-parallel trees per game and leaf-batched rollouts run too, and return visit-count policy targets
+    c = batched.selfplay_mcts(4, 16, seed=2, trees_per_game=3, leaf_batch=4, want_policy=True, max_turns=6)
+    v0, m0 = c["policy"][0]
+    assert v0.shape[0] == 4 and int(v0[0].sum()) == 3 * 16 * 4 and len(c["policy"]) == 6
