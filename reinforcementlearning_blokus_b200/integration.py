@@ -88,3 +88,70 @@ def uninstall() -> None:
 
     mg._SHARED_GENERATOR = _original
     _original = None
+
+
+# ---- the search agents of a live reference ---------------------------------------------------------------------------
+_patched = []        # (module, attribute, original object)
+
+
+def _to_host_board(board):
+    from .board import Board
+
+    return Board.from_packed(pack_reference_board(board))
+
+
+def make_agent_adapters():
+    """(MCTSAgent, FastMCTSAgent) classes for a live reference: same constructors as mcts/mcts_agent.py:194 and
+    agents/fast_mcts_agent.py:89, taking and returning the REFERENCE's Board / Player / Move objects; the search runs in
+    this package's device agents.  (A board handed over this way carries the exact frontier sets, like one rebuilt
+    from the wire; only the snapshot features of the learned evaluator look at them.)"""
+    from engine.move_generator import Move as RefMove
+
+    from . import agents as _agents
+    from . import mcts as _mcts
+    from .board import Player as HostPlayer
+    from .move_generator import Move as HostMove
+
+    def host_moves(legal_moves):
+        return [HostMove(m.piece_id, m.orientation, m.anchor_row, m.anchor_col) for m in legal_moves]
+
+    def ref_move(m):
+        return None if m is None else RefMove(m.piece_id, m.orientation, m.anchor_row, m.anchor_col)
+
+    class B200MCTSAgent(_mcts.MCTSAgent):
+        def select_action(self, board, player, legal_moves):
+            return ref_move(super().select_action(_to_host_board(board), HostPlayer(player.value), host_moves(legal_moves)))
+
+    class B200FastMCTSAgent(_agents.FastMCTSAgent):
+        def think(self, board, player, legal_moves, time_budget_ms):
+            out = super().think(_to_host_board(board), HostPlayer(player.value), host_moves(legal_moves), time_budget_ms)
+            return dict(out, move=ref_move(out.get("move")))
+
+    return B200MCTSAgent, B200FastMCTSAgent
+
+
+def install_agents():
+    """Replace MCTSAgent / FastMCTSAgent in every loaded module of the reference that holds them (their defining
+    modules, analytics.tournament.arena_runner, webapi ... import them by name) with the device-backed adapters.
+    Returns the two adapter classes; uninstall_agents() restores the originals."""
+    import sys
+
+    import agents.fast_mcts_agent as ref_fast
+    import mcts.mcts_agent as ref_mcts
+
+    new_mcts, new_fast = make_agent_adapters()
+    for old, new in ((ref_mcts.MCTSAgent, new_mcts), (ref_fast.FastMCTSAgent, new_fast)):
+        for mod in list(sys.modules.values()):
+            if mod is None or not getattr(mod, "__name__", "").split(".")[0] in {"mcts", "agents", "analytics", "webapi", "engine", "scripts"}:
+                continue
+            for attr, val in list(vars(mod).items()):
+                if val is old:
+                    _patched.append((mod, attr, old))
+                    setattr(mod, attr, new)
+    return new_mcts, new_fast
+
+
+def uninstall_agents() -> None:
+    while _patched:
+        mod, attr, old = _patched.pop()
+        setattr(mod, attr, old)

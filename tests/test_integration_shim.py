@@ -56,3 +56,45 @@ def test_adapter_packs_and_installs(reference_on_path, golden_dir):
     finally:
         integration.uninstall()
     assert mg._SHARED_GENERATOR is not installed
+
+
+def test_agent_adapters_patch_and_convert(reference_on_path, monkeypatch):
+    """install_agents() swaps MCTSAgent / FastMCTSAgent wherever the reference holds them; the adapters take the
+    reference's objects and hand back the reference's Move (the device search itself is stubbed here: no GPU)."""
+    import agents.fast_mcts_agent as ref_fast
+    import mcts.mcts_agent as ref_mcts
+    from engine.board import Board, Player
+    from engine.move_generator import Move
+
+    from reinforcementlearning_blokus_b200 import agents as my_agents
+    from reinforcementlearning_blokus_b200 import integration
+    from reinforcementlearning_blokus_b200 import mcts as my_mcts
+    seen = {}
+
+    def fake_select(self, board, player, legal_moves):
+        seen["board"], seen["player"], seen["n"] = board, player, len(legal_moves)
+        return legal_moves[1]
+
+    def fake_think(self, board, player, legal_moves, time_budget_ms):
+        return {"move": legal_moves[0], "stats": {"timeBudgetMs": time_budget_ms, "nodesEvaluated": 7}}
+
+    monkeypatch.setattr(my_mcts.MCTSAgent, "select_action", fake_select)
+    monkeypatch.setattr(my_agents.FastMCTSAgent, "think", fake_think)
+    orig_mcts, orig_fast = ref_mcts.MCTSAgent, ref_fast.FastMCTSAgent
+    try:
+        new_mcts, new_fast = integration.install_agents()
+        assert ref_mcts.MCTSAgent is new_mcts and ref_fast.FastMCTSAgent is new_fast
+        board = Board()
+        legal = [Move(1, 0, 0, 0), Move(2, 0, 0, 0), Move(2, 1, 0, 0)]
+        agent = ref_mcts.MCTSAgent(iterations=10, seed=1, use_transposition_table=False)
+        got = agent.select_action(board, Player.RED, legal)
+        assert isinstance(got, Move) and (got.piece_id, got.orientation) == (2, 0)
+        from reinforcementlearning_blokus_b200.board import Board as MyBoard
+
+        assert isinstance(seen["board"], MyBoard) and len(seen["board"].to_packed().tobytes()) == 256
+        assert seen["player"].value == 1 and seen["n"] == 3
+        out = ref_fast.FastMCTSAgent(iterations=5, time_limit=0.01, seed=2).think(board, Player.RED, legal, 25)
+        assert isinstance(out["move"], Move) and out["stats"]["timeBudgetMs"] == 25
+    finally:
+        integration.uninstall_agents()
+    assert ref_mcts.MCTSAgent is orig_mcts and ref_fast.FastMCTSAgent is orig_fast
