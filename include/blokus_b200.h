@@ -219,7 +219,12 @@ typedef struct bk_mcts_params {
                                    1: gain of the ROOT player measured from the root position (flat bandit);
                                    2: no rollout, every leaf is worth the constant 0.5 of the reference's dummy learned
                                       evaluator (mcts_agent.py:427-451, learned_evaluator.py:51-55); rewards are then
-                                      counted in halves (root_reward = number of halves) */
+                                      counted in halves (root_reward = number of halves);
+                                   3: no rollout, the leaf is worth the learned win probability of its player to move
+                                      (mcts_agent.py:427-451; LearnedWinProbabilityEvaluator with a pairwise logistic
+                                      model, mcts/learned_evaluator.py:97-143): the 4 x 34 snapshot features of the leaf
+                                      are computed in the kernel and fed to leaf_model.  Rewards are doubles:
+                                      root_reward then holds IEEE-754 bit patterns of the reward sums */
     int32_t  leaf_batch;        /* 1 (or 0): one rollout per iteration, one warp per tree -- the reference's search.
                                    2..16: leaf-batched rollouts -- a CTA of that many warps owns the tree; after each
                                    selection/expansion every warp rolls out from the new leaf with its own random stream
@@ -229,6 +234,12 @@ typedef struct bk_mcts_params {
     double   exploration;       /* 1.414 */
     uint64_t seed;
     uint64_t tree_offset;       /* global index of tree 0 (root-parallel sharding across GPUs) */
+    const double*   leaf_model;     /* reward_mode 3: DEVICE pointer to 35 doubles, weights of the 34 snapshot feature
+                                       differences + bias of a "pairwise_logreg" win-probability model */
+    const uint64_t* root_frontiers; /* reward_mode 3: DEVICE [n_roots][4][7] frontier sets of the roots (Board.get_frontier,
+                                       engine/board.py:247-259), or NULL for the sets of a freshly restored board */
+    int32_t  leaf_max_turns;        /* reward_mode 3: max_turns of the evaluator's progress features (2500) */
+    int32_t  reserved1;
 } bk_mcts_params;
 
 /* Bytes of device workspace per tree for a search of params->iterations_total iterations (host call). */

@@ -16,17 +16,18 @@
 #pragma once
 #include "movegen_core.cuh"
 #include "heuristic.cuh"
-// (included by blokus_b200.cu after zobrist_of / tt_lookup / tt_insert are defined)
+#include "snapshot.cuh"
+// (included by blokus_b200.cu after zobrist_of / tt_lookup / tt_insert / move_is_legal are defined)
 
 struct MctsLayout {            // byte offsets inside one tree's workspace slice
     uint32_t max_nodes, pool_slots;
     size_t off_states, off_parent, off_visits, off_reward, off_child_base, off_n_legal, off_n_expanded,
-           off_move, off_pool, off_header, total;
+           off_move, off_pool, off_header, off_frontier, total;
 };
 
 __host__ __device__ inline size_t bk_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline MctsLayout mcts_layout(int iterations_total) {
+__host__ __device__ inline MctsLayout mcts_layout(int iterations_total, bool with_frontier = false) {
     MctsLayout L;
     const size_t T = (size_t)(iterations_total > 0 ? iterations_total : 1);
     L.max_nodes = (uint32_t)(T + 1);
@@ -47,6 +48,8 @@ __host__ __device__ inline MctsLayout mcts_layout(int iterations_total) {
     L.off_move = o;        o += (size_t)L.max_nodes * 2;
     o = bk_align_up(o, 8);
     L.off_header = o;      o += 128;
+    // learned leaf evaluation: every node also keeps the four frontier sets of its board (28 words, engine/board.py:315-367)
+    L.off_frontier = o;    if (with_frontier) o += (size_t)L.max_nodes * 28 * 8;
     L.total = bk_align_up(o, 256);
     return L;
 }
@@ -95,9 +98,14 @@ __device__ __forceinline__ int32_t board_score_of(const WarpState& s, uint32_t q
 // before, then ALL W warps roll out from the new leaf with their own Philox streams (stream 1 + w of the tree) and the
 // W rewards are backed up together (visits += W).  One tree then advances ~W simulations per iteration latency, which
 // is what a single agent move needs (BASELINE config 4); W = 1 is bit-identical to BATCH = false.
-template <int POLICY, bool BATCH = false>
+// LEARNED = true: learned leaf evaluation in place of the rollout (mcts_agent.py:427-451) with a "pairwise_logreg"
+// win-probability model folded to 34 weights + bias (prm.leaf_model): the leaf's 4 x 34 snapshot features are computed in
+// shared memory (snapshot.cuh: four piece-count generations, flood fill) and the reward is the mean pairwise
+// probability of the player to move at the leaf.  Rewards are doubles then (same 8-byte slots), and every node carries
+// the frontier sets of its board, updated on expansion with the reference's rule.
+template <int POLICY, bool BATCH = false, bool LEARNED = false>
 __global__ void __launch_bounds__(BATCH ? 32 * BK_MCTS_MAX_WARPS : BK_MCTS_THREADS,
-                                  BATCH ? 1 : (POLICY == 0 ? BK_MCTS_CTAS_PER_SM : BK_MCTS_HEUR_CTAS_PER_SM))
+                                  BATCH ? 1 : (LEARNED ? 16 : (POLICY == 0 ? BK_MCTS_CTAS_PER_SM : BK_MCTS_HEUR_CTAS_PER_SM)))
 k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_params prm, MctsTT tt,
        unsigned char* __restrict__ workspace, int resume, int max_root_moves,
        int32_t* __restrict__ out_visits, long long* __restrict__ out_reward, uint32_t* __restrict__ out_counts,
@@ -107,12 +115,14 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
     __shared__ uint32_t sh_node, sh_stop, sh_root_player;
     __shared__ int32_t sh_root_score;
     __shared__ long long sh_r[BK_MCTS_MAX_WARPS];
+    __shared__ __align__(16) double s_feat[LEARNED ? 4 * BK_NFEAT : 1];      // leaf feature block (learned evaluation)
+    __shared__ uint16_t s_pc[LEARNED ? 4 * 24 : 1];
     const int lane = threadIdx.x & 31;
     const int wib = BATCH ? (int)(threadIdx.x >> 5) : 0;          // warp in block; warp 0 leads the tree
     const int W = BATCH ? (int)(blockDim.x >> 5) : 1;
     const bool lead = wib == 0;
     const uint32_t hs = (uint32_t)wib * HEUR_SMEM_PER_WARP;       // this warp's heuristic scratch
-    const MctsLayout L = mcts_layout(prm.iterations_total);
+    const MctsLayout L = mcts_layout(prm.iterations_total, LEARNED);
     // trees differ in cost (rollout lengths, tree depth): the next tree comes from a per-launch ticket counter so that
     // a batch larger than the resident CTAs has no idle tail; a tree's result depends on (seed, tree id) only
     for (;;) {
@@ -140,6 +150,9 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
         uint16_t* n_expanded = reinterpret_cast<uint16_t*>(base + L.off_n_expanded);
         uint16_t* move_of = reinterpret_cast<uint16_t*>(base + L.off_move);
         MctsHeader* hdr = reinterpret_cast<MctsHeader*>(base + L.off_header);
+        uint64_t* frontier = reinterpret_cast<uint64_t*>(base + L.off_frontier);       // [node][28], LEARNED only
+        double* reward_d = reinterpret_cast<double*>(reward);                          // the same slots as doubles
+        uint32_t F[4] = {0u, 0u, 0u, 0u};                                               // frontier rows of `s`
         const uint64_t tree_id = prm.tree_offset + (uint64_t)tree;
         // per-tree salt keeps concurrently searched trees from reading each other's cached rewards, so the
         // result of a tree depends on (seed, tree id) only
@@ -154,6 +167,13 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                 uint32_t A, C; make_masks(s, s.to_move, lane, A, C);
                 const Totals t0 = gen_totals<BATCH ? BK_MCTS_MAX_WARPS : 1>(A, C, sel4(s.used, s.to_move), lane);
                 store_state(states + 0, lane, s);
+                if (LEARNED) {
+                    if (prm.root_frontiers)
+                        unpack_rows4(lane < 28 ? __ldg(prm.root_frontiers + (size_t)(tree % n_roots) * 28 + lane) : 0ull, lane, F);
+                    else
+                        rebuild_frontiers(s, lane, F);
+                    store_rows4(frontier, lane, F);
+                }
                 if (lane == 0) {
                     parent[0] = -1; visits[0] = 0; reward[0] = 0; child_base[0] = 0xFFFFFFFFu;
                     n_legal[0] = (uint16_t)t0.n; n_expanded[0] = 0; move_of[0] = 0xFFFF;
@@ -201,7 +221,8 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                     const double v = (double)visits[ch];
                     double u;
                     if (visits[ch] == 0) u = __longlong_as_double(0x7FF0000000000000ll);
-                    else u = __dadd_rn(__ddiv_rn(__dmul_rn((double)reward[ch], unit), v), __dmul_rn(prm.exploration, sqrt(__ddiv_rn(logN, v))));
+                    else u = __dadd_rn(__ddiv_rn(LEARNED ? reward_d[ch] : __dmul_rn((double)reward[ch], unit), v),
+                                       __dmul_rn(prm.exploration, sqrt(__ddiv_rn(logN, v))));
                     if (!have || u > best) { best = u; best_k = k; have = true; }
                 }
                 // warp argmax, ties -> smallest k (Python's max keeps the first maximal child)
@@ -217,6 +238,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
             }
             // ---- expansion (mcts_agent.py:113-145): pop the last untried move of `node`
             load_state(states + node, lane, s);
+            if (LEARNED) unpack_rows4(lane < 28 ? frontier[(size_t)node * 28 + lane] : 0ull, lane, F);
             {
                 const uint32_t nl = n_legal[node], ne = n_expanded[node];
                 if (ne < nl && (prm.max_depth <= 0 || (int)depth < prm.max_depth)) {
@@ -225,7 +247,9 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                     const Totals tot = gen_totals<BATCH ? BK_MCTS_MAX_WARPS : 1>(A, C, sel4(s.used, p), lane);
                     int o, row, col;
                     const uint32_t id = select_move(tot, nl - 1 - ne, A, C, lane, o, row, col);
+                    const uint32_t own_before = sel4(s.P, p);
                     place_move(s, p, o, row, col, lane);
+                    if (LEARNED) update_frontier(s, p, sel4(s.P, p) & ~own_before, lane, F);
                     uint32_t A2, C2; make_masks(s, s.to_move, lane, A2, C2);
                     const Totals tc = gen_totals<BATCH ? BK_MCTS_MAX_WARPS : 1>(A2, C2, sel4(s.used, s.to_move), lane);
                     uint32_t cb = child_base[node];
@@ -240,6 +264,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                     if (!overflow) {
                         const uint32_t child = n_nodes++;
                         store_state(states + child, lane, s);
+                        if (LEARNED) store_rows4(frontier + (size_t)child * 28, lane, F);
                         if (lane == 0) {
                             child_base[node] = cb;
                             pool[cb + ne] = child;
@@ -264,14 +289,23 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
             if (overflow) break;
             // ---- simulation (mcts_agent.py:408-437); `s` holds the state of `node`
             long long r = 0;
+            double rd = 0.0;                         // the reward of learned evaluations
             bool cached = false;
             uint64_t key = 0;
             if (!BATCH && tt.keys) {
                 key = zobrist_of(s, tt.zobrist, lane) ^ salt;
                 double rv = 0.0;
-                if (tt_lookup(tt.keys, tt.rewards, tt.log2_slots, key, rv)) { r = (long long)rv; cached = true; }
+                if (tt_lookup(tt.keys, tt.rewards, tt.log2_slots, key, rv)) { r = (long long)rv; rd = rv; cached = true; }
             }
-            if (!cached && prm.reward_mode == 2) {
+            if (LEARNED) {
+                if (!cached) {
+                    // _evaluate_leaf(node.board, node.player) -> predict_player_win_probability (learned_evaluator.py:79-143)
+                    snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
+                    rd = win_probability(s_feat, prm.leaf_model, s.to_move, lane);
+                    __syncwarp();
+                    if (tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, rd);
+                }
+            } else if (!cached && prm.reward_mode == 2) {
                 // learned leaf evaluation in place of the rollout (mcts_agent.py:427-451) with the reference's dummy
                 // artifact (learned_evaluator.py:51-55,129-131): every leaf is worth 0.5, counted here as one half
                 r = 1;
@@ -309,7 +343,8 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
             }
             // ---- back-propagation (mcts_agent.py:572-582): W simulations at once in batch mode
             if (lead && lane == 0) {
-                for (int32_t v = (int32_t)node; v >= 0; v = parent[v]) { visits[v] += W; reward[v] += r; }
+                if (LEARNED) { for (int32_t v = (int32_t)node; v >= 0; v = parent[v]) { visits[v] += 1; reward_d[v] = __dadd_rn(reward_d[v], rd); } }
+                else { for (int32_t v = (int32_t)node; v >= 0; v = parent[v]) { visits[v] += W; reward[v] += r; } }
             }
             if (lead) iter_done++;
             __syncwarp();

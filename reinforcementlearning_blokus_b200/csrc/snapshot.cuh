@@ -133,10 +133,10 @@ __device__ __noinline__ void piece_totals(const uint32_t A, const uint32_t C, co
     bk_gen_all<PieceTotalSink, true>(A, C, used, sink);
 }
 
-// The 4 x 34 feature block of one board.  pc = uint16[4][24] and feat = double[4][34] are this warp's shared scratch;
-// the block is written to `out` with coalesced stores.
-__device__ __forceinline__ void snapshot_features(const WarpState& s, const uint32_t (&F)[4], int turn_index, int max_turns,
-                                                  int lane, uint16_t* pc, double* feat, double* __restrict__ out) {
+// The 4 x 34 feature block of one board, left in shared memory.  pc = uint16[4][24] and feat = double[4][34] are this
+// warp's shared scratch.
+__device__ __forceinline__ void snapshot_features_block(const WarpState& s, const uint32_t (&F)[4], int turn_index, int max_turns,
+                                                        int lane, uint16_t* pc, double* feat) {
     // ---- movegen-bound part: P_i for every player -------------------------------------------------------
     for (int k = lane; k < 4 * 24; k += 32) pc[k] = 0;
     __syncwarp();
@@ -226,8 +226,30 @@ __device__ __forceinline__ void snapshot_features(const WarpState& s, const uint
         f[33] = __ddiv_rn((double)sel4i(cells, p), 400.0);
     }
     __syncwarp();
+}
+
+// ... and written to `out` with coalesced stores.
+__device__ __forceinline__ void snapshot_features(const WarpState& s, const uint32_t (&F)[4], int turn_index, int max_turns,
+                                                  int lane, uint16_t* pc, double* feat, double* __restrict__ out) {
+    snapshot_features_block(s, F, turn_index, max_turns, lane, pc, feat);
     for (int k = lane; k < 4 * BK_NFEAT; k += 32) out[k] = feat[k];
     __syncwarp();
+}
+
+// LearnedWinProbabilityEvaluator.predict_player_win_probability (mcts/learned_evaluator.py:133-143) for a
+// "pairwise_logreg" model folded to 34 weights and a bias (model[0..33], model[34]): mean over the three opponents j of
+// sigmoid(bias + sum_c w_c * (f_player[c] - f_j[c])), terms added in column order, opponents in player order.
+__device__ __forceinline__ double win_probability(const double* feat, const double* __restrict__ model, uint32_t player, int lane) {
+    double p = 0.0;
+    if (lane < 3) {
+        const uint32_t j = (uint32_t)lane + ((uint32_t)lane >= player ? 1u : 0u);          // the lane-th opponent
+        double z = __ldg(model + BK_NFEAT);
+        for (int c = 0; c < BK_NFEAT; c++)
+            z = __dadd_rn(z, __dmul_rn(__ldg(model + c), __dsub_rn(feat[player * BK_NFEAT + c], feat[j * BK_NFEAT + c])));
+        p = __ddiv_rn(1.0, __dadd_rn(1.0, exp(-z)));
+    }
+    const double p0 = __shfl_sync(BK_FULL, p, 0), p1 = __shfl_sync(BK_FULL, p, 1), p2 = __shfl_sync(BK_FULL, p, 2);
+    return __ddiv_rn(__dadd_rn(__dadd_rn(p0, p1), p2), 3.0);
 }
 
 // Feature rows of n boards.  frontiers: uint64[n][28] bitboards (or NULL: rebuilt from the cells); turn_index: int32[n]

@@ -121,16 +121,25 @@ class DeviceUCT:
     def __init__(self, iterations_total: int, n_trees: int = 1, max_rollout_moves: int = 50, max_depth: int = 0,
                  ucb_variant: int = 0, exploration: float = 1.414, seed: int = 0, tree_offset: int = 0,
                  reward_mode: int = 0, rollout_policy: int = 0, tt: Optional[dev.DeviceTranspositionTable] = None, zobrist: Optional[ZobristHash] = None,
-                 max_root_moves: int = MAX_ROOT_MOVES, leaf_batch: int = 1):
+                 max_root_moves: int = MAX_ROOT_MOVES, leaf_batch: int = 1, leaf_model: Optional[torch.Tensor] = None,
+                 leaf_max_turns: int = 2500):
         if not torch.cuda.is_available():
             raise _lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
         self.lib = _lib.init(torch.cuda.current_device())
         self.p = _lib.MctsParams(iterations=0, iterations_total=int(iterations_total),
                                  max_rollout_moves=int(max_rollout_moves), rollout_policy=int(rollout_policy), max_depth=int(max_depth),
                                  ucb_variant=int(ucb_variant), resume=0, reward_mode=int(reward_mode), leaf_batch=int(leaf_batch),
-                                 reserved0=0, exploration=float(exploration),
+                                 reserved0=0, leaf_max_turns=int(leaf_max_turns), reserved1=0, exploration=float(exploration),
                                  seed=int(seed) & (2**64 - 1), tree_offset=int(tree_offset))
         self.n_trees = int(n_trees)
+        # reward_mode 3: learned leaf evaluation with a folded pairwise logistic model (float64[35] on the device)
+        self.leaf_model = None
+        if int(reward_mode) == 3:
+            if leaf_model is None or leaf_model.numel() != 35:
+                raise ValueError("reward_mode 3 needs leaf_model: 34 weights + bias")
+            self.leaf_model = leaf_model.to(device="cuda", dtype=torch.float64).contiguous()
+            self.p.leaf_model = self.leaf_model.data_ptr()
+        self.root_frontiers = None
         self.leaf_batch = max(1, int(leaf_batch))       # simulations per iteration (warps per tree)
         if self.leaf_batch > 16:
             raise ValueError("leaf_batch must be in [1, 16]")
@@ -153,13 +162,21 @@ class DeviceUCT:
         self.iterations_done = 0
         self._roots = None
 
-    def search(self, roots: Optional[torch.Tensor], iterations: int, resume: bool = False) -> Dict[str, torch.Tensor]:
-        """Run `iterations` more iterations on every tree (fresh trees from `roots` unless resume)."""
+    def search(self, roots: Optional[torch.Tensor], iterations: int, resume: bool = False,
+               root_frontiers: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Run `iterations` more iterations on every tree (fresh trees from `roots` unless resume).  root_frontiers
+        (int64[n_roots, 4, 7], learned leaf evaluation only): the roots' incremental frontier sets; None = rebuilt."""
         if not resume:
             if roots is None:
                 raise ValueError("roots required for a fresh search")
             self._roots = roots.contiguous()
             self.iterations_done = 0
+            self.root_frontiers = None
+            if root_frontiers is not None:
+                if tuple(root_frontiers.shape) != (self._roots.shape[0], 4, 7) or root_frontiers.dtype != torch.int64:
+                    raise ValueError("root_frontiers must be int64[n_roots, 4, 7]")
+                self.root_frontiers = root_frontiers.to(self._roots.device).contiguous()
+            self.p.root_frontiers = self.root_frontiers.data_ptr() if self.root_frontiers is not None else None
         if self.iterations_done + iterations > self.p.iterations_total:
             raise ValueError("search exceeds iterations_total")
         self.p.iterations = int(iterations)
@@ -175,7 +192,8 @@ class DeviceUCT:
             self.status.data_ptr(), torch.cuda.current_stream().cuda_stream))
         dev._count()
         self.iterations_done += iterations
-        return {"visits": self.visits, "reward": self.reward, "moves": self.moves, "counts": self.counts,
+        reward = self.reward.view(torch.float64) if self.p.reward_mode == 3 else self.reward
+        return {"visits": self.visits, "reward": reward, "moves": self.moves, "counts": self.counts,
                 "status": self.status}
 
 
@@ -209,9 +227,11 @@ class MCTSAgent:
     Learned-evaluator options (mcts_agent.py:427-466, 486-551): with the reference's ``dummy_model.json`` artifact --
     the only one its recorded arena runs use -- every probability is 0.5, so leaf evaluation is the kernel's constant
     leaf value (reward_mode 2), the progressive bias term is exactly 0 and the shaping term is exactly 0 for gamma = 1
-    or potential_mode "logit"; those combinations run on the device.  A fitted artifact is served out of tree by
-    ``winprob.LearnedWinProbabilityEvaluator`` (device features, scikit-learn model); using it INSIDE the tree would
-    need the estimator on the device and raises NotImplementedError.
+    or potential_mode "logit"; those combinations run on the device.  A fitted ``pairwise_logreg`` artifact whose
+    pipeline is [StandardScaler,] LogisticRegression also runs in the tree: leaf_evaluation_enabled evaluates the 34
+    snapshot features of every new leaf in the kernel and feeds the folded 34 weights + bias (reward_mode 3).  Other
+    estimators (gradient-boosted phase models) are served out of tree by ``winprob.LearnedWinProbabilityEvaluator``;
+    progressive bias and potential shaping with a fitted model raise NotImplementedError.
     """
 
     def __init__(self, iterations: int = 1000, time_limit: Optional[float] = None, exploration_constant: float = 1.414,
@@ -243,9 +263,14 @@ class MCTSAgent:
             from .winprob import LearnedWinProbabilityEvaluator
 
             self.learned_evaluator = LearnedWinProbabilityEvaluator(learned_model_path, potential_mode=potential_mode)
-            if self._requires_learned_evaluator and not self.learned_evaluator._is_dummy:
-                raise NotImplementedError("a fitted win-probability model inside the tree is not on the device path; "
-                                          "use winprob.LearnedWinProbabilityEvaluator for out-of-tree evaluation")
+            real = not self.learned_evaluator._is_dummy
+            if real and (self.progressive_bias_enabled or self.potential_shaping_enabled):
+                raise NotImplementedError("progressive bias / potential shaping with a fitted model are not on the "
+                                          "device path (leaf evaluation is); use the dummy artifact or disable them")
+            if real and self.leaf_evaluation_enabled and getattr(self.learned_evaluator, "device_model", None) is None:
+                raise NotImplementedError("in-tree leaf evaluation runs pairwise_logreg artifacts whose pipeline is "
+                                          "[StandardScaler,] LogisticRegression; this artifact has another shape -- "
+                                          "use winprob.LearnedWinProbabilityEvaluator out of tree")
             if (self.potential_shaping_enabled and potential_mode == "prob" and self.potential_shaping_gamma != 1.0
                     and self.potential_shaping_weight != 0.0):
                 raise NotImplementedError("potential shaping with gamma != 1 adds a non-zero constant to truncated "
@@ -288,9 +313,16 @@ class MCTSAgent:
         # every search of this agent gets its own block of Philox streams
         offset = self._searches * max(self.num_trees, 1)
         self._searches += 1
+        mode, model = 0, None
+        if self.leaf_evaluation_enabled:
+            if self.learned_evaluator._is_dummy:
+                mode = 2
+            else:
+                mode, model = 3, torch.from_numpy(self.learned_evaluator.device_model)
         return DeviceUCT(total, n_trees=self.num_trees, max_rollout_moves=self.max_rollout_moves,
                          exploration=self.exploration_constant, seed=self.seed, tree_offset=offset,
-                         reward_mode=2 if self.leaf_evaluation_enabled else 0, leaf_batch=self.leaf_batch,
+                         reward_mode=mode, leaf_model=model, leaf_max_turns=getattr(self.learned_evaluator, "max_turns", 2500),
+                         leaf_batch=self.leaf_batch,
                          rollout_policy=self.rollout_policy, tt=tt,
                          zobrist=self.zobrist_hash if tt is not None else None)
 
@@ -298,13 +330,16 @@ class MCTSAgent:
         """Root statistics (visits, reward sums) by ascending legal-move rank, summed over the trees."""
         start = time.time()
         root = _root_state(board, player)
+        frontiers = None
+        if self.leaf_evaluation_enabled and self.learned_evaluator is not None and not self.learned_evaluator._is_dummy:
+            frontiers = torch.from_numpy(board.frontier_words()[None].copy())     # the board's incremental sets
         if self.time_limit:
             # capacity for the time budget: one warp runs about 12-15 k simulations/s (profiles/r01_agent_latency.json)
             chunk = 64
             cap = min(60000, max(4 * chunk, int(self.time_limit * 30000)))
             eng = self._engine(cap)
             done = 0
-            res = eng.search(root, chunk)
+            res = eng.search(root, chunk, root_frontiers=frontiers)
             done += chunk
             torch.cuda.synchronize()
             while time.time() - start < self.time_limit and done + chunk <= cap:
@@ -313,7 +348,7 @@ class MCTSAgent:
                 torch.cuda.synchronize()
         else:
             eng = self._engine(max(1, int(self.iterations)))
-            res = eng.search(root, int(self.iterations))
+            res = eng.search(root, int(self.iterations), root_frontiers=frontiers)
             done = int(self.iterations)
         if int(res["status"].max().item()):
             raise _lib.BlokusB200Error("MCTS workspace exhausted")
@@ -323,7 +358,8 @@ class MCTSAgent:
         self.stats["iterations_run"] = done
         self.stats["time_elapsed"] = time.time() - start
         if self.leaf_evaluation_enabled:
-            reward = reward * 0.5                            # halves -> the evaluator's probabilities
+            if self.learned_evaluator._is_dummy:
+                reward = reward * 0.5                        # halves -> the dummy evaluator's probabilities
             self.stats["leaf_eval_calls"] = done
         if self.progressive_bias_enabled:
             self.stats["progressive_bias_updates"] = done    # one (zero-valued) prior per expansion

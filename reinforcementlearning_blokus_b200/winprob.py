@@ -140,6 +140,38 @@ def write_snapshots_dataset(run_dir: str, snapshot_rows: Sequence[Mapping[str, A
             "path_csv": csv_path, "parquet_written": written, "parquet_error": err}
 
 
+def fold_logistic_pipeline(artifact: Mapping[str, Any]) -> Optional[np.ndarray]:
+    """float64[35] (34 weights in SNAPSHOT_FEATURE_COLUMNS order + bias) of a "pairwise_logreg" artifact whose pipeline is
+    [StandardScaler,] LogisticRegression over (a subset of) the snapshot columns -- the form the device kernel evaluates:
+    logit = intercept + sum_c coef_c * (d_c - mean_c) / scale_c.  None when the pipeline has any other shape."""
+    if artifact.get("model_type") != "pairwise_logreg":
+        return None
+    pipe = artifact.get("pipeline")
+    steps = [st for _, st in getattr(pipe, "steps", [])] if hasattr(pipe, "steps") else [pipe]
+    if not steps or type(steps[-1]).__name__ != "LogisticRegression" or len(steps) > 2:
+        return None
+    clf = steps[-1]
+    coef = np.asarray(clf.coef_, dtype=np.float64).reshape(-1)
+    cols = list(artifact.get("feature_columns", SNAPSHOT_FEATURE_COLUMNS))
+    if len(coef) != len(cols) or any(c not in SNAPSHOT_FEATURE_COLUMNS for c in cols) or len(np.atleast_1d(clf.intercept_)) != 1:
+        return None
+    mean, scale = np.zeros(len(cols)), np.ones(len(cols))
+    if len(steps) == 2:
+        sc = steps[0]
+        if type(sc).__name__ != "StandardScaler":
+            return None
+        if getattr(sc, "with_mean", True) and getattr(sc, "mean_", None) is not None:
+            mean = np.asarray(sc.mean_, dtype=np.float64)
+        if getattr(sc, "with_std", True) and getattr(sc, "scale_", None) is not None:
+            scale = np.asarray(sc.scale_, dtype=np.float64)
+    w = coef / scale
+    out = np.zeros(35, dtype=np.float64)
+    for c, v in zip(cols, w):
+        out[SNAPSHOT_FEATURE_COLUMNS.index(c)] = v
+    out[34] = float(np.atleast_1d(clf.intercept_)[0]) - float(np.sum(w * mean))
+    return out
+
+
 # ---- learned leaf evaluator (mcts/learned_evaluator.py) ----------------------------------------------------------
 def _phase_bucket_from_occupancy(board_occupancy: float, *, early_max: float = 0.33, mid_max: float = 0.66) -> str:
     return "early" if board_occupancy < early_max else ("mid" if board_occupancy < mid_max else "late")
@@ -166,6 +198,7 @@ class LearnedWinProbabilityEvaluator:
         if self.model_type not in {"pairwise_logreg", "pairwise_gbt_phase"}:
             raise ValueError(f"Unsupported learned evaluator model_type '{self.model_type}' in {self.artifact_path}.")
         self._cols = [SNAPSHOT_FEATURE_COLUMNS.index(c) for c in self.feature_columns]
+        self.device_model = fold_logistic_pipeline(self.artifact)      # float64[35] for the UCT kernel, or None
 
     def _extract_features_for_all_players(self, board: Board) -> Dict[int, Dict[str, float]]:
         blk = board_feature_block(board, int(board.move_count), self.max_turns)

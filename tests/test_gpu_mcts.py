@@ -269,3 +269,88 @@ def test_batched_mcts_selfplay():
     c = batched.selfplay_mcts(4, 16, seed=2, trees_per_game=3, leaf_batch=4, want_policy=True, max_turns=6)
     v0, m0 = c["policy"][0]
     assert v0.shape[0] == 4 and int(v0[0].sum()) == 3 * 16 * 4 and len(c["policy"]) == 6
+
+
+def _logreg_artifact(golden_dir, tmp_path, scaler=True):
+    joblib = pytest.importorskip("joblib")
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+
+    from reinforcementlearning_blokus_b200 import winprob
+
+    rows = np.load(os.path.join(golden_dir, "snapshots.npz"))["state_features"]            # reference rows [240, 4, 34]
+    x = np.concatenate([rows[:, 0] - rows[:, 1], rows[:, 2] - rows[:, 3], rows[:, 1] - rows[:, 2]])
+    # a learnable target: the side with more mobility and more squares placed tends to win
+    c = winprob.SNAPSHOT_FEATURE_COLUMNS
+    y = (x[:, c.index("mobility_total_placements")] + 20 * x[:, c.index("player_board_occupancy")] * 400 > 0).astype(int)
+    steps = ([("scale", StandardScaler())] if scaler else []) + [("clf", LogisticRegression(max_iter=500))]
+    pipe = Pipeline(steps).fit(x, y)
+    path = str(tmp_path / ("logreg_scaled.joblib" if scaler else "logreg.joblib"))
+    joblib.dump({"model_type": "pairwise_logreg", "feature_columns": c, "pipeline": pipe}, path)
+    return path, pipe, rows
+
+
+def test_learned_leaf_evaluation_in_the_tree(golden_dir, tmp_path):
+    """mcts_agent.py:427-451 with a fitted pairwise logistic model: the kernel computes the leaf's snapshot features and
+    the folded model itself.  (1) the folded weights reproduce scikit-learn's predict_proba; (2) kernel == sequential
+    oracle (visits, moves, double reward sums) with and without root frontier sets and the transposition table;
+    (3) the agent accepts the reference's constructor arguments and its leaf values are the evaluator's probabilities."""
+    from reinforcementlearning_blokus_b200 import winprob
+
+    path, pipe, rows = _logreg_artifact(golden_dir, tmp_path)
+    ev = winprob.LearnedWinProbabilityEvaluator(path)
+    w = ev.device_model
+    assert w is not None and w.shape == (35,)
+    d = rows[7, 0] - rows[7, 2]
+    assert 1.0 / (1.0 + np.exp(-(w[34] + float(np.dot(w[:34], d))))) == pytest.approx(float(pipe.predict_proba(d[None])[0, 1]), abs=1e-12)
+    iters = 150
+    z = np.load(os.path.join(golden_dir, "snapshots.npz"))
+    for ri, root_np in enumerate(_roots(golden_dir)[:3]):
+        root = dev.to_device(np.atleast_1d(root_np))
+        want = orc.mcts_search_learned(root_np, iters, seed=17, model=w, tree_id=ri)
+        res = DeviceUCT(iters, n_trees=1, seed=17, tree_offset=ri, reward_mode=3, leaf_model=torch.from_numpy(w)).search(root, iters)
+        n = want["n_root"]
+        assert int(res["counts"][0]) == n and int(res["status"][0]) == 0
+        assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n]), ri
+        assert np.array_equal(res["moves"][0, :n].cpu().numpy(), want["moves"][:n])
+        assert np.allclose(res["reward"][0, :n].cpu().numpy(), want["reward"][:n], rtol=0, atol=1e-12)
+        assert int(res["visits"][0, :n].sum()) == iters
+    # a mid-game board captured by the reference WITH its incremental frontier sets (stale cells included)
+    g, k = 3, 4
+    st = z["snap_states"][g, k].view(STATE_DTYPE)[0]
+    fr_bits = np.unpackbits(z["frontiers"][g, k], axis=-1, bitorder="little")[:, :400]
+    fr_words = np.packbits(np.pad(fr_bits, ((0, 0), (0, 48))), axis=-1, bitorder="little").view("<i8").reshape(1, 4, 7)
+    want = orc.mcts_search_learned(st, iters, seed=4, model=w, root_frontier=fr_bits)
+    eng = DeviceUCT(iters, n_trees=1, seed=4, reward_mode=3, leaf_model=torch.from_numpy(w))
+    res = eng.search(dev.to_device(np.atleast_1d(st)), iters, root_frontiers=torch.from_numpy(fr_words.copy()))
+    n = want["n_root"]
+    assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n])
+    assert np.allclose(res["reward"][0, :n].cpu().numpy(), want["reward"][:n], rtol=0, atol=1e-12)
+    # transposition table: cached probabilities are reused by a second search
+    zob, tt, ott = ZobristHash(seed=42), TranspositionTable(max_size=1 << 16), orc.OracleTT(18)
+    for rep in range(2):
+        want = orc.mcts_search_learned(st, 100, seed=9, model=w, tt=ott, zobrist=zob.table)
+        res = DeviceUCT(100, n_trees=1, seed=9, reward_mode=3, leaf_model=torch.from_numpy(w), tt=tt.device, zobrist=zob).search(
+            dev.to_device(np.atleast_1d(st)), 100)
+        assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n]), rep
+    ott.close()
+    # the agent: leaf values are the evaluator's own probabilities of the children, for the player to move there
+    board = Board.from_packed(_roots(golden_dir)[1])
+    player = board.current_player
+    legal = get_shared_generator().get_legal_moves(board, player)
+    agent = MCTSAgent(iterations=len(legal), seed=2, learned_model_path=path, leaf_evaluation_enabled=True,
+                      use_transposition_table=False)
+    r = agent.search_root(board, player)
+    assert int(r["visits"].sum()) == len(legal) and (r["visits"] == 1).all()          # one visit per root move
+    ids = sorted(m.to_id() for m in legal)
+    for rank in (0, len(ids) // 2, len(ids) - 1):
+        child = board.copy()
+        mv = Move.from_id(ids[rank])
+        cells = get_shared_generator().piece_position_cache[mv.piece_id][mv.orientation]
+        from reinforcementlearning_blokus_b200 import Position
+        child.place_piece([Position(mv.anchor_row + a, mv.anchor_col + b) for a, b in cells], player, mv.piece_id, validate=False)
+        assert r["reward"][rank] == pytest.approx(ev.predict_player_win_probability(child, child.current_player), abs=1e-9)
+    assert agent.select_action(board, player, legal) in legal and agent.stats["leaf_eval_calls"] == len(legal)
+    with pytest.raises(NotImplementedError):
+        MCTSAgent(learned_model_path=path, progressive_bias_enabled=True)
