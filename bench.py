@@ -388,6 +388,8 @@ def _int_roofline(n, per_launch_s, clocks, sm_max):
 
 def _extras(dev, torch, n):
     """The other two parts of BASELINE.json's metric: legal-move generations/s (and later MCTS sims/s)."""
+    from reinforcementlearning_blokus_b200.state import empty_states as empty_states_fn
+
     def timeit(fn, reps=5):
         fn(); fn()
         torch.cuda.synchronize()
@@ -457,6 +459,16 @@ def _extras(dev, torch, n):
             eng.search(root, iters)
             torch.cuda.synchronize()
             ex[tag] = round(timeit(lambda: eng.search(root, iters), reps=3), 3)
+        # UCT with learned leaf evaluation in the kernel (reward_mode 3: a pairwise logistic win-probability model on the
+        # 34 snapshot features of every new leaf instead of a rollout); synthetic weights, trees from the empty board
+        wts = torch.from_numpy(np.random.default_rng(0).normal(0.0, 0.05, 35))
+        lt = 4 * 2368
+        leng = DeviceUCT(256, n_trees=lt, seed=SEED, reward_mode=3, leaf_model=wts)
+        start = dev.to_device(empty_states_fn(1))
+        leng.search(start, 256)
+        torch.cuda.synchronize()
+        ex["mcts_learned_leaf_sims_per_sec"] = lt * 256 / timeit(lambda: leng.search(start, 256), reps=2) * 1e3
+        del leng
     except Exception as exc:                                                # extras never break the headline line
         ex["mcts_move_error"] = str(exc)[:200]
     # win-probability snapshot rows (row N4): 4 x 34 float64 per board = four piece-count generations + a flood fill;
