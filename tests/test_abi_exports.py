@@ -74,3 +74,32 @@ def test_sass_is_sm100a_only(lib_path):
     out = subprocess.run([cuobjdump, "-lelf", lib_path], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/blokus_b200.h compiles as C11 (the boundary is a C ABI) and bk_mcts_params / bk_state have the byte
+    layout the ctypes binding assumes."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from reinforcementlearning_blokus_b200._lib import MctsParams
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    fields = [f[0] for f in MctsParams._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "blokus_b200.h"\nint main(void){\n'
+                   + 'printf("%zu %zu\\n", sizeof(bk_mcts_params), sizeof(bk_state));\n'
+                   + "".join(f'printf("{f} %zu\\n", offsetof(bk_mcts_params, {f}));\n' for f in fields) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call([gcc, "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    lines = subprocess.check_output([str(exe)], text=True).split("\n")
+    size_params, size_state = (int(x) for x in lines[0].split())
+    assert size_params == ctypes.sizeof(MctsParams) and size_state == 256
+    for line in lines[1:]:
+        if line:
+            name, off = line.split()
+            assert getattr(MctsParams, name).offset == int(off), name
