@@ -240,6 +240,9 @@ typedef struct bk_mcts_params {
                                        engine/board.py:247-259), or NULL for the sets of a freshly restored board */
     int32_t  leaf_max_turns;        /* reward_mode 3: max_turns of the evaluator's progress features (2500) */
     int32_t  reserved1;
+    double   progressive_bias_weight; /* reward_mode 3: w of the selection term w * prior/(1 + n) (mcts_agent.py:88, 453-468),
+                                         prior(child) = V(child board, parent player) - V(parent board, parent player);
+                                         0 = off */
 } bk_mcts_params;
 
 /* Bytes of device workspace per tree for a search of params->iterations_total iterations (host call). */

@@ -88,7 +88,7 @@ def lib() -> C.CDLL:
         L.orc_tt_size.argtypes = [vp]
         L.orc_tt_size.restype = u64
         L.orc_mcts_search.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, vp, vp]
-        L.orc_mcts_search_learned.argtypes = [vp, vp, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, i32, vp, vp, vp]
+        L.orc_mcts_search_learned.argtypes = [vp, vp, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, i32, C.c_double, vp, vp, vp]
         L.orc_mcts_search_batched.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, i32, vp, vp, vp]
         L.orc_check_moves_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp]
         L.orc_check_playouts.argtypes = [u64, u64, i32, i32, i32, vp, vp, vp]
@@ -328,7 +328,7 @@ def mcts_search(root: np.ndarray, iterations: int, seed: int, tree_id: int = 0, 
 def mcts_search_learned(root: np.ndarray, iterations: int, seed: int, model: np.ndarray, tree_id: int = 0, max_turns: int = 2500,
                         root_frontier: Optional[np.ndarray] = None, max_depth: int = 0, ucb_variant: int = 0,
                         exploration: float = 1.414, tt: Optional[OracleTT] = None, zobrist: Optional[np.ndarray] = None,
-                        max_root_moves: int = 2048):
+                        max_root_moves: int = 2048, bias_weight: float = 0.0):
     """UCT with learned leaf evaluation (mcts_agent.py:427-451): model = float64[35] (34 weights + bias of a folded
     pairwise logistic model), root_frontier = uint8[4, 400] incremental frontier sets or None.  reward sums are doubles."""
     st = np.ascontiguousarray(np.atleast_1d(root), dtype=STATE_DTYPE)
@@ -341,7 +341,7 @@ def mcts_search_learned(root: np.ndarray, iterations: int, seed: int, model: np.
     zt = None if zobrist is None else np.ascontiguousarray(zobrist, dtype=np.uint64)
     n = lib().orc_mcts_search_learned(_ptr(st), _ptr(fr), int(iterations), int(max_depth), int(ucb_variant), float(exploration),
                                       int(seed), int(tree_id), tt.h if tt else None, _ptr(zt), int(max_root_moves), _ptr(md),
-                                      int(max_turns), _ptr(vis), _ptr(rew), _ptr(mov))
+                                      int(max_turns), float(bias_weight), _ptr(vis), _ptr(rew), _ptr(mov))
     return {"n_root": int(n), "visits": vis, "reward": rew, "moves": mov}
 
 

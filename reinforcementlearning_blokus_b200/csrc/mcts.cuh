@@ -22,7 +22,7 @@
 struct MctsLayout {            // byte offsets inside one tree's workspace slice
     uint32_t max_nodes, pool_slots;
     size_t off_states, off_parent, off_visits, off_reward, off_child_base, off_n_legal, off_n_expanded,
-           off_move, off_pool, off_header, off_frontier, total;
+           off_move, off_pool, off_header, off_frontier, off_value, off_prior, total;
 };
 
 __host__ __device__ inline size_t bk_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -50,6 +50,9 @@ __host__ __device__ inline MctsLayout mcts_layout(int iterations_total, bool wit
     L.off_header = o;      o += 128;
     // learned leaf evaluation: every node also keeps the four frontier sets of its board (28 words, engine/board.py:315-367)
     L.off_frontier = o;    if (with_frontier) o += (size_t)L.max_nodes * 28 * 8;
+    // ... its own learned value V(board, player to move) and its progressive-bias prior (mcts_agent.py:453-468)
+    L.off_value = o;       if (with_frontier) o += (size_t)L.max_nodes * 8;
+    L.off_prior = o;       if (with_frontier) o += (size_t)L.max_nodes * 8;
     L.total = bk_align_up(o, 256);
     return L;
 }
@@ -152,6 +155,9 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
         MctsHeader* hdr = reinterpret_cast<MctsHeader*>(base + L.off_header);
         uint64_t* frontier = reinterpret_cast<uint64_t*>(base + L.off_frontier);       // [node][28], LEARNED only
         double* reward_d = reinterpret_cast<double*>(reward);                          // the same slots as doubles
+        double* node_value = reinterpret_cast<double*>(base + L.off_value);            // LEARNED only
+        double* node_prior = reinterpret_cast<double*>(base + L.off_prior);
+        const bool bias_on = LEARNED && prm.progressive_bias_weight != 0.0;
         uint32_t F[4] = {0u, 0u, 0u, 0u};                                               // frontier rows of `s`
         const uint64_t tree_id = prm.tree_offset + (uint64_t)tree;
         // per-tree salt keeps concurrently searched trees from reading each other's cached rewards, so the
@@ -173,6 +179,12 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                     else
                         rebuild_frontiers(s, lane, F);
                     store_rows4(frontier, lane, F);
+                    if (bias_on) {                 // V(root board, root player): the parent value of the root's children
+                        snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
+                        const double v0 = win_probability(s_feat, prm.leaf_model, s.to_move, lane);
+                        if (lane == 0) { node_value[0] = v0; node_prior[0] = 0.0; }
+                        __syncwarp();
+                    }
                 }
                 if (lane == 0) {
                     parent[0] = -1; visits[0] = 0; reward[0] = 0; child_base[0] = 0xFFFFFFFFu;
@@ -205,6 +217,8 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
         };
         for (int it = 0; it < prm.iterations; it++) {
             uint32_t node = 0, depth = 0;
+            bool have_value = false;               // learned value of the new leaf already computed during expansion
+            double leaf_value = 0.0;
             if (lead && !overflow) {
             // ---- selection (mcts_agent.py:384-406)
             while (true) {
@@ -221,8 +235,12 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                     const double v = (double)visits[ch];
                     double u;
                     if (visits[ch] == 0) u = __longlong_as_double(0x7FF0000000000000ll);
-                    else u = __dadd_rn(__ddiv_rn(LEARNED ? reward_d[ch] : __dmul_rn((double)reward[ch], unit), v),
-                                       __dmul_rn(prm.exploration, sqrt(__ddiv_rn(logN, v))));
+                    else {
+                        u = __dadd_rn(__ddiv_rn(LEARNED ? reward_d[ch] : __dmul_rn((double)reward[ch], unit), v),
+                                      __dmul_rn(prm.exploration, sqrt(__ddiv_rn(logN, v))));
+                        if (bias_on)               // + w * (prior / (1 + n)), mcts_agent.py:88-89
+                            u = __dadd_rn(u, __dmul_rn(prm.progressive_bias_weight, __ddiv_rn(node_prior[ch], __dadd_rn(1.0, v))));
+                    }
                     if (!have || u > best) { best = u; best_k = k; have = true; }
                 }
                 // warp argmax, ties -> smallest k (Python's max keeps the first maximal child)
@@ -265,6 +283,16 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                         const uint32_t child = n_nodes++;
                         store_state(states + child, lane, s);
                         if (LEARNED) store_rows4(frontier + (size_t)child * 28, lane, F);
+                        if (bias_on) {
+                            // _update_progressive_bias(parent, child): both values for the PARENT's player; the child's
+                            // feature block also gives its own value, which the simulation below reuses
+                            snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
+                            const double for_parent = win_probability(s_feat, prm.leaf_model, p, lane);
+                            leaf_value = win_probability(s_feat, prm.leaf_model, s.to_move, lane);
+                            have_value = true;
+                            if (lane == 0) { node_prior[child] = __dsub_rn(for_parent, node_value[node]); node_value[child] = leaf_value; }
+                            __syncwarp();
+                        }
                         if (lane == 0) {
                             child_base[node] = cb;
                             pool[cb + ne] = child;
@@ -300,9 +328,12 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
             if (LEARNED) {
                 if (!cached) {
                     // _evaluate_leaf(node.board, node.player) -> predict_player_win_probability (learned_evaluator.py:79-143)
-                    snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
-                    rd = win_probability(s_feat, prm.leaf_model, s.to_move, lane);
-                    __syncwarp();
+                    if (have_value) rd = leaf_value;
+                    else {
+                        snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
+                        rd = win_probability(s_feat, prm.leaf_model, s.to_move, lane);
+                        __syncwarp();
+                    }
                     if (tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, rd);
                 }
             } else if (!cached && prm.reward_mode == 2) {

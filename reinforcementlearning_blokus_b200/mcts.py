@@ -122,14 +122,16 @@ class DeviceUCT:
                  ucb_variant: int = 0, exploration: float = 1.414, seed: int = 0, tree_offset: int = 0,
                  reward_mode: int = 0, rollout_policy: int = 0, tt: Optional[dev.DeviceTranspositionTable] = None, zobrist: Optional[ZobristHash] = None,
                  max_root_moves: int = MAX_ROOT_MOVES, leaf_batch: int = 1, leaf_model: Optional[torch.Tensor] = None,
-                 leaf_max_turns: int = 2500):
+                 leaf_max_turns: int = 2500, progressive_bias_weight: float = 0.0):
         if not torch.cuda.is_available():
             raise _lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
         self.lib = _lib.init(torch.cuda.current_device())
         self.p = _lib.MctsParams(iterations=0, iterations_total=int(iterations_total),
                                  max_rollout_moves=int(max_rollout_moves), rollout_policy=int(rollout_policy), max_depth=int(max_depth),
                                  ucb_variant=int(ucb_variant), resume=0, reward_mode=int(reward_mode), leaf_batch=int(leaf_batch),
-                                 reserved0=0, leaf_max_turns=int(leaf_max_turns), reserved1=0, exploration=float(exploration),
+                                 reserved0=0, leaf_max_turns=int(leaf_max_turns), reserved1=0,
+                                 progressive_bias_weight=float(progressive_bias_weight) if int(reward_mode) == 3 else 0.0,
+                                 exploration=float(exploration),
                                  seed=int(seed) & (2**64 - 1), tree_offset=int(tree_offset))
         self.n_trees = int(n_trees)
         # reward_mode 3: learned leaf evaluation with a folded pairwise logistic model (float64[35] on the device)
@@ -229,9 +231,11 @@ class MCTSAgent:
     leaf value (reward_mode 2), the progressive bias term is exactly 0 and the shaping term is exactly 0 for gamma = 1
     or potential_mode "logit"; those combinations run on the device.  A fitted ``pairwise_logreg`` artifact whose
     pipeline is [StandardScaler,] LogisticRegression also runs in the tree: leaf_evaluation_enabled evaluates the 34
-    snapshot features of every new leaf in the kernel and feeds the folded 34 weights + bias (reward_mode 3).  Other
-    estimators (gradient-boosted phase models) are served out of tree by ``winprob.LearnedWinProbabilityEvaluator``;
-    progressive bias and potential shaping with a fitted model raise NotImplementedError.
+    snapshot features of every new leaf in the kernel and feeds the folded 34 weights + bias (reward_mode 3), and
+    progressive_bias_enabled adds the selection term w * prior / (1 + n) with prior = V(child, parent player) -
+    V(parent, parent player) from the same feature block.  Other estimators (gradient-boosted phase models) are served
+    out of tree by ``winprob.LearnedWinProbabilityEvaluator``; potential shaping with a fitted model raises
+    NotImplementedError.
     """
 
     def __init__(self, iterations: int = 1000, time_limit: Optional[float] = None, exploration_constant: float = 1.414,
@@ -264,9 +268,12 @@ class MCTSAgent:
 
             self.learned_evaluator = LearnedWinProbabilityEvaluator(learned_model_path, potential_mode=potential_mode)
             real = not self.learned_evaluator._is_dummy
-            if real and (self.progressive_bias_enabled or self.potential_shaping_enabled):
-                raise NotImplementedError("progressive bias / potential shaping with a fitted model are not on the "
-                                          "device path (leaf evaluation is); use the dummy artifact or disable them")
+            if real and self.potential_shaping_enabled:
+                raise NotImplementedError("potential shaping with a fitted model is not on the device path (leaf "
+                                          "evaluation and progressive bias are); use the dummy artifact or disable it")
+            if real and self.progressive_bias_enabled and not self.leaf_evaluation_enabled:
+                raise NotImplementedError("progressive bias with a fitted model runs together with learned leaf "
+                                          "evaluation (the kernel shares the leaf's feature block); enable both")
             if real and self.leaf_evaluation_enabled and getattr(self.learned_evaluator, "device_model", None) is None:
                 raise NotImplementedError("in-tree leaf evaluation runs pairwise_logreg artifacts whose pipeline is "
                                           "[StandardScaler,] LogisticRegression; this artifact has another shape -- "
@@ -322,6 +329,7 @@ class MCTSAgent:
         return DeviceUCT(total, n_trees=self.num_trees, max_rollout_moves=self.max_rollout_moves,
                          exploration=self.exploration_constant, seed=self.seed, tree_offset=offset,
                          reward_mode=mode, leaf_model=model, leaf_max_turns=getattr(self.learned_evaluator, "max_turns", 2500),
+                         progressive_bias_weight=self.progressive_bias_weight if self.progressive_bias_enabled else 0.0,
                          leaf_batch=self.leaf_batch,
                          rollout_policy=self.rollout_policy, tt=tt,
                          zobrist=self.zobrist_hash if tt is not None else None)

@@ -353,4 +353,25 @@ def test_learned_leaf_evaluation_in_the_tree(golden_dir, tmp_path):
         assert r["reward"][rank] == pytest.approx(ev.predict_player_win_probability(child, child.current_player), abs=1e-9)
     assert agent.select_action(board, player, legal) in legal and agent.stats["leaf_eval_calls"] == len(legal)
     with pytest.raises(NotImplementedError):
-        MCTSAgent(learned_model_path=path, progressive_bias_enabled=True)
+        MCTSAgent(learned_model_path=path, progressive_bias_enabled=True)            # needs leaf evaluation too
+    with pytest.raises(NotImplementedError):
+        MCTSAgent(learned_model_path=path, leaf_evaluation_enabled=True, potential_shaping_enabled=True)
+    # progressive bias (mcts_agent.py:88, 453-468) on top of leaf evaluation: kernel == oracle, and it changes the search
+    for ri, root_np in enumerate(_roots(golden_dir)[1:3]):
+        root = dev.to_device(np.atleast_1d(root_np))
+        want = orc.mcts_search_learned(root_np, 300, seed=23, model=w, tree_id=ri, bias_weight=0.25)
+        res = DeviceUCT(300, n_trees=1, seed=23, tree_offset=ri, reward_mode=3, leaf_model=torch.from_numpy(w),
+                        progressive_bias_weight=0.25).search(root, 300)
+        n = want["n_root"]
+        assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n]), ri
+        assert np.allclose(res["reward"][0, :n].cpu().numpy(), want["reward"][:n], rtol=0, atol=1e-12)
+    late = z["snap_states"][0, 7].view(STATE_DTYPE)[0]                       # ply 56: few root moves, so selection happens
+    plain = orc.mcts_search_learned(late, 300, seed=23, model=w)
+    strong = orc.mcts_search_learned(late, 300, seed=23, model=w, bias_weight=5.0)
+    assert 0 < plain["n_root"] < 150 and not np.array_equal(plain["visits"], strong["visits"])
+    res = DeviceUCT(300, n_trees=1, seed=23, reward_mode=3, leaf_model=torch.from_numpy(w), progressive_bias_weight=5.0).search(
+        dev.to_device(np.atleast_1d(late)), 300)
+    assert np.array_equal(res["visits"][0, :plain["n_root"]].cpu().numpy(), strong["visits"][:plain["n_root"]])
+    biased = MCTSAgent(iterations=120, seed=2, learned_model_path=path, leaf_evaluation_enabled=True,
+                       progressive_bias_enabled=True, progressive_bias_weight=0.25, use_transposition_table=False)
+    assert biased.select_action(board, player, legal) in legal and biased.stats["progressive_bias_updates"] == 120
