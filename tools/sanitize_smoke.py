@@ -34,5 +34,15 @@ for pol in (0, 1):
     eng = DeviceUCT(24, n_trees=4, seed=5, rollout_policy=pol, tt=tt, zobrist=z)
     eng.search(mid[:2].contiguous(), 12)
     eng.search(None, 12, resume=True)
+for pol in (0, 1):                                   # leaf-batched rollouts: a CTA of warps per tree
+    eng = DeviceUCT(16, n_trees=3, seed=6, rollout_policy=pol, leaf_batch=8 if pol else 16)
+    eng.search(mid[:2].contiguous(), 8)
+    eng.search(None, 8, resume=True)
+eng = DeviceUCT(32, n_trees=3, seed=7, reward_mode=3, leaf_model=torch.linspace(-0.1, 0.1, 35, dtype=torch.float64),
+                progressive_bias_weight=0.25, tt=tt, zobrist=z)   # learned leaf evaluation + progressive bias
+eng.search(mid[:3].contiguous(), 32)
+dev.piece_counts(st)
+dev.snapshot_features(st)
+dev.replay_snapshots(r["trace"], (0, 8, 40, 64), want_states=True)
 torch.cuda.synchronize()
 print("sanitize smoke ok", int(counts.sum()))
