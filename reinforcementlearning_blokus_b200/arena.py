@@ -463,8 +463,11 @@ def run_experiment(run_config: RunConfig, *, verbose: bool = False, device_batch
 
     When every agent is of a built-in policy type ("random" / "heuristic", default weights) and `device_batch` is set,
     the whole experiment is ONE device batch (run_device_arena): same seeds, seat assignments, record keys and
-    snapshot rows, moves drawn with Philox.  Any other agent mix runs the reference's per-game loop over agent objects
-    (a fresh agent per game and name, seeded with the reference's agent_seed)."""
+    snapshot rows, moves drawn with Philox.  Mixes that include search agents ("mcts", "fast_mcts",
+    "gameplay_fast_mcts" -- the reference's own arena configs) run as device batches too, one search launch per agent and
+    turn over all games (run_device_arena_agents).  Anything else (custom heuristic weights, learned models,
+    device_batch=False) runs the reference's per-game loop over agent objects (a fresh agent per game and name, seeded
+    with the reference's agent_seed)."""
     import os
     from datetime import datetime
 
@@ -484,8 +487,15 @@ def run_experiment(run_config: RunConfig, *, verbose: bool = False, device_batch
         json.dump(payload, f, indent=2, sort_keys=True)
         f.write("\n")
     builtin = all(a.type.lower() in POLICY_OF and not a.params.get("weights") for a in run_config.agents)
+    batchable = all((a.type.lower() in POLICY_OF and not a.params.get("weights")) or
+                    (a.type.lower() in _SEARCH_TYPES and not a.params.get("learned_model_path")) for a in run_config.agents)
     snaps = run_config.snapshots.checkpoints if run_config.snapshots.enabled else None
-    if builtin and device_batch:
+    if batchable and not builtin and device_batch:
+        out = run_device_arena_agents(run_config, run_id=run_id)
+        records, rows = out["records"], out.get("snapshot_rows", [])
+        for rec in records:
+            rec["agent_move_stats"] = {n: out["agent_move_stats"][n] for n in set(rec["seat_assignment"].values())}
+    elif builtin and device_batch:
         out = run_device_arena({a.name: a.type.lower() for a in run_config.agents}, run_config.num_games,
                                run_seed=run_config.seed, seat_policy=run_config.seat_policy, run_id=run_id,
                                snapshots=snaps, max_turns=run_config.max_turns)
@@ -530,3 +540,135 @@ def run_experiment(run_config: RunConfig, *, verbose: bool = False, device_batch
         json.dump(summary, f, indent=2, sort_keys=True)
         f.write("\n")
     return {"run_id": run_id, "run_dir": run_dir, "summary": summary, "snapshot_rows": len(rows)}
+
+
+# ---- whole experiments with search agents as device batches ------------------------------------------------------------
+_SEARCH_TYPES = {"mcts", "fast_mcts", "gameplay_fast_mcts", "gameplay_mcts"}
+
+
+def _iteration_cap(cfg: AgentConfig) -> int:
+    """Simulations per move of a search agent under the reference's deterministic budget rule (arena_runner.py:334-356,
+    446-450): round(iterations_per_ms * thinking_time_ms), else its `iterations` parameter."""
+    p = cfg.params
+    kind = cfg.type.lower()
+    ipm = float(p.get("iterations_per_ms", 10.0 if kind == "mcts" else 20.0))
+    default_iters = int(p.get("iterations", 1000 if kind == "mcts" else 5000))
+    if cfg.thinking_time_ms is not None and bool(p.get("deterministic_time_budget", True)):
+        return max(1, int(round(ipm * cfg.thinking_time_ms)))
+    if cfg.thinking_time_ms is not None:                    # wall-clock budgets have no meaning inside one batch
+        return max(1, min(default_iters, int(round(ipm * cfg.thinking_time_ms))))
+    return max(1, default_iters)
+
+
+def run_device_arena_agents(run_config: RunConfig, run_id: str = "device_arena") -> Dict[str, Any]:
+    """All games of a RunConfig at once on the device, for any mix of "random", "heuristic", "mcts", "fast_mcts" and
+    "gameplay_fast_mcts" agents (the reference's scripts/arena_config.json seats four gameplay_fast_mcts agents with
+    25 / 50 / 100 / 200 ms budgets).  Per turn: one single-turn playout launch draws the moves of the built-in policies
+    (same Philox streams as run_device_arena), one search launch per search agent covers all games where that agent is
+    to move (flat UCB bandit with 50-ply rollouts for the fast types, UCT with HeuristicAgent rollouts for "mcts",
+    simulations per move from the deterministic budget rule), then one bk_step applies every move.  Seeds, seat
+    assignments, record keys and snapshot rows are those of run_experiment."""
+    import torch
+
+    from . import device as dev
+    from .batched import PASS, BatchedBlokus
+    from .mcts import MAX_ROOT_MOVES, DeviceUCT
+
+    names, n = run_config.agent_names, run_config.num_games
+    cfgs = list(run_config.agents)
+    for a in cfgs:
+        if a.type.lower() not in POLICY_OF and a.type.lower() not in _SEARCH_TYPES:
+            raise ValueError(f"Unsupported agent type for the device arena: {a.type}")
+    seats, agent_at = [], np.zeros((n, 4), dtype=np.int64)
+    packed = np.zeros(n, dtype=np.int32)
+    for i in range(n):
+        gs = game_seed_from_run_seed(run_config.seed, i)
+        sa = seat_assignment_for_game(names, i, gs, run_config.seat_policy)
+        seats.append((gs, sa))
+        for p in range(4):
+            k = names.index(sa[str(p + 1)])
+            agent_at[i, p] = k
+            packed[i] |= POLICY_OF.get(cfgs[k].type.lower(), 0) << (8 * p)       # search seats: placeholder policy
+    t0 = time.perf_counter()
+    games = BatchedBlokus(n)
+    device = games.states.device
+    agent_at_d = torch.from_numpy(agent_at).to(device)
+    packed_d = torch.from_numpy(packed).to(device)
+    engines: Dict[int, Any] = {}
+    caps = {k: _iteration_cap(c) for k, c in enumerate(cfgs) if c.type.lower() in _SEARCH_TYPES}
+    for k, c in enumerate(cfgs):
+        if k in caps:
+            flat = c.type.lower() != "mcts"
+            lb = int(c.params.get("leaf_batch", 1))
+            iters = -(-caps[k] // lb)
+            engines[k] = (DeviceUCT(iters, n_trees=n, max_rollout_moves=int(c.params.get("max_rollout_moves", 50)),
+                                    max_depth=1 if flat else 0, ucb_variant=1 if flat else 0, reward_mode=1 if flat else 0,
+                                    exploration=float(c.params.get("exploration_constant", 1.414)),
+                                    seed=stable_hash_int(run_config.seed, c.name, "device_arena"),
+                                    rollout_policy=dev.POLICY_UNIFORM if flat else dev.POLICY_HEURISTIC, leaf_batch=lb), iters, lb)
+    max_t = 96
+    trace = torch.full((n, max_t), PASS, dtype=torch.int32, device=device)
+    turns = torch.zeros(n, dtype=torch.int32, device=device)
+    moves_by = np.zeros(len(cfgs), dtype=np.int64)
+    rank_weight = torch.arange(MAX_ROOT_MOVES, device=device, dtype=torch.int64)
+    scratch: Dict[str, Any] = {}
+    for t in range(max_t):
+        running = games.alive_mask() != 0
+        if not bool(running.any()):
+            break
+        mover = games.states[:, 240].to(torch.int64)
+        who = agent_at_d.gather(1, mover[:, None])[:, 0]
+        counts = games.legal_move_counts()
+        can = running & (counts > 0)
+        r = dev.playout(n, seed=run_config.seed, start_states=games.states, seat_policies=packed_d, first_turn=t,
+                        max_turns=t + 1, want_trace=True, want_board_scores=False, out=scratch)
+        move = r["trace"][:, t].to(torch.int32)                                  # built-in seats (and placeholders)
+        for k, (eng, iters, lb) in engines.items():
+            idx = torch.nonzero(can & (who == k))[:, 0]
+            m = int(idx.numel())
+            if m == 0:
+                continue
+            eng.p.tree_offset = t * (1 << 24)
+            res = eng.search(games.states[idx].contiguous(), iters, active_trees=m)
+            visits = res["visits"][:m]
+            key = visits.to(torch.int64) * MAX_ROOT_MOVES + rank_weight[None, : visits.shape[1]]
+            best = key.argmax(dim=1)                                             # most visited, ties to the highest rank
+            ids = res["moves"][:m].view(torch.int16).gather(1, best[:, None]).view(torch.uint16)[:, 0]
+            move[idx] = ids.to(torch.int32)
+            moves_by[k] += m
+        for k, c in enumerate(cfgs):
+            if k not in engines:
+                moves_by[k] += int((can & (who == k)).sum())
+        move = torch.where(can, move, torch.full_like(move, PASS))
+        games.step(move.to(torch.int16).view(torch.uint16).contiguous())
+        trace[:, t] = torch.where(running, move, trace[:, t])
+        turns += running.to(torch.int32)
+    duration = time.perf_counter() - t0
+    gsc, _ = games.scores()
+    scores = gsc.cpu().numpy()
+    tr = trace.cpu().numpy()
+    nturns = turns.cpu().numpy()
+    finals = games.states.cpu().numpy()
+    per_agent = {c.name: {"moves": float(moves_by[k]), "total_simulations": float(moves_by[k] * engines[k][1] * engines[k][2]) if k in engines else None,
+                          "avg_simulations_per_move": float(engines[k][1] * engines[k][2]) if k in engines else None}
+                 for k, c in enumerate(cfgs)}
+    records = []
+    for i, (gs, sa) in enumerate(seats):
+        by_player = {str(p + 1): int(scores[i, p]) for p in range(4)}
+        placed = tr[i, : nturns[i]] != PASS
+        rec = _record(run_id, i, gs, sa, run_config.seat_policy, by_player, int(placed.sum()), int(nturns[i]),
+                      int((~placed).sum()), 0, duration / max(n, 1), False, {}, None)
+        rec["moves_made"] = int(finals[i, 242]) | (int(finals[i, 243]) << 8)
+        records.append(rec)
+    out = {"records": records, "summary": summarize(records, names), "agent_move_stats": per_agent,
+           "trace": trace.to(torch.int16).view(torch.uint16)}
+    if run_config.snapshots.enabled:
+        from . import winprob
+
+        replay = dev.replay_snapshots(out["trace"], run_config.snapshots.checkpoints, max_turns=run_config.max_turns)
+        hit = (replay["turn_index"] >= 0).cpu().numpy()
+        for i, rec in enumerate(records):
+            rec["snapshot_checkpoints_hit"] = [int(c) for c, h in zip(replay["checkpoints"], hit[i]) if h]
+        out["snapshot_rows"] = winprob.snapshot_rows_from_replay(replay, records)
+        out["snapshot_features"] = replay
+    return out

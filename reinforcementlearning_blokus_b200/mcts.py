@@ -165,9 +165,11 @@ class DeviceUCT:
         self._roots = None
 
     def search(self, roots: Optional[torch.Tensor], iterations: int, resume: bool = False,
-               root_frontiers: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+               root_frontiers: Optional[torch.Tensor] = None, active_trees: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """Run `iterations` more iterations on every tree (fresh trees from `roots` unless resume).  root_frontiers
-        (int64[n_roots, 4, 7], learned leaf evaluation only): the roots' incremental frontier sets; None = rebuilt."""
+        (int64[n_roots, 4, 7], learned leaf evaluation only): the roots' incremental frontier sets; None = rebuilt.
+        active_trees (<= n_trees) searches only the first so many trees (a batch whose size changes from call to call);
+        rows beyond it in the returned tensors are stale."""
         if not resume:
             if roots is None:
                 raise ValueError("roots required for a fresh search")
@@ -184,9 +186,13 @@ class DeviceUCT:
         self.p.iterations = int(iterations)
         self.p.resume = 1 if resume else 0
         n_roots = self._roots.shape[0]
+        if not resume:
+            self._active = self.n_trees if active_trees is None else int(active_trees)
+            if not 1 <= self._active <= self.n_trees:
+                raise ValueError("active_trees must be in [1, n_trees]")
         check = _lib.check
         check(self.lib.bk_mcts_search(
-            self._roots.data_ptr(), n_roots, self.n_trees, C.byref(self.p),
+            self._roots.data_ptr(), n_roots, self._active, C.byref(self.p),
             self.tt.handle if self.tt is not None else None,
             self.zobrist.device_table().data_ptr() if self.zobrist is not None else None,
             self.workspace.data_ptr(), self.ws_bytes, self.max_root_moves,

@@ -197,3 +197,49 @@ def test_run_experiment_device_batch_and_object_agents(tmp_path):
                                 device_batch=False)
     rec = json.loads(open(os.path.join(loop["run_dir"], "games.jsonl")).readline())
     assert set(rec) == set(games[0])
+
+
+def test_device_arena_with_search_agents(tmp_path):
+    """The shape of the reference's scripts/arena_config.json (four gameplay_fast_mcts agents with different budgets,
+    round robin, snapshots) as device batches: legal complete games (replayed by the oracle), deterministic, the
+    simulations per move follow the budget rule, and a mixed table of random / heuristic / mcts / fast_mcts agents."""
+    import json
+    import os
+
+    from oracle import orc
+    from reinforcementlearning_blokus_b200 import arena
+
+    cfg = arena.RunConfig.from_dict({
+        "agents": [{"name": f"mcts_{ms}ms", "type": "gameplay_fast_mcts", "thinking_time_ms": ms, "iterations_per_ms": 8}
+                   for ms in (2, 4, 6, 8)],
+        "num_games": 10, "seed": 20260301, "seat_policy": "round_robin", "output_root": str(tmp_path / "runs"),
+        "snapshots": {"enabled": True, "checkpoints": [8, 32]}})
+    a = arena.run_device_arena_agents(cfg)
+    b = arena.run_device_arena_agents(cfg)
+    assert torch.equal(a["trace"], b["trace"])
+    assert {n: s["avg_simulations_per_move"] for n, s in a["agent_move_stats"].items()} == {
+        "mcts_2ms": 16.0, "mcts_4ms": 32.0, "mcts_6ms": 48.0, "mcts_8ms": 64.0}
+    tr = a["trace"].cpu().numpy()
+    for g, rec in enumerate(a["records"]):
+        board = orc.OracleBoard()
+        for t in range(rec["turn_count"]):
+            if tr[g, t] == 0xFFFF:
+                assert not board.has_legal_moves(board.current_player)
+                board.pass_turn()
+            else:
+                assert board.make_move(board.current_player, int(tr[g, t]))
+        assert board.check_game_over()
+        assert {str(p + 1): board.game_score(p) for p in range(4)} == rec["final_scores"]
+        assert rec["seat_assignment"] == arena.seat_assignment_for_game(cfg.agent_names, g, rec["game_seed"], "round_robin")
+    assert len(a["snapshot_rows"]) == 4 * sum(len(r["snapshot_checkpoints_hit"]) for r in a["records"]) > 0
+    # through run_experiment, with a mixed table
+    mixed = arena.RunConfig.from_dict({
+        "agents": [{"name": "rnd", "type": "random"}, {"name": "heur", "type": "heuristic"},
+                   {"name": "uct", "type": "mcts", "thinking_time_ms": 3, "use_transposition_table": False},
+                   {"name": "fast", "type": "fast_mcts", "thinking_time_ms": 2, "leaf_batch": 4}],
+        "num_games": 8, "seed": 3, "seat_policy": "randomized", "output_root": str(tmp_path / "runs")})
+    out = arena.run_experiment(mixed)
+    games = [json.loads(line) for line in open(os.path.join(out["run_dir"], "games.jsonl"))]
+    assert len(games) == 8 and out["summary"]["completed_games"] == 8
+    assert games[0]["agent_move_stats"]["uct"]["avg_simulations_per_move"] == 30.0       # 10 iterations/ms x 3 ms
+    assert games[0]["agent_move_stats"]["fast"]["avg_simulations_per_move"] == 40.0      # 20/ms x 2 ms
