@@ -560,14 +560,19 @@ def _iteration_cap(cfg: AgentConfig) -> int:
     return max(1, default_iters)
 
 
-def run_device_arena_agents(run_config: RunConfig, run_id: str = "device_arena") -> Dict[str, Any]:
+def run_device_arena_agents(run_config: RunConfig, run_id: str = "device_arena", auto_leaf_batch: bool = True) -> Dict[str, Any]:
     """All games of a RunConfig at once on the device, for any mix of "random", "heuristic", "mcts", "fast_mcts" and
     "gameplay_fast_mcts" agents (the reference's scripts/arena_config.json seats four gameplay_fast_mcts agents with
     25 / 50 / 100 / 200 ms budgets).  Per turn: one single-turn playout launch draws the moves of the built-in policies
     (same Philox streams as run_device_arena), one search launch per search agent covers all games where that agent is
     to move (flat UCB bandit with 50-ply rollouts for the fast types, UCT with HeuristicAgent rollouts for "mcts",
     simulations per move from the deterministic budget rule), then one bk_step applies every move.  Seeds, seat
-    assignments, record keys and snapshot rows are those of run_experiment."""
+    assignments, record keys and snapshot rows are those of run_experiment.
+
+    auto_leaf_batch: a flat-bandit agent (fast types) without an explicit "leaf_batch" parameter gets leaf-batched rollouts (up to 16
+    warps per tree) when the games alone would leave most of the GPU idle -- about a quarter of the games are searched
+    per launch, and one warp per tree fills the device only from ~14 000 games on.  Its budget stays the same number
+    of simulations per move."""
     import torch
 
     from . import device as dev
@@ -599,7 +604,9 @@ def run_device_arena_agents(run_config: RunConfig, run_id: str = "device_arena")
     for k, c in enumerate(cfgs):
         if k in caps:
             flat = c.type.lower() != "mcts"
-            lb = int(c.params.get("leaf_batch", 1))
+            lb = int(c.params.get("leaf_batch", 0))
+            if lb <= 0:                          # only the flat bandits: batching changes how a UCT tree grows
+                lb = min(16, max(1, 3552 // max(1, -(-n // 4)))) if (auto_leaf_batch and flat) else 1
             iters = -(-caps[k] // lb)
             engines[k] = (DeviceUCT(iters, n_trees=n, max_rollout_moves=int(c.params.get("max_rollout_moves", 50)),
                                     max_depth=1 if flat else 0, ucb_variant=1 if flat else 0, reward_mode=1 if flat else 0,

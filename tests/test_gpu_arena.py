@@ -217,6 +217,10 @@ def test_device_arena_with_search_agents(tmp_path):
     a = arena.run_device_arena_agents(cfg)
     b = arena.run_device_arena_agents(cfg)
     assert torch.equal(a["trace"], b["trace"])
+    one_warp = arena.run_device_arena_agents(cfg, auto_leaf_batch=False)         # one rollout per iteration, as the reference
+    assert one_warp["summary"]["completed_games"] == 10
+    assert {n: s["avg_simulations_per_move"] for n, s in one_warp["agent_move_stats"].items()} == {
+        "mcts_2ms": 16.0, "mcts_4ms": 32.0, "mcts_6ms": 48.0, "mcts_8ms": 64.0}
     assert {n: s["avg_simulations_per_move"] for n, s in a["agent_move_stats"].items()} == {
         "mcts_2ms": 16.0, "mcts_4ms": 32.0, "mcts_6ms": 48.0, "mcts_8ms": 64.0}
     tr = a["trace"].cpu().numpy()
