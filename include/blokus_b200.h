@@ -224,7 +224,9 @@ typedef struct bk_mcts_params {
                                       (mcts_agent.py:427-451; LearnedWinProbabilityEvaluator with a pairwise logistic
                                       model, mcts/learned_evaluator.py:97-143): the 4 x 34 snapshot features of the leaf
                                       are computed in the kernel and fed to leaf_model.  Rewards are doubles:
-                                      root_reward then holds IEEE-754 bit patterns of the reward sums */
+                                      root_reward then holds IEEE-754 bit patterns of the reward sums;
+                                   4: rollout as in mode 0 plus potential-based shaping with the same learned model
+                                      (leaf_model, shaping_weight, shaping_gamma, potential_mode); rewards are doubles */
     int32_t  leaf_batch;        /* 1 (or 0): one rollout per iteration, one warp per tree -- the reference's search.
                                    2..16: leaf-batched rollouts -- a CTA of that many warps owns the tree; after each
                                    selection/expansion every warp rolls out from the new leaf with its own random stream
@@ -243,6 +245,10 @@ typedef struct bk_mcts_params {
     double   progressive_bias_weight; /* reward_mode 3: w of the selection term w * prior/(1 + n) (mcts_agent.py:88, 453-468),
                                          prior(child) = V(child board, parent player) - V(parent board, parent player);
                                          0 = off */
+    double   shaping_weight;          /* reward_mode 4: w and gamma of the potential-based shaping term added to TRUNCATED */
+    double   shaping_gamma;           /*   rollouts, w * (gamma * Phi(final) - Phi(initial)) (mcts_agent.py:486-551) */
+    int32_t  potential_mode;          /* reward_mode 4: Phi = clamped win probability (0, "prob") or its logit (1, "logit") */
+    int32_t  reserved2;
 } bk_mcts_params;
 
 /* Bytes of device workspace per tree for a search of params->iterations_total iterations (host call). */

@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
         L.orc_tt_size.restype = u64
         L.orc_mcts_search.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, vp, vp]
         L.orc_mcts_search_learned.argtypes = [vp, vp, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, i32, C.c_double, vp, vp, vp]
+        L.orc_mcts_search_shaped.argtypes = [vp, vp, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, i32, C.c_double, C.c_double,
+                                             C.c_double, i32, vp, vp, vp]
         L.orc_mcts_search_batched.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, i32, vp, vp, vp]
         L.orc_check_moves_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp]
         L.orc_check_playouts.argtypes = [u64, u64, i32, i32, i32, vp, vp, vp]
@@ -342,6 +344,26 @@ def mcts_search_learned(root: np.ndarray, iterations: int, seed: int, model: np.
     n = lib().orc_mcts_search_learned(_ptr(st), _ptr(fr), int(iterations), int(max_depth), int(ucb_variant), float(exploration),
                                       int(seed), int(tree_id), tt.h if tt else None, _ptr(zt), int(max_root_moves), _ptr(md),
                                       int(max_turns), float(bias_weight), _ptr(vis), _ptr(rew), _ptr(mov))
+    return {"n_root": int(n), "visits": vis, "reward": rew, "moves": mov}
+
+
+def mcts_search_shaped(root: np.ndarray, iterations: int, seed: int, model: np.ndarray, tree_id: int = 0, max_turns: int = 2500,
+                       root_frontier: Optional[np.ndarray] = None, max_rollout_moves: int = 50, rollout_policy: int = 0,
+                       exploration: float = 1.414, shaping_weight: float = 1.0, shaping_gamma: float = 1.0,
+                       potential_mode: int = 0, bias_weight: float = 0.0, tt: Optional[OracleTT] = None,
+                       zobrist: Optional[np.ndarray] = None, max_root_moves: int = 2048):
+    """UCT with rollouts and potential-based shaping from the learned model (mcts_agent.py:470-554); reward sums are doubles."""
+    st = np.ascontiguousarray(np.atleast_1d(root), dtype=STATE_DTYPE)
+    md = np.ascontiguousarray(model, dtype=np.float64)
+    fr = None if root_frontier is None else np.ascontiguousarray(root_frontier, dtype=np.uint8)
+    vis = np.zeros(max_root_moves, dtype=np.int32)
+    rew = np.zeros(max_root_moves, dtype=np.float64)
+    mov = np.zeros(max_root_moves, dtype=np.uint16)
+    zt = None if zobrist is None else np.ascontiguousarray(zobrist, dtype=np.uint64)
+    n = lib().orc_mcts_search_shaped(_ptr(st), _ptr(fr), int(iterations), int(max_rollout_moves), int(rollout_policy),
+                                     float(exploration), int(seed), int(tree_id), tt.h if tt else None, _ptr(zt),
+                                     int(max_root_moves), _ptr(md), int(max_turns), float(bias_weight), float(shaping_weight),
+                                     float(shaping_gamma), int(potential_mode), _ptr(vis), _ptr(rew), _ptr(mov))
     return {"n_root": int(n), "visits": vis, "reward": rew, "moves": mov}
 
 

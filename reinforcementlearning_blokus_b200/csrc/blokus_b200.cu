@@ -969,7 +969,7 @@ extern "C" int bk_tt_stats(bk_tt* tt, uint64_t* out_host, void* stream) {
 
 extern "C" int64_t bk_mcts_workspace_bytes(const bk_mcts_params* params) {
     if (!params || params->iterations_total <= 0) return 0;
-    return (int64_t)mcts_layout(params->iterations_total, params->reward_mode == 3).total;
+    return (int64_t)mcts_layout(params->iterations_total, params->reward_mode >= 3).total;
 }
 
 extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, const bk_mcts_params* params, bk_tt* tt,
@@ -983,7 +983,7 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
     REQUIRE(params->rollout_policy == BK_POLICY_UNIFORM || params->rollout_policy == BK_POLICY_HEURISTIC,
             "bk_mcts_search: unknown rollout policy");
     REQUIRE(!tt || zobrist_table, "bk_mcts_search: a transposition table needs a Zobrist table");
-    const bool learned = params->reward_mode == 3;
+    const bool learned = params->reward_mode >= 3;
     const MctsLayout L = mcts_layout(params->iterations_total, learned);
     if ((int64_t)L.total * n_trees > workspace_bytes) return fail(BK_ERR_CAPACITY, "%s", "bk_mcts_search: workspace too small");
     MctsTT t; t.keys = nullptr; t.rewards = nullptr; t.occupied = nullptr; t.log2_slots = 0; t.zobrist = zobrist_table;
@@ -995,14 +995,18 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     long long* rr = reinterpret_cast<long long*>(root_reward);
     cudaStream_t st = as_stream(stream);
-    REQUIRE(params->reward_mode >= 0 && params->reward_mode <= 3, "bk_mcts_search: unknown reward_mode");
+    REQUIRE(params->reward_mode >= 0 && params->reward_mode <= 4, "bk_mcts_search: unknown reward_mode");
     if (learned) {
-        REQUIRE(params->leaf_model != nullptr, "bk_mcts_search: reward_mode 3 needs leaf_model (34 weights + bias on the device)");
-        REQUIRE(W == 1, "bk_mcts_search: learned leaf evaluation has no rollouts to batch (leaf_batch must be 1)");
-        const int cap = g_sms * 16;
+        REQUIRE(params->leaf_model != nullptr, "bk_mcts_search: reward_mode 3/4 needs leaf_model (34 weights + bias on the device)");
+        REQUIRE(W == 1, "bk_mcts_search: the learned modes run one warp per tree (leaf_batch must be 1)");
+        const int cap = g_sms * (heur && params->reward_mode == 4 ? 12 : 16);
         const int grid = n_trees < cap ? n_trees : cap;
-        k_mcts<0, false, true><<<grid, BK_MCTS_THREADS, 0, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
-            ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
+        if (heur && params->reward_mode == 4)
+            k_mcts<1, false, true><<<grid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+                ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
+        else
+            k_mcts<0, false, true><<<grid, BK_MCTS_THREADS, 0, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+                ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
     } else if (W == 1) {
         const int cap = g_sms * (heur ? BK_MCTS_HEUR_CTAS_PER_SM : BK_MCTS_CTAS_PER_SM);
         const int grid = n_trees < cap ? n_trees : cap;

@@ -327,8 +327,47 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
             }
             if (LEARNED) {
                 if (!cached) {
+                    if (prm.reward_mode == 4) {
+                        // _rollout with potential-based shaping (mcts_agent.py:470-554): Phi of the leaf, the rollout
+                        // (frontier sets follow every placement), and on a TRUNCATED rollout w * (gamma * Phi(end) - Phi(leaf))
+                        const uint32_t me = s.to_move;
+                        const int32_t before = board_score_of(s, me);
+                        snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
+                        const double phi0 = potential_of(win_probability(s_feat, prm.leaf_model, me, lane), prm.potential_mode);
+                        __syncwarp();
+                        const int limit = prm.max_rollout_moves > 0 ? prm.max_rollout_moves : 1 << 30;
+                        int moves_made = 0;
+                        for (int ply = 0; ply < limit; ply++) {
+                            const uint32_t p = s.to_move;
+                            int o, row, col;
+                            if (POLICY == BK_POLICY_HEURISTIC) {
+                                uint32_t id = 0, idx = 0;
+                                const uint32_t before_draws = draws;
+                                const uint32_t rnd = next_draw();
+                                if (heuristic_pick(s, p, rnd, hs, lane, id, idx) == 0) { draws = before_draws; break; }
+                                o = (int)(id / 400u); row = (int)((id % 400u) / 20u); col = (int)(id % 20u);
+                            } else {
+                                uint32_t A, C; make_masks(s, p, lane, A, C);
+                                const Totals tot = gen_totals<1>(A, C, sel4(s.used, p), lane);
+                                if (tot.n == 0) break;
+                                const uint32_t rnd = next_draw();
+                                select_move(tot, __umulhi(rnd, tot.n), A, C, lane, o, row, col);
+                            }
+                            const uint32_t own_before = sel4(s.P, p);
+                            place_move(s, p, o, row, col, lane);
+                            update_frontier(s, p, sel4(s.P, p) & ~own_before, lane, F);
+                            moves_made++;
+                        }
+                        rd = (double)(board_score_of(s, me) - before);
+                        if (moves_made >= limit) {
+                            snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
+                            const double phi1 = potential_of(win_probability(s_feat, prm.leaf_model, me, lane), prm.potential_mode);
+                            __syncwarp();
+                            rd = __dadd_rn(rd, __dmul_rn(prm.shaping_weight, __dsub_rn(__dmul_rn(prm.shaping_gamma, phi1), phi0)));
+                        }
+                    }
                     // _evaluate_leaf(node.board, node.player) -> predict_player_win_probability (learned_evaluator.py:79-143)
-                    if (have_value) rd = leaf_value;
+                    else if (have_value) rd = leaf_value;
                     else {
                         snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
                         rd = win_probability(s_feat, prm.leaf_model, s.to_move, lane);

@@ -321,3 +321,9 @@ k_replay_snapshots(const bk_state* __restrict__ start, const uint16_t* __restric
         }
     }
 }
+
+// LearnedWinProbabilityEvaluator.potential (mcts/learned_evaluator.py:145-152): the clamped probability or its logit
+__device__ __forceinline__ double potential_of(double p, int mode) {
+    p = fmin(fmax(p, 1e-6), 1.0 - 1e-6);
+    return mode == 1 ? log(__ddiv_rn(p, __dsub_rn(1.0, p))) : p;
+}

@@ -122,7 +122,8 @@ class DeviceUCT:
                  ucb_variant: int = 0, exploration: float = 1.414, seed: int = 0, tree_offset: int = 0,
                  reward_mode: int = 0, rollout_policy: int = 0, tt: Optional[dev.DeviceTranspositionTable] = None, zobrist: Optional[ZobristHash] = None,
                  max_root_moves: int = MAX_ROOT_MOVES, leaf_batch: int = 1, leaf_model: Optional[torch.Tensor] = None,
-                 leaf_max_turns: int = 2500, progressive_bias_weight: float = 0.0):
+                 leaf_max_turns: int = 2500, progressive_bias_weight: float = 0.0, shaping_weight: float = 1.0,
+                 shaping_gamma: float = 1.0, potential_mode: str = "prob"):
         if not torch.cuda.is_available():
             raise _lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
         self.lib = _lib.init(torch.cuda.current_device())
@@ -130,15 +131,18 @@ class DeviceUCT:
                                  max_rollout_moves=int(max_rollout_moves), rollout_policy=int(rollout_policy), max_depth=int(max_depth),
                                  ucb_variant=int(ucb_variant), resume=0, reward_mode=int(reward_mode), leaf_batch=int(leaf_batch),
                                  reserved0=0, leaf_max_turns=int(leaf_max_turns), reserved1=0,
-                                 progressive_bias_weight=float(progressive_bias_weight) if int(reward_mode) == 3 else 0.0,
+                                 progressive_bias_weight=float(progressive_bias_weight) if int(reward_mode) >= 3 else 0.0,
+                                 shaping_weight=float(shaping_weight), shaping_gamma=float(shaping_gamma),
+                                 potential_mode=1 if potential_mode == "logit" else 0, reserved2=0,
                                  exploration=float(exploration),
                                  seed=int(seed) & (2**64 - 1), tree_offset=int(tree_offset))
         self.n_trees = int(n_trees)
-        # reward_mode 3: learned leaf evaluation with a folded pairwise logistic model (float64[35] on the device)
+        # reward_mode 3 / 4: learned leaf evaluation / rollouts with potential shaping, both with a folded pairwise
+        # logistic model (float64[35] on the device)
         self.leaf_model = None
-        if int(reward_mode) == 3:
+        if int(reward_mode) >= 3:
             if leaf_model is None or leaf_model.numel() != 35:
-                raise ValueError("reward_mode 3 needs leaf_model: 34 weights + bias")
+                raise ValueError("reward_mode 3 / 4 needs leaf_model: 34 weights + bias")
             self.leaf_model = leaf_model.to(device="cuda", dtype=torch.float64).contiguous()
             self.p.leaf_model = self.leaf_model.data_ptr()
         self.root_frontiers = None
@@ -200,7 +204,7 @@ class DeviceUCT:
             self.status.data_ptr(), torch.cuda.current_stream().cuda_stream))
         dev._count()
         self.iterations_done += iterations
-        reward = self.reward.view(torch.float64) if self.p.reward_mode == 3 else self.reward
+        reward = self.reward.view(torch.float64) if self.p.reward_mode >= 3 else self.reward
         return {"visits": self.visits, "reward": reward, "moves": self.moves, "counts": self.counts,
                 "status": self.status}
 
@@ -239,9 +243,9 @@ class MCTSAgent:
     pipeline is [StandardScaler,] LogisticRegression also runs in the tree: leaf_evaluation_enabled evaluates the 34
     snapshot features of every new leaf in the kernel and feeds the folded 34 weights + bias (reward_mode 3), and
     progressive_bias_enabled adds the selection term w * prior / (1 + n) with prior = V(child, parent player) -
-    V(parent, parent player) from the same feature block.  Other estimators (gradient-boosted phase models) are served
-    out of tree by ``winprob.LearnedWinProbabilityEvaluator``; potential shaping with a fitted model raises
-    NotImplementedError.
+    V(parent, parent player) from the same feature block; potential_shaping_enabled (without leaf evaluation) keeps
+    the rollouts and adds w * (gamma * Phi(end) - Phi(leaf)) to truncated ones (reward_mode 4).  Other estimators
+    (gradient-boosted phase models) are served out of tree by ``winprob.LearnedWinProbabilityEvaluator``.
     """
 
     def __init__(self, iterations: int = 1000, time_limit: Optional[float] = None, exploration_constant: float = 1.414,
@@ -274,18 +278,15 @@ class MCTSAgent:
 
             self.learned_evaluator = LearnedWinProbabilityEvaluator(learned_model_path, potential_mode=potential_mode)
             real = not self.learned_evaluator._is_dummy
-            if real and self.potential_shaping_enabled:
-                raise NotImplementedError("potential shaping with a fitted model is not on the device path (leaf "
-                                          "evaluation and progressive bias are); use the dummy artifact or disable it")
-            if real and self.progressive_bias_enabled and not self.leaf_evaluation_enabled:
-                raise NotImplementedError("progressive bias with a fitted model runs together with learned leaf "
-                                          "evaluation (the kernel shares the leaf's feature block); enable both")
-            if real and self.leaf_evaluation_enabled and getattr(self.learned_evaluator, "device_model", None) is None:
+            if real and self.progressive_bias_enabled and not (self.leaf_evaluation_enabled or self.potential_shaping_enabled):
+                raise NotImplementedError("progressive bias with a fitted model runs in the learned kernels: enable "
+                                          "leaf evaluation or potential shaping with it")
+            if real and self._requires_learned_evaluator and getattr(self.learned_evaluator, "device_model", None) is None:
                 raise NotImplementedError("in-tree leaf evaluation runs pairwise_logreg artifacts whose pipeline is "
                                           "[StandardScaler,] LogisticRegression; this artifact has another shape -- "
                                           "use winprob.LearnedWinProbabilityEvaluator out of tree")
-            if (self.potential_shaping_enabled and potential_mode == "prob" and self.potential_shaping_gamma != 1.0
-                    and self.potential_shaping_weight != 0.0):
+            if (not real and self.potential_shaping_enabled and potential_mode == "prob"
+                    and self.potential_shaping_gamma != 1.0 and self.potential_shaping_weight != 0.0):
                 raise NotImplementedError("potential shaping with gamma != 1 adds a non-zero constant to truncated "
                                           "rollouts; only the zero-term configurations run on the device")
         self.iterations = iterations
@@ -327,15 +328,20 @@ class MCTSAgent:
         offset = self._searches * max(self.num_trees, 1)
         self._searches += 1
         mode, model = 0, None
+        real = self.learned_evaluator is not None and not self.learned_evaluator._is_dummy
         if self.leaf_evaluation_enabled:
             if self.learned_evaluator._is_dummy:
                 mode = 2
             else:
                 mode, model = 3, torch.from_numpy(self.learned_evaluator.device_model)
+        elif self.potential_shaping_enabled and real:            # rollouts + shaping term on truncated ones
+            mode, model = 4, torch.from_numpy(self.learned_evaluator.device_model)
         return DeviceUCT(total, n_trees=self.num_trees, max_rollout_moves=self.max_rollout_moves,
                          exploration=self.exploration_constant, seed=self.seed, tree_offset=offset,
                          reward_mode=mode, leaf_model=model, leaf_max_turns=getattr(self.learned_evaluator, "max_turns", 2500),
                          progressive_bias_weight=self.progressive_bias_weight if self.progressive_bias_enabled else 0.0,
+                         shaping_weight=self.potential_shaping_weight, shaping_gamma=self.potential_shaping_gamma,
+                         potential_mode=self.potential_mode,
                          leaf_batch=self.leaf_batch,
                          rollout_policy=self.rollout_policy, tt=tt,
                          zobrist=self.zobrist_hash if tt is not None else None)
@@ -345,7 +351,7 @@ class MCTSAgent:
         start = time.time()
         root = _root_state(board, player)
         frontiers = None
-        if self.leaf_evaluation_enabled and self.learned_evaluator is not None and not self.learned_evaluator._is_dummy:
+        if self._requires_learned_evaluator and self.learned_evaluator is not None and not self.learned_evaluator._is_dummy:
             frontiers = torch.from_numpy(board.frontier_words()[None].copy())     # the board's incremental sets
         if self.time_limit:
             # capacity for the time budget: one warp runs about 12-15 k simulations/s (profiles/r01_agent_latency.json)

@@ -354,8 +354,23 @@ def test_learned_leaf_evaluation_in_the_tree(golden_dir, tmp_path):
     assert agent.select_action(board, player, legal) in legal and agent.stats["leaf_eval_calls"] == len(legal)
     with pytest.raises(NotImplementedError):
         MCTSAgent(learned_model_path=path, progressive_bias_enabled=True)            # needs leaf evaluation too
-    with pytest.raises(NotImplementedError):
-        MCTSAgent(learned_model_path=path, leaf_evaluation_enabled=True, potential_shaping_enabled=True)
+    # potential-based shaping (mcts_agent.py:486-551): rollouts stay, truncated ones get w * (gamma * Phi(end) - Phi(leaf))
+    for pol, mode, gamma in ((0, 0, 1.0), (0, 1, 0.9), (1, 0, 0.95)):
+        root_np = _roots(golden_dir)[2]
+        root = dev.to_device(np.atleast_1d(root_np))
+        kw = dict(max_rollout_moves=6, rollout_policy=pol, shaping_weight=1.5, shaping_gamma=gamma)
+        want = orc.mcts_search_shaped(root_np, 120, seed=31, model=w, potential_mode=mode, **kw)
+        res = DeviceUCT(120, n_trees=1, seed=31, reward_mode=4, leaf_model=torch.from_numpy(w),
+                        potential_mode="logit" if mode else "prob", **kw).search(root, 120)
+        n = want["n_root"]
+        assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n]), (pol, mode)
+        assert np.allclose(res["reward"][0, :n].cpu().numpy(), want["reward"][:n], rtol=0, atol=1e-9)
+        frac = res["reward"][0, :n].cpu().numpy()
+        assert np.abs(frac - np.round(frac)).max() > 1e-6                      # the shaping term is really in the rewards
+    shaped = MCTSAgent(iterations=60, seed=2, learned_model_path=path, potential_shaping_enabled=True,
+                       potential_shaping_gamma=0.9, progressive_bias_enabled=True, use_transposition_table=False,
+                       max_rollout_moves=8)
+    assert shaped.select_action(board, player, legal) in legal
     # progressive bias (mcts_agent.py:88, 453-468) on top of leaf evaluation: kernel == oracle, and it changes the search
     for ri, root_np in enumerate(_roots(golden_dir)[1:3]):
         root = dev.to_device(np.atleast_1d(root_np))
