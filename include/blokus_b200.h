@@ -241,7 +241,8 @@ typedef struct bk_mcts_params {
     const uint64_t* root_frontiers; /* reward_mode 3: DEVICE [n_roots][4][7] frontier sets of the roots (Board.get_frontier,
                                        engine/board.py:247-259), or NULL for the sets of a freshly restored board */
     int32_t  leaf_max_turns;        /* reward_mode 3: max_turns of the evaluator's progress features (2500) */
-    int32_t  reserved1;
+    int32_t  leaf_model_kind;       /* 0: leaf_model = 35 doubles (logistic); 1: flattened gradient-boosted phase models
+                                       ("pairwise_gbt_phase"; layout in csrc/snapshot.cuh / winprob.flatten_gbt_phase_models) */
     double   progressive_bias_weight; /* reward_mode 3: w of the selection term w * prior/(1 + n) (mcts_agent.py:88, 453-468),
                                          prior(child) = V(child board, parent player) - V(parent board, parent player);
                                          0 = off */

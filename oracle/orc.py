@@ -89,6 +89,9 @@ def lib() -> C.CDLL:
         L.orc_tt_size.restype = u64
         L.orc_mcts_search.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, vp, vp]
         L.orc_mcts_search_learned.argtypes = [vp, vp, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, i32, C.c_double, vp, vp, vp]
+        L.orc_set_model_kind.argtypes = [i32]
+        L.orc_win_probability_packed.argtypes = [vp, vp, i32, vp, i32, i32]
+        L.orc_win_probability_packed.restype = C.c_double
         L.orc_mcts_search_shaped.argtypes = [vp, vp, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, i32, C.c_double, C.c_double,
                                              C.c_double, i32, vp, vp, vp]
         L.orc_mcts_search_batched.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, i32, vp, vp, vp]
@@ -330,12 +333,13 @@ def mcts_search(root: np.ndarray, iterations: int, seed: int, tree_id: int = 0, 
 def mcts_search_learned(root: np.ndarray, iterations: int, seed: int, model: np.ndarray, tree_id: int = 0, max_turns: int = 2500,
                         root_frontier: Optional[np.ndarray] = None, max_depth: int = 0, ucb_variant: int = 0,
                         exploration: float = 1.414, tt: Optional[OracleTT] = None, zobrist: Optional[np.ndarray] = None,
-                        max_root_moves: int = 2048, bias_weight: float = 0.0):
+                        max_root_moves: int = 2048, bias_weight: float = 0.0, model_kind: int = 0):
     """UCT with learned leaf evaluation (mcts_agent.py:427-451): model = float64[35] (34 weights + bias of a folded
     pairwise logistic model), root_frontier = uint8[4, 400] incremental frontier sets or None.  reward sums are doubles."""
     st = np.ascontiguousarray(np.atleast_1d(root), dtype=STATE_DTYPE)
     md = np.ascontiguousarray(model, dtype=np.float64)
-    assert md.size == 35
+    assert model_kind == 1 or md.size == 35
+    lib().orc_set_model_kind(int(model_kind))           # thread-local: applies to the call below
     fr = None if root_frontier is None else np.ascontiguousarray(root_frontier, dtype=np.uint8)
     vis = np.zeros(max_root_moves, dtype=np.int32)
     rew = np.zeros(max_root_moves, dtype=np.float64)
@@ -347,14 +351,24 @@ def mcts_search_learned(root: np.ndarray, iterations: int, seed: int, model: np.
     return {"n_root": int(n), "visits": vis, "reward": rew, "moves": mov}
 
 
+def win_probability(state: np.ndarray, player: int, model: np.ndarray, model_kind: int = 0, max_turns: int = 2500,
+                    frontiers: Optional[np.ndarray] = None) -> float:
+    """LearnedWinProbabilityEvaluator.predict_player_win_probability for one packed state (logistic or GBT model form)."""
+    st = np.ascontiguousarray(np.atleast_1d(state), dtype=STATE_DTYPE)
+    md = np.ascontiguousarray(model, dtype=np.float64)
+    fr = None if frontiers is None else np.ascontiguousarray(frontiers, dtype=np.uint8)
+    return float(lib().orc_win_probability_packed(_ptr(st), _ptr(fr), int(player), _ptr(md), int(model_kind), int(max_turns)))
+
+
 def mcts_search_shaped(root: np.ndarray, iterations: int, seed: int, model: np.ndarray, tree_id: int = 0, max_turns: int = 2500,
                        root_frontier: Optional[np.ndarray] = None, max_rollout_moves: int = 50, rollout_policy: int = 0,
                        exploration: float = 1.414, shaping_weight: float = 1.0, shaping_gamma: float = 1.0,
                        potential_mode: int = 0, bias_weight: float = 0.0, tt: Optional[OracleTT] = None,
-                       zobrist: Optional[np.ndarray] = None, max_root_moves: int = 2048):
+                       zobrist: Optional[np.ndarray] = None, max_root_moves: int = 2048, model_kind: int = 0):
     """UCT with rollouts and potential-based shaping from the learned model (mcts_agent.py:470-554); reward sums are doubles."""
     st = np.ascontiguousarray(np.atleast_1d(root), dtype=STATE_DTYPE)
     md = np.ascontiguousarray(model, dtype=np.float64)
+    lib().orc_set_model_kind(int(model_kind))
     fr = None if root_frontier is None else np.ascontiguousarray(root_frontier, dtype=np.uint8)
     vis = np.zeros(max_root_moves, dtype=np.int32)
     rew = np.zeros(max_root_moves, dtype=np.float64)

@@ -69,7 +69,7 @@ class MctsParams(C.Structure):
         ("resume", C.c_int32), ("reward_mode", C.c_int32), ("leaf_batch", C.c_int32), ("reserved0", C.c_int32),
         ("exploration", C.c_double),
         ("seed", C.c_uint64), ("tree_offset", C.c_uint64),
-        ("leaf_model", C.c_void_p), ("root_frontiers", C.c_void_p), ("leaf_max_turns", C.c_int32), ("reserved1", C.c_int32),
+        ("leaf_model", C.c_void_p), ("root_frontiers", C.c_void_p), ("leaf_max_turns", C.c_int32), ("leaf_model_kind", C.c_int32),
         ("progressive_bias_weight", C.c_double), ("shaping_weight", C.c_double), ("shaping_gamma", C.c_double),
         ("potential_mode", C.c_int32), ("reserved2", C.c_int32),
     ]

@@ -181,7 +181,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                     store_rows4(frontier, lane, F);
                     if (bias_on) {                 // V(root board, root player): the parent value of the root's children
                         snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
-                        const double v0 = win_probability(s_feat, prm.leaf_model, s.to_move, lane);
+                        const double v0 = win_probability_any(s_feat, prm.leaf_model, prm.leaf_model_kind, s.to_move, lane);
                         if (lane == 0) { node_value[0] = v0; node_prior[0] = 0.0; }
                         __syncwarp();
                     }
@@ -287,8 +287,8 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                             // _update_progressive_bias(parent, child): both values for the PARENT's player; the child's
                             // feature block also gives its own value, which the simulation below reuses
                             snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
-                            const double for_parent = win_probability(s_feat, prm.leaf_model, p, lane);
-                            leaf_value = win_probability(s_feat, prm.leaf_model, s.to_move, lane);
+                            const double for_parent = win_probability_any(s_feat, prm.leaf_model, prm.leaf_model_kind, p, lane);
+                            leaf_value = win_probability_any(s_feat, prm.leaf_model, prm.leaf_model_kind, s.to_move, lane);
                             have_value = true;
                             if (lane == 0) { node_prior[child] = __dsub_rn(for_parent, node_value[node]); node_value[child] = leaf_value; }
                             __syncwarp();
@@ -333,7 +333,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                         const uint32_t me = s.to_move;
                         const int32_t before = board_score_of(s, me);
                         snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
-                        const double phi0 = potential_of(win_probability(s_feat, prm.leaf_model, me, lane), prm.potential_mode);
+                        const double phi0 = potential_of(win_probability_any(s_feat, prm.leaf_model, prm.leaf_model_kind, me, lane), prm.potential_mode);
                         __syncwarp();
                         const int limit = prm.max_rollout_moves > 0 ? prm.max_rollout_moves : 1 << 30;
                         int moves_made = 0;
@@ -361,7 +361,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                         rd = (double)(board_score_of(s, me) - before);
                         if (moves_made >= limit) {
                             snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
-                            const double phi1 = potential_of(win_probability(s_feat, prm.leaf_model, me, lane), prm.potential_mode);
+                            const double phi1 = potential_of(win_probability_any(s_feat, prm.leaf_model, prm.leaf_model_kind, me, lane), prm.potential_mode);
                             __syncwarp();
                             rd = __dadd_rn(rd, __dmul_rn(prm.shaping_weight, __dsub_rn(__dmul_rn(prm.shaping_gamma, phi1), phi0)));
                         }
@@ -370,7 +370,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                     else if (have_value) rd = leaf_value;
                     else {
                         snapshot_features_block(s, F, (int)s.move_count, prm.leaf_max_turns, lane, s_pc, s_feat);
-                        rd = win_probability(s_feat, prm.leaf_model, s.to_move, lane);
+                        rd = win_probability_any(s_feat, prm.leaf_model, prm.leaf_model_kind, s.to_move, lane);
                         __syncwarp();
                     }
                     if (tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, rd);

@@ -322,6 +322,50 @@ k_replay_snapshots(const bk_state* __restrict__ start, const uint16_t* __restric
     }
 }
 
+// The same for a "pairwise_gbt_phase" artifact (mcts/learned_evaluator.py:112-127) flattened by
+// winprob.flatten_gbt_phase_models: the pair's phase (mean board occupancy < 0.33 / < 0.66 / else) picks the model, lane L
+// walks trees L, L+32, ... (left when float32(x[feature]) <= threshold), the lane sums are combined with a butterfly of
+// _rn additions (the oracle uses the same order), p = sigmoid(init + learning_rate * sum).
+__device__ __forceinline__ double win_probability_gbt(const double* feat, const double* __restrict__ blob, uint32_t player, int lane) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (uint32_t n = 0; n < 3; n++) {
+        const uint32_t j = n + (n >= player ? 1u : 0u);
+        const double* fi = feat + player * BK_NFEAT;
+        const double* fj = feat + j * BK_NFEAT;
+        const double occ = __ddiv_rn(__dadd_rn(fi[29], fj[29]), 2.0);          // phase_board_occupancy of the pair
+        const int phase = occ < 0.33 ? 0 : (occ < 0.66 ? 1 : 2);
+        const double* m = blob + (int)__ldg(blob + phase);
+        const int nt = (int)__ldg(m);
+        const double init = __ldg(m + 1), lr = __ldg(m + 2);
+        const double* roots = m + 4;
+        const double* nodes = roots + nt;
+        double partial = 0.0;
+        for (int t = lane; t < nt; t += 32) {
+            int k = (int)__ldg(roots + t);
+            for (;;) {
+                const double* rec = nodes + 5 * k;
+                const int f = (int)__ldg(rec);
+                if (f < 0) { partial = __dadd_rn(partial, __ldg(rec + 4)); break; }
+                const double x = (double)(float)__dsub_rn(fi[f], fj[f]);
+                k = (int)__ldg(rec + ((x <= __ldg(rec + 1)) ? 2 : 3));
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) partial = __dadd_rn(partial, __shfl_xor_sync(BK_FULL, partial, d));
+        const double raw = __dadd_rn(init, __dmul_rn(lr, partial));
+        const double p = __ddiv_rn(1.0, __dadd_rn(1.0, exp(-raw)));
+        acc = (n == 0) ? p : __dadd_rn(acc, p);
+    }
+    return __ddiv_rn(acc, 3.0);
+}
+
+// the evaluator's probability for either model form
+__device__ __forceinline__ double win_probability_any(const double* feat, const double* __restrict__ model, int kind,
+                                                      uint32_t player, int lane) {
+    return kind == 1 ? win_probability_gbt(feat, model, player, lane) : win_probability(feat, model, player, lane);
+}
+
 // LearnedWinProbabilityEvaluator.potential (mcts/learned_evaluator.py:145-152): the clamped probability or its logit
 __device__ __forceinline__ double potential_of(double p, int mode) {
     p = fmin(fmax(p, 1e-6), 1.0 - 1e-6);

@@ -123,14 +123,14 @@ class DeviceUCT:
                  reward_mode: int = 0, rollout_policy: int = 0, tt: Optional[dev.DeviceTranspositionTable] = None, zobrist: Optional[ZobristHash] = None,
                  max_root_moves: int = MAX_ROOT_MOVES, leaf_batch: int = 1, leaf_model: Optional[torch.Tensor] = None,
                  leaf_max_turns: int = 2500, progressive_bias_weight: float = 0.0, shaping_weight: float = 1.0,
-                 shaping_gamma: float = 1.0, potential_mode: str = "prob"):
+                 shaping_gamma: float = 1.0, potential_mode: str = "prob", leaf_model_kind: int = 0):
         if not torch.cuda.is_available():
             raise _lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
         self.lib = _lib.init(torch.cuda.current_device())
         self.p = _lib.MctsParams(iterations=0, iterations_total=int(iterations_total),
                                  max_rollout_moves=int(max_rollout_moves), rollout_policy=int(rollout_policy), max_depth=int(max_depth),
                                  ucb_variant=int(ucb_variant), resume=0, reward_mode=int(reward_mode), leaf_batch=int(leaf_batch),
-                                 reserved0=0, leaf_max_turns=int(leaf_max_turns), reserved1=0,
+                                 reserved0=0, leaf_max_turns=int(leaf_max_turns), leaf_model_kind=int(leaf_model_kind),
                                  progressive_bias_weight=float(progressive_bias_weight) if int(reward_mode) >= 3 else 0.0,
                                  shaping_weight=float(shaping_weight), shaping_gamma=float(shaping_gamma),
                                  potential_mode=1 if potential_mode == "logit" else 0, reserved2=0,
@@ -141,8 +141,8 @@ class DeviceUCT:
         # logistic model (float64[35] on the device)
         self.leaf_model = None
         if int(reward_mode) >= 3:
-            if leaf_model is None or leaf_model.numel() != 35:
-                raise ValueError("reward_mode 3 / 4 needs leaf_model: 34 weights + bias")
+            if leaf_model is None or (int(leaf_model_kind) == 0 and leaf_model.numel() != 35):
+                raise ValueError("reward_mode 3 / 4 needs leaf_model: 34 weights + bias, or a flattened GBT blob (kind 1)")
             self.leaf_model = leaf_model.to(device="cuda", dtype=torch.float64).contiguous()
             self.p.leaf_model = self.leaf_model.data_ptr()
         self.root_frontiers = None
@@ -244,8 +244,9 @@ class MCTSAgent:
     snapshot features of every new leaf in the kernel and feeds the folded 34 weights + bias (reward_mode 3), and
     progressive_bias_enabled adds the selection term w * prior / (1 + n) with prior = V(child, parent player) -
     V(parent, parent player) from the same feature block; potential_shaping_enabled (without leaf evaluation) keeps
-    the rollouts and adds w * (gamma * Phi(end) - Phi(leaf)) to truncated ones (reward_mode 4).  Other estimators
-    (gradient-boosted phase models) are served out of tree by ``winprob.LearnedWinProbabilityEvaluator``.
+    the rollouts and adds w * (gamma * Phi(end) - Phi(leaf)) to truncated ones (reward_mode 4).  ``pairwise_gbt_phase``
+    artifacts (GradientBoostingClassifier per game phase) run the same way with their trees flattened for the kernel.
+    Artifacts of any other shape are served out of tree by ``winprob.LearnedWinProbabilityEvaluator``.
     """
 
     def __init__(self, iterations: int = 1000, time_limit: Optional[float] = None, exploration_constant: float = 1.414,
@@ -282,9 +283,10 @@ class MCTSAgent:
                 raise NotImplementedError("progressive bias with a fitted model runs in the learned kernels: enable "
                                           "leaf evaluation or potential shaping with it")
             if real and self._requires_learned_evaluator and getattr(self.learned_evaluator, "device_model", None) is None:
-                raise NotImplementedError("in-tree leaf evaluation runs pairwise_logreg artifacts whose pipeline is "
-                                          "[StandardScaler,] LogisticRegression; this artifact has another shape -- "
-                                          "use winprob.LearnedWinProbabilityEvaluator out of tree")
+                raise NotImplementedError("the learned options run in the kernel for pairwise_logreg artifacts whose "
+                                          "pipeline is [StandardScaler,] LogisticRegression and for pairwise_gbt_phase "
+                                          "artifacts of scikit-learn GradientBoostingClassifier models; this artifact has "
+                                          "another shape -- use winprob.LearnedWinProbabilityEvaluator out of tree")
             if (not real and self.potential_shaping_enabled and potential_mode == "prob"
                     and self.potential_shaping_gamma != 1.0 and self.potential_shaping_weight != 0.0):
                 raise NotImplementedError("potential shaping with gamma != 1 adds a non-zero constant to truncated "
@@ -340,6 +342,7 @@ class MCTSAgent:
                          exploration=self.exploration_constant, seed=self.seed, tree_offset=offset,
                          reward_mode=mode, leaf_model=model, leaf_max_turns=getattr(self.learned_evaluator, "max_turns", 2500),
                          progressive_bias_weight=self.progressive_bias_weight if self.progressive_bias_enabled else 0.0,
+                         leaf_model_kind=getattr(self.learned_evaluator, "device_model_kind", 0),
                          shaping_weight=self.potential_shaping_weight, shaping_gamma=self.potential_shaping_gamma,
                          potential_mode=self.potential_mode,
                          leaf_batch=self.leaf_batch,

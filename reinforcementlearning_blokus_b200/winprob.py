@@ -172,6 +172,52 @@ def fold_logistic_pipeline(artifact: Mapping[str, Any]) -> Optional[np.ndarray]:
     return out
 
 
+def flatten_gbt_phase_models(artifact: Mapping[str, Any]) -> Optional[np.ndarray]:
+    """One float64 blob for the UCT kernel from a "pairwise_gbt_phase" artifact (mcts/learned_evaluator.py:112-127) whose
+    phase / fallback models are scikit-learn GradientBoostingClassifier (binary) over all 34 snapshot columns:
+
+        blob[0:3]            offsets of the early / mid / late model (a missing phase points at the fallback model)
+        model: n_trees, init_raw, learning_rate, 0, roots[n_trees], nodes[*][5] = (feature or -1, threshold, left, right, value)
+
+    raw = init_raw + learning_rate * sum_t value(leaf_t(x)), p = sigmoid(raw); a tree goes left when float32(x[feature])
+    <= threshold, as scikit-learn's trees do.  None when the artifact has any other shape."""
+    if artifact.get("model_type") != "pairwise_gbt_phase":
+        return None
+    cols = list(artifact.get("feature_columns", SNAPSHOT_FEATURE_COLUMNS))
+    if cols != SNAPSHOT_FEATURE_COLUMNS:
+        return None
+    phases = artifact.get("phase_models", {}) or {}
+    fallback = artifact.get("fallback_model")
+    chosen = [phases.get(ph) or fallback for ph in ("early", "mid", "late")]
+    if any(m is None for m in chosen):
+        return None
+    parts, offsets, seen = [], [], {}
+    pos = 3
+    for m in chosen:
+        if id(m) in seen:
+            offsets.append(seen[id(m)])
+            continue
+        if type(m).__name__ != "GradientBoostingClassifier" or getattr(m, "n_classes_", 2) != 2 or m.estimators_.shape[1] != 1:
+            return None
+        init_raw = float(np.asarray(m._raw_predict_init(np.zeros((1, len(cols))))).ravel()[0])
+        roots, nodes, base = [], [], 0
+        for est in m.estimators_[:, 0]:
+            t = est.tree_
+            roots.append(float(base))
+            for k in range(t.node_count):
+                leaf = t.children_left[k] < 0
+                nodes.append([-1.0 if leaf else float(t.feature[k]), float(t.threshold[k]),
+                              -1.0 if leaf else float(base + t.children_left[k]), -1.0 if leaf else float(base + t.children_right[k]),
+                              float(t.value[k, 0, 0])])
+            base += t.node_count
+        block = np.concatenate([[float(len(roots)), init_raw, float(m.learning_rate), 0.0], roots, np.asarray(nodes).ravel()])
+        seen[id(m)] = pos
+        offsets.append(pos)
+        parts.append(block)
+        pos += len(block)
+    return np.concatenate([np.asarray(offsets, dtype=np.float64)] + parts).astype(np.float64)
+
+
 # ---- learned leaf evaluator (mcts/learned_evaluator.py) ----------------------------------------------------------
 def _phase_bucket_from_occupancy(board_occupancy: float, *, early_max: float = 0.33, mid_max: float = 0.66) -> str:
     return "early" if board_occupancy < early_max else ("mid" if board_occupancy < mid_max else "late")
@@ -198,7 +244,12 @@ class LearnedWinProbabilityEvaluator:
         if self.model_type not in {"pairwise_logreg", "pairwise_gbt_phase"}:
             raise ValueError(f"Unsupported learned evaluator model_type '{self.model_type}' in {self.artifact_path}.")
         self._cols = [SNAPSHOT_FEATURE_COLUMNS.index(c) for c in self.feature_columns]
-        self.device_model = fold_logistic_pipeline(self.artifact)      # float64[35] for the UCT kernel, or None
+        # the model in the form the UCT kernel evaluates: float64[35] (logistic) or a flattened tree blob (GBT), or None
+        self.device_model = fold_logistic_pipeline(self.artifact)
+        self.device_model_kind = 0
+        if self.device_model is None:
+            self.device_model = flatten_gbt_phase_models(self.artifact)
+            self.device_model_kind = 1
 
     def _extract_features_for_all_players(self, board: Board) -> Dict[int, Dict[str, float]]:
         blk = board_feature_block(board, int(board.move_count), self.max_turns)

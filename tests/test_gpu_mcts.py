@@ -390,3 +390,57 @@ def test_learned_leaf_evaluation_in_the_tree(golden_dir, tmp_path):
     biased = MCTSAgent(iterations=120, seed=2, learned_model_path=path, leaf_evaluation_enabled=True,
                        progressive_bias_enabled=True, progressive_bias_weight=0.25, use_transposition_table=False)
     assert biased.select_action(board, player, legal) in legal and biased.stats["progressive_bias_updates"] == 120
+
+
+def test_learned_gbt_phase_models_in_the_tree(golden_dir, tmp_path):
+    """The other artifact type of the reference's evaluator, "pairwise_gbt_phase" (mcts/learned_evaluator.py:112-127):
+    flattened scikit-learn gradient-boosted trees are walked inside the kernel.  Kernel == oracle for leaf evaluation
+    (+ progressive bias) and for rollouts with potential shaping; the agent's leaf values equal scikit-learn's."""
+    joblib = pytest.importorskip("joblib")
+    from sklearn.ensemble import GradientBoostingClassifier
+
+    from reinforcementlearning_blokus_b200 import Position, winprob
+
+    rows = np.load(os.path.join(golden_dir, "snapshots.npz"))["state_features"]
+    cols = winprob.SNAPSHOT_FEATURE_COLUMNS
+    x = np.concatenate([rows[:, 0] - rows[:, 1], rows[:, 2] - rows[:, 3], rows[:, 1] - rows[:, 2]])
+    y = (x[:, cols.index("mobility_total_placements")] + 8000 * x[:, cols.index("player_board_occupancy")] > 0).astype(int)
+    occ = np.concatenate([(rows[:, a, 29] + rows[:, b, 29]) / 2 for a, b in ((0, 1), (2, 3), (1, 2))])
+    early = GradientBoostingClassifier(n_estimators=45, max_depth=3, random_state=1).fit(x[occ < 0.4], y[occ < 0.4])
+    rest = GradientBoostingClassifier(n_estimators=30, max_depth=2, random_state=2).fit(x, y)
+    path = str(tmp_path / "gbt.joblib")
+    joblib.dump({"model_type": "pairwise_gbt_phase", "feature_columns": cols, "phase_models": {"early": early},
+                 "fallback_model": rest}, path)
+    ev = winprob.LearnedWinProbabilityEvaluator(path)
+    blob = ev.device_model
+    assert ev.device_model_kind == 1 and blob is not None
+    tb = torch.from_numpy(blob)
+    for ri, root_np in enumerate(_roots(golden_dir)[:3]):
+        root = dev.to_device(np.atleast_1d(root_np))
+        want = orc.mcts_search_learned(root_np, 120, seed=41, model=blob, model_kind=1, tree_id=ri, bias_weight=0.25)
+        res = DeviceUCT(120, n_trees=1, seed=41, tree_offset=ri, reward_mode=3, leaf_model=tb, leaf_model_kind=1,
+                        progressive_bias_weight=0.25).search(root, 120)
+        n = want["n_root"]
+        assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n]), ri
+        assert np.allclose(res["reward"][0, :n].cpu().numpy(), want["reward"][:n], rtol=0, atol=1e-12)
+    root_np = _roots(golden_dir)[2]
+    kw = dict(max_rollout_moves=5, rollout_policy=1, shaping_weight=2.0, shaping_gamma=0.9)
+    want = orc.mcts_search_shaped(root_np, 80, seed=5, model=blob, model_kind=1, potential_mode=1, **kw)
+    res = DeviceUCT(80, n_trees=1, seed=5, reward_mode=4, leaf_model=tb, leaf_model_kind=1, potential_mode="logit", **kw).search(
+        dev.to_device(np.atleast_1d(root_np)), 80)
+    n = want["n_root"]
+    assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n])
+    assert np.allclose(res["reward"][0, :n].cpu().numpy(), want["reward"][:n], rtol=0, atol=1e-9)
+    board = Board.from_packed(_roots(golden_dir)[1])
+    player = board.current_player
+    legal = get_shared_generator().get_legal_moves(board, player)
+    agent = MCTSAgent(iterations=len(legal), seed=2, learned_model_path=path, leaf_evaluation_enabled=True,
+                      use_transposition_table=False)
+    r = agent.search_root(board, player)
+    ids = sorted(m.to_id() for m in legal)
+    for rank in (0, len(ids) // 3, len(ids) - 1):
+        child = board.copy()
+        mv = Move.from_id(ids[rank])
+        cells = get_shared_generator().piece_position_cache[mv.piece_id][mv.orientation]
+        child.place_piece([Position(mv.anchor_row + a, mv.anchor_col + b) for a, b in cells], player, mv.piece_id, validate=False)
+        assert r["reward"][rank] == pytest.approx(ev.predict_player_win_probability(child, child.current_player), abs=1e-9)

@@ -171,3 +171,55 @@ def test_pairwise_dataset_matches_reference(golden_dir):
     train, test, split = winprob.split_pairwise_by_game(out, test_size=0.25, seed=3)
     assert split == json.loads(str(z["meta"][1]))
     assert np.array_equal(train.index.to_numpy(), z["train_index"]) and np.array_equal(test.index.to_numpy(), z["test_index"])
+
+
+def test_device_model_forms_match_sklearn(golden_dir, tmp_path):
+    """The two model forms handed to the UCT kernel -- folded logistic weights and flattened gradient-boosted phase
+    models -- evaluated by the CPU oracle (the kernel's restatement) agree with scikit-learn's predict_proba used the way
+    mcts/learned_evaluator.py:97-143 uses it, on reference feature rows."""
+    import os
+
+    import pytest
+
+    joblib = pytest.importorskip("joblib")
+    from sklearn.ensemble import GradientBoostingClassifier
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+
+    from oracle import orc
+    from reinforcementlearning_blokus_b200 import winprob
+
+    z = np.load(os.path.join(golden_dir, "snapshots.npz"))
+    rows = z["state_features"]                                                   # [240, 4, 34]
+    states = np.load(os.path.join(golden_dir, "random_states.npz"))["states"].view(orc.STATE_DTYPE).reshape(-1)
+    cols = winprob.SNAPSHOT_FEATURE_COLUMNS
+    x = np.concatenate([rows[:, 0] - rows[:, 1], rows[:, 2] - rows[:, 3], rows[:, 1] - rows[:, 2]])
+    y = (x[:, cols.index("mobility_total_placements")] + 8000 * x[:, cols.index("player_board_occupancy")] > 0).astype(int)
+    logreg = Pipeline([("scale", StandardScaler()), ("clf", LogisticRegression(max_iter=500))]).fit(x, y)
+    occ = np.concatenate([(rows[:, a, 29] + rows[:, b, 29]) / 2 for a, b in ((0, 1), (2, 3), (1, 2))])
+    early = GradientBoostingClassifier(n_estimators=40, max_depth=3, random_state=1).fit(x[occ < 0.4], y[occ < 0.4])
+    late = GradientBoostingClassifier(n_estimators=25, max_depth=2, random_state=2).fit(x, y)
+    art_l = {"model_type": "pairwise_logreg", "feature_columns": cols, "pipeline": logreg}
+    art_g = {"model_type": "pairwise_gbt_phase", "feature_columns": cols, "phase_models": {"early": early}, "fallback_model": late}
+    w, blob = winprob.fold_logistic_pipeline(art_l), winprob.flatten_gbt_phase_models(art_g)
+    assert w.shape == (35,) and blob is not None and blob[1] == blob[2] != blob[0]           # mid and late share the fallback
+    for i in (0, 17, 101, 230):
+        for player in (0, 3):
+            want_l, want_g = [], []
+            for j in range(4):
+                if j == player:
+                    continue
+                d = (rows[i, player] - rows[i, j])[None]
+                want_l.append(logreg.predict_proba(d)[0, 1])
+                o = (rows[i, player, 29] + rows[i, j, 29]) / 2.0
+                want_g.append((early if o < 0.33 else late).predict_proba(d)[0, 1])
+            assert orc.win_probability(states[i], player, w, 0) == pytest.approx(float(np.mean(want_l)), abs=1e-12)
+            assert orc.win_probability(states[i], player, blob, 1) == pytest.approx(float(np.mean(want_g)), abs=1e-12)
+    # artifacts of another shape are declined (the host evaluator still serves them out of tree)
+    assert winprob.fold_logistic_pipeline(art_g) is None and winprob.flatten_gbt_phase_models(art_l) is None
+    assert winprob.flatten_gbt_phase_models({"model_type": "pairwise_gbt_phase", "phase_models": {"early": early}}) is None
+    p = str(tmp_path / "gbt.joblib")
+    joblib.dump(art_g, p)
+    ev = winprob.LearnedWinProbabilityEvaluator(p)
+    assert ev.device_model_kind == 1 and np.array_equal(ev.device_model, blob)
