@@ -205,6 +205,11 @@ int bk_tt_stats(bk_tt* tt, uint64_t* out_host, void* stream);
 int bk_heuristic_scores(const bk_state* states, const uint8_t* players, const uint32_t* offsets,
                         const uint16_t* move_ids, int n, double* scores, void* stream);
 
+/* The same with HeuristicAgent.set_weights (agents/heuristic_agent.py:268-282): weights_host = HOST array
+ * {piece_size, corner_creation, edge_avoidance, center_preference}; products and sums in the reference's order. */
+int bk_heuristic_scores_weighted(const bk_state* states, const uint8_t* players, const uint32_t* offsets,
+                                 const uint16_t* move_ids, int n, const double* weights_host, double* scores, void* stream);
+
 /* ---- K5: UCT search (mcts/mcts_agent.py:304-582; flat variant agents/fast_mcts_agent.py:112-338) -- */
 
 typedef struct bk_mcts_params {

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "bk_tt_put": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "bk_tt_stats": (_i32, [_vp, _vp, _vp]),
     "bk_heuristic_scores": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "bk_heuristic_scores_weighted": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bk_mcts_workspace_bytes": (_i64, [_vp]),
     "bk_mcts_search": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -48,8 +48,8 @@ class HeuristicAgent:
     """Softmax(T=1) sample over 1.0*size + 2.0*corner_creation - 1.5*edge + 0.5*centre.
 
     The float64 scores come from ``bk_heuristic_scores`` (one launch for the whole move list) and equal the
-    reference's ``_evaluate_move`` bit for bit.  The kernel implements the reference's default weights;
-    non-default weights are rejected rather than evaluated somewhere else.
+    reference's ``_evaluate_move`` bit for bit, for the default weights and for any ``set_weights`` (the four weights
+    are kernel arguments; products and sums in the reference's order).
     """
 
     def __init__(self, seed: Optional[int] = None):
@@ -65,13 +65,13 @@ class HeuristicAgent:
                 self.center_preference_weight) == (1.0, 2.0, -1.5, 0.5)
 
     def evaluate_moves(self, board: Board, player: Player, legal_moves: List[Move]) -> np.ndarray:
-        if not self._default_weights():
-            raise NotImplementedError("the device kernel implements the reference's default heuristic weights")
+        weights = None if self._default_weights() else (self.piece_size_weight, self.corner_creation_weight,
+                                                        self.edge_avoidance_weight, self.center_preference_weight)
         ids = np.array([m.to_id() for m in legal_moves], dtype=np.uint16)
         st = dev.to_device(np.atleast_1d(board.to_packed()))
         players = torch.tensor([player.value - 1], dtype=torch.uint8, device="cuda")
         offsets = torch.tensor([0, len(ids)], dtype=torch.int32, device="cuda")
-        scores = dev.heuristic_scores(st, offsets, torch.from_numpy(ids).cuda(), players)
+        scores = dev.heuristic_scores(st, offsets, torch.from_numpy(ids).cuda(), players, weights=weights)
         return scores.cpu().numpy()
 
     def _evaluate_move(self, board: Board, player: Player, move: Move) -> float:

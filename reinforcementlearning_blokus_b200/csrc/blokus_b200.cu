@@ -660,7 +660,8 @@ __global__ void k_tt_put(unsigned long long* keys, double* rewards, uint32_t log
 //   centre  = 1 - sqrt((ar-9.5)^2 + (ac-9.5)^2) / sqrt(2*9.5^2), from the ANCHOR (:185-198)
 // Explicit _rn intrinsics keep the compiler from contracting to FMA, so the doubles equal numpy's bit for bit.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double heuristic_score(const uint32_t* __restrict__ arows, uint32_t move_count, uint32_t id) {
+__device__ __forceinline__ double heuristic_score(const uint32_t* __restrict__ arows, uint32_t move_count, uint32_t id,
+                                                  double w_size = 1.0, double w_corner = 2.0, double w_edge = -1.5, double w_centre = 0.5) {
     const int o = id / 400, cell = id - o * 400, ar = cell / 20, ac = cell - ar * 20;
     const int n = c_orient_ncells[o];
     int corners = 0, edge = 0;
@@ -675,22 +676,22 @@ __device__ __forceinline__ double heuristic_score(const uint32_t* __restrict__ a
         const int m = min(min(r, c), min(19 - r, 19 - c));
         edge += (m <= 2);
     }
-    double score = __dadd_rn(0.0, __dmul_rn(1.0, (double)n));
-    score = __dadd_rn(score, __dmul_rn(2.0, (double)corners));
+    double score = __dadd_rn(0.0, __dmul_rn(w_size, (double)n));
+    score = __dadd_rn(score, __dmul_rn(w_corner, (double)corners));
     const double progress = __ddiv_rn((double)move_count, 100.0);
     const double edge_score = (progress < 0.3) ? (double)edge : __dmul_rn((double)edge, 0.5);
-    score = __dadd_rn(score, __dmul_rn(-1.5, edge_score));
+    score = __dadd_rn(score, __dmul_rn(w_edge, edge_score));
     const double dr = __dsub_rn((double)ar, 9.5), dc = __dsub_rn((double)ac, 9.5);
     const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc)));
     const double maxd = __dsqrt_rn(__dmul_rn(2.0, __dmul_rn(9.5, 9.5)));
     const double centre = __dsub_rn(1.0, __ddiv_rn(dist, maxd));
-    return __dadd_rn(score, __dmul_rn(0.5, centre));
+    return __dadd_rn(score, __dmul_rn(w_centre, centre));
 }
 
 __global__ void __launch_bounds__(BK_THREADS)
 k_heuristic_scores(const bk_state* __restrict__ states, const uint8_t* __restrict__ players,
                    const uint32_t* __restrict__ offsets, const uint16_t* __restrict__ ids, int n,
-                   double* __restrict__ out) {
+                   double* __restrict__ out, double w_size, double w_corner, double w_edge, double w_centre) {
     __shared__ uint32_t s_a[BK_WARPS][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -706,7 +707,8 @@ k_heuristic_scores(const bk_state* __restrict__ states, const uint8_t* __restric
         s_a[wib][lane] = A;
         __syncwarp();
         const uint32_t lo = offsets[i], hi = offsets[i + 1];
-        for (uint32_t k = lo + lane; k < hi; k += 32) out[k] = heuristic_score(s_a[wib], s.move_count, ids[k]);
+        for (uint32_t k = lo + lane; k < hi; k += 32)
+            out[k] = heuristic_score(s_a[wib], s.move_count, ids[k], w_size, w_corner, w_edge, w_centre);
     }
 }
 
@@ -1034,7 +1036,18 @@ extern "C" int bk_heuristic_scores(const bk_state* states, const uint8_t* player
                                    const uint16_t* move_ids, int n, double* scores, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids && scores)), "bk_heuristic_scores: null buffer");
     if (n == 0) return BK_OK;
-    k_heuristic_scores<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, offsets, move_ids, n, scores);
+    k_heuristic_scores<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, offsets, move_ids, n, scores, 1.0, 2.0, -1.5, 0.5);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int bk_heuristic_scores_weighted(const bk_state* states, const uint8_t* players, const uint32_t* offsets,
+                                            const uint16_t* move_ids, int n, const double* weights_host, double* scores, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids && scores)), "bk_heuristic_scores_weighted: null buffer");
+    REQUIRE(weights_host != nullptr, "bk_heuristic_scores_weighted: weights_host = {piece_size, corner_creation, edge_avoidance, center_preference}");
+    if (n == 0) return BK_OK;
+    k_heuristic_scores<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, offsets, move_ids, n, scores,
+        weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
     LAUNCH_CHECK();
     return BK_OK;
 }

@@ -7,7 +7,8 @@ CUDA tensors holding packed ``bk_state`` records (see ``state.py``).
 
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -309,12 +310,18 @@ def playout(n: int, seed: int, game_offset: int = 0, start_states: Optional[torc
 
 
 def heuristic_scores(states: torch.Tensor, offsets: torch.Tensor, move_ids: torch.Tensor,
-                     players: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """float64 HeuristicAgent._evaluate_move score of every listed move (agents/heuristic_agent.py:68-103)."""
+                     players: Optional[torch.Tensor] = None, weights: Optional[Sequence[float]] = None) -> torch.Tensor:
+    """float64 HeuristicAgent._evaluate_move score of every listed move (agents/heuristic_agent.py:68-103).  weights =
+    (piece_size, corner_creation, edge_avoidance, center_preference) of set_weights; None = the defaults 1, 2, -1.5, 0.5."""
     n = _check_states(states)
     _check_players(players, n)
     lib = _lib_for(states)
     out = torch.empty(max(move_ids.numel(), 1), dtype=torch.float64, device=states.device)
+    if weights is not None:
+        w = (C.c_double * 4)(*[float(v) for v in weights])
+        check(lib.bk_heuristic_scores_weighted(_ptr(states), _ptr(players), _ptr(offsets), _ptr(move_ids), n, w, _ptr(out), _stream()))
+        _count()
+        return out[:move_ids.numel()]
     check(lib.bk_heuristic_scores(_ptr(states), _ptr(players), _ptr(offsets), _ptr(move_ids), n, _ptr(out), _stream()))
     _count()
     return out[:move_ids.numel()]

@@ -181,3 +181,36 @@ def test_fast_mcts_think_schema_and_budget():
     assert one["move"] == legal[0] and one["stats"]["nodesEvaluated"] == 1
     mv, stats = GameplayFastMCTSAgent(iterations=64, seed=1).choose_move(board, Player.RED, legal, 200)
     assert mv in legal and "topMoves" in stats
+
+
+def test_heuristic_agent_custom_weights():
+    """HeuristicAgent.set_weights (agents/heuristic_agent.py:268-282; the arena's "weights" parameter): the kernel takes
+    the four weights and combines the same features in the reference's order -- checked against the default-weight
+    scores recombined on the host, and through select_action."""
+    from reinforcementlearning_blokus_b200 import BlokusGame, HeuristicAgent, RandomAgent
+    from reinforcementlearning_blokus_b200 import device as dev
+
+    game = BlokusGame()
+    rnd = RandomAgent(seed=3)
+    for _ in range(14):
+        p = game.get_current_player()
+        game.make_move(rnd.select_action(game.board, p, game.get_legal_moves(p)), p)
+    board, player = game.board, game.get_current_player()
+    legal = game.get_legal_moves(player)
+    base = HeuristicAgent(seed=1)
+    s_default = base.evaluate_moves(board, player, legal)
+    # isolate each feature with unit weights, then recombine with arbitrary ones
+    parts = []
+    for k in range(4):
+        a = HeuristicAgent(seed=1)
+        w = [0.0, 0.0, 0.0, 0.0]; w[k] = 1.0
+        a.set_weights(dict(zip(("piece_size", "corner_creation", "edge_avoidance", "center_preference"), w)))
+        parts.append(a.evaluate_moves(board, player, legal))
+    assert np.array_equal(((0.0 + 1.0 * parts[0]) + 2.0 * parts[1] + -1.5 * parts[2]) + 0.5 * parts[3], s_default)
+    custom = HeuristicAgent(seed=1)
+    custom.set_weights({"piece_size": 0.7, "corner_creation": 3.25, "edge_avoidance": -0.4, "center_preference": 1.9})
+    got = custom.evaluate_moves(board, player, legal)
+    want = (((0.0 + 0.7 * parts[0]) + 3.25 * parts[1]) + -0.4 * parts[2]) + 1.9 * parts[3]
+    assert np.array_equal(got, want) and not np.array_equal(got, s_default)
+    assert custom.select_action(board, player, legal) in legal
+    assert custom.get_action_info()["weights"]["corner_creation"] == 3.25
