@@ -26,5 +26,9 @@ dev.replay_snapshots(tr, (8, 16, 24, 32, 40, 48, 56, 64))
 roots = dev.to_device(empty_states(1))
 DeviceUCT(256, n_trees=3552, seed=42).search(roots, 256)
 DeviceUCT(256, n_trees=2072, seed=42, rollout_policy=dev.POLICY_HEURISTIC).search(roots, 256)
+DeviceUCT(64, n_trees=444, seed=42, leaf_batch=8).search(roots, 64)                                  # k_mcts<0,true,false>
+import numpy as np
+w = torch.from_numpy(np.random.default_rng(0).normal(0, 0.05, 35))
+DeviceUCT(256, n_trees=2368, seed=42, reward_mode=3, leaf_model=w, progressive_bias_weight=0.25).search(roots, 256)   # k_mcts<0,false,true>
 torch.cuda.synchronize()
 print("ok")
