@@ -401,13 +401,17 @@ def _extras(dev, torch, n):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    # mid-game corpus: 2^20 states = random self-play stopped after k turns; 256 MiB of states,
-    # twice the L2, so every generation streams its state from HBM
+    # corpus of SURVEY 8d C1-ii: 2^20 states, game g = uniform-random self-play from the empty board stopped after k
+    # turns, k spread evenly over 0..60 (every stage of the game, terminal states included); 256 MiB of states, twice
+    # the L2, so every generation streams its state from HBM
     parts = []
-    per = (1 << 20) // 8
-    for k in (6, 12, 18, 24, 30, 36, 42, 48):
-        parts.append(dev.playout(per, seed=7, game_offset=k * 1_000_000, max_turns=k, want_final=True)["final_states"].clone())
-    corpus = torch.cat(parts).contiguous()
+    per = -(-(1 << 20) // 61)
+    for k in range(61):
+        if k == 0:
+            parts.append(dev.to_device(empty_states_fn(per)))
+        else:
+            parts.append(dev.playout(per, seed=0xB10C05, game_offset=k * per, max_turns=k, want_final=True)["final_states"].clone())
+    corpus = torch.cat(parts)[: 1 << 20].contiguous()
     del parts
     m = corpus.shape[0]
     ex = {"movegen_states": m, "movegen_mean_legal_moves": float(dev.movegen_count(corpus).float().mean())}
@@ -453,7 +457,7 @@ def _extras(dev, torch, n):
     try:
         from reinforcementlearning_blokus_b200.mcts import DeviceUCT
 
-        root = corpus[3 * per + 17: 3 * per + 18].contiguous()              # a 24-turn position
+        root = corpus[24 * per + 17: 24 * per + 18].contiguous()            # a 24-turn position
         for tag, iters, wb in (("mcts_move_1000_sims_ms_one_warp", 1000, 1), ("mcts_move_1008_sims_ms_leaf_batch16", 63, 16)):
             eng = DeviceUCT(iters, n_trees=1, max_depth=1, ucb_variant=1, reward_mode=1, seed=SEED, leaf_batch=wb)
             eng.search(root, iters)
@@ -473,7 +477,7 @@ def _extras(dev, torch, n):
         ex["mcts_move_error"] = str(exc)[:200]
     # win-probability snapshot rows (row N4): 4 x 34 float64 per board = four piece-count generations + a flood fill;
     # and a whole dataset pass: replay recorded games, capture 8 checkpoints each
-    sub = corpus[: 1 << 18]
+    sub = corpus[::4].contiguous()                      # every fourth state: all game stages
     ms = timeit(lambda: dev.snapshot_features(sub), reps=3)
     ex["snapshot_boards_per_sec"] = sub.shape[0] / ms * 1e3
     tr = dev.playout(n, seed=SEED, want_trace=True)["trace"]
