@@ -444,3 +444,35 @@ def test_learned_gbt_phase_models_in_the_tree(golden_dir, tmp_path):
         cells = get_shared_generator().piece_position_cache[mv.piece_id][mv.orientation]
         child.place_piece([Position(mv.anchor_row + a, mv.anchor_col + b) for a, b in cells], player, mv.piece_id, validate=False)
         assert r["reward"][rank] == pytest.approx(ev.predict_player_win_probability(child, child.current_player), abs=1e-9)
+
+
+def test_config4_fast_mcts_1000_sims_on_kat1_roots(golden_dir):
+    """BASELINE config 4 as SURVEY 8d C4 spells it out: roots = the five KAT-1 benchmark states and the empty board,
+    FastMCTS-interface agent with 1,000 simulations per move (leaf-batched rollouts), device transposition keys from the
+    reference-order Zobrist table.  Checks: move in the legal set, stats keys of fast_mcts_agent.py:204-225, root visits
+    add up to the simulations, seed determinism, TT keys == ZobristHash(seed).hash_board on the roots."""
+    import json
+
+    from reinforcementlearning_blokus_b200 import FastMCTSAgent
+
+    with open(os.path.join(golden_dir, "kat1_states.json")) as f:
+        kat = json.load(f)
+    roots = [empty_states(1)[0]] + [np.frombuffer(bytes.fromhex(k["packed_hex"]), dtype=STATE_DTYPE)[0] for k in kat]
+    zob = ZobristHash(seed=42)
+    keys = zob.hash_states(dev.to_device(np.array(roots))).cpu().numpy().view(np.uint64)
+    gen = get_shared_generator()
+    for i, st in enumerate(roots):
+        board = Board.from_packed(st)
+        player = board.current_player
+        assert zob.hash_board(board) == int(keys[i])
+        legal = gen.get_legal_moves(board, player)
+        outs = [FastMCTSAgent(iterations=1000, time_limit=30.0, seed=7, leaf_batch=8).think(board, player, legal, 30000)
+                for _ in range(2)]
+        a, b = outs
+        assert a["move"] in legal and a["move"] == b["move"] and a["stats"]["topMoves"] == b["stats"]["topMoves"]
+        st_ = a["stats"]
+        assert {"timeBudgetMs", "timeSpentMs", "nodesEvaluated", "maxDepthReached", "topMoves"} <= set(st_)
+        assert st_["nodesEvaluated"] == 1000 and len(st_["topMoves"]) <= 10
+        eng = DeviceUCT(125, n_trees=1, seed=7, max_depth=1, ucb_variant=1, reward_mode=1, leaf_batch=8)
+        res = eng.search(dev.to_device(np.atleast_1d(st)), 125)
+        assert int(res["visits"][0].sum()) == 1000 and int(res["counts"][0]) == len(legal)
