@@ -235,8 +235,8 @@ typedef struct bk_mcts_params {
     int32_t  leaf_batch;        /* 1 (or 0): one rollout per iteration, one warp per tree -- the reference's search.
                                    2..16: leaf-batched rollouts -- a CTA of that many warps owns the tree; after each
                                    selection/expansion every warp rolls out from the new leaf with its own random stream
-                                   and the rewards are backed up together (visits += leaf_batch).  Not combinable with a
-                                   transposition table. */
+                                   and the rewards are backed up together (visits += leaf_batch); a transposition
+                                   table then caches the SUM of a leaf's rewards. */
     int32_t  reserved0;
     double   exploration;       /* 1.414 */
     uint64_t seed;

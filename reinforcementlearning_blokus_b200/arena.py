@@ -413,7 +413,7 @@ def build_agent(config: AgentConfig, seed: int):
         return MCTSAgent(
             iterations=iterations, time_limit=float(time_limit) if time_limit is not None else None,
             exploration_constant=float(p.get("exploration_constant", 1.414)),
-            use_transposition_table=bool(p.get("use_transposition_table", leaf_batch <= 1)), seed=seed,
+            use_transposition_table=bool(p.get("use_transposition_table", True)), seed=seed,
             learned_model_path=p.get("learned_model_path"), leaf_evaluation_enabled=bool(p.get("leaf_evaluation_enabled", False)),
             progressive_bias_enabled=bool(p.get("progressive_bias_enabled", False)),
             progressive_bias_weight=float(p.get("progressive_bias_weight", 0.25)),

@@ -993,7 +993,6 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
     const bool heur = params->rollout_policy == BK_POLICY_HEURISTIC;
     const int W = params->leaf_batch > 1 ? params->leaf_batch : 1;
     REQUIRE(W <= BK_MCTS_MAX_WARPS, "bk_mcts_search: leaf_batch must be in [0, 16]");
-    REQUIRE(W == 1 || !tt, "bk_mcts_search: leaf-batched rollouts cannot use a transposition table");
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     long long* rr = reinterpret_cast<long long*>(root_reward);
     cudaStream_t st = as_stream(stream);

@@ -115,7 +115,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
        uint16_t* __restrict__ out_moves, uint32_t* __restrict__ out_status) {
     extern __shared__ __align__(16) unsigned char heur_smem[];    // HEUR_SMEM_PER_WARP bytes per warp when rollout_policy == 1
     __shared__ int sh_tree;
-    __shared__ uint32_t sh_node, sh_stop, sh_root_player;
+    __shared__ uint32_t sh_node, sh_stop, sh_cached, sh_root_player;
     __shared__ int32_t sh_root_score;
     __shared__ long long sh_r[BK_MCTS_MAX_WARPS];
     __shared__ __align__(16) double s_feat[LEARNED ? 4 * BK_NFEAT : 1];      // leaf feature block (learned evaluation)
@@ -308,23 +308,24 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                 }
             }
             }   // lead && !overflow
-            if (BATCH) {
-                if (lead && lane == 0) { sh_node = node; sh_stop = overflow; }
-                __syncthreads();                    // the leaf's state (global) and its index are visible to all warps
-                overflow = sh_stop; node = sh_node;
-                if (!lead && !overflow) load_state(states + node, lane, s);
-            }
-            if (overflow) break;
-            // ---- simulation (mcts_agent.py:408-437); `s` holds the state of `node`
+            // ---- simulation (mcts_agent.py:408-437); `s` holds the state of `node`.  The transposition table is probed
+            // by the tree's leading warp; a leaf-batched search caches the SUM of a leaf's W rewards.
             long long r = 0;
             double rd = 0.0;                         // the reward of learned evaluations
             bool cached = false;
             uint64_t key = 0;
-            if (!BATCH && tt.keys) {
+            if (tt.keys && lead && !overflow) {
                 key = zobrist_of(s, tt.zobrist, lane) ^ salt;
                 double rv = 0.0;
                 if (tt_lookup(tt.keys, tt.rewards, tt.log2_slots, key, rv)) { r = (long long)rv; rd = rv; cached = true; }
             }
+            if (BATCH) {
+                if (lead && lane == 0) { sh_node = node; sh_stop = overflow; sh_cached = cached ? 1u : 0u; }
+                __syncthreads();                    // the leaf's state (global) and its index are visible to all warps
+                overflow = sh_stop; node = sh_node; cached = sh_cached != 0u;
+                if (!lead && !overflow && !cached) load_state(states + node, lane, s);
+            }
+            if (overflow) break;
             if (LEARNED) {
                 if (!cached) {
                     if (prm.reward_mode == 4) {
@@ -407,9 +408,12 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                 if (!BATCH && tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, (double)r);
             }
             if (BATCH) {
-                if (lane == 0) sh_r[wib] = r;
+                if (lane == 0) sh_r[wib] = r;       // (cached: the leading warp holds the cached sum, the others 0)
                 __syncthreads();
-                if (lead) { r = 0; for (int w = 0; w < W; w++) r += sh_r[w]; }
+                if (lead) {
+                    r = 0; for (int w = 0; w < W; w++) r += sh_r[w];
+                    if (tt.keys && !cached && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, (double)r);
+                }
             }
             // ---- back-propagation (mcts_agent.py:572-582): W simulations at once in batch mode
             if (lead && lane == 0) {

@@ -149,8 +149,6 @@ class DeviceUCT:
         self.leaf_batch = max(1, int(leaf_batch))       # simulations per iteration (warps per tree)
         if self.leaf_batch > 16:
             raise ValueError("leaf_batch must be in [1, 16]")
-        if self.leaf_batch > 1 and tt is not None:
-            raise ValueError("leaf-batched rollouts cannot use a transposition table")
         self.max_root_moves = int(max_root_moves)
         self.tt, self.zobrist = tt, zobrist
         if tt is not None and zobrist is None:
@@ -297,11 +295,9 @@ class MCTSAgent:
         self.use_transposition_table = use_transposition_table
         self.max_rollout_moves = int(max_rollout_moves)
         self.num_trees = int(num_trees)
-        # leaf-batched rollouts: every iteration rolls out `leaf_batch` times from the new leaf (1 = the reference)
+        # leaf-batched rollouts: every iteration rolls out `leaf_batch` times from the new leaf (1 = the reference);
+        # with the transposition table a batch caches the sum of its rewards
         self.leaf_batch = max(1, int(leaf_batch))
-        if self.leaf_batch > 1 and use_transposition_table:
-            raise ValueError("leaf_batch > 1 needs use_transposition_table=False (a batch of rollouts has no single "
-                             "reward to cache)")
         self.seed = 0 if seed is None else int(seed)
         self.move_generator = get_shared_generator()
         self.zobrist_hash = ZobristHash(seed=seed)

@@ -216,8 +216,17 @@ def test_leaf_batched_rollouts_match_oracle(golden_dir):
     eng.search(root, 32); eng.search(None, 40, resume=True)
     res = eng.search(None, 24, resume=True)
     assert torch.equal(res["visits"], v) and torch.equal(res["reward"], w)
-    with pytest.raises(ValueError):
-        DeviceUCT(8, leaf_batch=4, tt=TranspositionTable(max_size=1 << 10).device, zobrist=ZobristHash(seed=1))
+    # with a transposition table a batch caches the sum of its rewards; a second search hits the entries of the first
+    zob, tt, ott = ZobristHash(seed=42), TranspositionTable(max_size=1 << 16), orc.OracleTT(18)
+    root_np = roots[2]
+    for rep in range(2):
+        want = orc.mcts_search(root_np, 80, seed=8, tree_id=0, leaf_batch=4, tt=ott, zobrist=zob.table)
+        res = DeviceUCT(80, n_trees=1, seed=8, leaf_batch=4, tt=tt.device, zobrist=zob).search(dev.to_device(np.atleast_1d(root_np)), 80)
+        n = want["n_root"]
+        assert np.array_equal(res["visits"][0, :n].cpu().numpy(), want["visits"][:n]), rep
+        assert np.array_equal(res["reward"][0, :n].cpu().numpy(), want["reward"][:n]), rep
+        assert len(tt) == ott.size()
+    ott.close()
     # the agent: same budget in simulations, spent 8 at a time
     from reinforcementlearning_blokus_b200 import FastMCTSAgent
     board = Board.from_packed(roots[1])
