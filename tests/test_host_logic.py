@@ -223,3 +223,27 @@ def test_device_model_forms_match_sklearn(golden_dir, tmp_path):
     joblib.dump(art_g, p)
     ev = winprob.LearnedWinProbabilityEvaluator(p)
     assert ev.device_model_kind == 1 and np.array_equal(ev.device_model, blob)
+
+
+def test_arena_budget_rule_and_summary():
+    """Deterministic budget rule of the arena adapters (arena_runner.py:334-356, 446-450) and the per-agent summary."""
+    from reinforcementlearning_blokus_b200 import arena
+
+    cap = arena._iteration_cap
+    assert cap(arena.AgentConfig("a", "gameplay_fast_mcts", 25, {"iterations_per_ms": 20.0})) == 500
+    assert cap(arena.AgentConfig("a", "fast_mcts", 200)) == 4000                       # default 20 iterations per ms
+    assert cap(arena.AgentConfig("a", "mcts", 30)) == 300                              # default 10 iterations per ms
+    assert cap(arena.AgentConfig("a", "mcts", None, {"iterations": 64})) == 64
+    assert cap(arena.AgentConfig("a", "fast_mcts", 100, {"deterministic_time_budget": False, "iterations": 500})) == 500
+    recs = [
+        {"error": None, "agent_scores": {"x": 70, "y": 60, "z": 60, "w": 10}, "agent_ranks": {"x": 1, "y": 2, "z": 2, "w": 3},
+         "winner_agents": ["x"]},
+        {"error": None, "agent_scores": {"x": 50, "y": 80, "z": 80, "w": 20}, "agent_ranks": {"x": 2, "y": 1, "z": 1, "w": 3},
+         "winner_agents": ["y", "z"]},
+        {"error": "boom", "agent_scores": {}, "agent_ranks": {}, "winner_agents": []},
+    ]
+    s = arena.summarize(recs, ["x", "y", "z", "w"])
+    assert s["completed_games"] == 2 and s["error_games"] == 1
+    assert s["agents"]["x"] == {"games": 2, "wins": 1.0, "win_rate": 0.5, "mean_score": 60.0, "mean_rank": 1.5}
+    assert s["agents"]["y"]["wins"] == 0.5 and s["agents"]["w"]["win_rate"] == 0.0
+    assert arena.compute_ranks({"1": 30, "2": 30, "3": 10, "4": 50}) == {"1": 2, "2": 2, "3": 3, "4": 1}       # dense ranks
