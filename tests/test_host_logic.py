@@ -247,3 +247,31 @@ def test_arena_budget_rule_and_summary():
     assert s["agents"]["x"] == {"games": 2, "wins": 1.0, "win_rate": 0.5, "mean_score": 60.0, "mean_rank": 1.5}
     assert s["agents"]["y"]["wins"] == 0.5 and s["agents"]["w"]["win_rate"] == 0.0
     assert arena.compute_ranks({"1": 30, "2": 30, "3": 10, "4": 50}) == {"1": 2, "2": 2, "3": 3, "4": 1}       # dense ranks
+
+
+def test_snapshot_rows_schema():
+    """Rows of snapshots.csv: key order of arena_runner.py:_build_snapshot_rows_for_checkpoint (:552-575) followed by the
+    34 feature columns, labels filled in from the finished game (:722-731); checkpoints a game never reached are skipped."""
+    import torch
+
+    from reinforcementlearning_blokus_b200 import winprob
+
+    feats = torch.arange(2 * 2 * 4 * 34, dtype=torch.float64).reshape(2, 2, 4, 34)
+    replay = {"features": feats, "turn_index": torch.tensor([[8, 17], [9, -1]], dtype=torch.int32), "checkpoints": np.array([8, 16])}
+    recs = [{"run_id": "r", "game_id": "r_g0000", "game_index": 0, "game_seed": 5, "seat_assignment": {"1": "a", "2": "b", "3": "c", "4": "d"},
+             "final_scores": {"1": 50, "2": 60, "3": 60, "4": 10}, "final_ranks": {"1": 2, "2": 1, "3": 1, "4": 3},
+             "winner_ids": [2, 3], "winner_id": None, "is_tie": True},
+            {"run_id": "r", "game_id": "r_g0001", "game_index": 1, "game_seed": 6, "seat_assignment": {"1": "b", "2": "c", "3": "d", "4": "a"},
+             "final_scores": {"1": 90, "2": 60, "3": 61, "4": 10}, "final_ranks": {"1": 1, "2": 3, "3": 2, "4": 4},
+             "winner_ids": [1], "winner_id": 1, "is_tie": False}]
+    rows = winprob.snapshot_rows_from_replay(replay, recs)
+    assert len(rows) == 4 * 3                                              # game 1 never reached ply 16
+    assert list(rows[0])[:20] == ["run_id", "game_id", "game_index", "game_seed", "checkpoint_index", "checkpoint_ply", "ply",
+                                  "turn_index", "current_player_id", "player_id", "player_name", "agent_name", "seat_index",
+                                  "winner_id", "winner_ids_json", "label_is_winner", "final_score", "final_rank",
+                                  "final_scores_json", "is_tie"]
+    assert list(rows[0])[20:] == winprob.SNAPSHOT_FEATURE_COLUMNS
+    r = rows[5]                                                            # game 0, checkpoint 1 (ply 16), player 2
+    assert (r["checkpoint_index"], r["checkpoint_ply"], r["turn_index"], r["player_id"], r["player_name"], r["agent_name"]) == (1, 16, 17, 2, "BLUE", "b")
+    assert r["current_player_id"] == 17 % 4 + 1 and r["label_is_winner"] == 1 and r["winner_ids_json"] == "[2, 3]" and r["is_tie"] is True
+    assert r["frontier_size"] == float(feats[0, 1, 1, 0]) and rows[-1]["winner_id"] == 1 and rows[-1]["final_rank"] == 4
