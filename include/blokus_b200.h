@@ -97,6 +97,11 @@ int bk_movegen_emit(const bk_state* states, const uint8_t* players, int n,
 int bk_movegen_fixed(const bk_state* states, const uint8_t* players, int n, uint32_t cap,
                      uint32_t* counts, uint16_t* move_ids, void* stream);
 
+/* One-pass CSR: after bk_movegen_fixed (ids in rows of `cap` slots, full lengths in counts) and bk_exclusive_scan_u32 of
+ * min(counts, cap), copy every row's ids to its CSR range move_ids[offsets[i] .. offsets[i+1]).  Rows longer than cap
+ * must be regenerated with bk_movegen_emit (the host wrapper does that when it happens). */
+int bk_compact_rows(const uint16_t* slots, uint32_t cap, const uint32_t* offsets, int n, uint16_t* move_ids, void* stream);
+
 /* Legal-anchor bitmap: bitmap[i][o*20+row] has bit col set iff move (o,row,col) is legal.  `bitmap` must be 16-byte
  * aligned (each state's 7 280 bytes leave as 16-byte stores). */
 int bk_movegen_bitmap(const bk_state* states, const uint8_t* players, int n,

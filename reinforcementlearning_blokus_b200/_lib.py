@@ -38,6 +38,7 @@ PROTOTYPES = {
     "bk_movegen_fixed": (_i32, [_vp, _vp, _i32, _u32, _vp, _vp, _vp]),
     "bk_can_place_mask": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "bk_movegen_bitmap": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "bk_compact_rows": (_i32, [_vp, _u32, _vp, _i32, _vp, _vp]),
     "bk_movegen_piece_counts": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "bk_has_moves": (_i32, [_vp, _i32, _vp, _vp]),
     "bk_snapshot_features": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),

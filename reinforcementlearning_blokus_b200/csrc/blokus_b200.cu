@@ -762,6 +762,28 @@ extern "C" int bk_movegen_fixed(const bk_state* states, const uint8_t* players, 
     return BK_OK;
 }
 
+// Fixed-capacity rows -> CSR: state i's first (offsets[i+1] - offsets[i]) ids move from slots[i*cap ...] to ids[offsets[i] ...].
+__global__ void __launch_bounds__(BK_THREADS)
+k_compact_rows(const uint16_t* __restrict__ slots, uint32_t cap, const uint32_t* __restrict__ offsets, int n,
+               uint16_t* __restrict__ ids) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        const uint32_t lo = offsets[i], cnt = offsets[i + 1] - lo;
+        const uint16_t* src = slots + (size_t)i * cap;
+        for (uint32_t k = lane; k < cnt; k += 32) ids[lo + k] = __ldcs(src + k);      // read once
+    }
+}
+
+extern "C" int bk_compact_rows(const uint16_t* slots, uint32_t cap, const uint32_t* offsets, int n, uint16_t* move_ids, void* stream) {
+    REQUIRE_INIT(); REQUIRE(n >= 0 && cap > 0 && (n == 0 || (slots && offsets && move_ids)), "bk_compact_rows: bad argument");
+    if (n == 0) return BK_OK;
+    k_compact_rows<<<grid_for(n, 8), BK_THREADS, 0, as_stream(stream)>>>(slots, cap, offsets, n, move_ids);
+    LAUNCH_CHECK();
+    return BK_OK;
+}
+
 extern "C" int bk_movegen_bitmap(const bk_state* states, const uint8_t* players, int n, uint32_t* bitmap, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && bitmap)), "bk_movegen_bitmap: null buffer");
     REQUIRE(reinterpret_cast<uintptr_t>(bitmap) % 16 == 0, "bk_movegen_bitmap: bitmap must be 16-byte aligned");

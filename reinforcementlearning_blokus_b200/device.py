@@ -80,15 +80,38 @@ def movegen_count(states: torch.Tensor, players: Optional[torch.Tensor] = None) 
     return counts
 
 
-def movegen(states: torch.Tensor, players: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+ONE_PASS_CAP = 1280          # row capacity of the one-pass CSR path (longest list seen in 10^7 states: 1 052)
+ONE_PASS_MAX_BYTES = 6 << 30  # temporary rows beyond this size: use the two-pass path
+
+
+def movegen(states: torch.Tensor, players: Optional[torch.Tensor] = None,
+            one_pass: Optional[bool] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Legal moves of every state as CSR: (counts int32[N], offsets int32[N+1], move_ids uint16[total]),
-    ids ascending = the (piece, orientation, row, col) order of the reference's naive generator."""
+    ids ascending = the (piece, orientation, row, col) order of the reference's naive generator.
+
+    one_pass (default: whenever the temporary rows fit ONE_PASS_MAX_BYTES): ONE generation per state writes ids into
+    fixed rows of ONE_PASS_CAP slots, a scan of the counts gives the offsets and a copy kernel packs the rows; a list
+    longer than the cap (never seen) falls back to the two-pass path (count, scan, second generation that emits)."""
     n = _check_states(states)
     _check_players(players, n)
     lib = _lib_for(states)
-    counts = torch.empty(n, dtype=torch.int32, device=states.device)
-    offsets = torch.empty(n + 1, dtype=torch.int32, device=states.device)
     st = _stream()
+    offsets = torch.empty(n + 1, dtype=torch.int32, device=states.device)
+    if one_pass is None:
+        one_pass = n * ONE_PASS_CAP * 2 <= ONE_PASS_MAX_BYTES
+    if one_pass and n > 0:
+        counts, rows = movegen_fixed(states, ONE_PASS_CAP, players)
+        check(lib.bk_exclusive_scan_u32(_ptr(counts), n, _ptr(offsets), st))
+        _count(3)
+        total, longest = (int(v) for v in torch.stack([offsets[n], counts.max()]).tolist())
+        ids = torch.empty(max(total, 1), dtype=torch.uint16, device=states.device)
+        if longest <= ONE_PASS_CAP:
+            check(lib.bk_compact_rows(_ptr(rows), ONE_PASS_CAP, _ptr(offsets), n, _ptr(ids), st))
+        else:
+            check(lib.bk_movegen_emit(_ptr(states), _ptr(players), n, _ptr(offsets), _ptr(ids), st))
+        _count()
+        return counts, offsets, ids[:total]
+    counts = torch.empty(n, dtype=torch.int32, device=states.device)
     check(lib.bk_movegen_count(_ptr(states), _ptr(players), n, _ptr(counts), st))
     check(lib.bk_exclusive_scan_u32(_ptr(counts), n, _ptr(offsets), st))
     _count(4)

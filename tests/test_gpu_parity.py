@@ -398,3 +398,21 @@ def test_policy_distributions_are_the_references(golden_dir):
         dof = int(big.sum()) - 1
         assert abs(chi2 - dof) < 6.0 * np.sqrt(2.0 * dof), (policy, chi2, dof)
         assert abs(freq[~big].sum() - expect[~big].sum()) < 6.0 * np.sqrt(expect[~big].sum() + 1.0)
+
+
+def test_csr_one_pass_equals_two_pass(golden_dir):
+    """device.movegen: the one-pass path (fixed rows + compaction) and the two-pass path (count, scan, emit) return the
+    same CSR, also when rows overflow the capacity and the wrapper falls back."""
+    z = np.load(os.path.join(golden_dir, "random_states.npz"))
+    st = dev.to_device(z["states"])
+    one, two = dev.movegen(st, one_pass=True), dev.movegen(st, one_pass=False)
+    assert all(torch.equal(a, b) for a, b in zip(one, two))
+    keep = dev.ONE_PASS_CAP
+    try:
+        dev.ONE_PASS_CAP = 64                                   # most rows overflow: fallback
+        small = dev.movegen(st, one_pass=True)
+    finally:
+        dev.ONE_PASS_CAP = keep
+    assert all(torch.equal(a, b) for a, b in zip(small, two))
+    empty = dev.movegen(st[:0].contiguous())
+    assert empty[2].numel() == 0 and empty[1].tolist() == [0]
