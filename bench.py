@@ -5,8 +5,8 @@ Workload (BASELINE.json configs[1]): batched uniform-random 4-player self-play, 
 games from the empty board to terminal score per GPU.  One "step" = one such batch.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # CUDA arm (this repo)
-  python bench.py --impl reference [...]                          # CPU arm: the oracle port of the
-                                                                  # reference engine on all host cores
+  python bench.py --impl reference [...]                          # CPU arm: the reference's own Python engine
+                                                                  # (oracle/_ref) on all host cores
 
 For N > 1 the driver launches one rank per GPU with torch.distributed.run; games are sharded by global
 game index (rank r plays games [r*G, (r+1)*G) of every step: weak scaling, no data-path collective).
@@ -132,28 +132,58 @@ def _cpu_playouts(n_games: int, threads: int, game_offset: int) -> float:
     return time.perf_counter() - t0
 
 
+def _reference_available() -> bool:
+    from oracle import make_ref
+
+    return make_ref.available()
+
+
+REF_SOURCE = ("oracle/_ref: the reference's own Python engine (engine/game.py BlokusGame(enable_telemetry=False), default "
+              "frontier+bitboard generator, uniform random.Random choice), byte-compiled by oracle/make_ref.py")
+
+
 def run_reference(args) -> None:
+    """CPU arm.  With oracle/_ref present (built in the build container, ships with the tree) this times the PYTHON
+    reference itself, one process per host core; otherwise the C port of it (oracle/blokus_oracle.c) on all threads."""
     rank = _env_int("RANK", 0)
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = max(cores * 16, 64)                      # games per step: a bounded sample of the workload
-    for w in range(args.warmup):
-        _cpu_playouts(max(cores, 8), cores, 10_000_000 + w * 1000)
-    t = 0.0
-    for k in range(args.steps):
-        t += _cpu_playouts(sample, cores, k * sample)
+    extra = {}
+    if _reference_available():
+        from oracle import ref_bench
+
+        kind, per_worker = "reference", 2
+        pool = ref_bench.PlayoutPool(cores)
+        sample = cores * per_worker
+        for _ in range(args.warmup):
+            pool.step(1)
+        t = 0.0
+        for _ in range(args.steps):
+            t += pool.step(per_worker)[1]
+        pool.close()
+        what = (f"{sample} games/step ({per_worker} per process, {cores} processes) x {args.steps} steps of the same "
+                f"workload; {REF_SOURCE}")
+        # the C port beside it, same box, all threads (what round 1 reported as the reference arm)
+        tp = _cpu_playouts(max(cores * 8, 64), cores, 0)
+        extra["port_playouts_per_sec"] = max(cores * 8, 64) / tp
+    else:
+        kind = "port"
+        sample = max(cores * 16, 64)                  # games per step: a bounded sample of the workload
+        for w in range(args.warmup):
+            _cpu_playouts(max(cores, 8), cores, 10_000_000 + w * 1000)
+        t = 0.0
+        for k in range(args.steps):
+            t += _cpu_playouts(sample, cores, k * sample)
+        what = (f"{sample} games/step x {args.steps} steps of the same workload (oracle/blokus_oracle.c: C restatement "
+                "of the reference's default frontier+bitboard engine; oracle/_ref was not built in this tree)")
     value = sample * args.steps / t
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic", "config": {"workload": WORKLOAD, "games_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} games/step x {args.steps} steps of the same workload "
-                                   "(oracle/blokus_oracle.c: C restatement of the reference's default "
-                                   "frontier+bitboard engine; the Python reference itself cannot travel "
-                                   "to the GPU box and runs 2.5 playouts/s/core, BASELINE.md section 2)"},
+        "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": what}, **extra),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -487,8 +517,39 @@ def _extras(dev, torch, n):
 
 
 def _cpu_baseline():
-    """Oracle port on ONE host core, bounded sample (~10-15 s)."""
-    budget = float(os.environ.get("BLOKUS_CPU_BASELINE_SECONDS", "12"))
+    """The reference's Python engine on all host cores (oracle/_ref, bounded sample) with its movegen benchmark and
+    search agents on one core; beside it the C port of the engine (oracle/blokus_oracle.c) on one core."""
+    out = {}
+    if _reference_available():
+        from oracle import ref_bench
+
+        cores = os.cpu_count() or 1
+        budget = float(os.environ.get("BLOKUS_CPU_BASELINE_SECONDS", "12"))
+        pool = ref_bench.PlayoutPool(cores)
+        pool.step(1)
+        games, t = 0, 0.0
+        while t < budget:
+            g, dt = pool.step(2)
+            games, t = games + g, t + dt
+        pool.close()
+        out = {"value": games / t, "unit": UNIT, "cores": cores, "kind": "reference",
+               "sample": f"{games} games of the same workload in {t:.1f} s on {cores} processes; {REF_SOURCE}",
+               "playouts_per_sec_per_core": games / t / cores}
+        # BASELINE configs[0]: benchmarks/benchmark_move_generation.py's protocol, one core
+        mg = ref_bench.movegen_benchmark(num_runs=10)
+        out["movegen_frontier_bitboard_gens_per_sec_one_core"] = mg["frontier_bitboard_gens_per_sec"]
+        out["movegen_naive_gens_per_sec_one_core"] = mg["naive_gens_per_sec"]
+        out["movegen_benchmark_ms"] = [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()} for r in mg["states"]]
+        out.update({k: round(v, 3) for k, v in ref_bench.search_rates(4.0).items()})
+    out["port"] = _cpu_port_baseline()
+    if not out.get("kind"):
+        out.update({k: out["port"][k] for k in ("value", "unit", "cores", "kind", "sample")})
+    return out
+
+
+def _cpu_port_baseline():
+    """Oracle port on ONE host core, bounded sample (~8 s)."""
+    budget = float(os.environ.get("BLOKUS_CPU_PORT_SECONDS", "8"))
     from oracle import orc
     orc.lib()
     t0 = time.perf_counter()

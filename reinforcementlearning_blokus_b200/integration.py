@@ -43,15 +43,28 @@ def pack_reference_board(board) -> np.ndarray:
     return s
 
 
-def make_adapter():
-    """A subclass of the reference's LegalMoveGenerator whose three public queries run on the device."""
+def adapter_class():
+    """A subclass of the reference's LegalMoveGenerator whose queries run on the device: the public three
+    (``get_legal_moves`` / ``is_move_legal`` / ``has_legal_moves``, engine/move_generator.py:130, 912, 961), the
+    frontier + bitboard generator they dispatch to (``_get_legal_moves_frontier`` :261, ``_has_any_legal_move_frontier``
+    :977, ``get_move_count`` :948) and the coordinate legality test (``is_placement_legal_bitboard_coords`` :682).
+    ``_get_legal_moves_naive`` stays the reference's: it is the trusted oracle of the reference's own tests."""
     from engine.move_generator import LegalMoveGenerator as RefGenerator
     from engine.move_generator import Move as RefMove
 
-    class B200LegalMoveGenerator(RefGenerator):
+    base = getattr(RefGenerator, "_b200_base", RefGenerator)       # never stack adapters on adapters
+
+    class B200LegalMoveGenerator(base):
+        _b200_base = base
+
         def get_legal_moves(self, board, player) -> List:
             ids = single.legal_move_ids(pack_reference_board(board), player.value - 1)
             return [RefMove(*P.decode_move(int(i))) for i in ids]
+
+        _get_legal_moves_frontier = get_legal_moves
+
+        def get_move_count(self, board, player) -> int:
+            return single.count_moves(pack_reference_board(board), player.value - 1)
 
         def is_move_legal(self, board, player, move) -> bool:
             if move.piece_id in board.player_pieces_used[player]:
@@ -68,17 +81,72 @@ def make_adapter():
         def has_legal_moves(self, board, player) -> bool:
             return bool((single.has_moves_mask(pack_reference_board(board)) >> (player.value - 1)) & 1)
 
-    return B200LegalMoveGenerator()
+        _has_any_legal_move_frontier = has_legal_moves
+
+        def is_placement_legal_bitboard_coords(self, board, player, placement_coords, *, is_first_move: bool = False) -> bool:
+            mask = _cells_to_mask(placement_coords)
+            if mask is None:
+                return False
+            s = pack_reference_board(board)
+            k = player.value - 1                        # the caller states whether this is a first move (:688)
+            s["first_mask"] = (int(s["first_mask"]) & ~(1 << k)) | (int(bool(is_first_move)) << k)
+            return single.can_place(s, k, mask)
+
+    return B200LegalMoveGenerator
 
 
-def install() -> Optional[object]:
-    """Swap the reference's shared generator for the device-backed adapter; returns the adapter."""
+def make_adapter():
+    """One device-backed generator object (see adapter_class)."""
+    return adapter_class()()
+
+
+def _cells_to_mask(cells) -> Optional[int]:
+    """(row, col) pairs -> 400-bit mask, bit row*20+col; None when a cell is off the board or there is none."""
+    mask = 0
+    for r, c in cells:
+        if not (0 <= r < 20 and 0 <= c < 20):
+            return None
+        mask |= 1 << (r * 20 + c)
+    return mask or None
+
+
+def _device_can_place_piece(self, piece_positions, player) -> bool:
+    """Board.can_place_piece (engine/board.py:136-172) on the device: bk_can_place_mask."""
+    mask = _cells_to_mask((p.row, p.col) for p in piece_positions) if piece_positions else None
+    if mask is None:
+        return False
+    return single.can_place(pack_reference_board(self), player.value - 1, mask)
+
+
+def install(replace_class: bool = False, patch_board: bool = False) -> Optional[object]:
+    """Swap the reference's shared generator for the device-backed adapter; returns the adapter.
+
+    replace_class: also rebind ``engine.move_generator.LegalMoveGenerator`` (and every loaded module attribute that
+    holds the class), so code that builds its own ``LegalMoveGenerator()`` -- the reference's tests and its benchmark
+    do -- gets the device generator too.  patch_board: ``Board.can_place_piece`` runs on the device as well."""
     global _original
+    import sys
+
     import engine.move_generator as mg
 
     if _original is None:
-        _original = mg._SHARED_GENERATOR
-    mg._SHARED_GENERATOR = make_adapter()
+        _original = {"shared": mg._SHARED_GENERATOR, "class": getattr(mg.LegalMoveGenerator, "_b200_base", mg.LegalMoveGenerator),
+                     "rebound": [], "can_place": None}
+    cls = adapter_class()
+    mg._SHARED_GENERATOR = cls()
+    if replace_class:
+        old = _original["class"]
+        for mod in list(sys.modules.values()):
+            for attr, val in list(vars(mod).items()) if mod is not None and hasattr(mod, "__dict__") else ():
+                if val is old and attr != "_b200_base":
+                    _original["rebound"].append((mod, attr))
+                    setattr(mod, attr, cls)
+    if patch_board:
+        import engine.board as eb
+
+        if _original["can_place"] is None:
+            _original["can_place"] = eb.Board.can_place_piece
+        eb.Board.can_place_piece = _device_can_place_piece
     return mg._SHARED_GENERATOR
 
 
@@ -86,7 +154,15 @@ def uninstall() -> None:
     global _original
     import engine.move_generator as mg
 
-    mg._SHARED_GENERATOR = _original
+    if _original is None:
+        return
+    mg._SHARED_GENERATOR = _original["shared"]
+    for mod, attr in _original["rebound"]:
+        setattr(mod, attr, _original["class"])
+    if _original["can_place"] is not None:
+        import engine.board as eb
+
+        eb.Board.can_place_piece = _original["can_place"]
     _original = None
 
 

@@ -6,6 +6,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(1, os.path.join(ROOT, "tests"))
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -24,6 +26,13 @@ def pytest_sessionstart(session):
             build.build()
     except Exception as exc:  # report, and let the tests that need the library fail loudly
         sys.stderr.write(f"[conftest] could not build libblokus_b200.so: {exc}\n")
+    try:  # the byte-compiled reference (checker / CPU baseline); only the build container has the sources
+        from oracle import make_ref
+
+        if os.path.isdir(os.path.join(make_ref.REF, "engine")):
+            make_ref.build()
+    except Exception as exc:
+        sys.stderr.write(f"[conftest] could not build oracle/_ref: {exc}\n")
 
 
 @pytest.fixture(scope="session")

@@ -460,6 +460,191 @@ def gen_pairwise():
     print("pairwise", meta, split)
 
 
+# ---------------------------------------------------------------------------------------------
+# UCT search of the reference itself (mcts/mcts_agent.py), made reproducible without touching its code
+# ---------------------------------------------------------------------------------------------
+class _AscendingGenerator:
+    """Context manager: the SHARED generator (engine/move_generator.py get_shared_generator, used by MCTSNode and
+    MCTSAgent) returns its legal moves in ascending canonical id.  The reference's order is CPython set order; any
+    order is a valid run of its algorithm, this one is the order the oracle and the kernel use."""
+
+    def __enter__(self):
+        from engine.move_generator import get_shared_generator
+
+        self.gen = get_shared_generator()
+        orig = self.gen.get_legal_moves            # bound method of the unmodified class
+
+        def ascending(board, player):
+            return sorted(orig(board, player), key=move_id)
+
+        self.gen.get_legal_moves = ascending       # instance attribute shadows the method
+        return self
+
+    def __exit__(self, *a):
+        del self.gen.get_legal_moves
+
+
+class PhiloxIndexAgent:
+    """Rollout agent (the `rollout_agent` argument of MCTSAgent, mcts_agent.py:207,275-278): RandomAgent's uniform
+    index choice with the draw taken from Philox stream 1 of (seed, tree): draw number n is this agent's n-th call."""
+
+    def __init__(self, seed: int, tree: int = 0):
+        self.seed, self.tree, self.n = seed, tree, 0
+
+    def select_action(self, board, player, legal_moves):
+        r = draw(self.seed, self.tree, self.n, 1)
+        self.n += 1
+        return legal_moves[(r * len(legal_moves)) >> 32]
+
+    def set_seed(self, seed):
+        self.seed = seed
+
+
+class _PhiloxChoice:
+    """Stands in for HeuristicAgent.rng (agents/heuristic_agent.py:29,65): choice(n, p=probs) turns the next Philox
+    draw of stream 1 into a categorical sample.  The probabilities are the reference's own softmax; the cumulative
+    order is the device's (32 interleaved lanes: all moves k = L mod 32 of lane 0, then lane 1, ...)."""
+
+    def __init__(self, seed: int, tree: int = 0):
+        self.seed, self.tree, self.n = seed, tree, 0
+
+    def choice(self, n, p):
+        r = draw(self.seed, self.tree, self.n, 1)
+        self.n += 1
+        order = np.concatenate([np.arange(L, n, 32) for L in range(min(32, n))])
+        cdf = np.cumsum(np.asarray(p, dtype=np.float64)[order])
+        target = cdf[-1] * (r * 2.0 ** -32)
+        k = int(np.searchsorted(cdf, target, side="right"))
+        return int(order[min(k, n - 1)])
+
+
+def _root_children(root):
+    ch = sorted(root.children, key=lambda c: move_id(c.move))
+    return (np.array([move_id(c.move) for c in ch], dtype=np.uint16), np.array([c.visits for c in ch], dtype=np.int32),
+            np.array([float(c.total_reward) for c in ch], dtype=np.float64))
+
+
+def _tree_digest(root):
+    """(nodes, max depth, sum over nodes of visits*(depth+1)) -- a cheap fingerprint of the whole tree's shape."""
+    n = d_max = acc = 0
+    stack = [(root, 0)]
+    while stack:
+        nd, d = stack.pop()
+        n += 1
+        d_max = max(d_max, d)
+        acc += nd.visits * (d + 1)
+        stack.extend((c, d + 1) for c in nd.children)
+    return np.array([n, d_max, acc], dtype=np.int64)
+
+
+def _fit_logreg_artifact(path):
+    """A fitted pairwise_logreg artifact in the reference's format (analytics/winprob/train.py writes
+    {"model_type", "feature_columns", "pipeline"}): StandardScaler + LogisticRegression on pairwise.npz."""
+    import joblib
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+
+    from analytics.winprob.features import SNAPSHOT_FEATURE_COLUMNS
+
+    z = np.load(os.path.join(HERE, "pairwise.npz"))
+    pipe = Pipeline([("scaler", StandardScaler()), ("clf", LogisticRegression(max_iter=500))]).fit(z["X"], z["label"])
+    joblib.dump({"model_type": "pairwise_logreg", "feature_columns": list(SNAPSHOT_FEATURE_COLUMNS), "pipeline": pipe}, path)
+    sc, clf = pipe.named_steps["scaler"], pipe.named_steps["clf"]
+    w = clf.coef_[0] / sc.scale_
+    return np.concatenate([w, [clf.intercept_[0] - float(np.dot(w, sc.mean_))]]).astype(np.float64)
+
+
+def gen_mcts(iterations=200, seed=42):
+    """Runs the UNMODIFIED MCTSAgent / MCTSNode (mcts/mcts_agent.py:19-191, 304-582) and records the root statistics.
+    Only two inputs are pinned from outside, through the reference's own extension points: the order of the shared
+    generator's move list (ascending id) and the rollout agent's random draw (Philox).  Selection, UCB1, pop-last
+    expansion, transposition-table probe/store, rollout loop, reward and back-propagation are the reference's code."""
+    import tempfile
+
+    from mcts.mcts_agent import MCTSAgent, MCTSNode
+
+    roots = [("empty", Board())] + [("kat1_%d" % n, generate_random_valid_state(n, seed=n)[0]) for n in (5, 10, 20, 30, 40)]
+    out = {"iterations": np.array([iterations]), "seed": np.array([seed], dtype=np.uint64)}
+    names = []
+
+    def record(tag, board, player, agent, its, frontier=True):
+        root = MCTSNode(board, player)
+        agent.iterations = its
+        agent._run_mcts_with_iterations(root)
+        mv, vis, rew = _root_children(root)
+        out[tag + "/state"] = np.frombuffer(_packed_for(board, player).tobytes(), dtype=np.uint8)
+        out[tag + "/frontier"] = _frontier_bytes(board)
+        out[tag + "/moves"], out[tag + "/visits"], out[tag + "/reward"] = mv, vis, rew
+        out[tag + "/digest"] = _tree_digest(root)
+        out[tag + "/tt"] = np.array([agent.stats["transposition_hits"],
+                                     len(agent.transposition_table.table) if agent.transposition_table else 0], dtype=np.int64)
+        best = root.get_best_move()
+        out[tag + "/best"] = np.array([move_id(best)], dtype=np.uint16)
+        names.append(tag)
+        print(tag, "n_root", len(mv), "visited", int((vis > 0).sum()), "digest", out[tag + "/digest"].tolist(),
+              "tt", out[tag + "/tt"].tolist(), flush=True)
+        return root, best
+
+    with _AscendingGenerator():
+        for name, board in roots:
+            player = board.current_player
+            # 1. uniform Philox rollouts, no transposition table
+            ag = MCTSAgent(iterations=iterations, rollout_agent=PhiloxIndexAgent(seed), use_transposition_table=False, seed=seed)
+            record("uct/%s" % name, board, player, ag, iterations)
+            # 2. with the transposition table; then a SECOND search of the same agent (same table, mcts_agent.py:337-339
+            #    clears it only past 500 000 entries) on the position after the chosen move
+            rag = PhiloxIndexAgent(seed)
+            ag = MCTSAgent(iterations=iterations, rollout_agent=rag, use_transposition_table=True, seed=seed)
+            _, best = record("tt1/%s" % name, board, player, ag, iterations)
+            nxt = board.copy()
+            nxt.place_piece(ag._get_move_positions(best), player, best.piece_id, validate=False)
+            rag.tree, rag.n = 1, 0                  # the agent's second search draws from the next stream block
+            record("tt2/%s" % name, nxt, nxt.current_player, ag, iterations)
+        # 3. the default rollout policy: HeuristicAgent with its RandomState replaced by the Philox categorical draw
+        for name, board in roots[:3]:
+            from agents.heuristic_agent import HeuristicAgent as _H
+
+            h = _H(seed=seed)
+            h.rng = _PhiloxChoice(seed)
+            ag = MCTSAgent(iterations=60, rollout_agent=h, use_transposition_table=False, seed=seed)
+            record("heur/%s" % name, board, board.current_player, ag, 60)
+        # 4. learned options: the reference's dummy artifact, and a fitted pairwise_logreg pipeline
+        with tempfile.TemporaryDirectory() as td:
+            dummy = os.path.join(td, "dummy_model.json")
+            with open(dummy, "w") as f:
+                f.write("{}")
+            art = os.path.join(td, "pairwise_logreg.pkl")
+            out["model"] = _fit_logreg_artifact(art)
+            for name, board in roots[:3]:
+                player = board.current_player
+                ag = MCTSAgent(iterations=iterations, rollout_agent=PhiloxIndexAgent(seed), use_transposition_table=False, seed=seed,
+                               learned_model_path=dummy, leaf_evaluation_enabled=True)
+                record("dummy/%s" % name, board, player, ag, iterations)
+                ag = MCTSAgent(iterations=80, rollout_agent=PhiloxIndexAgent(seed), use_transposition_table=False, seed=seed,
+                               learned_model_path=art, leaf_evaluation_enabled=True)
+                record("leaf/%s" % name, board, player, ag, 80)
+                ag = MCTSAgent(iterations=80, rollout_agent=PhiloxIndexAgent(seed), use_transposition_table=True, seed=seed,
+                               learned_model_path=art, leaf_evaluation_enabled=True, progressive_bias_enabled=True,
+                               progressive_bias_weight=0.25)
+                record("bias/%s" % name, board, player, ag, 80)
+            for name, board in roots[:2]:
+                for mode in ("prob", "logit"):
+                    ag = MCTSAgent(iterations=40, rollout_agent=PhiloxIndexAgent(seed), use_transposition_table=False, seed=seed,
+                                   learned_model_path=art, potential_shaping_enabled=True, potential_shaping_gamma=0.9,
+                                   potential_shaping_weight=2.0, potential_mode=mode, max_rollout_moves=6)
+                    record("shape_%s/%s" % (mode, name), board, board.current_player, ag, 40)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "mcts.npz"), **out)
+    print("mcts", len(names), "searches")
+
+
+def _packed_for(board: Board, player: Player) -> np.ndarray:
+    s = pack(board)
+    s["to_move"] = player.value - 1
+    return s
+
+
 def random_state_from_packed(s) -> Board:
     """Rebuild a reference Board from a packed state (the recipe of engine-service/app.py:27-50)."""
     board = Board()
@@ -486,8 +671,8 @@ def random_state_from_packed(s) -> Board:
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise"]
+    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise", "mcts"]
     for w in which:
         {"tables": gen_tables, "kat1": gen_kat1, "kat2": gen_kat2, "random": gen_random_states,
          "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic, "mobility": gen_mobility,
-         "snapshots": gen_snapshots, "pairwise": gen_pairwise}[w]()
+         "snapshots": gen_snapshots, "pairwise": gen_pairwise, "mcts": gen_mcts}[w]()
