@@ -71,8 +71,11 @@ enum bk_policy {
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
 
-/* Select `device`, upload the piece tables.  Replaces the import-time table construction of
- * engine/pieces.py:496-513 and LegalMoveGenerator.__init__ (engine/move_generator.py:112-128). */
+/* Create the library's context for `device` (piece tables in its constant memory, per-launch work counters); the
+ * caller's current device is left unchanged and other devices' contexts are untouched.  Every other entry point works
+ * on the CALLER'S CURRENT DEVICE (the one its stream and buffers belong to) and returns BK_ERR_NOT_INIT if bk_init was
+ * not called for it.  Replaces the import-time table construction of engine/pieces.py:496-513 and
+ * LegalMoveGenerator.__init__ (engine/move_generator.py:112-128). */
 int bk_init(int device);
 const char* bk_last_error(void);
 /* Library build id string (arch, build flags). */
@@ -199,8 +202,11 @@ int bk_tt_destroy(bk_tt* tt);
 /* TranspositionTable.get / put (mcts/zobrist.py:171-202); found[i]=1 and rewards[i] set on a hit. */
 int bk_tt_get(bk_tt* tt, const uint64_t* keys, int n, double* rewards, uint8_t* found, void* stream);
 int bk_tt_put(bk_tt* tt, const uint64_t* keys, const double* rewards, int n, void* stream);
-/* host out: [0]=slots, [1]=occupied */
+/* host out[4]: [0]=slots, [1]=entries, [2]=hits and [3]=probes of the searches that used the table
+ * (TranspositionTable.hit_count / access_count, mcts/zobrist.py:181-185; reset by bk_tt_clear) */
 int bk_tt_stats(bk_tt* tt, uint64_t* out_host, void* stream);
+/* TranspositionTable.put's eviction (mcts/zobrist.py:196-200): remove the n_evict entries inserted first. */
+int bk_tt_evict_oldest(bk_tt* tt, uint64_t n_evict, void* stream);
 
 /* ---- N1: HeuristicAgent move scores (agents/heuristic_agent.py:68-198) ---------------------- */
 
@@ -242,7 +248,11 @@ typedef struct bk_mcts_params {
                                    selection/expansion every warp rolls out from the new leaf with its own random stream
                                    and the rewards are backed up together (visits += leaf_batch); a transposition
                                    table then caches the SUM of a leaf's rewards. */
-    int32_t  reserved0;
+    int32_t  tt_tree_base;      /* transposition-table namespace of tree k = tt_tree_base + k (independent of tree_offset):
+                                   an agent keeps it constant over its searches so that a later search finds what an
+                                   earlier one cached (mcts_agent.py:337-339, 418-434); concurrently searched trees get
+                                   different namespaces and never read each other's entries.  Namespace 0 = plain Zobrist
+                                   keys, the reference's single table. */
     double   exploration;       /* 1.414 */
     uint64_t seed;
     uint64_t tree_offset;       /* global index of tree 0 (root-parallel sharding across GPUs) */

@@ -87,6 +87,15 @@ def lib() -> C.CDLL:
         L.orc_tt_destroy.argtypes = [vp]
         L.orc_tt_size.argtypes = [vp]
         L.orc_tt_size.restype = u64
+        for name in ("orc_tt_hits", "orc_tt_probes"):
+            getattr(L, name).argtypes = [vp]
+            getattr(L, name).restype = u64
+        L.orc_tt_get.argtypes = [vp, u64, vp]
+        L.orc_tt_put.argtypes = [vp, u64, C.c_double]
+        L.orc_tt_put.restype = None
+        L.orc_tt_evict_oldest.argtypes = [vp, u64]
+        L.orc_tt_evict_oldest.restype = None
+        L.orc_set_tt_namespace.argtypes = [i32]
         L.orc_mcts_search.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, vp, vp]
         L.orc_mcts_search_learned.argtypes = [vp, vp, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, i32, C.c_double, vp, vp, vp]
         L.orc_set_model_kind.argtypes = [i32]
@@ -309,6 +318,24 @@ class OracleTT:
     def size(self) -> int:
         return int(lib().orc_tt_size(self.h))
 
+    def hits(self) -> int:
+        """hit_count of the searches that used the table (mcts_agent.py:423)."""
+        return int(lib().orc_tt_hits(self.h))
+
+    def probes(self) -> int:
+        return int(lib().orc_tt_probes(self.h))
+
+    def get(self, key: int):
+        v = C.c_double()
+        return float(v.value) if lib().orc_tt_get(self.h, int(key), C.byref(v)) else None
+
+    def put(self, key: int, reward: float) -> None:
+        lib().orc_tt_put(self.h, int(key), float(reward))
+
+    def evict_oldest(self, n: int) -> None:
+        """TranspositionTable.put's eviction (mcts/zobrist.py:196-200): the n entries inserted first go."""
+        lib().orc_tt_evict_oldest(self.h, int(n))
+
     def close(self):
         if self.h:
             lib().orc_tt_destroy(self.h)
@@ -317,8 +344,10 @@ class OracleTT:
 
 def mcts_search(root: np.ndarray, iterations: int, seed: int, tree_id: int = 0, max_rollout_moves: int = 50,
                 max_depth: int = 0, ucb_variant: int = 0, reward_mode: int = 0, rollout_policy: int = 0, exploration: float = 1.414, tt: Optional[OracleTT] = None,
-                zobrist: Optional[np.ndarray] = None, max_root_moves: int = 2048, leaf_batch: int = 1):
-    """Sequential UCT with canonical untried order and Philox rollouts; returns dict(n_root, visits, reward, moves)."""
+                zobrist: Optional[np.ndarray] = None, max_root_moves: int = 2048, leaf_batch: int = 1, tt_namespace: int = 0):
+    """Sequential UCT with canonical untried order and Philox rollouts; returns dict(n_root, visits, reward, moves).
+    tt_namespace: the tree's namespace in the transposition table (the kernel's tt_tree_base + tree index; 0 = plain keys)."""
+    lib().orc_set_tt_namespace(int(tt_namespace))       # thread-local: applies to the call below
     st = np.ascontiguousarray(np.atleast_1d(root), dtype=STATE_DTYPE)
     vis = np.zeros(max_root_moves, dtype=np.int32)
     rew = np.zeros(max_root_moves, dtype=np.int64)
@@ -333,13 +362,14 @@ def mcts_search(root: np.ndarray, iterations: int, seed: int, tree_id: int = 0, 
 def mcts_search_learned(root: np.ndarray, iterations: int, seed: int, model: np.ndarray, tree_id: int = 0, max_turns: int = 2500,
                         root_frontier: Optional[np.ndarray] = None, max_depth: int = 0, ucb_variant: int = 0,
                         exploration: float = 1.414, tt: Optional[OracleTT] = None, zobrist: Optional[np.ndarray] = None,
-                        max_root_moves: int = 2048, bias_weight: float = 0.0, model_kind: int = 0):
+                        max_root_moves: int = 2048, bias_weight: float = 0.0, model_kind: int = 0, tt_namespace: int = 0):
     """UCT with learned leaf evaluation (mcts_agent.py:427-451): model = float64[35] (34 weights + bias of a folded
     pairwise logistic model), root_frontier = uint8[4, 400] incremental frontier sets or None.  reward sums are doubles."""
     st = np.ascontiguousarray(np.atleast_1d(root), dtype=STATE_DTYPE)
     md = np.ascontiguousarray(model, dtype=np.float64)
     assert model_kind == 1 or md.size == 35
     lib().orc_set_model_kind(int(model_kind))           # thread-local: applies to the call below
+    lib().orc_set_tt_namespace(int(tt_namespace))
     fr = None if root_frontier is None else np.ascontiguousarray(root_frontier, dtype=np.uint8)
     vis = np.zeros(max_root_moves, dtype=np.int32)
     rew = np.zeros(max_root_moves, dtype=np.float64)
@@ -364,11 +394,12 @@ def mcts_search_shaped(root: np.ndarray, iterations: int, seed: int, model: np.n
                        root_frontier: Optional[np.ndarray] = None, max_rollout_moves: int = 50, rollout_policy: int = 0,
                        exploration: float = 1.414, shaping_weight: float = 1.0, shaping_gamma: float = 1.0,
                        potential_mode: int = 0, bias_weight: float = 0.0, tt: Optional[OracleTT] = None,
-                       zobrist: Optional[np.ndarray] = None, max_root_moves: int = 2048, model_kind: int = 0):
+                       zobrist: Optional[np.ndarray] = None, max_root_moves: int = 2048, model_kind: int = 0, tt_namespace: int = 0):
     """UCT with rollouts and potential-based shaping from the learned model (mcts_agent.py:470-554); reward sums are doubles."""
     st = np.ascontiguousarray(np.atleast_1d(root), dtype=STATE_DTYPE)
     md = np.ascontiguousarray(model, dtype=np.float64)
     lib().orc_set_model_kind(int(model_kind))
+    lib().orc_set_tt_namespace(int(tt_namespace))
     fr = None if root_frontier is None else np.ascontiguousarray(root_frontier, dtype=np.uint8)
     vis = np.zeros(max_root_moves, dtype=np.int32)
     rew = np.zeros(max_root_moves, dtype=np.float64)

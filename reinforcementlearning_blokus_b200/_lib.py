@@ -55,6 +55,7 @@ PROTOTYPES = {
     "bk_tt_get": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "bk_tt_put": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "bk_tt_stats": (_i32, [_vp, _vp, _vp]),
+    "bk_tt_evict_oldest": (_i32, [_vp, _u64, _vp]),
     "bk_heuristic_scores": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "bk_heuristic_scores_weighted": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bk_mcts_workspace_bytes": (_i64, [_vp]),
@@ -68,7 +69,7 @@ class MctsParams(C.Structure):
     _fields_ = [
         ("iterations", C.c_int32), ("iterations_total", C.c_int32), ("max_rollout_moves", C.c_int32),
         ("rollout_policy", C.c_int32), ("max_depth", C.c_int32), ("ucb_variant", C.c_int32),
-        ("resume", C.c_int32), ("reward_mode", C.c_int32), ("leaf_batch", C.c_int32), ("reserved0", C.c_int32),
+        ("resume", C.c_int32), ("reward_mode", C.c_int32), ("leaf_batch", C.c_int32), ("tt_tree_base", C.c_int32),
         ("exploration", C.c_double),
         ("seed", C.c_uint64), ("tree_offset", C.c_uint64),
         ("leaf_model", C.c_void_p), ("root_frontiers", C.c_void_p), ("leaf_max_turns", C.c_int32), ("leaf_model_kind", C.c_int32),
@@ -101,15 +102,19 @@ def load() -> C.CDLL:
 
 def check(code: int) -> None:
     if code != 0:
-        msg = load().bk_last_error().decode("utf-8", "replace")
+        lib = _lib if _lib is not None else load()       # never re-enter load()'s lock from an error path
+        msg = lib.bk_last_error().decode("utf-8", "replace")
         raise BlokusB200Error(f"blokus_b200 error {code}: {msg}")
 
 
 def init(device: int = 0) -> C.CDLL:
-    """bk_init once per device; raises when no CUDA device is available."""
+    """bk_init once per device (the C library keeps one context per device and leaves the current device alone);
+    raises BlokusB200Error when the device does not exist or cannot run the kernels."""
     lib = load()
+    if device in _inited_devices:
+        return lib
+    code = lib.bk_init(int(device))          # outside the module lock: check() reads the library's error string
+    check(code)
     with _lock:
-        if device not in _inited_devices:
-            check(lib.bk_init(int(device)))
-            _inited_devices.add(device)
+        _inited_devices.add(device)
     return lib

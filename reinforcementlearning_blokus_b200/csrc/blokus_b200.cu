@@ -6,6 +6,7 @@
 // nothing falls back to the CPU.  One process drives one GPU (bk_init(device) binds the library to it).
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include "movegen_core.cuh"
 
@@ -19,11 +20,20 @@
 // error plumbing / lifecycle
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static unsigned int* g_tickets = nullptr;      // per-launch work counters of the playout kernels (device, BK_TICKETS of them)
-static unsigned int g_ticket_next = 0;
+
+// One context per CUDA device, created by bk_init(device) and selected by the CALLER'S current device at every entry
+// point (the device whose stream and buffers the call names).  Nothing else in this library is mutable: the piece
+// tables live in per-device constant memory written by bk_init, errors are thread-local.
 #define BK_TICKETS 256
-static int g_device = -1;
-static int g_sms = 0;
+#define BK_MAX_DEVICES 64
+struct BkCtx {
+    int inited;
+    int sms;
+    unsigned int* tickets;      // per-launch work counters of the playout / search kernels (device, BK_TICKETS of them)
+    unsigned int next;
+};
+static BkCtx g_ctx[BK_MAX_DEVICES];
+static std::mutex g_init_mutex;
 
 static int fail(int code, const char* fmt, const char* detail) {
     snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -34,8 +44,14 @@ static int fail(int code, const char* fmt, const char* detail) {
         cudaError_t e__ = (expr);                                                        \
         if (e__ != cudaSuccess) return fail(BK_ERR_CUDA, #expr ": %s", cudaGetErrorString(e__)); \
     } while (0)
+static BkCtx* current_ctx() {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= BK_MAX_DEVICES || !g_ctx[d].inited) return nullptr;
+    return &g_ctx[d];
+}
 #define REQUIRE_INIT() \
-    do { if (g_device < 0) return fail(BK_ERR_NOT_INIT, "%s", "bk_init has not been called"); } while (0)
+    BkCtx* cx = current_ctx(); \
+    do { if (!cx) return fail(BK_ERR_NOT_INIT, "%s", "bk_init has not been called for the current CUDA device"); } while (0)
 #define REQUIRE(cond, msg) \
     do { if (!(cond)) return fail(BK_ERR_ARG, "%s", msg); } while (0)
 
@@ -43,21 +59,21 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 // A zeroed work counter for one launch on `st` (round-robin over a small pool so that launches in flight on
 // different streams never share one).
-static unsigned int* fresh_ticket(cudaStream_t st) {
-    unsigned int* t = g_tickets + (__sync_fetch_and_add(&g_ticket_next, 1u) % BK_TICKETS);
-    cudaMemsetAsync(t, 0, sizeof(unsigned int), st);
-    return t;
+static cudaError_t fresh_ticket(BkCtx* cx, cudaStream_t st, unsigned int** out) {
+    unsigned int* t = cx->tickets + (__sync_fetch_and_add(&cx->next, 1u) % BK_TICKETS);
+    *out = t;
+    return cudaMemsetAsync(t, 0, sizeof(unsigned int), st);
 }
 
-static inline int grid_for(int n_items, int ctas_per_sm) {
+static inline int grid_for(const BkCtx* cx, int n_items, int ctas_per_sm) {
     long long need = ((long long)n_items + BK_WARPS - 1) / BK_WARPS;
-    long long cap = (long long)g_sms * ctas_per_sm;
+    long long cap = (long long)cx->sms * ctas_per_sm;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
 }
 
 extern "C" const char* bk_last_error(void) { return g_err; }
-extern "C" const char* bk_version(void) { return "blokus_b200 r1 sm_100a (row-sliced warp-per-game)"; }
+extern "C" const char* bk_version(void) { return "blokus_b200 r2 sm_100a (row-sliced warp-per-game)"; }
 
 __global__ void k_movegen_emit(const bk_state* __restrict__, const uint8_t* __restrict__, int, const uint32_t* __restrict__,
                                uint32_t, uint32_t* __restrict__, uint16_t* __restrict__);
@@ -67,13 +83,22 @@ __global__ void k_movegen_bitmap(const bk_state* __restrict__, const uint8_t* __
 static cudaError_t bk_init_policies_impl();
 static cudaError_t bk_init_policies() { return bk_init_policies_impl(); }
 
+struct DeviceGuard {            // bk_init works on `device` and leaves the caller's current device as it found it
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 extern "C" int bk_init(int device) {
     int count = 0;
     CUDA_TRY(cudaGetDeviceCount(&count));
-    if (device < 0 || device >= count) return fail(BK_ERR_ARG, "%s", "bk_init: no such CUDA device");
+    if (device < 0 || device >= count || device >= BK_MAX_DEVICES) return fail(BK_ERR_ARG, "%s", "bk_init: no such CUDA device");
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    BkCtx* cx = &g_ctx[device];
+    if (cx->inited) return BK_OK;
+    DeviceGuard guard;
+    if (cudaGetDevice(&guard.prev) != cudaSuccess) guard.prev = -1;
     CUDA_TRY(cudaSetDevice(device));
-    if (g_device >= 0 && g_device != device) g_tickets = nullptr;      // re-bound to another GPU: its own counters
-    CUDA_TRY(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&cx->sms, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_piece, BK_TBL_ORIENT_PIECE, sizeof(BK_TBL_ORIENT_PIECE)));
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_ncells, BK_TBL_ORIENT_NCELLS, sizeof(BK_TBL_ORIENT_NCELLS)));
     CUDA_TRY(cudaMemcpyToSymbol(c_orient_cells, BK_TBL_ORIENT_CELLS, sizeof(BK_TBL_ORIENT_CELLS)));
@@ -84,8 +109,9 @@ extern "C" int bk_init(int device) {
     CUDA_TRY(cudaFuncSetAttribute(k_movegen_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_movegen_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
     CUDA_TRY(bk_init_policies());
-    if (!g_tickets) CUDA_TRY(cudaMalloc(&g_tickets, BK_TICKETS * sizeof(unsigned int)));
-    g_device = device;
+    if (!cx->tickets) CUDA_TRY(cudaMalloc(&cx->tickets, BK_TICKETS * sizeof(unsigned int)));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cx->inited = 1;
     return BK_OK;
 }
 
@@ -598,10 +624,14 @@ k_zobrist(const bk_state* __restrict__ states, int n, const uint64_t* __restrict
 }
 
 struct bk_tt {
-    unsigned long long* keys;   // 0 = empty slot
+    unsigned long long* keys;      // 0 = empty slot
     double* rewards;
+    uint32_t* stamps;              // insertion number of the slot's entry (the dict order of the reference's table)
     uint32_t log2_slots;
-    unsigned long long* occupied;  // device counter
+    unsigned long long* occupied;  // device counters: [0] live entries, [1] entries ever inserted (next stamp),
+                                   //                  [2] hits and [3] probes of the searches (hit_count / access_count)
+    unsigned long long evicted;    // entries removed by bk_tt_evict_oldest: live stamps are [evicted, inserted)
+    int device;
 };
 #define TT_MAX_PROBE 128
 __device__ __forceinline__ uint64_t tt_norm(uint64_t k) { return k ? k : 0x9E3779B97F4A7C15ull; }
@@ -620,8 +650,10 @@ __device__ __forceinline__ bool tt_lookup(const unsigned long long* keys, const 
     }
     return false;
 }
-__device__ __forceinline__ bool tt_insert(unsigned long long* keys, double* rewards, uint32_t log2_slots,
-                                          unsigned long long* occupied, uint64_t key, double reward) {
+// stamp_in = 0xFFFFFFFF: a new entry takes the next insertion number; otherwise the given one (rebuild after eviction)
+__device__ __forceinline__ bool tt_insert(unsigned long long* keys, double* rewards, uint32_t* stamps, uint32_t log2_slots,
+                                          unsigned long long* occupied, uint64_t key, double reward,
+                                          uint32_t stamp_in = 0xFFFFFFFFu) {
     key = tt_norm(key);
     const uint32_t mask = (1u << log2_slots) - 1u;
     uint32_t slot = tt_home(key, log2_slots);
@@ -629,11 +661,16 @@ __device__ __forceinline__ bool tt_insert(unsigned long long* keys, double* rewa
         unsigned long long k = keys[slot];
         if (k == 0ull) {
             k = atomicCAS(&keys[slot], 0ull, (unsigned long long)key);
-            if (k == 0ull) { rewards[slot] = reward; atomicAdd(occupied, 1ull); return true; }
+            if (k == 0ull) {
+                rewards[slot] = reward;
+                stamps[slot] = stamp_in != 0xFFFFFFFFu ? stamp_in : (uint32_t)atomicAdd(occupied + 1, 1ull);
+                atomicAdd(occupied, 1ull);
+                return true;
+            }
         }
-        if (k == key) { rewards[slot] = reward; return true; }   // dict semantics: last put wins
+        if (k == key) { rewards[slot] = reward; return true; }   // dict semantics: last put wins, the entry keeps its place
     }
-    return false;   // neighbourhood full: entry dropped (the reference evicts instead, mcts/zobrist.py:196-200)
+    return false;   // neighbourhood full (the table holds 2x max_size slots; callers evict at max_size, see bk_tt_evict_oldest)
 }
 __global__ void k_tt_get(const unsigned long long* keys, const double* rewards, uint32_t log2_slots,
                          const uint64_t* q, int n, double* out, uint8_t* found) {
@@ -644,11 +681,33 @@ __global__ void k_tt_get(const unsigned long long* keys, const double* rewards, 
     found[i] = hit ? 1 : 0;
     if (hit) out[i] = r;
 }
-__global__ void k_tt_put(unsigned long long* keys, double* rewards, uint32_t log2_slots, unsigned long long* occupied,
+__global__ void k_tt_put(unsigned long long* keys, double* rewards, uint32_t* stamps, uint32_t log2_slots, unsigned long long* occupied,
                          const uint64_t* q, const double* r, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    tt_insert(keys, rewards, log2_slots, occupied, q[i], r[i]);
+    if (gridDim.x == 1) {       // small batch: one thread, in order -- the puts enter the table in the order given
+        if (threadIdx.x == 0)
+            for (int i = 0; i < n; i++) tt_insert(keys, rewards, stamps, log2_slots, occupied, q[i], r[i]);
+        return;
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // large batch: its entries count as inserted together
+    if (i < n) tt_insert(keys, rewards, stamps, log2_slots, occupied, q[i], r[i]);
+}
+// TranspositionTable.put's eviction (mcts/zobrist.py:196-200): drop the entries with the lowest insertion numbers.
+// Survivors are copied out, the table is wiped and they are inserted again with their insertion numbers.
+__global__ void k_tt_collect(const unsigned long long* keys, const double* rewards, const uint32_t* stamps, uint32_t slots,
+                             uint32_t first_kept, unsigned long long* tmp_keys, double* tmp_rewards, uint32_t* tmp_stamps,
+                             unsigned int* n_kept) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slots || keys[i] == 0ull) return;
+    if ((int32_t)(stamps[i] - first_kept) < 0) return;            // older than the cut (wrap-safe)
+    const unsigned int k = atomicAdd(n_kept, 1u);
+    tmp_keys[k] = keys[i]; tmp_rewards[k] = rewards[i]; tmp_stamps[k] = stamps[i];
+}
+__global__ void k_tt_reinsert(unsigned long long* keys, double* rewards, uint32_t* stamps, uint32_t log2_slots,
+                              unsigned long long* occupied, const unsigned long long* tmp_keys, const double* tmp_rewards,
+                              const uint32_t* tmp_stamps, const unsigned int* n_kept) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n_kept) return;
+    tt_insert(keys, rewards, stamps, log2_slots, occupied, tmp_keys[i], tmp_rewards[i], tmp_stamps[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -739,7 +798,7 @@ static cudaError_t bk_init_policies_impl() {
 extern "C" int bk_movegen_count(const bk_state* states, const uint8_t* players, int n, uint32_t* counts, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && counts)), "bk_movegen_count: null buffer");
     if (n == 0) return BK_OK;
-    k_movegen_count<<<grid_for(n, BK_COUNT_CTAS), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, counts);
+    k_movegen_count<<<grid_for(cx, n, BK_COUNT_CTAS), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, counts);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -748,7 +807,7 @@ extern "C" int bk_movegen_emit(const bk_state* states, const uint8_t* players, i
                                uint16_t* move_ids, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids)), "bk_movegen_emit: null buffer");
     if (n == 0) return BK_OK;
-    k_movegen_emit<<<grid_for(n, 3), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, offsets, 0u, nullptr, move_ids);
+    k_movegen_emit<<<grid_for(cx, n, 3), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, offsets, 0u, nullptr, move_ids);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -757,7 +816,7 @@ extern "C" int bk_movegen_fixed(const bk_state* states, const uint8_t* players, 
                                 uint16_t* move_ids, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && cap > 0 && (n == 0 || (states && counts && move_ids)), "bk_movegen_fixed: bad argument");
     if (n == 0) return BK_OK;
-    k_movegen_emit<<<grid_for(n, 3), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, nullptr, cap, counts, move_ids);
+    k_movegen_emit<<<grid_for(cx, n, 3), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, nullptr, cap, counts, move_ids);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -779,7 +838,7 @@ k_compact_rows(const uint16_t* __restrict__ slots, uint32_t cap, const uint32_t*
 extern "C" int bk_compact_rows(const uint16_t* slots, uint32_t cap, const uint32_t* offsets, int n, uint16_t* move_ids, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && cap > 0 && (n == 0 || (slots && offsets && move_ids)), "bk_compact_rows: bad argument");
     if (n == 0) return BK_OK;
-    k_compact_rows<<<grid_for(n, 8), BK_THREADS, 0, as_stream(stream)>>>(slots, cap, offsets, n, move_ids);
+    k_compact_rows<<<grid_for(cx, n, 8), BK_THREADS, 0, as_stream(stream)>>>(slots, cap, offsets, n, move_ids);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -788,7 +847,7 @@ extern "C" int bk_movegen_bitmap(const bk_state* states, const uint8_t* players,
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && bitmap)), "bk_movegen_bitmap: null buffer");
     REQUIRE(reinterpret_cast<uintptr_t>(bitmap) % 16 == 0, "bk_movegen_bitmap: bitmap must be 16-byte aligned");
     if (n == 0) return BK_OK;
-    k_movegen_bitmap<<<grid_for(n, 3), BK_THREADS, BK_WARPS * BITMAP_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, bitmap);
+    k_movegen_bitmap<<<grid_for(cx, n, 3), BK_THREADS, BK_WARPS * BITMAP_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, bitmap);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -797,7 +856,7 @@ extern "C" int bk_movegen_piece_counts(const bk_state* states, const uint8_t* pl
                                        uint16_t* anchor_max, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && piece_counts)), "bk_movegen_piece_counts: null buffer");
     if (n == 0) return BK_OK;
-    k_piece_counts<<<grid_for(n, 3), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, piece_counts, anchor_max);
+    k_piece_counts<<<grid_for(cx, n, 3), BK_THREADS, 0, as_stream(stream)>>>(states, players, n, piece_counts, anchor_max);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -806,7 +865,7 @@ extern "C" int bk_snapshot_features(const bk_state* states, const uint64_t* fron
                                     int max_turns, double* features, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && features)), "bk_snapshot_features: null buffer");
     if (n == 0) return BK_OK;
-    k_snapshot_features<<<grid_for(n, 3), BK_THREADS, BK_WARPS * BK_SNAP_SMEM_PER_WARP, as_stream(stream)>>>(
+    k_snapshot_features<<<grid_for(cx, n, 3), BK_THREADS, BK_WARPS * BK_SNAP_SMEM_PER_WARP, as_stream(stream)>>>(
         states, frontiers, turn_index, n, max_turns, features);
     LAUNCH_CHECK();
     return BK_OK;
@@ -824,7 +883,7 @@ extern "C" int bk_replay_snapshots(const bk_state* start, const uint16_t* traces
     for (int k = 0; k < n_checkpoints; k++)
         for (int j = 0; j < k; j++) REQUIRE(ck.ply[j] != ck.ply[k], "bk_replay_snapshots: duplicate checkpoint ply");
     if (n == 0) return BK_OK;
-    k_replay_snapshots<<<grid_for(n, 3), BK_THREADS, BK_WARPS * BK_SNAP_SMEM_PER_WARP, as_stream(stream)>>>(
+    k_replay_snapshots<<<grid_for(cx, n, 3), BK_THREADS, BK_WARPS * BK_SNAP_SMEM_PER_WARP, as_stream(stream)>>>(
         start, traces, n, n_turns, ck, max_turns, features, turn_index, snap_states, snap_frontiers);
     LAUNCH_CHECK();
     return BK_OK;
@@ -833,7 +892,7 @@ extern "C" int bk_replay_snapshots(const bk_state* start, const uint16_t* traces
 extern "C" int bk_has_moves(const bk_state* states, int n, uint8_t* out_mask, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && out_mask)), "bk_has_moves: null buffer");
     if (n == 0) return BK_OK;
-    k_has_moves<<<grid_for(n, 3), BK_THREADS, 0, as_stream(stream)>>>(states, n, out_mask);
+    k_has_moves<<<grid_for(cx, n, 3), BK_THREADS, 0, as_stream(stream)>>>(states, n, out_mask);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -842,7 +901,7 @@ extern "C" int bk_is_move_legal(const bk_state* states, const uint8_t* players, 
                                 uint8_t* out, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && move_ids && out)), "bk_is_move_legal: null buffer");
     if (n == 0) return BK_OK;
-    k_is_move_legal<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, move_ids, n, out);
+    k_is_move_legal<<<grid_for(cx, n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, move_ids, n, out);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -851,7 +910,7 @@ extern "C" int bk_can_place_mask(const bk_state* states, const uint8_t* players,
                                  uint8_t* out, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && cell_masks && out)), "bk_can_place_mask: null buffer");
     if (n == 0) return BK_OK;
-    k_can_place_mask<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, cell_masks, n, out);
+    k_can_place_mask<<<grid_for(cx, n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, cell_masks, n, out);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -860,7 +919,7 @@ extern "C" int bk_step(bk_state* states, const uint8_t* players, const uint16_t*
                        uint8_t* alive, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && move_ids)), "bk_step: null buffer");
     if (n == 0) return BK_OK;
-    k_step<<<grid_for(n, 3), BK_THREADS, 0, as_stream(stream)>>>(states, players, move_ids, n, ok, alive);
+    k_step<<<grid_for(cx, n, 3), BK_THREADS, 0, as_stream(stream)>>>(states, players, move_ids, n, ok, alive);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -868,7 +927,7 @@ extern "C" int bk_step(bk_state* states, const uint8_t* players, const uint16_t*
 extern "C" int bk_scores(const bk_state* states, int n, int32_t* game_scores, int32_t* board_scores, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || states), "bk_scores: null buffer");
     if (n == 0) return BK_OK;
-    k_scores<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, n, game_scores, board_scores);
+    k_scores<<<grid_for(cx, n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, n, game_scores, board_scores);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -883,17 +942,19 @@ extern "C" int bk_playout(const bk_state* start_states, int n, uint64_t seed, ui
     if (max_turns == 0) max_turns = BK_MAX_TURNS;
     REQUIRE(first_turn >= 0 && first_turn <= max_turns, "bk_playout: first_turn out of range");
     const int pw = BK_PLAYOUT_THREADS / 32;
-    long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)g_sms * BK_PLAYOUT_MIN_BLOCKS;
+    unsigned int* ticket = nullptr;
+    CUDA_TRY(fresh_ticket(cx, as_stream(stream), &ticket));
+    long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)cx->sms * BK_PLAYOUT_MIN_BLOCKS;
     if (policy == BK_POLICY_UNIFORM && !trace && !choice) {     // scores only: no per-turn output code at all
         k_playout<0, false><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, 0, as_stream(stream)>>>(
-            fresh_ticket(as_stream(stream)), nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+            ticket, nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     } else if (policy == BK_POLICY_UNIFORM) {
         k_playout<0><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, 0, as_stream(stream)>>>(
-            fresh_ticket(as_stream(stream)), nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+            ticket, nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     } else {
-        pcap = (long long)g_sms * 2;
+        pcap = (long long)cx->sms * 2;
         k_playout<1><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, BK_HEUR_PLAYOUT_SMEM, as_stream(stream)>>>(
-            fresh_ticket(as_stream(stream)), nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
+            ticket, nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     }
     LAUNCH_CHECK();
     return BK_OK;
@@ -909,9 +970,11 @@ extern "C" int bk_playout_seats(const bk_state* start_states, int n, uint64_t se
     if (max_turns == 0) max_turns = BK_MAX_TURNS;
     REQUIRE(first_turn >= 0 && first_turn <= max_turns, "bk_playout_seats: first_turn out of range");
     const int pw = BK_PLAYOUT_THREADS / 32;
-    long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)g_sms * 2;
+    unsigned int* ticket = nullptr;
+    CUDA_TRY(fresh_ticket(cx, as_stream(stream), &ticket));
+    long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)cx->sms * 2;
     k_playout<2><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, BK_HEUR_PLAYOUT_SMEM, as_stream(stream)>>>(
-        fresh_ticket(as_stream(stream)), seat_policies, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice,
+        ticket, seat_policies, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice,
         final_states);
     LAUNCH_CHECK();
     return BK_OK;
@@ -932,7 +995,7 @@ extern "C" int bk_exclusive_scan_u32(const uint32_t* counts, int n, uint32_t* of
 extern "C" int bk_zobrist_hash(const bk_state* states, int n, const uint64_t* table, uint64_t* keys, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && table && (n == 0 || (states && keys)), "bk_zobrist_hash: null buffer");
     if (n == 0) return BK_OK;
-    k_zobrist<<<grid_for(n, 8), BK_THREADS, 0, as_stream(stream)>>>(states, n, table, keys);
+    k_zobrist<<<grid_for(cx, n, 8), BK_THREADS, 0, as_stream(stream)>>>(states, n, table, keys);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -942,52 +1005,96 @@ extern "C" int bk_tt_create(bk_tt** out, uint32_t log2_slots) {
     bk_tt* t = new (std::nothrow) bk_tt();
     if (!t) return fail(BK_ERR_ARG, "%s", "bk_tt_create: out of host memory");
     const size_t slots = (size_t)1 << log2_slots;
-    t->log2_slots = log2_slots; t->keys = nullptr; t->rewards = nullptr; t->occupied = nullptr;
+    t->log2_slots = log2_slots; t->keys = nullptr; t->rewards = nullptr; t->occupied = nullptr; t->stamps = nullptr; t->evicted = 0;
+    cudaGetDevice(&t->device);
     cudaError_t e = cudaMalloc(&t->keys, slots * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&t->rewards, slots * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&t->occupied, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&t->stamps, slots * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&t->occupied, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(t->keys, 0, slots * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(t->occupied, 0, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(t->occupied, 0, 4 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
-        cudaFree(t->keys); cudaFree(t->rewards); cudaFree(t->occupied); delete t;
+        cudaFree(t->keys); cudaFree(t->rewards); cudaFree(t->stamps); cudaFree(t->occupied); delete t;
         return fail(BK_ERR_CUDA, "bk_tt_create: %s", cudaGetErrorString(e));
     }
     *out = t;
     return BK_OK;
 }
+#define REQUIRE_TT_DEVICE(tt) \
+    do { int d__ = -1; cudaGetDevice(&d__); if ((tt) && (tt)->device != d__) return fail(BK_ERR_ARG, "%s", "transposition table belongs to another CUDA device"); } while (0)
 extern "C" int bk_tt_clear(bk_tt* tt, void* stream) {
-    REQUIRE_INIT(); REQUIRE(tt, "bk_tt_clear: null table");
+    REQUIRE_INIT(); REQUIRE(tt, "bk_tt_clear: null table"); REQUIRE_TT_DEVICE(tt);
     CUDA_TRY(cudaMemsetAsync(tt->keys, 0, ((size_t)1 << tt->log2_slots) * sizeof(unsigned long long), as_stream(stream)));
-    CUDA_TRY(cudaMemsetAsync(tt->occupied, 0, sizeof(unsigned long long), as_stream(stream)));
+    CUDA_TRY(cudaMemsetAsync(tt->occupied, 0, 4 * sizeof(unsigned long long), as_stream(stream)));
+    tt->evicted = 0;
     return BK_OK;
 }
 extern "C" int bk_tt_destroy(bk_tt* tt) {
     if (!tt) return BK_OK;
-    cudaFree(tt->keys); cudaFree(tt->rewards); cudaFree(tt->occupied);
+    cudaFree(tt->keys); cudaFree(tt->rewards); cudaFree(tt->stamps); cudaFree(tt->occupied);
     delete tt;
     return BK_OK;
 }
 extern "C" int bk_tt_get(bk_tt* tt, const uint64_t* keys, int n, double* rewards, uint8_t* found, void* stream) {
-    REQUIRE_INIT(); REQUIRE(tt && n >= 0 && (n == 0 || (keys && rewards && found)), "bk_tt_get: null buffer");
+    REQUIRE_INIT(); REQUIRE(tt && n >= 0 && (n == 0 || (keys && rewards && found)), "bk_tt_get: null buffer"); REQUIRE_TT_DEVICE(tt);
     if (n == 0) return BK_OK;
     k_tt_get<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(tt->keys, tt->rewards, tt->log2_slots, keys, n, rewards, found);
     LAUNCH_CHECK();
     return BK_OK;
 }
 extern "C" int bk_tt_put(bk_tt* tt, const uint64_t* keys, const double* rewards, int n, void* stream) {
-    REQUIRE_INIT(); REQUIRE(tt && n >= 0 && (n == 0 || (keys && rewards)), "bk_tt_put: null buffer");
+    REQUIRE_INIT(); REQUIRE(tt && n >= 0 && (n == 0 || (keys && rewards)), "bk_tt_put: null buffer"); REQUIRE_TT_DEVICE(tt);
     if (n == 0) return BK_OK;
-    k_tt_put<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(tt->keys, tt->rewards, tt->log2_slots, tt->occupied, keys, rewards, n);
+    k_tt_put<<<n <= 1024 ? 1 : (n + 255) / 256, n <= 1024 ? 32 : 256, 0, as_stream(stream)>>>(tt->keys, tt->rewards, tt->stamps, tt->log2_slots, tt->occupied, keys, rewards, n);
     LAUNCH_CHECK();
     return BK_OK;
 }
 extern "C" int bk_tt_stats(bk_tt* tt, uint64_t* out_host, void* stream) {
-    REQUIRE_INIT(); REQUIRE(tt && out_host, "bk_tt_stats: null buffer");
-    unsigned long long occ = 0;
-    CUDA_TRY(cudaMemcpyAsync(&occ, tt->occupied, sizeof(occ), cudaMemcpyDeviceToHost, as_stream(stream)));
+    REQUIRE_INIT(); REQUIRE(tt && out_host, "bk_tt_stats: null buffer"); REQUIRE_TT_DEVICE(tt);
+    unsigned long long c[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(c, tt->occupied, sizeof(c), cudaMemcpyDeviceToHost, as_stream(stream)));
     CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
     out_host[0] = (uint64_t)1 << tt->log2_slots;
-    out_host[1] = (uint64_t)occ;
+    out_host[1] = (uint64_t)c[0];
+    out_host[2] = (uint64_t)c[2];
+    out_host[3] = (uint64_t)c[3];
+    return BK_OK;
+}
+extern "C" int bk_tt_evict_oldest(bk_tt* tt, uint64_t n_evict, void* stream) {
+    REQUIRE_INIT(); REQUIRE(tt, "bk_tt_evict_oldest: null table"); REQUIRE_TT_DEVICE(tt);
+    cudaStream_t st = as_stream(stream);
+    unsigned long long c[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(c, tt->occupied, sizeof(c), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (n_evict == 0 || c[0] == 0) return BK_OK;
+    if (n_evict >= c[0]) {                       // everything goes; hit / probe counters stay
+        CUDA_TRY(cudaMemsetAsync(tt->keys, 0, ((size_t)1 << tt->log2_slots) * sizeof(unsigned long long), st));
+        CUDA_TRY(cudaMemsetAsync(tt->occupied, 0, sizeof(unsigned long long), st));
+        tt->evicted = c[1];
+        return BK_OK;
+    }
+    const size_t keep = (size_t)(c[0] - n_evict);
+    const uint32_t slots = 1u << tt->log2_slots;
+    unsigned long long* tk = nullptr; double* tr = nullptr; uint32_t* ts = nullptr; unsigned int* nk = nullptr;
+    cudaError_t e = cudaMalloc(&tk, keep * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&tr, keep * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&ts, keep * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&nk, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(nk, 0, sizeof(unsigned int), st);
+    if (e == cudaSuccess) {
+        const uint32_t first_kept = (uint32_t)(tt->evicted + n_evict);
+        k_tt_collect<<<(slots + 255) / 256, 256, 0, st>>>(tt->keys, tt->rewards, tt->stamps, slots, first_kept, tk, tr, ts, nk);
+        e = cudaMemsetAsync(tt->keys, 0, (size_t)slots * sizeof(unsigned long long), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(tt->occupied, 0, sizeof(unsigned long long), st);
+        if (e == cudaSuccess) {
+            k_tt_reinsert<<<(unsigned int)((keep + 255) / 256), 256, 0, st>>>(tt->keys, tt->rewards, tt->stamps, tt->log2_slots, tt->occupied, tk, tr, ts, nk);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(tk); cudaFree(tr); cudaFree(ts); cudaFree(nk);
+    if (e != cudaSuccess) return fail(BK_ERR_CUDA, "bk_tt_evict_oldest: %s", cudaGetErrorString(e));
+    tt->evicted += n_evict;
     return BK_OK;
 }
 
@@ -1010,8 +1117,8 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
     const bool learned = params->reward_mode >= 3;
     const MctsLayout L = mcts_layout(params->iterations_total, learned);
     if ((int64_t)L.total * n_trees > workspace_bytes) return fail(BK_ERR_CAPACITY, "%s", "bk_mcts_search: workspace too small");
-    MctsTT t; t.keys = nullptr; t.rewards = nullptr; t.occupied = nullptr; t.log2_slots = 0; t.zobrist = zobrist_table;
-    if (tt) { t.keys = tt->keys; t.rewards = tt->rewards; t.occupied = tt->occupied; t.log2_slots = tt->log2_slots; }
+    MctsTT t; t.keys = nullptr; t.rewards = nullptr; t.occupied = nullptr; t.stamps = nullptr; t.log2_slots = 0; t.zobrist = zobrist_table;
+    if (tt) { REQUIRE_TT_DEVICE(tt); t.keys = tt->keys; t.rewards = tt->rewards; t.occupied = tt->occupied; t.stamps = tt->stamps; t.log2_slots = tt->log2_slots; }
     const bool heur = params->rollout_policy == BK_POLICY_HEURISTIC;
     const int W = params->leaf_batch > 1 ? params->leaf_batch : 1;
     REQUIRE(W <= BK_MCTS_MAX_WARPS, "bk_mcts_search: leaf_batch must be in [0, 16]");
@@ -1019,34 +1126,36 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
     long long* rr = reinterpret_cast<long long*>(root_reward);
     cudaStream_t st = as_stream(stream);
     REQUIRE(params->reward_mode >= 0 && params->reward_mode <= 4, "bk_mcts_search: unknown reward_mode");
+    unsigned int* ticket = nullptr;
+    CUDA_TRY(fresh_ticket(cx, st, &ticket));
     if (learned) {
         REQUIRE(params->leaf_model != nullptr, "bk_mcts_search: reward_mode 3/4 needs leaf_model (34 weights + bias on the device)");
         REQUIRE(W == 1, "bk_mcts_search: the learned modes run one warp per tree (leaf_batch must be 1)");
-        const int cap = g_sms * (heur && params->reward_mode == 4 ? 12 : 16);
+        const int cap = cx->sms * (heur && params->reward_mode == 4 ? 12 : 16);
         const int grid = n_trees < cap ? n_trees : cap;
         if (heur && params->reward_mode == 4)
-            k_mcts<1, false, true><<<grid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+            k_mcts<1, false, true><<<grid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, st>>>(ticket, roots, n_roots, n_trees, *params, t,
                 ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
         else
-            k_mcts<0, false, true><<<grid, BK_MCTS_THREADS, 0, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+            k_mcts<0, false, true><<<grid, BK_MCTS_THREADS, 0, st>>>(ticket, roots, n_roots, n_trees, *params, t,
                 ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
     } else if (W == 1) {
-        const int cap = g_sms * (heur ? BK_MCTS_HEUR_CTAS_PER_SM : BK_MCTS_CTAS_PER_SM);
+        const int cap = cx->sms * (heur ? BK_MCTS_HEUR_CTAS_PER_SM : BK_MCTS_CTAS_PER_SM);
         const int grid = n_trees < cap ? n_trees : cap;
         if (heur)
-            k_mcts<1, false><<<grid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+            k_mcts<1, false><<<grid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, st>>>(ticket, roots, n_roots, n_trees, *params, t,
                 ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
         else
-            k_mcts<0, false><<<grid, BK_MCTS_THREADS, 0, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+            k_mcts<0, false><<<grid, BK_MCTS_THREADS, 0, st>>>(ticket, roots, n_roots, n_trees, *params, t,
                 ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
     } else {
-        const int cap = g_sms * ((heur ? 16 : 24) / W);                       // CTAs of W warps: 16-24 warps per SM
+        const int cap = cx->sms * ((heur ? 16 : 24) / W);                       // CTAs of W warps: 16-24 warps per SM
         const int grid = n_trees < cap ? n_trees : cap;
         if (heur)
-            k_mcts<1, true><<<grid, 32 * W, W * HEUR_SMEM_PER_WARP, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+            k_mcts<1, true><<<grid, 32 * W, W * HEUR_SMEM_PER_WARP, st>>>(ticket, roots, n_roots, n_trees, *params, t,
                 ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
         else
-            k_mcts<0, true><<<grid, 32 * W, 0, st>>>(fresh_ticket(st), roots, n_roots, n_trees, *params, t,
+            k_mcts<0, true><<<grid, 32 * W, 0, st>>>(ticket, roots, n_roots, n_trees, *params, t,
                 ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
     }
     LAUNCH_CHECK();
@@ -1057,7 +1166,7 @@ extern "C" int bk_heuristic_scores(const bk_state* states, const uint8_t* player
                                    const uint16_t* move_ids, int n, double* scores, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids && scores)), "bk_heuristic_scores: null buffer");
     if (n == 0) return BK_OK;
-    k_heuristic_scores<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, offsets, move_ids, n, scores, 1.0, 2.0, -1.5, 0.5);
+    k_heuristic_scores<<<grid_for(cx, n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, offsets, move_ids, n, scores, 1.0, 2.0, -1.5, 0.5);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -1067,7 +1176,7 @@ extern "C" int bk_heuristic_scores_weighted(const bk_state* states, const uint8_
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids && scores)), "bk_heuristic_scores_weighted: null buffer");
     REQUIRE(weights_host != nullptr, "bk_heuristic_scores_weighted: weights_host = {piece_size, corner_creation, edge_avoidance, center_preference}");
     if (n == 0) return BK_OK;
-    k_heuristic_scores<<<grid_for(n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, offsets, move_ids, n, scores,
+    k_heuristic_scores<<<grid_for(cx, n, 6), BK_THREADS, 0, as_stream(stream)>>>(states, players, offsets, move_ids, n, scores,
         weights_host[0], weights_host[1], weights_host[2], weights_host[3]);
     LAUNCH_CHECK();
     return BK_OK;

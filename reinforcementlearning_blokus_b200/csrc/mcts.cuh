@@ -67,7 +67,7 @@ struct MctsHeader {            // persistent between launches of the same search
 static_assert(sizeof(MctsHeader) <= 128, "MctsHeader must fit its workspace slot");
 
 struct MctsTT {                // optional transposition table (mcts/zobrist.py:155-220); keys == nullptr: off
-    unsigned long long* keys; double* rewards; unsigned long long* occupied; uint32_t log2_slots;
+    unsigned long long* keys; double* rewards; unsigned long long* occupied; uint32_t* stamps; uint32_t log2_slots;
     const uint64_t* zobrist;   // 2088-entry table, reference order
 };
 
@@ -160,9 +160,13 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
         const bool bias_on = LEARNED && prm.progressive_bias_weight != 0.0;
         uint32_t F[4] = {0u, 0u, 0u, 0u};                                               // frontier rows of `s`
         const uint64_t tree_id = prm.tree_offset + (uint64_t)tree;
-        // per-tree salt keeps concurrently searched trees from reading each other's cached rewards, so the
-        // result of a tree depends on (seed, tree id) only
-        const uint64_t salt = tree_id * 0xD6E8FEB86659FD93ull;
+        // Transposition-table namespace: tree k of a launch reads and writes keys salted with tt_tree_base + k, so trees
+        // searched concurrently never see each other's entries (a tree's result depends on (seed, tree id, table
+        // contents of its namespace) only).  The namespace does NOT follow tree_offset: an agent keeps it constant over
+        // its searches, and search k+1 finds what search k cached (mcts_agent.py:337-339, 418-434).  Namespace 0 uses
+        // the plain Zobrist key -- the reference's one table.
+        const uint64_t salt = (uint64_t)(uint32_t)(prm.tt_tree_base + tree) * 0xD6E8FEB86659FD93ull;
+        uint32_t tt_hits = 0, tt_probes = 0;
 
         uint32_t n_nodes = 0, pool_used = 0, iter_done = 0, draws = 0, overflow = 0, root_player = 0;
         int32_t root_score = 0;
@@ -317,7 +321,8 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
             if (tt.keys && lead && !overflow) {
                 key = zobrist_of(s, tt.zobrist, lane) ^ salt;
                 double rv = 0.0;
-                if (tt_lookup(tt.keys, tt.rewards, tt.log2_slots, key, rv)) { r = (long long)rv; rd = rv; cached = true; }
+                tt_probes++;
+                if (tt_lookup(tt.keys, tt.rewards, tt.log2_slots, key, rv)) { r = (long long)rv; rd = rv; cached = true; tt_hits++; }
             }
             if (BATCH) {
                 if (lead && lane == 0) { sh_node = node; sh_stop = overflow; sh_cached = cached ? 1u : 0u; }
@@ -374,13 +379,13 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                         rd = win_probability_any(s_feat, prm.leaf_model, prm.leaf_model_kind, s.to_move, lane);
                         __syncwarp();
                     }
-                    if (tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, rd);
+                    if (tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.stamps, tt.log2_slots, tt.occupied, key, rd);
                 }
             } else if (!cached && prm.reward_mode == 2) {
                 // learned leaf evaluation in place of the rollout (mcts_agent.py:427-451) with the reference's dummy
                 // artifact (learned_evaluator.py:51-55,129-131): every leaf is worth 0.5, counted here as one half
                 r = 1;
-                if (!BATCH && tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, (double)r);
+                if (!BATCH && tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.stamps, tt.log2_slots, tt.occupied, key, (double)r);
             } else if (!cached) {
                 const uint32_t me = prm.reward_mode ? root_player : s.to_move;      // node.player (mcts_agent.py:483)
                 const int32_t before = prm.reward_mode ? root_score : board_score_of(s, me);
@@ -405,14 +410,14 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                     place_move(s, p, o, row, col, lane);
                 }
                 r = (long long)(board_score_of(s, me) - before);
-                if (!BATCH && tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, (double)r);
+                if (!BATCH && tt.keys && lane == 0) tt_insert(tt.keys, tt.rewards, tt.stamps, tt.log2_slots, tt.occupied, key, (double)r);
             }
             if (BATCH) {
                 if (lane == 0) sh_r[wib] = r;       // (cached: the leading warp holds the cached sum, the others 0)
                 __syncthreads();
                 if (lead) {
                     r = 0; for (int w = 0; w < W; w++) r += sh_r[w];
-                    if (tt.keys && !cached && lane == 0) tt_insert(tt.keys, tt.rewards, tt.log2_slots, tt.occupied, key, (double)r);
+                    if (tt.keys && !cached && lane == 0) tt_insert(tt.keys, tt.rewards, tt.stamps, tt.log2_slots, tt.occupied, key, (double)r);
                 }
             }
             // ---- back-propagation (mcts_agent.py:572-582): W simulations at once in batch mode
@@ -431,6 +436,10 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
             hdr->root_player = root_player; hdr->root_score = root_score;
             if (out_status) out_status[tree] = overflow;
             if (out_counts) out_counts[tree] = n_legal[0];
+            if (tt.keys && tt_probes) {           // TranspositionTable.access_count / hit_count (mcts/zobrist.py:181-185)
+                atomicAdd(tt.occupied + 2, (unsigned long long)tt_hits);
+                atomicAdd(tt.occupied + 3, (unsigned long long)tt_probes);
+            }
         }
         __syncwarp();
         // ---- root statistics by ascending legal-move rank (child k of the root is rank n_legal-1-k)

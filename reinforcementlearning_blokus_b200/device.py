@@ -34,8 +34,12 @@ def _count(n: int = 1) -> None:
 def _lib_for(t: Optional[torch.Tensor] = None):
     if not torch.cuda.is_available():
         raise _lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
-    dev = t.device.index if (t is not None and t.is_cuda) else torch.cuda.current_device()
-    return _lib.init(dev)
+    cur = torch.cuda.current_device()
+    if t is not None and t.is_cuda and t.device.index != cur:
+        # the C ABI launches on the caller's current device and torch's current stream belongs to it
+        raise ValueError(f"tensor lives on cuda:{t.device.index} but the current device is cuda:{cur}; "
+                         f"wrap the call in `with torch.cuda.device({t.device.index}):`")
+    return _lib.init(cur)
 
 
 def _stream() -> int:
@@ -103,7 +107,8 @@ def movegen(states: torch.Tensor, players: Optional[torch.Tensor] = None,
         counts, rows = movegen_fixed(states, ONE_PASS_CAP, players)
         check(lib.bk_exclusive_scan_u32(_ptr(counts), n, _ptr(offsets), st))
         _count(3)
-        total, longest = (int(v) for v in torch.stack([offsets[n], counts.max()]).tolist())
+        total, longest = (int(v) for v in torch.stack([counts.sum(dtype=torch.int64), counts.max().to(torch.int64)]).tolist())
+        _check_total(total)
         ids = torch.empty(max(total, 1), dtype=torch.uint16, device=states.device)
         if longest <= ONE_PASS_CAP:
             check(lib.bk_compact_rows(_ptr(rows), ONE_PASS_CAP, _ptr(offsets), n, _ptr(ids), st))
@@ -115,11 +120,19 @@ def movegen(states: torch.Tensor, players: Optional[torch.Tensor] = None,
     check(lib.bk_movegen_count(_ptr(states), _ptr(players), n, _ptr(counts), st))
     check(lib.bk_exclusive_scan_u32(_ptr(counts), n, _ptr(offsets), st))
     _count(4)
-    total = int(offsets[n].item())
+    total = int(counts.sum(dtype=torch.int64).item())     # not offsets[n]: the 32-bit scan wraps on huge batches
+    _check_total(total)
     ids = torch.empty(max(total, 1), dtype=torch.uint16, device=states.device)
     check(lib.bk_movegen_emit(_ptr(states), _ptr(players), n, _ptr(offsets), _ptr(ids), st))
     _count()
     return counts, offsets, ids[:total]
+
+
+def _check_total(total: int) -> None:
+    """CSR offsets are 32-bit: refuse a batch whose move ids do not fit instead of writing out of bounds."""
+    if total >= 2**31:
+        raise ValueError(f"the batch holds {total} legal moves; CSR offsets are int32 -- split it into batches below 2^31 ids "
+                         "(about 10 M mid-game states)")
 
 
 def exclusive_scan(counts: torch.Tensor) -> torch.Tensor:
@@ -461,9 +474,14 @@ class DeviceTranspositionTable:
     def stats(self) -> Dict[str, int]:
         import ctypes as C
 
-        out = (C.c_uint64 * 2)()
+        out = (C.c_uint64 * 4)()
         check(self._lib.bk_tt_stats(self._h, out, _stream()))
-        return {"max_size": int(out[0]), "size": int(out[1])}
+        return {"max_size": int(out[0]), "size": int(out[1]), "hits": int(out[2]), "probes": int(out[3])}
+
+    def evict_oldest(self, n: int) -> None:
+        """Remove the n entries inserted first (TranspositionTable.put's eviction, mcts/zobrist.py:196-200)."""
+        check(self._lib.bk_tt_evict_oldest(self._h, int(n), _stream()))
+        _count(2)
 
     def close(self) -> None:
         if self._h is not None:

@@ -96,8 +96,21 @@ class TranspositionTable:
         return None
 
     def put(self, hash_value: int, entry: Dict):
+        self.evict_if_full()
         k = torch.tensor([np.uint64(hash_value).astype(np.int64)], dtype=torch.int64, device="cuda")
         self._t.put(k, torch.tensor([float(entry["reward"])], dtype=torch.float64, device="cuda"))
+
+    def evict_if_full(self) -> None:
+        """mcts/zobrist.py:196-200: a put into a full table first removes the max_size // 10 entries inserted first.
+        The search kernel inserts without this check (the device table has >= 2 x max_size slots); DeviceUCT callers
+        run it between searches."""
+        if len(self) >= self.max_size:
+            self._t.evict_oldest(self.max_size // 10)
+
+    def search_counters(self) -> Dict[str, int]:
+        """Hits / probes of the search kernels that used this table (counted on the device)."""
+        st = self._t.stats()
+        return {"hits": st["hits"], "probes": st["probes"]}
 
     def clear(self):
         self._t.clear()
@@ -108,8 +121,10 @@ class TranspositionTable:
         return self._t.stats()["size"]
 
     def get_stats(self) -> Dict[str, float]:
-        return {"size": len(self), "max_size": self.max_size, "access_count": self.access_count,
-                "hit_count": self.hit_count, "hit_rate": self.hit_count / max(self.access_count, 1)}
+        st = self._t.stats()
+        access, hits = self.access_count + st["probes"], self.hit_count + st["hits"]     # host calls + in-kernel probes
+        return {"size": st["size"], "max_size": self.max_size, "access_count": access,
+                "hit_count": hits, "hit_rate": hits / max(access, 1)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -123,14 +138,14 @@ class DeviceUCT:
                  reward_mode: int = 0, rollout_policy: int = 0, tt: Optional[dev.DeviceTranspositionTable] = None, zobrist: Optional[ZobristHash] = None,
                  max_root_moves: int = MAX_ROOT_MOVES, leaf_batch: int = 1, leaf_model: Optional[torch.Tensor] = None,
                  leaf_max_turns: int = 2500, progressive_bias_weight: float = 0.0, shaping_weight: float = 1.0,
-                 shaping_gamma: float = 1.0, potential_mode: str = "prob", leaf_model_kind: int = 0):
+                 shaping_gamma: float = 1.0, potential_mode: str = "prob", leaf_model_kind: int = 0, tt_tree_base: int = 0):
         if not torch.cuda.is_available():
             raise _lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
         self.lib = _lib.init(torch.cuda.current_device())
         self.p = _lib.MctsParams(iterations=0, iterations_total=int(iterations_total),
                                  max_rollout_moves=int(max_rollout_moves), rollout_policy=int(rollout_policy), max_depth=int(max_depth),
                                  ucb_variant=int(ucb_variant), resume=0, reward_mode=int(reward_mode), leaf_batch=int(leaf_batch),
-                                 reserved0=0, leaf_max_turns=int(leaf_max_turns), leaf_model_kind=int(leaf_model_kind),
+                                 tt_tree_base=int(tt_tree_base), leaf_max_turns=int(leaf_max_turns), leaf_model_kind=int(leaf_model_kind),
                                  progressive_bias_weight=float(progressive_bias_weight) if int(reward_mode) >= 3 else 0.0,
                                  shaping_weight=float(shaping_weight), shaping_gamma=float(shaping_gamma),
                                  potential_mode=1 if potential_mode == "logit" else 0, reserved2=0,
@@ -322,9 +337,20 @@ class MCTSAgent:
 
     def _engine(self, total: int) -> DeviceUCT:
         tt = self.transposition_table.device if self.transposition_table is not None else None
-        # every search of this agent gets its own block of Philox streams
+        # every search of this agent gets its own block of Philox streams; the transposition-table namespaces stay
+        # 0 .. num_trees-1 over all its searches, so a later search finds what an earlier one cached
+        # (mcts_agent.py:337-339: the reference keeps one table per agent and clears it only past 500 000 entries)
         offset = self._searches * max(self.num_trees, 1)
         self._searches += 1
+        if self.transposition_table is not None:
+            self.transposition_table.evict_if_full()
+        # the engine (workspace, result buffers) is kept across the moves of the agent; only the stream block changes
+        key = (int(total), self.seed, id(self.zobrist_hash), self.exploration_constant, self.max_rollout_moves)
+        cached = getattr(self, "_engine_cache", None)
+        if cached is not None and cached[0] == key:
+            cached[1].p.tree_offset = int(offset)
+            return cached[1]
+        self._engine_cache = None
         mode, model = 0, None
         real = self.learned_evaluator is not None and not self.learned_evaluator._is_dummy
         if self.leaf_evaluation_enabled:
@@ -334,28 +360,32 @@ class MCTSAgent:
                 mode, model = 3, torch.from_numpy(self.learned_evaluator.device_model)
         elif self.potential_shaping_enabled and real:            # rollouts + shaping term on truncated ones
             mode, model = 4, torch.from_numpy(self.learned_evaluator.device_model)
-        return DeviceUCT(total, n_trees=self.num_trees, max_rollout_moves=self.max_rollout_moves,
+        eng = DeviceUCT(total, n_trees=self.num_trees, max_rollout_moves=self.max_rollout_moves,
                          exploration=self.exploration_constant, seed=self.seed, tree_offset=offset,
                          reward_mode=mode, leaf_model=model, leaf_max_turns=getattr(self.learned_evaluator, "max_turns", 2500),
                          progressive_bias_weight=self.progressive_bias_weight if self.progressive_bias_enabled else 0.0,
                          leaf_model_kind=getattr(self.learned_evaluator, "device_model_kind", 0),
                          shaping_weight=self.potential_shaping_weight, shaping_gamma=self.potential_shaping_gamma,
                          potential_mode=self.potential_mode,
-                         leaf_batch=self.leaf_batch,
+                         leaf_batch=self.leaf_batch, tt_tree_base=0,
                          rollout_policy=self.rollout_policy, tt=tt,
                          zobrist=self.zobrist_hash if tt is not None else None)
+        self._engine_cache = (key, eng)
+        return eng
 
     def search_root(self, board: Board, player: Player) -> Dict[str, np.ndarray]:
         """Root statistics (visits, reward sums) by ascending legal-move rank, summed over the trees."""
         start = time.time()
         root = _root_state(board, player)
+        hits0 = self.transposition_table.search_counters()["hits"] if self.transposition_table is not None else 0
         frontiers = None
         if self._requires_learned_evaluator and self.learned_evaluator is not None and not self.learned_evaluator._is_dummy:
             frontiers = torch.from_numpy(board.frontier_words()[None].copy())     # the board's incremental sets
         if self.time_limit:
-            # capacity for the time budget: one warp runs about 12-15 k simulations/s (profiles/r01_agent_latency.json)
+            # capacity for the time budget: one warp runs about 12-15 k simulations/s (profiles/r01_agent_latency.json);
+            # the workspace grows with the capacity (child pool up to 2048 slots per iteration), so the bound is tight
             chunk = 64
-            cap = min(60000, max(4 * chunk, int(self.time_limit * 30000)))
+            cap = min(60000, max(4 * chunk, int(self.time_limit * 16000)))
             eng = self._engine(cap)
             done = 0
             res = eng.search(root, chunk, root_frontiers=frontiers)
@@ -376,6 +406,8 @@ class MCTSAgent:
         reward = res["reward"][:, :n_root].sum(dim=0).cpu().numpy()
         self.stats["iterations_run"] = done
         self.stats["time_elapsed"] = time.time() - start
+        if self.transposition_table is not None:         # mcts_agent.py:423, counted by the kernel
+            self.stats["transposition_hits"] += self.transposition_table.search_counters()["hits"] - hits0
         if self.leaf_evaluation_enabled:
             if self.learned_evaluator._is_dummy:
                 reward = reward * 0.5                        # halves -> the dummy evaluator's probabilities

@@ -103,3 +103,27 @@ def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
         if line:
             name, off = line.split()
             assert getattr(MctsParams, name).offset == int(off), name
+
+
+def test_init_failure_raises_and_does_not_deadlock(lib_path):
+    """a failing bk_init used to re-enter the module lock.  Without a GPU (or with a device index that does
+    not exist) init() must raise BlokusB200Error, twice in a row."""
+    import threading
+
+    from reinforcementlearning_blokus_b200 import _lib
+
+    result = []
+
+    def run():
+        for _ in range(2):
+            try:
+                _lib.init(9999)
+                result.append("no error")
+            except _lib.BlokusB200Error as exc:
+                result.append(str(exc))
+
+    t = threading.Thread(target=run, daemon=True)
+    t.start()
+    t.join(timeout=60)
+    assert not t.is_alive(), "init() hung"
+    assert len(result) == 2 and all("blokus_b200 error" in r for r in result), result

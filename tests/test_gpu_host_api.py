@@ -214,3 +214,43 @@ def test_heuristic_agent_custom_weights():
     assert np.array_equal(got, want) and not np.array_equal(got, s_default)
     assert custom.select_action(board, player, legal) in legal
     assert custom.get_action_info()["weights"]["corner_creation"] == 3.25
+
+
+# ---- the C ABI keeps one context per device -------------------------------------------------------------------------------
+def test_bad_device_raises_instead_of_hanging():
+    from reinforcementlearning_blokus_b200 import _lib
+
+    with pytest.raises(_lib.BlokusB200Error):
+        _lib.init(9999)
+    with pytest.raises(_lib.BlokusB200Error):          # a second failure must not dead-lock either
+        _lib.init(9999)
+
+
+def test_tensor_on_another_device_is_refused():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from reinforcementlearning_blokus_b200 import device as dev
+    from reinforcementlearning_blokus_b200.state import empty_states
+
+    with torch.cuda.device(1):
+        s1 = dev.to_device(empty_states(2))
+    with torch.cuda.device(0), pytest.raises(ValueError):
+        dev.movegen_count(s1)
+
+
+def test_two_devices_in_one_process():
+    """bk_init(1) after bk_init(0) must not disturb device 0 (per-device contexts; the current device is left alone)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from reinforcementlearning_blokus_b200 import device as dev
+
+    outs = {}
+    for d in (0, 1, 0, 1):
+        with torch.cuda.device(d):
+            r = dev.playout(256, seed=5, want_trace=True)
+            got = (r["game_scores"].cpu(), r["trace"].cpu())
+            assert torch.cuda.current_device() == d
+        if d in outs:
+            assert torch.equal(outs[d][0], got[0]) and torch.equal(outs[d][1], got[1])
+        outs[d] = got
+    assert torch.equal(outs[0][0], outs[1][0])

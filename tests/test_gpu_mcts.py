@@ -485,3 +485,83 @@ def test_config4_fast_mcts_1000_sims_on_kat1_roots(golden_dir):
         eng = DeviceUCT(125, n_trees=1, seed=7, max_depth=1, ucb_variant=1, reward_mode=1, leaf_batch=8)
         res = eng.search(dev.to_device(np.atleast_1d(st)), 125)
         assert int(res["visits"][0].sum()) == 1000 and int(res["counts"][0]) == len(legal)
+
+
+# ---- transposition table across the moves of ONE agent (mcts_agent.py:337-339, 418-434) -----------------------------------
+def test_agent_reuses_its_transposition_table_across_moves(golden_dir):
+    """The second select_action of an agent -- on the position after its first move -- hits what the first search
+    cached, reports the hits in stats["transposition_hits"], and equals the oracle run with ONE persistent table whose
+    second search draws from the agent's next stream block."""
+    board = Board.from_packed(_roots(golden_dir)[2])
+    gen = get_shared_generator()
+    agent = MCTSAgent(iterations=160, seed=6, rollout_agent=RandomAgent(seed=6))
+    ott = orc.OracleTT(18)
+    zt = orc.zobrist_table(6)
+    total_hits = 0
+    for k in range(3):
+        player = board.current_player
+        legal = gen.get_legal_moves(board, player)
+        r = agent.search_root(board, player)
+        want = orc.mcts_search(board.to_packed(), 160, seed=6, tree_id=k, tt=ott, zobrist=zt, tt_namespace=0)
+        n = want["n_root"]
+        assert r["n_root"] == n == len(legal)
+        assert np.array_equal(r["visits"], want["visits"][:n]), k
+        assert np.array_equal(r["reward"], want["reward"][:n]), k
+        assert agent.stats["transposition_hits"] == ott.hits(), k
+        assert len(agent.transposition_table) == ott.size()
+        if k:
+            assert agent.stats["transposition_hits"] > total_hits, "a later search must find the earlier searches' entries"
+        total_hits = agent.stats["transposition_hits"]
+        mv = agent.select_action(board, player, legal[:1])          # (one legal move: returned without a search)
+        best = int(np.argmax(r["visits"]))
+        ids = sorted(m.to_id() for m in legal)
+        m = Move.from_id(ids[best])
+        assert board.place_piece(m.get_positions(gen.piece_orientations_cache[m.piece_id]), player, m.piece_id)
+    st = agent.get_action_info()["transposition_stats"]
+    assert st["hit_count"] == ott.hits() and st["access_count"] == ott.probes()
+    ott.close()
+
+
+def test_table_namespaces_isolate_concurrent_trees_and_persist(golden_dir):
+    """Tree k of a launch uses namespace tt_tree_base + k whatever its tree_offset: concurrently searched trees do not
+    see each other's entries, and a second launch with other stream ids finds the first launch's entries."""
+    root_np = _roots(golden_dir)[3]
+    root = dev.to_device(np.atleast_1d(root_np))
+    zob = ZobristHash(seed=3)
+    tt = TranspositionTable(max_size=1 << 16)
+    otts = [orc.OracleTT(18) for _ in range(3)]             # the oracle runs the trees one by one: one table per namespace
+    for launch, offset in enumerate((0, 40)):
+        res = DeviceUCT(90, n_trees=3, seed=2, tree_offset=offset, tt=tt.device, zobrist=zob).search(root, 90)
+        for k in range(3):
+            want = orc.mcts_search(root_np, 90, seed=2, tree_id=offset + k, tt=otts[k], zobrist=zob.table, tt_namespace=k)
+            n = want["n_root"]
+            assert np.array_equal(res["visits"][k, :n].cpu().numpy(), want["visits"][:n]), (launch, k)
+            assert np.array_equal(res["reward"][k, :n].cpu().numpy(), want["reward"][:n]), (launch, k)
+    st = tt.device.stats()
+    assert st["hits"] == sum(o.hits() for o in otts) > 0
+    assert st["size"] == sum(o.size() for o in otts)
+    for o in otts:
+        o.close()
+
+
+def test_transposition_table_evicts_oldest_tenth_when_full():
+    """mcts/zobrist.py:196-200: a put into a full table first removes the max_size // 10 entries inserted first."""
+    tt = TranspositionTable(max_size=50)
+    ott = orc.OracleTT(8)
+    keys = [int(k) for k in np.random.default_rng(0).integers(1, 2**63, size=120)]
+    for i, k in enumerate(keys):
+        if ott.size() >= 50:
+            ott.evict_oldest(5)
+        ott.put(k, float(i))
+        tt.put(k, {"reward": float(i)})
+        if i == 30:                                   # overwriting an entry does not renew it (dict order)
+            ott.put(keys[2], -1.0)
+            tt.put(keys[2], {"reward": -1.0})
+    assert len(tt) == ott.size() <= 50
+    for k in keys:
+        got, want = tt.get(k), ott.get(k)
+        assert (got is None) == (want is None)
+        if got is not None:
+            assert got["reward"] == want
+    assert tt.get(keys[0]) is None and tt.get(keys[-1]) is not None
+    ott.close()
