@@ -24,7 +24,7 @@ _LAZY = {
 
 
 _SUBMODULES = ("agents", "arena", "batched", "board", "device", "dist", "game", "integration", "mcts", "move_generator",
-               "mobility", "service", "single", "winprob")
+               "mobility", "service", "single", "telemetry", "winprob")
 
 
 def __getattr__(name):

@@ -34,7 +34,9 @@ class BlokusGame:
         self.move_generator: LegalMoveGenerator = get_shared_generator()
         self.game_history: List[dict] = []
         self.winner: Optional[Player] = None
-        self.enable_telemetry = False
+        # engine/game.py:44-48: with telemetry every move records the four players' metrics before and after it
+        # (telemetry.collect_all_player_metrics: four device launches per board) and their deltas
+        self.enable_telemetry = bool(enable_telemetry)
         self.telemetry_fast_mode = telemetry_fast_mode
 
     # ---- moves ------------------------------------------------------------------------------------------
@@ -46,6 +48,11 @@ class BlokusGame:
         move_id = move.to_id()            # None for bad piece / orientation indices and off-board anchors
         if move_id is None or move.piece_id in self.board.player_pieces_used[player]:
             return False
+        before = None
+        if self.enable_telemetry:
+            from . import telemetry
+
+            before = telemetry.collect_all_player_metrics(self.board, self.move_generator, self.telemetry_fast_mode)
         ok, alive = single.step_check(self.board.to_packed(), player.value - 1, move_id)
         if not ok:
             return False
@@ -61,6 +68,15 @@ class BlokusGame:
                        "anchor_row": move.anchor_row, "anchor_col": move.anchor_col},
             "board_state": self.board.grid.tolist(),
         })
+        if before:
+            after = telemetry.collect_all_player_metrics(self.board, self.move_generator, self.telemetry_fast_mode)
+            payload = telemetry.compute_move_telemetry_delta(
+                ply=idx + 1, mover_id=player.name,
+                move_id=f"{move.piece_id}-{move.orientation}-{move.anchor_row}-{move.anchor_col}", before=before, after=after)
+            if payload:
+                payload["before"] = [{"playerId": pid, "metrics": m} for pid, m in before.items()]
+                payload["after"] = [{"playerId": pid, "metrics": m} for pid, m in after.items()]
+                self.game_history[-1]["telemetry"] = payload
         if alive == 0:
             self._set_game_over()
         return True

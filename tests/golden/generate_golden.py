@@ -645,6 +645,57 @@ def _packed_for(board: Board, player: Player) -> np.ndarray:
     return s
 
 
+def gen_telemetry():
+    """engine/telemetry.py collect_all_player_metrics (fast and full sampling) on boards replayed from the golden games,
+    i.e. with the reference's incremental frontier sets.  The generator handed to it lists moves in ascending id (the
+    order simulate_mobility_stability's seeded shuffle then starts from)."""
+    from engine.telemetry import collect_all_player_metrics
+
+    class Ascending:
+        def __init__(self):
+            self.piece_orientations_cache = GEN.piece_orientations_cache
+
+        def get_legal_moves(self, board, player):
+            return sorted(GEN.get_legal_moves(board, player), key=move_id)
+
+    z = np.load(os.path.join(HERE, "games.npz"))
+    traces = z["traces"]
+    rows = []
+    for gi, plies in ((0, (0, 3, 9, 22, 41, 60)), (1, (5, 14, 33, 52)), (2, (1, 27, 47, 70)), (5, (12, 36, 64))):
+        game = BlokusGame(enable_telemetry=False)
+        t = 0
+        for stop in plies:
+            while t < stop and t < int(z["turns"][gi]):
+                pl = game.get_current_player()
+                if traces[gi, t] == 0xFFFF:
+                    game.board._update_current_player()
+                else:
+                    assert game.make_move(id_to_move(traces[gi, t]), pl)
+                t += 1
+            board = game.board
+            for fast in (True, False):
+                if not fast and stop % 2:
+                    continue
+                m = collect_all_player_metrics(board, Ascending(), fast_mode=fast)
+                rows.append({"game": gi, "turn": t, "fast_mode": fast, "packed_hex": pack(board).tobytes().hex(),
+                             "frontier": [sorted([list(x) for x in board.get_frontier(Player(p + 1))]) for p in range(4)],
+                             "metrics": m, "no_generator": collect_all_player_metrics(board, None) if fast else None})
+            print("telemetry game", gi, "turn", t, flush=True)
+    # BlokusGame(enable_telemetry=True): the per-move payload of engine/game.py:72-141 for the first plies of golden game 3
+    moves = []
+    with _AscendingGenerator():
+        game = BlokusGame(enable_telemetry=True, telemetry_fast_mode=True)
+        for t in range(7):
+            pl = game.get_current_player()
+            assert game.make_move(id_to_move(traces[3, t]), pl)
+            tel = game.game_history[-1]["telemetry"]
+            moves.append({"move_id": int(traces[3, t]), "telemetry": {k: tel[k] for k in
+                          ("ply", "moverId", "moveId", "deltaSelf", "deltaOppTotal", "deltaOppByPlayer", "deltaAdvantage", "winProxyDelta")}})
+    with open(os.path.join(HERE, "telemetry.json"), "w") as f:
+        json.dump({"source": "engine/telemetry.py collect_all_player_metrics", "rows": rows, "game_moves": moves}, f)
+    print("telemetry", len(rows), "rows")
+
+
 def random_state_from_packed(s) -> Board:
     """Rebuild a reference Board from a packed state (the recipe of engine-service/app.py:27-50)."""
     board = Board()
@@ -671,8 +722,8 @@ def random_state_from_packed(s) -> Board:
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise", "mcts"]
+    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise", "mcts", "telemetry"]
     for w in which:
         {"tables": gen_tables, "kat1": gen_kat1, "kat2": gen_kat2, "random": gen_random_states,
          "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic, "mobility": gen_mobility,
-         "snapshots": gen_snapshots, "pairwise": gen_pairwise, "mcts": gen_mcts}[w]()
+         "snapshots": gen_snapshots, "pairwise": gen_pairwise, "mcts": gen_mcts, "telemetry": gen_telemetry}[w]()

@@ -10,7 +10,7 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 from oracle import orc  # noqa: E402
-from reinforcementlearning_blokus_b200 import Board, MCTSAgent, Move, Player, ZobristHash, get_shared_generator  # noqa: E402
+from reinforcementlearning_blokus_b200 import Board, MCTSAgent, Move, Player, RandomAgent, ZobristHash, get_shared_generator  # noqa: E402
 from reinforcementlearning_blokus_b200 import device as dev  # noqa: E402
 from reinforcementlearning_blokus_b200.mcts import DeviceUCT, TranspositionTable  # noqa: E402
 from reinforcementlearning_blokus_b200.state import STATE_DTYPE, empty_states  # noqa: E402
@@ -512,7 +512,6 @@ def test_agent_reuses_its_transposition_table_across_moves(golden_dir):
         if k:
             assert agent.stats["transposition_hits"] > total_hits, "a later search must find the earlier searches' entries"
         total_hits = agent.stats["transposition_hits"]
-        mv = agent.select_action(board, player, legal[:1])          # (one legal move: returned without a search)
         best = int(np.argmax(r["visits"]))
         ids = sorted(m.to_id() for m in legal)
         m = Move.from_id(ids[best])
