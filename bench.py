@@ -150,11 +150,18 @@ def run_reference(args) -> None:
         return
     cores = os.cpu_count() or 1
     extra = {}
-    if _reference_available():
+    use_ref = _reference_available()
+    pool = None
+    if use_ref:
         from oracle import ref_bench
 
+        try:
+            pool = ref_bench.PlayoutPool(cores)
+        except Exception as exc:                      # report and time the port instead
+            extra["reference_error"] = repr(exc)[:200]
+            use_ref = False
+    if use_ref:
         kind, per_worker = "reference", 2
-        pool = ref_bench.PlayoutPool(cores)
         sample = cores * per_worker
         for _ in range(args.warmup):
             pool.step(1)
@@ -520,30 +527,39 @@ def _cpu_baseline():
     """The reference's Python engine on all host cores (oracle/_ref, bounded sample) with its movegen benchmark and
     search agents on one core; beside it the C port of the engine (oracle/blokus_oracle.c) on one core."""
     out = {}
-    if _reference_available():
-        from oracle import ref_bench
-
-        cores = os.cpu_count() or 1
-        budget = float(os.environ.get("BLOKUS_CPU_BASELINE_SECONDS", "12"))
-        pool = ref_bench.PlayoutPool(cores)
-        pool.step(1)
-        games, t = 0, 0.0
-        while t < budget:
-            g, dt = pool.step(2)
-            games, t = games + g, t + dt
-        pool.close()
-        out = {"value": games / t, "unit": UNIT, "cores": cores, "kind": "reference",
-               "sample": f"{games} games of the same workload in {t:.1f} s on {cores} processes; {REF_SOURCE}",
-               "playouts_per_sec_per_core": games / t / cores}
-        # BASELINE configs[0]: benchmarks/benchmark_move_generation.py's protocol, one core
-        mg = ref_bench.movegen_benchmark(num_runs=10)
-        out["movegen_frontier_bitboard_gens_per_sec_one_core"] = mg["frontier_bitboard_gens_per_sec"]
-        out["movegen_naive_gens_per_sec_one_core"] = mg["naive_gens_per_sec"]
-        out["movegen_benchmark_ms"] = [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()} for r in mg["states"]]
-        out.update({k: round(v, 3) for k, v in ref_bench.search_rates(4.0).items()})
+    try:
+        if _reference_available():
+            out = _cpu_reference_baseline()
+    except Exception as exc:
+        out = {"reference_error": repr(exc)[:200]}
     out["port"] = _cpu_port_baseline()
     if not out.get("kind"):
         out.update({k: out["port"][k] for k in ("value", "unit", "cores", "kind", "sample")})
+    return out
+
+
+def _cpu_reference_baseline():
+    """oracle/_ref on all host cores (playouts), and on one core: its movegen benchmark and its search agents."""
+    from oracle import ref_bench
+
+    cores = os.cpu_count() or 1
+    budget = float(os.environ.get("BLOKUS_CPU_BASELINE_SECONDS", "12"))
+    pool = ref_bench.PlayoutPool(cores)
+    pool.step(1)
+    games, t = 0, 0.0
+    while t < budget:
+        g, dt = pool.step(2)
+        games, t = games + g, t + dt
+    pool.close()
+    out = {"value": games / t, "unit": UNIT, "cores": cores, "kind": "reference",
+           "sample": f"{games} games of the same workload in {t:.1f} s on {cores} processes; {REF_SOURCE}",
+           "playouts_per_sec_per_core": games / t / cores}
+    # BASELINE configs[0]: benchmarks/benchmark_move_generation.py's protocol, one core
+    mg = ref_bench.movegen_benchmark(num_runs=10)
+    out["movegen_frontier_bitboard_gens_per_sec_one_core"] = mg["frontier_bitboard_gens_per_sec"]
+    out["movegen_naive_gens_per_sec_one_core"] = mg["naive_gens_per_sec"]
+    out["movegen_benchmark_ms"] = [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()} for r in mg["states"]]
+    out.update({k: round(v, 3) for k, v in ref_bench.search_rates(4.0).items()})
     return out
 
 

@@ -3,8 +3,10 @@
 
 TEST INFRASTRUCTURE ONLY (like everything under oracle/).  The reference is pure Python, so "compiling it from the
 sources where they lie" means byte-compiling: every module listed below is compiled with ``py_compile`` straight from
-``/root/reference`` into a source-less ``.pyc`` tree under ``oracle/_ref/pyref`` (git-ignored, NOT gpurun-ignored, so
-it travels to the GPU box exactly like a built ``.so``).  No reference source file is copied into the repository.
+``/root/reference`` and stored source-less in ONE importable archive, ``oracle/_ref/pyref.zip`` (zipimport loads
+``.pyc`` members; loose ``*.pyc`` files do not survive the transfer to the GPU box).  ``oracle/_ref/`` is git-ignored,
+NOT gpurun-ignored, so it travels to the GPU box exactly like a built ``.so``.  No reference source file is copied into
+the repository.
 
 Who may use the result (and only as checker / baseline, never on the product path):
   * ``tests/test_gpu_reference_suite.py`` -- runs the reference's OWN hot-path tests with the device generator and
@@ -25,11 +27,13 @@ import os
 import py_compile
 import shutil
 import sys
+import tempfile
+import zipfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("BLOKUS_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
-TREE = os.path.join(OUT, "pyref")
+TREE = os.path.join(OUT, "pyref.zip")
 MANIFEST = os.path.join(OUT, "MANIFEST.json")
 
 # The hot path of SURVEY.md section 8(a) and its callers, the benchmark of BASELINE configs[0] and the reference's own
@@ -65,7 +69,7 @@ def _files():
 
 
 def build(force: bool = False) -> str:
-    """Byte-compile the listed reference modules into oracle/_ref/pyref.  Needs /root/reference (build container)."""
+    """Byte-compile the listed reference modules into oracle/_ref/pyref.zip.  Needs /root/reference (build container)."""
     if not os.path.isdir(os.path.join(REF, "engine")):
         raise FileNotFoundError(f"no reference checkout at {REF}: oracle/_ref can only be built in the build container")
     files = _files()
@@ -79,12 +83,14 @@ def build(force: bool = False) -> str:
             old = json.load(f)
         if old.get("sha256") == digest and old.get("magic") == magic:
             return TREE
-    shutil.rmtree(TREE, ignore_errors=True)
-    for rel in files:
-        dst = os.path.join(TREE, rel[:-3] + ".pyc")
-        os.makedirs(os.path.dirname(dst), exist_ok=True)
-        py_compile.compile(os.path.join(REF, rel), cfile=dst, dfile="reference:/" + rel, doraise=True,
-                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+    shutil.rmtree(OUT, ignore_errors=True)
+    os.makedirs(OUT, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp, zipfile.ZipFile(TREE, "w", zipfile.ZIP_DEFLATED) as z:
+        for rel in files:
+            dst = os.path.join(tmp, "m.pyc")
+            py_compile.compile(os.path.join(REF, rel), cfile=dst, dfile="reference:/" + rel, doraise=True,
+                               invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+            z.write(dst, rel[:-3] + ".pyc")
     with open(MANIFEST, "w") as f:
         json.dump({"what": "byte-compiled modules of the reference (TGALLOWAY1/ReinforcementLearning_Blokus), built by "
                            "oracle/make_ref.py from " + REF, "python": sys.version.split()[0], "magic": magic,
@@ -102,6 +108,8 @@ def ref_path() -> str:
         m = json.load(f)
     if m.get("magic") != importlib.util.MAGIC_NUMBER.hex():
         raise RuntimeError(f"oracle/_ref was built by Python {m.get('python')}; this is {sys.version.split()[0]}")
+    if not os.path.isfile(TREE):
+        raise FileNotFoundError("oracle/_ref/pyref.zip is missing (manifest present): rebuild with oracle/make_ref.py")
     return TREE
 
 

@@ -639,6 +639,51 @@ def gen_mcts(iterations=200, seed=42):
     print("mcts", len(names), "searches")
 
 
+def gen_mcts_deep(seed=42):
+    """More searches of the unmodified MCTSAgent on late-game roots with few legal moves, where 300 iterations build
+    trees several plies deep (UCB1 selection below the root, terminal nodes, in-search transpositions).  Added to the
+    entries gen_mcts wrote."""
+    from agents.heuristic_agent import HeuristicAgent as _H
+    from mcts.mcts_agent import MCTSAgent, MCTSNode
+
+    path = os.path.join(HERE, "mcts.npz")
+    out = {k: v for k, v in np.load(path).items()}
+    names = [str(n) for n in out["names"] if not str(n).split("/")[0].startswith("deep")]
+    states = np.load(os.path.join(HERE, "random_states.npz"))["states"].view(STATE_DTYPE).reshape(-1)
+
+    def record(tag, board, player, agent, its):
+        root = MCTSNode(board, player)
+        agent.iterations = its
+        agent._run_mcts_with_iterations(root)
+        mv, vis, rew = _root_children(root)
+        out[tag + "/state"] = np.frombuffer(_packed_for(board, player).tobytes(), dtype=np.uint8)
+        out[tag + "/frontier"] = _frontier_bytes(board)
+        out[tag + "/moves"], out[tag + "/visits"], out[tag + "/reward"] = mv, vis, rew
+        out[tag + "/digest"] = _tree_digest(root)
+        out[tag + "/tt"] = np.array([agent.stats["transposition_hits"],
+                                     len(agent.transposition_table.table) if agent.transposition_table else 0], dtype=np.int64)
+        out[tag + "/best"] = np.array([move_id(root.get_best_move())], dtype=np.uint16)
+        names.append(tag)
+        print(tag, "children", len(mv), "digest", out[tag + "/digest"].tolist(), "tt", out[tag + "/tt"].tolist(), flush=True)
+
+    with _AscendingGenerator():
+        for idx in (42, 74, 80, 54):
+            board = random_state_from_packed(states[idx])
+            player = board.current_player
+            name = "rs%d" % idx
+            ag = MCTSAgent(iterations=300, rollout_agent=PhiloxIndexAgent(seed), use_transposition_table=False, seed=seed)
+            record("deep_uct/" + name, board, player, ag, 300)
+            ag = MCTSAgent(iterations=300, rollout_agent=PhiloxIndexAgent(seed), use_transposition_table=True, seed=seed)
+            record("deep_tt/" + name, board, player, ag, 300)
+            h = _H(seed=seed)
+            h.rng = _PhiloxChoice(seed)
+            ag = MCTSAgent(iterations=150, rollout_agent=h, use_transposition_table=True, seed=seed)
+            record("deep_heur/" + name, board, player, ag, 150)
+    out["names"] = np.array(names)
+    np.savez_compressed(path, **out)
+    print("mcts", len(names), "searches")
+
+
 def _packed_for(board: Board, player: Player) -> np.ndarray:
     s = pack(board)
     s["to_move"] = player.value - 1
@@ -722,8 +767,8 @@ def random_state_from_packed(s) -> Board:
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise", "mcts", "telemetry"]
+    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise", "mcts", "mcts_deep", "telemetry"]
     for w in which:
         {"tables": gen_tables, "kat1": gen_kat1, "kat2": gen_kat2, "random": gen_random_states,
          "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic, "mobility": gen_mobility,
-         "snapshots": gen_snapshots, "pairwise": gen_pairwise, "mcts": gen_mcts, "telemetry": gen_telemetry}[w]()
+         "snapshots": gen_snapshots, "pairwise": gen_pairwise, "mcts": gen_mcts, "mcts_deep": gen_mcts_deep, "telemetry": gen_telemetry}[w]()

@@ -492,8 +492,9 @@ def test_agent_reuses_its_transposition_table_across_moves(golden_dir):
     """The second select_action of an agent -- on the position after its first move -- hits what the first search
     cached, reports the hits in stats["transposition_hits"], and equals the oracle run with ONE persistent table whose
     second search draws from the agent's next stream block."""
-    board = Board.from_packed(_roots(golden_dir)[2])
-    gen = get_shared_generator()
+    z = np.load(os.path.join(golden_dir, "random_states.npz"))
+    board = Board.from_packed(z["states"].view(STATE_DTYPE).reshape(-1)[74])      # 48 moves played, 16 legal moves: the
+    gen = get_shared_generator()                                                  # second search re-visits the first one's nodes
     agent = MCTSAgent(iterations=160, seed=6, rollout_agent=RandomAgent(seed=6))
     ott = orc.OracleTT(18)
     zt = orc.zobrist_table(6)
@@ -564,3 +565,55 @@ def test_transposition_table_evicts_oldest_tenth_when_full():
             assert got["reward"] == want
     assert tt.get(keys[0]) is None and tt.get(keys[-1]) is not None
     ott.close()
+
+
+# ---- the kernel against the REFERENCE's own MCTSAgent (tests/golden/mcts.npz) ----------------------------------------------
+def _frontier_words(fr_bytes):
+    bits = np.zeros((4, 448), dtype=np.uint8)
+    bits[:, :400] = fr_bytes
+    return torch.from_numpy(np.packbits(bits.reshape(4, 7, 64), axis=-1, bitorder="little").view("<i8").reshape(1, 4, 7).copy()).cuda()
+
+
+def test_kernel_matches_reference_uct(golden_dir):
+    """Every search the unmodified reference recorded (uniform / HeuristicAgent rollouts, transposition table and a second
+    search of the same agent, dummy and fitted learned leaf evaluation, progressive bias, potential shaping, deep
+    late-game trees): the kernel returns the same expanded moves, visits, reward sums, best move, hits and table sizes."""
+    import uct_golden as U
+
+    z, names, seed = U.load(golden_dir)
+    zob = ZobristHash(seed=seed)
+    model = torch.from_numpy(z["model"].copy())
+    tables = {}
+    for tag in names:
+        sp = U.spec(tag)
+        name = tag.split("/")[1]
+        st, fr = U.root(z, tag)
+        root = dev.to_device(np.atleast_1d(st))
+        tt = None
+        if sp.get("tt"):
+            tt = tables[name] if sp.get("second") else tables.setdefault(name + tag.split("/")[0], TranspositionTable(max_size=1 << 15))
+            if not sp.get("second"):
+                tables[name] = tt
+        kw = dict(n_trees=1, seed=seed, tree_offset=1 if sp.get("second") else 0, tt=tt.device if tt else None,
+                  zobrist=zob if tt else None)
+        before = tt.device.stats() if tt else None
+        if sp["family"] == "plain":
+            eng = DeviceUCT(sp["iterations"], rollout_policy=sp.get("rollout_policy", 0), reward_mode=sp.get("reward_mode", 0), **kw)
+            res = eng.search(root, sp["iterations"])
+        elif sp["family"] == "learned":
+            eng = DeviceUCT(sp["iterations"], reward_mode=3, leaf_model=model, progressive_bias_weight=sp.get("bias_weight", 0.0), **kw)
+            res = eng.search(root, sp["iterations"], root_frontiers=_frontier_words(fr))
+        else:
+            eng = DeviceUCT(sp["iterations"], reward_mode=4, leaf_model=model, max_rollout_moves=6, shaping_weight=2.0,
+                            shaping_gamma=0.9, potential_mode="logit" if sp["potential_mode"] else "prob", **kw)
+            res = eng.search(root, sp["iterations"], root_frontiers=_frontier_words(fr))
+        assert int(res["status"][0]) == 0
+        n = int(res["counts"][0])
+        U.compare(z, tag, n, res["moves"][0].cpu().numpy(), res["visits"][0].cpu().numpy(), res["reward"][0].cpu().numpy(),
+                  scale=sp.get("scale", 1.0))
+        if tt is not None:
+            after = tt.device.stats()
+            want_hits, want_size = z[tag + "/tt"].tolist()
+            first = 0 if not sp.get("second") else int(z["tt1/" + name + "/tt"][0])
+            assert after["hits"] - before["hits"] == want_hits - first, tag
+            assert after["size"] == want_size, tag

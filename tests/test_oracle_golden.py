@@ -194,3 +194,43 @@ def test_snapshot_features_of_state_corpus_match_reference(golden_dir):
     states = np.load(os.path.join(golden_dir, "random_states.npz"))["states"].view(orc.STATE_DTYPE).reshape(-1)
     for i in range(len(states)):
         assert (orc.snapshot_features(states[i]) == z["state_features"][i]).all(), i
+
+
+# ---- UCT: the oracle's restatement against the reference's own MCTSAgent -------------------------------------------------
+def test_uct_matches_reference(golden_dir):
+    """mcts/mcts_agent.py:19-191, 304-582 executed by the reference (tests/golden/mcts.npz: uniform and HeuristicAgent
+    rollouts, transposition table incl. a second search of the same agent, dummy / fitted learned leaf evaluation,
+    progressive bias, potential shaping, deep late-game trees): identical expanded moves, visits, reward sums, best
+    move, transposition hits and table sizes."""
+    import uct_golden as U
+
+    z, names, seed = U.load(golden_dir)
+    zt = orc.zobrist_table(seed)
+    model = z["model"]
+    tables = {}
+    assert len(names) >= 40
+    for tag in names:
+        sp = U.spec(tag)
+        name = tag.split("/")[1]
+        st, fr = U.root(z, tag)
+        tt = None
+        if sp.get("tt"):
+            if sp.get("second"):
+                tt = tables[name]                                   # the first search's table (tt1/<name> ran before)
+            else:
+                tt = tables[name] = orc.OracleTT(16)
+        kw = dict(tree_id=1 if sp.get("second") else 0, tt=tt, zobrist=zt if tt else None)
+        if sp["family"] == "plain":
+            w = orc.mcts_search(st, sp["iterations"], seed=seed, rollout_policy=sp.get("rollout_policy", 0),
+                                reward_mode=sp.get("reward_mode", 0), **kw)
+        elif sp["family"] == "learned":
+            w = orc.mcts_search_learned(st, sp["iterations"], seed=seed, model=model, root_frontier=fr,
+                                        bias_weight=sp.get("bias_weight", 0.0), **kw)
+        else:
+            w = orc.mcts_search_shaped(st, sp["iterations"], seed=seed, model=model, root_frontier=fr, max_rollout_moves=6,
+                                       shaping_weight=2.0, shaping_gamma=0.9, potential_mode=sp["potential_mode"], **kw)
+        U.compare(z, tag, w["n_root"], w["moves"], w["visits"], w["reward"], scale=sp.get("scale", 1.0))
+        if tt is not None:
+            assert [tt.hits(), tt.size()] == z[tag + "/tt"].tolist(), tag
+    for t in tables.values():
+        t.close()
