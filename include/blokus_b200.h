@@ -269,7 +269,7 @@ typedef struct bk_mcts_params {
     double   shaping_weight;          /* reward_mode 4: w and gamma of the potential-based shaping term added to TRUNCATED */
     double   shaping_gamma;           /*   rollouts, w * (gamma * Phi(final) - Phi(initial)) (mcts_agent.py:486-551) */
     int32_t  potential_mode;          /* reward_mode 4: Phi = clamped win probability (0, "prob") or its logit (1, "logit") */
-    int32_t  reserved2;
+    int32_t  round_width;             /* bk_mcts_wide_search only: simulations planned per round (1..4096) */
 } bk_mcts_params;
 
 /* Bytes of device workspace per tree for a search of params->iterations_total iterations (host call). */
@@ -286,6 +286,23 @@ int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, const bk_mct
                    bk_tt* tt, const uint64_t* zobrist_table, void* workspace, int64_t workspace_bytes,
                    int max_root_moves, int32_t* root_visits, int64_t* root_reward, uint32_t* root_counts,
                    uint16_t* root_move_ids, uint32_t* status, void* stream);
+
+/* ---- K6: one tree over the whole GPU (csrc/mcts_wide.cuh) ------------------------------------------------------------
+ * The searches above run the reference's sequential iteration, one warp (or CTA) per tree.  A caller that needs ONE move
+ * fast -- FastMCTSAgent.think (agents/fast_mcts_agent.py:112), POST /think (engine-service/app.py:53-72), a single
+ * MCTSAgent.select_action (mcts/mcts_agent.py:304) -- uses this round-synchronous search instead: per round one warp
+ * plans params->round_width simulations by UCB1 walks with virtual loss (expanding in the reference's pop-last order), the
+ * whole grid executes them (expansion + Philox rollout of simulation number j + integer back-propagation), repeat.
+ * Deterministic: the result depends on (seed, tree_offset + k, round_width and the sequence of calls) only.
+ * params: iterations = simulations to add in THIS call, iterations_total = capacity, resume, max_depth, ucb_variant,
+ * reward_mode 0/1/2, rollout_policy, max_rollout_moves (<= 96), exploration, seed, tree_offset, round_width.  No
+ * transposition table and no learned modes here.  The call returns after the search has finished (it synchronises the
+ * stream to learn how many rounds were needed).  Outputs as bk_mcts_search, plus sims_done [n_trees]. */
+int64_t bk_mcts_wide_workspace_bytes(const bk_mcts_params* params);
+int bk_mcts_wide_search(const bk_state* roots, int n_roots, int n_trees, const bk_mcts_params* params,
+                        void* workspace, int64_t workspace_bytes, int max_root_moves, int32_t* root_visits,
+                        int64_t* root_reward, uint32_t* root_counts, uint16_t* root_move_ids, uint32_t* status,
+                        uint32_t* sims_done, void* stream);
 
 #ifdef __cplusplus
 }

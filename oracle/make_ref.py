@@ -54,8 +54,10 @@ TEST_MODULES = [
     "tests/test_bitboard_basic.py", "tests/test_frontier_basic.py", "tests/test_pieces_orientations.py",
     "tests/test_piece_shapes_match.py", "tests/test_engine.py", "tests/test_game_over_logic.py",
     "tests/test_game_result.py", "tests/test_fast_mcts_think.py", "tests/test_mcts_diagnostics.py",
-    "tests/test_telemetry.py", "tests/test_mobility_metrics.py",
+    "tests/test_telemetry.py",
 ]
+# (tests/test_mobility_metrics.py is left out: it opens a JSON fixture next to its own source file, which an archive
+#  of byte-code does not have; the formula it checks is pinned by tests/golden/mobility.npz instead)
 
 
 def _files():
@@ -86,6 +88,13 @@ def build(force: bool = False) -> str:
     shutil.rmtree(OUT, ignore_errors=True)
     os.makedirs(OUT, exist_ok=True)
     with tempfile.TemporaryDirectory() as tmp, zipfile.ZipFile(TREE, "w", zipfile.ZIP_DEFLATED) as z:
+        dirs = set()
+        for rel in files:                              # explicit directory entries: zipimport needs them to see the
+            parts = rel.split("/")[:-1]                # packages without __init__ (analytics, benchmarks) as namespaces
+            for i in range(1, len(parts) + 1):
+                dirs.add("/".join(parts[:i]) + "/")
+        for d in sorted(dirs):
+            z.writestr(zipfile.ZipInfo(d), b"")
         for rel in files:
             dst = os.path.join(tmp, "m.pyc")
             py_compile.compile(os.path.join(REF, rel), cfile=dst, dfile="reference:/" + rel, doraise=True,

@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
         L.orc_mcts_search_shaped.argtypes = [vp, vp, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, vp, i32, C.c_double, C.c_double,
                                              C.c_double, i32, vp, vp, vp]
         L.orc_mcts_search_batched.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, vp, vp, i32, i32, vp, vp, vp]
+        L.orc_mcts_wide.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, C.c_double, u64, u64, i32, vp, vp, vp, vp]
         L.orc_check_moves_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp]
         L.orc_check_playouts.argtypes = [u64, u64, i32, i32, i32, vp, vp, vp]
         L.orc_num_snapshot_features.restype = i32
@@ -410,6 +411,24 @@ def mcts_search_shaped(root: np.ndarray, iterations: int, seed: int, model: np.n
                                      int(max_root_moves), _ptr(md), int(max_turns), float(bias_weight), float(shaping_weight),
                                      float(shaping_gamma), int(potential_mode), _ptr(vis), _ptr(rew), _ptr(mov))
     return {"n_root": int(n), "visits": vis, "reward": rew, "moves": mov}
+
+
+def mcts_wide(root: np.ndarray, call_sims: Sequence[int], width: int, seed: int, tree_id: int = 0, max_rollout_moves: int = 50,
+              max_depth: int = 0, ucb_variant: int = 0, reward_mode: int = 0, rollout_policy: int = 0, exploration: float = 1.414,
+              max_root_moves: int = 2048):
+    """Sequential restatement of the round-synchronous search (csrc/mcts_wide.cuh): call_sims = simulations added by each
+    search call.  Returns dict(n_root, visits, reward, moves, rounds, sims, nodes)."""
+    st = np.ascontiguousarray(np.atleast_1d(root), dtype=STATE_DTYPE)
+    calls = np.ascontiguousarray(call_sims, dtype=np.int32)
+    vis = np.zeros(max_root_moves, dtype=np.int32)
+    rew = np.zeros(max_root_moves, dtype=np.int64)
+    mov = np.zeros(max_root_moves, dtype=np.uint16)
+    info = np.zeros(3, dtype=np.int32)
+    n = lib().orc_mcts_wide(_ptr(st), _ptr(calls), len(calls), int(width), int(max_rollout_moves), int(max_depth), int(ucb_variant),
+                            int(reward_mode), int(rollout_policy), float(exploration), int(seed), int(tree_id), int(max_root_moves),
+                            _ptr(vis), _ptr(rew), _ptr(mov), _ptr(info))
+    return {"n_root": int(n), "visits": vis, "reward": rew, "moves": mov, "rounds": int(info[0]), "sims": int(info[1]),
+            "nodes": int(info[2])}
 
 
 def check_moves_batch(states: np.ndarray, offsets: np.ndarray, ids: np.ndarray, naive: bool = False,

@@ -60,6 +60,8 @@ PROTOTYPES = {
     "bk_heuristic_scores_weighted": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bk_mcts_workspace_bytes": (_i64, [_vp]),
     "bk_mcts_search": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bk_mcts_wide_workspace_bytes": (_i64, [_vp]),
+    "bk_mcts_wide_search": (_i32, [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -74,7 +76,7 @@ class MctsParams(C.Structure):
         ("seed", C.c_uint64), ("tree_offset", C.c_uint64),
         ("leaf_model", C.c_void_p), ("root_frontiers", C.c_void_p), ("leaf_max_turns", C.c_int32), ("leaf_model_kind", C.c_int32),
         ("progressive_bias_weight", C.c_double), ("shaping_weight", C.c_double), ("shaping_gamma", C.c_double),
-        ("potential_mode", C.c_int32), ("reserved2", C.c_int32),
+        ("potential_mode", C.c_int32), ("round_width", C.c_int32),
     ]
 
 _lock = threading.Lock()

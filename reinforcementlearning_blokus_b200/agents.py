@@ -18,7 +18,7 @@ import torch
 
 from . import device as dev
 from .board import Board, Player
-from .mcts import DeviceUCT, _root_state
+from .mcts import DeviceUCT, WideUCT, _root_state
 from .move_generator import Move, get_shared_generator
 
 
@@ -135,7 +135,7 @@ class FastMCTSAgent:
 
     def __init__(self, iterations: int = 30, time_limit: float = 0.5, exploration_constant: float = 1.414,
                  seed: Optional[int] = None, enable_diagnostics: bool = False, diagnostics_sample_interval: int = 100,
-                 rollout_plies: int = 50, leaf_batch: int = 1):
+                 rollout_plies: int = 50, leaf_batch: int = 1, search_width: Optional[int] = None):
         self.iterations = iterations
         self.time_limit = time_limit
         self.exploration_constant = exploration_constant
@@ -147,7 +147,13 @@ class FastMCTSAgent:
         # GPU-batched leaf rollouts: `leaf_batch` warps roll out from every selected child at once (1 = the reference's
         # one simulation per iteration); `iterations` stays the budget in SIMULATIONS
         self.leaf_batch = max(1, min(16, int(leaf_batch)))
+        # One move at a time is what this agent is asked for, so by default the search is the round-synchronous one
+        # that spreads ONE tree over the whole GPU (mcts.WideUCT, csrc/mcts_wide.cuh): `search_width` simulations are
+        # planned per round (default: a quarter of the budget, 64..1024).  search_width=0 (or leaf_batch > 1) selects
+        # the sequential one-warp / one-CTA search instead.
+        self.search_width = search_width
         self._thinks = 0
+        self._wide_cache = None
 
     def select_action(self, board: Board, player: Player, legal_moves: List[Move]) -> Optional[Move]:
         return self.think(board, player, legal_moves, int(self.time_limit * 1000))["move"]
@@ -170,11 +176,25 @@ class FastMCTSAgent:
                                          "nodesEvaluated": 1, "maxDepthReached": 1,
                                          "topMoves": [dict(self._move_dict(m, 1, 0.0), q_value=0.0)]}}
         ordered = sorted(legal_moves, key=lambda m: m.to_id())      # rank <-> move (ascending id)
-        W = self.leaf_batch
-        total = max(1, -(-int(self.iterations) // W))            # device iterations of W simulations each
-        eng = DeviceUCT(total, n_trees=1, max_rollout_moves=self.rollout_plies, max_depth=1, ucb_variant=1,
-                        exploration=self.exploration_constant, seed=self.seed, tree_offset=self._thinks,
-                        reward_mode=1, leaf_batch=W)
+        wide = self.leaf_batch == 1 and (self.search_width is None or int(self.search_width) > 0)
+        if wide:
+            W = 1
+            total = max(1, int(self.iterations))
+            width = int(self.search_width) if self.search_width else max(64, min(1024, total // 4))
+            key = (total, width, self.exploration_constant, self.rollout_plies, self.seed)
+            if self._wide_cache is not None and self._wide_cache[0] == key:
+                eng = self._wide_cache[1]                         # workspace and tables are kept between moves
+                eng.p.tree_offset = self._thinks
+            else:
+                eng = WideUCT(total, width=width, max_rollout_moves=self.rollout_plies, max_depth=1, ucb_variant=1,
+                              exploration=self.exploration_constant, seed=self.seed, tree_offset=self._thinks, reward_mode=1)
+                self._wide_cache = (key, eng)
+        else:
+            W = self.leaf_batch
+            total = max(1, -(-int(self.iterations) // W))            # device iterations of W simulations each
+            eng = DeviceUCT(total, n_trees=1, max_rollout_moves=self.rollout_plies, max_depth=1, ucb_variant=1,
+                            exploration=self.exploration_constant, seed=self.seed, tree_offset=self._thinks,
+                            reward_mode=1, leaf_batch=W)
         self._thinks += 1
         root = _root_state(board, player)
         n_root = len(ordered)
@@ -183,8 +203,9 @@ class FastMCTSAgent:
         res = None
         interval = max(1, self.diagnostics_sample_interval // W)    # in device iterations
         next_sample = interval
+        chunk = max(self.CHUNK, 4 * width) if wide else self.CHUNK
         while done < total and (done == 0 or time.perf_counter() - start < budget_s):
-            n = min(self.CHUNK, total - done)
+            n = min(chunk, total - done)
             if self.enable_diagnostics:
                 n = min(n, next_sample - done)          # land exactly on the sampling points (:164-175)
             res = eng.search(root if done == 0 else None, n, resume=done > 0)

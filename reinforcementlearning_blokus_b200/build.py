@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libblokus_b200.so")
 SOURCES = ["blokus_b200.cu"]
-DEPS = ["blokus_b200.cu", "movegen_core.cuh", "orient_gen.cuh", "tables_gen.h", "mcts.cuh", "heuristic.cuh",
+DEPS = ["blokus_b200.cu", "movegen_core.cuh", "orient_gen.cuh", "tables_gen.h", "mcts.cuh", "mcts_wide.cuh", "heuristic.cuh",
         "snapshot.cuh", "probe.cu", os.path.join("..", "..", "include", "blokus_b200.h")]
 PROBE_LIB = os.path.join(HERE, "libbk_probe.so")
 STAMP = LIB + ".srchash"          # hash of the sources the library was built from (mtimes do not survive a copy)

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <vector>
 #include "movegen_core.cuh"
 
 #define BK_THREADS 256
@@ -773,6 +774,7 @@ k_heuristic_scores(const bk_state* __restrict__ states, const uint8_t* __restric
 
 #include "snapshot.cuh"
 #include "mcts.cuh"
+#include "mcts_wide.cuh"
 
 #define BK_HEUR_PLAYOUT_SMEM ((BK_PLAYOUT_THREADS / 32) * HEUR_SMEM_PER_WARP)
 static cudaError_t bk_init_policies_impl() {
@@ -1100,7 +1102,7 @@ extern "C" int bk_tt_evict_oldest(bk_tt* tt, uint64_t n_evict, void* stream) {
 
 extern "C" int64_t bk_mcts_workspace_bytes(const bk_mcts_params* params) {
     if (!params || params->iterations_total <= 0) return 0;
-    return (int64_t)mcts_layout(params->iterations_total, params->reward_mode >= 3).total;
+    return (int64_t)mcts_layout(params->iterations_total, params->reward_mode >= 3, params->max_depth).total;
 }
 
 extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, const bk_mcts_params* params, bk_tt* tt,
@@ -1115,7 +1117,7 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
             "bk_mcts_search: unknown rollout policy");
     REQUIRE(!tt || zobrist_table, "bk_mcts_search: a transposition table needs a Zobrist table");
     const bool learned = params->reward_mode >= 3;
-    const MctsLayout L = mcts_layout(params->iterations_total, learned);
+    const MctsLayout L = mcts_layout(params->iterations_total, learned, params->max_depth);
     if ((int64_t)L.total * n_trees > workspace_bytes) return fail(BK_ERR_CAPACITY, "%s", "bk_mcts_search: workspace too small");
     MctsTT t; t.keys = nullptr; t.rewards = nullptr; t.occupied = nullptr; t.stamps = nullptr; t.log2_slots = 0; t.zobrist = zobrist_table;
     if (tt) { REQUIRE_TT_DEVICE(tt); t.keys = tt->keys; t.rewards = tt->rewards; t.occupied = tt->occupied; t.stamps = tt->stamps; t.log2_slots = tt->log2_slots; }
@@ -1159,6 +1161,83 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
                 ws, params->resume, max_root_moves, root_visits, rr, root_counts, root_move_ids, status);
     }
     LAUNCH_CHECK();
+    return BK_OK;
+}
+
+extern "C" int64_t bk_mcts_wide_workspace_bytes(const bk_mcts_params* params) {
+    if (!params || params->iterations_total <= 0) return 0;
+    return (int64_t)wide_layout(params->iterations_total, params->round_width, params->max_depth).total;
+}
+
+extern "C" int bk_mcts_wide_search(const bk_state* roots, int n_roots, int n_trees, const bk_mcts_params* params,
+                                   void* workspace, int64_t workspace_bytes, int max_root_moves, int32_t* root_visits,
+                                   int64_t* root_reward, uint32_t* root_counts, uint16_t* root_move_ids, uint32_t* status,
+                                   uint32_t* sims_done, void* stream) {
+    REQUIRE_INIT();
+    REQUIRE(params && workspace && n_trees > 0 && max_root_moves >= 0 && sims_done, "bk_mcts_wide_search: bad argument");
+    REQUIRE(params->resume || (roots && n_roots > 0), "bk_mcts_wide_search: a fresh search needs roots");
+    REQUIRE(params->iterations >= 0 && params->iterations_total > 0 && params->iterations_total <= 1000000,
+            "bk_mcts_wide_search: iterations_total must be in [1, 1000000]");
+    REQUIRE(params->round_width >= 1 && params->round_width <= BK_WIDE_MAX_WIDTH, "bk_mcts_wide_search: round_width must be in [1, 4096]");
+    REQUIRE(params->rollout_policy == BK_POLICY_UNIFORM || params->rollout_policy == BK_POLICY_HEURISTIC,
+            "bk_mcts_wide_search: unknown rollout policy");
+    REQUIRE(params->reward_mode >= 0 && params->reward_mode <= 2, "bk_mcts_wide_search: reward_mode must be 0, 1 or 2 (integer rewards)");
+    REQUIRE(params->max_rollout_moves >= 0 && params->max_rollout_moves <= 96, "bk_mcts_wide_search: max_rollout_moves must be in [0, 96]");
+    const WideLayout L = wide_layout(params->iterations_total, params->round_width, params->max_depth);
+    if ((int64_t)L.total * n_trees > workspace_bytes) return fail(BK_ERR_CAPACITY, "%s", "bk_mcts_wide_search: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    const bool heur = params->rollout_policy == BK_POLICY_HEURISTIC;
+    // simulations finished before this call (a resumed search continues where the header says)
+    std::vector<uint32_t> done((size_t)n_trees, 0u);
+    uint32_t before = 0;
+    if (params->resume) {
+        k_wide_finish<<<n_trees, 32, 0, st>>>(n_trees, *params, ws, 0, nullptr, nullptr, nullptr, nullptr, nullptr, sims_done);
+        CUDA_TRY(cudaMemcpyAsync(done.data(), sims_done, sizeof(uint32_t) * (size_t)n_trees, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        before = done[0];
+        for (int t = 1; t < n_trees; t++) REQUIRE(done[t] == before, "bk_mcts_wide_search: trees of one workspace must be resumed together");
+    }
+    const long long target_ll = (long long)before + params->iterations;
+    REQUIRE(target_ll <= params->iterations_total, "bk_mcts_wide_search: search exceeds iterations_total");
+    const uint32_t target = (uint32_t)target_ll;
+    const int per_sm = heur ? BK_MCTS_HEUR_CTAS_PER_SM : BK_MCTS_CTAS_PER_SM;
+    int gx = (cx->sms * per_sm + n_trees - 1) / n_trees;
+    if (gx > (int)L.width) gx = (int)L.width;
+    if (gx < 1) gx = 1;
+    const dim3 wgrid((unsigned)gx, (unsigned)n_trees);
+    int fresh = params->resume ? 0 : 1;
+    uint32_t reached = before;
+    if (fresh) {
+        const unsigned tb = (L.table_len + 255u) / 256u;
+        k_wide_tables<<<dim3(tb < 64u ? tb : 64u, (unsigned)n_trees), 256, 0, st>>>(n_trees, *params, ws);
+    }
+    // enqueue the rounds this call needs, then look at the counters (a tree that ran out of workspace stops early)
+    for (int attempt = 0; attempt < 64 && reached < target; attempt++) {
+        const uint32_t left = target - reached;
+        int rounds = (int)((left + L.width - 1) / L.width);
+        for (int r = 0; r < rounds; r++) {
+            k_wide_plan<<<n_trees, 32, 0, st>>>(roots, n_roots > 0 ? n_roots : 1, n_trees, *params, ws, fresh, target);
+            fresh = 0;
+            if (heur) k_wide_work<1><<<wgrid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, st>>>(n_trees, *params, ws);
+            else k_wide_work<0><<<wgrid, BK_MCTS_THREADS, 0, st>>>(n_trees, *params, ws);
+        }
+        k_wide_finish<<<n_trees, 32, 0, st>>>(n_trees, *params, ws, max_root_moves, root_visits,
+                                              reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status, sims_done);
+        LAUNCH_CHECK();
+        CUDA_TRY(cudaMemcpyAsync(done.data(), sims_done, sizeof(uint32_t) * (size_t)n_trees, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        uint32_t lo = done[0];
+        for (int t = 1; t < n_trees; t++) lo = done[t] < lo ? done[t] : lo;
+        if (lo == reached) break;             // no progress: a tree ran out of workspace (status says so) or has no moves
+        reached = lo;
+    }
+    if (params->iterations == 0 || fresh) {    // nothing ran: still build the root (fresh) and report
+        if (fresh) k_wide_plan<<<n_trees, 32, 0, st>>>(roots, n_roots, n_trees, *params, ws, 1, 0u);
+        k_wide_finish<<<n_trees, 32, 0, st>>>(n_trees, *params, ws, max_root_moves, root_visits,
+                                              reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status, sims_done);
+        LAUNCH_CHECK();
+    }
     return BK_OK;
 }
 

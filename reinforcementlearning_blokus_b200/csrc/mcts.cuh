@@ -27,14 +27,17 @@ struct MctsLayout {            // byte offsets inside one tree's workspace slice
 
 __host__ __device__ inline size_t bk_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline MctsLayout mcts_layout(int iterations_total, bool with_frontier = false) {
+__host__ __device__ inline MctsLayout mcts_layout(int iterations_total, bool with_frontier = false, int max_depth = 0) {
     MctsLayout L;
-    const size_t T = (size_t)(iterations_total > 0 ? iterations_total : 1);
+    size_t T = (size_t)(iterations_total > 0 ? iterations_total : 1);
+    // a flat bandit (max_depth 1) never holds more than the root and one node per root move, however long it runs
+    if (max_depth == 1 && T > 2048) T = 2048;
     L.max_nodes = (uint32_t)(T + 1);
     // a node first expanded at iteration t can still gain at most T - t children, and never more than its number
     // of legal moves (largest list seen in 10^6 states: 1003); a tree that outgrows the pool reports status 1
     size_t pool = T * (T + 1) / 2 + 1;
     if (pool > T * 2048) pool = T * 2048;
+    if (max_depth == 1 && pool > 2049) pool = 2049;          // only the root has children
     L.pool_slots = (uint32_t)(pool > 0xFFFFFF00ull ? 0xFFFFFF00ull : pool);
     size_t o = 0;
     L.off_states = o;      o += (size_t)L.max_nodes * sizeof(bk_state);
@@ -125,7 +128,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
     const int W = BATCH ? (int)(blockDim.x >> 5) : 1;
     const bool lead = wib == 0;
     const uint32_t hs = (uint32_t)wib * HEUR_SMEM_PER_WARP;       // this warp's heuristic scratch
-    const MctsLayout L = mcts_layout(prm.iterations_total, LEARNED);
+    const MctsLayout L = mcts_layout(prm.iterations_total, LEARNED, prm.max_depth);
     // trees differ in cost (rollout lengths, tree depth): the next tree comes from a per-launch ticket counter so that
     // a batch larger than the resident CTAs has no idle tail; a tree's result depends on (seed, tree id) only
     for (;;) {

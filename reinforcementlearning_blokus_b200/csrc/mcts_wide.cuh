@@ -1,0 +1,364 @@
+// mcts_wide.cuh -- K6: ONE search tree spread over the whole GPU ("round-synchronous" tree-parallel UCT).
+//
+// k_mcts (mcts.cuh) runs the reference's sequential iteration, one warp (or one CTA) per tree: exact, but a single move of
+// 1,000 simulations keeps 1 of 148 SMs busy.  The callers that ask for ONE move at a time (FastMCTSAgent.think, POST /think,
+// the arena's gameplay agents) get this search instead.  It is a different -- deterministic, oracle-restated -- schedule
+// of the same ingredients (UCB1 selection, pop-last expansion in ascending move order, Philox rollouts, integer rewards):
+//
+//   round:  PLAN   one warp walks the tree `width` times.  A walk descends through fully expanded nodes by
+//                  u = W * (1/m) + (c * sqrt(L)) * (1/sqrt(n)),   W, m = reward sum and number of the child's FINISHED
+//                  simulations (0 while it has none), n = m + its pending ones ("watch the unobserved": pending
+//                  simulations shrink the exploration term, they do not count as losses),
+//                  L = ln(N) (or 2 ln N, fast_mcts_agent.py:52) with N = finished + pending of the parent; first maximum wins.
+//                  At a node with an untried move it claims the last one (mcts_agent.py:124) for a NEW child; at a terminal /
+//                  depth-limit node it schedules another simulation of that node.  A child created in this round is a LEAF
+//                  until the round ends (its state does not exist yet): a walk that reaches it schedules one more
+//                  simulation of it, which re-derives the child from (parent, rank) like the creating one.
+//           WORK   every scheduled simulation runs on its own warp anywhere on the GPU: build the new child's state
+//                  (re-derive the claimed move by rank, place it, count its legal moves), roll out with the Philox stream
+//                  of (seed, tree, simulation number), add visit and reward to the leaf and all its ancestors (integer
+//                  atomics: order-independent, hence deterministic).
+//   The result depends on (seed, tree id, width, the sequence of search calls) only -- not on the grid or the SM count.
+//
+// Restated sequentially in oracle/blokus_oracle.c (orc_mcts_wide); tests/test_gpu_mcts_wide.py compares bit for bit.
+#pragma once
+#include "mcts.cuh"
+
+#define BK_WIDE_NONE 0xFFFFFFFFu
+#define BK_WIDE_STREAM 0x57u        /* Philox stream id of the wide search's rollouts */
+#define BK_WIDE_MAX_WIDTH 4096
+#define BK_WIDE_PENDING 0xFFFFu     /* n_legal of a node whose state the current round is still building */
+
+struct WideLayout {
+    uint32_t max_nodes, pool_slots, width, table_len;
+    size_t off_states, off_reward, off_q, off_inv, off_parent, off_visits, off_virt, off_child_base, off_pool,
+           off_n_legal, off_n_expanded, off_move, off_item_leaf, off_item_parent, off_item_rank, off_header,
+           off_rcp, off_invtab, off_stab, total;
+};
+
+__host__ __device__ inline WideLayout wide_layout(int sims_total, int width, int max_depth) {
+    WideLayout L;
+    const size_t T = (size_t)(sims_total > 0 ? sims_total : 1);          // simulations (sizes the tables)
+    const size_t TN = (max_depth == 1 && T > 2048) ? 2048 : T;           // nodes: a flat bandit has at most 2048 + root
+    L.max_nodes = (uint32_t)(TN + 1);
+    size_t pool = TN * (TN + 1) / 2 + 1;
+    if (pool > TN * 2048) pool = TN * 2048;
+    if (max_depth == 1 && pool > 2049) pool = 2049;                      // only the root has children
+    L.pool_slots = (uint32_t)(pool > 0xFFFFFF00ull ? 0xFFFFFF00ull : pool);
+    L.width = (uint32_t)(width < 1 ? 1 : (width > BK_WIDE_MAX_WIDTH ? BK_WIDE_MAX_WIDTH : width));
+    size_t o = 0;
+    L.off_states = o;       o += (size_t)L.max_nodes * sizeof(bk_state);
+    L.off_reward = o;       o += (size_t)L.max_nodes * 8;
+    L.off_q = o;            o += (size_t)L.max_nodes * 8;
+    L.off_inv = o;          o += (size_t)L.max_nodes * 8;
+    L.table_len = (uint32_t)(T + L.width + 2);              // simulation counts 0 .. T + width (finished + pending)
+    L.off_rcp = o;          o += (size_t)L.table_len * 8;
+    L.off_invtab = o;       o += (size_t)L.table_len * 8;
+    L.off_stab = o;         o += (size_t)L.table_len * 8;
+    L.off_parent = o;       o += (size_t)L.max_nodes * 4;
+    L.off_visits = o;       o += (size_t)L.max_nodes * 4;
+    L.off_virt = o;         o += (size_t)L.max_nodes * 4;
+    L.off_child_base = o;   o += (size_t)L.max_nodes * 4;
+    L.off_pool = o;         o += (size_t)L.pool_slots * 4;
+    L.off_item_leaf = o;    o += (size_t)L.width * 4;
+    L.off_item_parent = o;  o += (size_t)L.width * 4;
+    L.off_n_legal = o;      o += (size_t)L.max_nodes * 2;
+    L.off_n_expanded = o;   o += (size_t)L.max_nodes * 2;
+    L.off_move = o;         o += (size_t)L.max_nodes * 2;
+    L.off_item_rank = o;    o += (size_t)L.width * 2;
+    o = bk_align_up(o, 8);
+    L.off_header = o;       o += 128;
+    L.total = bk_align_up(o, 256);
+    return L;
+}
+
+struct WideHeader {            // persistent between the launches of one search and between resumed calls
+    uint32_t n_nodes, pool_used, sims_done, round, round_items, ticket, sims_base, overflow, root_player;
+    int32_t root_score;
+    uint32_t inited;
+};
+static_assert(sizeof(WideHeader) <= 128, "WideHeader must fit its workspace slot");
+
+struct WideView {              // typed pointers into one tree's workspace slice
+    bk_state* states; long long* reward; double* q; double* inv; int32_t* parent; int32_t* visits; int32_t* virt;
+    uint32_t* child_base; uint32_t* pool; uint16_t* n_legal; uint16_t* n_expanded; uint16_t* move_of;
+    uint32_t* item_leaf; uint32_t* item_parent; uint16_t* item_rank; WideHeader* hdr;
+    const double* rcp; const double* invtab; const double* stab;
+};
+__device__ __forceinline__ WideView wide_view(unsigned char* base, const WideLayout& L) {
+    WideView v;
+    v.states = reinterpret_cast<bk_state*>(base + L.off_states);
+    v.reward = reinterpret_cast<long long*>(base + L.off_reward);
+    v.q = reinterpret_cast<double*>(base + L.off_q);
+    v.inv = reinterpret_cast<double*>(base + L.off_inv);
+    v.parent = reinterpret_cast<int32_t*>(base + L.off_parent);
+    v.visits = reinterpret_cast<int32_t*>(base + L.off_visits);
+    v.virt = reinterpret_cast<int32_t*>(base + L.off_virt);
+    v.child_base = reinterpret_cast<uint32_t*>(base + L.off_child_base);
+    v.pool = reinterpret_cast<uint32_t*>(base + L.off_pool);
+    v.n_legal = reinterpret_cast<uint16_t*>(base + L.off_n_legal);
+    v.n_expanded = reinterpret_cast<uint16_t*>(base + L.off_n_expanded);
+    v.move_of = reinterpret_cast<uint16_t*>(base + L.off_move);
+    v.item_leaf = reinterpret_cast<uint32_t*>(base + L.off_item_leaf);
+    v.item_parent = reinterpret_cast<uint32_t*>(base + L.off_item_parent);
+    v.item_rank = reinterpret_cast<uint16_t*>(base + L.off_item_rank);
+    v.hdr = reinterpret_cast<WideHeader*>(base + L.off_header);
+    v.rcp = reinterpret_cast<const double*>(base + L.off_rcp);
+    v.invtab = reinterpret_cast<const double*>(base + L.off_invtab);
+    v.stab = reinterpret_cast<const double*>(base + L.off_stab);
+    return v;
+}
+
+// Selection terms.  Everything expensive is tabulated once per search (k_wide_tables): for n = finished + pending
+// simulations of a child and N of its parent
+//     u = q + s[N] * inv[n],   q = (w * unit) * rcp[m],   rcp[m] = 1/m,   inv[n] = 1/sqrt(n),   s[N] = c * sqrt(L(N))
+// (m = finished simulations of the child, w their reward sum)
+// so that a walk is loads, one multiply-add per child and one warp arg-max.
+__global__ void __launch_bounds__(256)
+k_wide_tables(int n_trees, bk_mcts_params prm, unsigned char* __restrict__ workspace) {
+    const int tree = blockIdx.y;
+    if (tree >= n_trees) return;
+    const WideLayout L = wide_layout(prm.iterations_total, prm.round_width, prm.max_depth);
+    unsigned char* base = workspace + (size_t)tree * L.total;
+    double* rcp = reinterpret_cast<double*>(base + L.off_rcp);
+    double* inv = reinterpret_cast<double*>(base + L.off_invtab);
+    double* stab = reinterpret_cast<double*>(base + L.off_stab);
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < L.table_len; n += gridDim.x * blockDim.x) {
+        const double dn = (double)(n ? n : 1u);
+        rcp[n] = __ddiv_rn(1.0, dn);
+        inv[n] = __ddiv_rn(1.0, sqrt(dn));
+        stab[n] = __dmul_rn(prm.exploration, sqrt(__dmul_rn(log(dn), prm.ucb_variant ? 2.0 : 1.0)));
+    }
+}
+
+// 64-bit key whose unsigned order is the order of the doubles (finite values and infinities)
+__device__ __forceinline__ unsigned long long wide_key(double u) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(u);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// ---- PLAN: one warp per tree --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_params prm, unsigned char* __restrict__ workspace,
+            int fresh, uint32_t sims_target) {
+    const int lane = threadIdx.x & 31;
+    const int tree = blockIdx.x;
+    if (tree >= n_trees) return;
+    const WideLayout L = wide_layout(prm.iterations_total, prm.round_width, prm.max_depth);
+    const WideView V = wide_view(workspace + (size_t)tree * L.total, L);
+    WideHeader* hdr = V.hdr;
+    const double unit = prm.reward_mode == 2 ? 0.5 : 1.0;
+
+    if (fresh) {
+        WarpState s;
+        load_state(roots + (tree % n_roots), lane, s);
+        uint32_t A, C; make_masks(s, s.to_move, lane, A, C);
+        const Totals t0 = gen_totals<1>(A, C, sel4(s.used, s.to_move), lane);
+        store_state(V.states + 0, lane, s);
+        const int32_t rs = board_score_of(s, s.to_move);
+        if (lane == 0) {
+            V.parent[0] = -1; V.visits[0] = 0; V.virt[0] = 0; V.reward[0] = 0; V.child_base[0] = BK_WIDE_NONE;
+            V.n_legal[0] = (uint16_t)t0.n; V.n_expanded[0] = 0; V.move_of[0] = 0xFFFF; V.q[0] = 0.0; V.inv[0] = 0.0;
+            hdr->n_nodes = 1; hdr->pool_used = 0; hdr->sims_done = 0; hdr->round = 0; hdr->round_items = 0; hdr->ticket = 0;
+            hdr->sims_base = 0; hdr->overflow = 0; hdr->root_player = s.to_move; hdr->root_score = rs; hdr->inited = 1;
+        }
+        __syncwarp();
+    }
+    // ---- the previous round is complete: drop its pending counts and refresh the selection terms along its paths
+    const uint32_t prev = hdr->round_items;
+    for (uint32_t i = lane; i < prev; i += 32) {
+        for (int32_t v = (int32_t)V.item_leaf[i]; v > 0; v = V.parent[v]) {      // the root is nobody's child: no terms
+            const int32_t n = V.visits[v];
+            V.virt[v] = 0;
+            V.q[v] = __dmul_rn(__dmul_rn((double)V.reward[v], unit), V.rcp[n]);
+            V.inv[v] = V.invtab[n];
+        }
+    }
+    __syncwarp();
+    if (lane == 0) V.virt[0] = 0;
+    uint32_t n_nodes = hdr->n_nodes, pool_used = hdr->pool_used, overflow = hdr->overflow;
+    const uint32_t sims_done = hdr->sims_done;
+    const uint32_t room = sims_target > sims_done ? sims_target - sims_done : 0u;
+    const uint32_t want_items = overflow ? 0u : (room < L.width ? room : L.width);
+    uint32_t n_items = 0;
+    __syncwarp();
+    while (n_items < want_items) {
+        uint32_t node = 0, depth = 0;
+        bool may_expand = false, pending = false;
+        for (;;) {
+            const uint32_t nl = V.n_legal[node], ne = V.n_expanded[node];
+            if (nl == BK_WIDE_PENDING) { pending = true; break; }        // created in this round: a leaf until the round ends
+            may_expand = ne < nl && (prm.max_depth <= 0 || (int)depth < prm.max_depth);
+            if (may_expand || ne == 0) break;
+            const double s = V.stab[V.visits[node] + V.virt[node]];
+            const uint32_t cb = V.child_base[node];
+            double best = 0.0; uint32_t best_k = BK_WIDE_NONE;
+            for (uint32_t k = lane; k < ne; k += 32) {
+                const uint32_t ch = V.pool[cb + k];
+                const double u = __dadd_rn(V.q[ch], __dmul_rn(s, V.inv[ch]));
+                if (best_k == BK_WIDE_NONE || u > best) { best = u; best_k = k; }
+            }
+            // first maximum over the warp: largest key, then smallest k (three integer reductions)
+            const unsigned long long key = best_k == BK_WIDE_NONE ? 0ull : wide_key(best);
+            const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+            const uint32_t mh = __reduce_max_sync(BK_FULL, hi);
+            const uint32_t ml = __reduce_max_sync(BK_FULL, hi == mh ? lo : 0u);
+            const uint32_t kk = __reduce_min_sync(BK_FULL, (hi == mh && lo == ml) ? best_k : BK_WIDE_NONE);
+            node = V.pool[cb + kk];
+            depth++;
+        }
+        uint32_t leaf = node, par = BK_WIDE_NONE, rank = 0;
+        if (pending) {                                                   // another simulation of a child that is being built
+            par = (uint32_t)V.parent[node]; rank = V.move_of[node];      // (its rank sits in move_of until the work kernel runs)
+        } else if (may_expand) {
+            const uint32_t nl = V.n_legal[node], ne = V.n_expanded[node];
+            uint32_t cb = V.child_base[node];
+            if (cb == BK_WIDE_NONE) {
+                const uint32_t remaining = (uint32_t)prm.iterations_total - (sims_done + n_items);
+                const uint32_t want = nl < remaining ? nl : remaining;
+                cb = pool_used;
+                if (pool_used + want > L.pool_slots) overflow = 1;
+                pool_used += want;
+            }
+            if (n_nodes >= L.max_nodes) overflow = 1;
+            if (overflow) break;
+            const uint32_t child = n_nodes++;
+            rank = nl - 1 - ne;
+            if (lane == 0) {
+                V.child_base[node] = cb; V.pool[cb + ne] = child; V.n_expanded[node] = (uint16_t)(ne + 1);
+                V.parent[child] = (int32_t)node; V.visits[child] = 0; V.virt[child] = 0; V.reward[child] = 0;
+                V.child_base[child] = BK_WIDE_NONE; V.n_legal[child] = BK_WIDE_PENDING; V.n_expanded[child] = 0;
+                V.move_of[child] = (uint16_t)rank; V.q[child] = 0.0; V.inv[child] = 0.0;
+            }
+            leaf = child; par = node;
+        }
+        if (lane == 0) {
+            V.item_leaf[n_items] = leaf; V.item_parent[n_items] = par; V.item_rank[n_items] = (uint16_t)rank;
+            // one more pending simulation on every node of the path
+            for (int32_t v = (int32_t)leaf; v >= 0; v = V.parent[v]) {
+                const int32_t pend = V.virt[v] + 1;
+                V.virt[v] = pend;
+                if (v > 0) V.inv[v] = V.invtab[V.visits[v] + pend];     // Q stays the mean of the finished simulations
+            }
+        }
+        n_items++;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        hdr->n_nodes = n_nodes; hdr->pool_used = pool_used; hdr->overflow = overflow;
+        hdr->round = hdr->round + 1; hdr->round_items = n_items; hdr->ticket = 0; hdr->sims_base = sims_done;
+        hdr->sims_done = sims_done + n_items;
+    }
+}
+
+// ---- WORK: every warp of the grid takes simulations of tree blockIdx.y from the round's list ---------------------------
+template <int POLICY>
+__global__ void __launch_bounds__(BK_MCTS_THREADS, POLICY == 0 ? BK_MCTS_CTAS_PER_SM : BK_MCTS_HEUR_CTAS_PER_SM)
+k_wide_work(int n_trees, bk_mcts_params prm, unsigned char* __restrict__ workspace) {
+    extern __shared__ __align__(16) unsigned char heur_smem[];    // HEUR_SMEM_PER_WARP bytes when POLICY == 1
+    const int lane = threadIdx.x & 31;
+    const int tree = blockIdx.y;
+    if (tree >= n_trees) return;
+    const WideLayout L = wide_layout(prm.iterations_total, prm.round_width, prm.max_depth);
+    const WideView V = wide_view(workspace + (size_t)tree * L.total, L);
+    WideHeader* hdr = V.hdr;
+    const uint32_t n_items = hdr->round_items, sims_base = hdr->sims_base;
+    const uint32_t root_player = hdr->root_player;
+    const int32_t root_score = hdr->root_score;
+    const uint64_t tree_id = prm.tree_offset + (uint64_t)tree;
+    for (;;) {
+        uint32_t t0 = 0;
+        if (lane == 0) t0 = atomicAdd(&hdr->ticket, 1u);
+        const uint32_t i = uni(t0);
+        if (i >= n_items) break;
+        const uint32_t leaf = V.item_leaf[i], par = V.item_parent[i];
+        WarpState s;
+        if (par != BK_WIDE_NONE) {                                       // expansion (mcts_agent.py:113-145)
+            load_state(V.states + par, lane, s);
+            const uint32_t p = s.to_move;
+            uint32_t A, C; make_masks(s, p, lane, A, C);
+            const Totals tot = gen_totals<1>(A, C, sel4(s.used, p), lane);
+            int o, row, col;
+            const uint32_t id = select_move(tot, V.item_rank[i], A, C, lane, o, row, col);
+            place_move(s, p, o, row, col, lane);
+            uint32_t A2, C2; make_masks(s, s.to_move, lane, A2, C2);
+            const Totals tc = gen_totals<1>(A2, C2, sel4(s.used, s.to_move), lane);
+            store_state(V.states + leaf, lane, s);
+            if (lane == 0) { V.n_legal[leaf] = (uint16_t)tc.n; V.move_of[leaf] = (uint16_t)id; }
+        } else {
+            load_state(V.states + leaf, lane, s);
+        }
+        // ---- simulation (mcts_agent.py:470-554): simulation number j draws from its own Philox blocks
+        long long r = 0;
+        if (prm.reward_mode == 2) {
+            r = 1;                                                       // the dummy evaluator's 0.5, counted as one half
+        } else {
+            const uint32_t j = sims_base + i;
+            uint32_t draws = 0, blk_of = 0;
+            PhiloxBlock blk = philox_block(prm.seed, tree_id, j << 5, BK_WIDE_STREAM);
+            auto next_draw = [&]() -> uint32_t {
+                if ((draws >> 2) != blk_of) { blk_of = draws >> 2; blk = philox_block(prm.seed, tree_id, (j << 5) | blk_of, BK_WIDE_STREAM); }
+                return philox_word(blk, draws++);
+            };
+            const uint32_t me = prm.reward_mode ? root_player : s.to_move;
+            const int32_t before = prm.reward_mode ? root_score : board_score_of(s, me);
+            const int limit = prm.max_rollout_moves > 0 ? prm.max_rollout_moves : 96;    // a game has at most 84 placements
+            for (int ply = 0; ply < limit; ply++) {
+                const uint32_t p = s.to_move;
+                if (POLICY == BK_POLICY_HEURISTIC) {
+                    uint32_t id = 0, idx = 0;
+                    const uint32_t before_draws = draws;
+                    const uint32_t rnd = next_draw();
+                    if (heuristic_pick(s, p, rnd, 0u, lane, id, idx) == 0) { draws = before_draws; break; }
+                    place_move(s, p, (int)(id / 400u), (int)((id % 400u) / 20u), (int)(id % 20u), lane);
+                    continue;
+                }
+                uint32_t A, C; make_masks(s, p, lane, A, C);
+                const Totals tot = gen_totals<1>(A, C, sel4(s.used, p), lane);
+                if (tot.n == 0) break;
+                const uint32_t rnd = next_draw();
+                int o, row, col;
+                select_move(tot, __umulhi(rnd, tot.n), A, C, lane, o, row, col);
+                place_move(s, p, o, row, col, lane);
+            }
+            r = (long long)(board_score_of(s, me) - before);
+        }
+        // ---- back-propagation (mcts_agent.py:572-582) with integer atomics: any order gives the same sums
+        if (lane == 0) {
+            for (int32_t v = (int32_t)leaf; v >= 0; v = V.parent[v]) {
+                atomicAdd(&V.visits[v], 1);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&V.reward[v]), (unsigned long long)r);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- root statistics by ascending legal-move rank (child k of the root is rank n_legal-1-k) ----------------------------
+__global__ void __launch_bounds__(32)
+k_wide_finish(int n_trees, bk_mcts_params prm, unsigned char* __restrict__ workspace, int max_root_moves,
+              int32_t* __restrict__ out_visits, long long* __restrict__ out_reward, uint32_t* __restrict__ out_counts,
+              uint16_t* __restrict__ out_moves, uint32_t* __restrict__ out_status, uint32_t* __restrict__ out_done) {
+    const int lane = threadIdx.x & 31;
+    const int tree = blockIdx.x;
+    if (tree >= n_trees) return;
+    const WideLayout L = wide_layout(prm.iterations_total, prm.round_width, prm.max_depth);
+    const WideView V = wide_view(workspace + (size_t)tree * L.total, L);
+    const uint32_t nl0 = V.n_legal[0], ne0 = V.n_expanded[0], cb0 = V.child_base[0];
+    if (lane == 0) {
+        if (out_status) out_status[tree] = V.hdr->overflow;
+        if (out_counts) out_counts[tree] = nl0;
+        if (out_done) out_done[tree] = V.hdr->sims_done;
+    }
+    for (uint32_t rank = lane; rank < (uint32_t)max_root_moves; rank += 32) {
+        int32_t v = 0; long long w = 0; uint16_t m = 0xFFFF;
+        if (rank < nl0) {
+            const uint32_t k = nl0 - 1 - rank;
+            if (k < ne0) { const uint32_t ch = V.pool[cb0 + k]; v = V.visits[ch]; w = V.reward[ch]; m = V.move_of[ch]; }
+        }
+        const size_t oi = (size_t)tree * max_root_moves + rank;
+        if (out_visits) out_visits[oi] = v;
+        if (out_reward) out_reward[oi] = w;
+        if (out_moves) out_moves[oi] = m;
+    }
+}

@@ -148,7 +148,7 @@ class DeviceUCT:
                                  tt_tree_base=int(tt_tree_base), leaf_max_turns=int(leaf_max_turns), leaf_model_kind=int(leaf_model_kind),
                                  progressive_bias_weight=float(progressive_bias_weight) if int(reward_mode) >= 3 else 0.0,
                                  shaping_weight=float(shaping_weight), shaping_gamma=float(shaping_gamma),
-                                 potential_mode=1 if potential_mode == "logit" else 0, reserved2=0,
+                                 potential_mode=1 if potential_mode == "logit" else 0, round_width=0,
                                  exploration=float(exploration),
                                  seed=int(seed) & (2**64 - 1), tree_offset=int(tree_offset))
         self.n_trees = int(n_trees)
@@ -222,6 +222,65 @@ class DeviceUCT:
                 "status": self.status}
 
 
+class WideUCT:
+    """ONE tree (per root) spread over the whole GPU: the round-synchronous search of csrc/mcts_wide.cuh.
+
+    ``DeviceUCT`` runs the reference's sequential iteration with one warp per tree -- the right shape for thousands of
+    trees, 1 of 148 SMs for a single move.  ``WideUCT`` plans ``width`` simulations per round with UCB1 walks under
+    virtual loss and runs them on the whole grid; 1,000 simulations take a few rounds instead of 1,000 sequential
+    rollouts.  Deterministic in (seed, tree_offset, width, sequence of search calls); integer reward modes only
+    (0 = MCTSAgent's leaf-player gain, 1 = root-player gain of the flat bandit, 2 = constant leaf), no transposition
+    table.  ``search`` returns when the search has finished (the C call synchronises the stream)."""
+
+    def __init__(self, sims_total: int, width: int = 256, n_trees: int = 1, max_rollout_moves: int = 50, max_depth: int = 0,
+                 ucb_variant: int = 0, exploration: float = 1.414, seed: int = 0, tree_offset: int = 0, reward_mode: int = 0,
+                 rollout_policy: int = 0, max_root_moves: int = MAX_ROOT_MOVES):
+        if not torch.cuda.is_available():
+            raise _lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
+        if int(reward_mode) not in (0, 1, 2):
+            raise ValueError("the wide search backs rewards up with integer atomics: reward_mode must be 0, 1 or 2")
+        self.lib = _lib.init(torch.cuda.current_device())
+        self.p = _lib.MctsParams(iterations=0, iterations_total=int(sims_total), max_rollout_moves=int(max_rollout_moves),
+                                 rollout_policy=int(rollout_policy), max_depth=int(max_depth), ucb_variant=int(ucb_variant),
+                                 resume=0, reward_mode=int(reward_mode), leaf_batch=1, tt_tree_base=0,
+                                 exploration=float(exploration), seed=int(seed) & (2**64 - 1), tree_offset=int(tree_offset),
+                                 round_width=int(width))
+        self.n_trees, self.width, self.max_root_moves = int(n_trees), int(width), int(max_root_moves)
+        self.ws_bytes = int(self.lib.bk_mcts_wide_workspace_bytes(C.byref(self.p))) * self.n_trees
+        d = torch.device("cuda", torch.cuda.current_device())
+        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=d)
+        m = self.max_root_moves
+        self.visits = torch.zeros((self.n_trees, m), dtype=torch.int32, device=d)
+        self.reward = torch.zeros((self.n_trees, m), dtype=torch.int64, device=d)
+        self.moves = torch.zeros((self.n_trees, m), dtype=torch.uint16, device=d)
+        self.counts = torch.zeros(self.n_trees, dtype=torch.int32, device=d)
+        self.status = torch.zeros(self.n_trees, dtype=torch.int32, device=d)
+        self.done = torch.zeros(self.n_trees, dtype=torch.int32, device=d)
+        self.sims_done = 0
+        self._roots = None
+
+    def search(self, roots: Optional[torch.Tensor], sims: int, resume: bool = False) -> Dict[str, torch.Tensor]:
+        """Add `sims` simulations to every tree (fresh trees from `roots` unless resume); tree k searches roots[k % n]."""
+        if not resume:
+            if roots is None:
+                raise ValueError("roots required for a fresh search")
+            self._roots = roots.contiguous()
+            self.sims_done = 0
+        if self.sims_done + sims > self.p.iterations_total:
+            raise ValueError("search exceeds sims_total")
+        self.p.iterations = int(sims)
+        self.p.resume = 1 if resume else 0
+        _lib.check(self.lib.bk_mcts_wide_search(
+            self._roots.data_ptr(), self._roots.shape[0], self.n_trees, C.byref(self.p), self.workspace.data_ptr(), self.ws_bytes,
+            self.max_root_moves, self.visits.data_ptr(), self.reward.data_ptr(), self.counts.data_ptr(), self.moves.data_ptr(),
+            self.status.data_ptr(), self.done.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        rounds = -(-int(sims) // self.width) + 1
+        dev._count(2 * rounds + 1)
+        self.sims_done += int(sims)
+        return {"visits": self.visits, "reward": self.reward, "moves": self.moves, "counts": self.counts,
+                "status": self.status, "sims_done": self.done}
+
+
 def _root_state(board: Board, player: Player) -> torch.Tensor:
     s = board.to_packed()
     s["to_move"] = player.value - 1          # MCTSNode(board, player): the root player moves (mcts_agent.py:325)
@@ -268,7 +327,7 @@ class MCTSAgent:
                  progressive_bias_enabled: bool = False, progressive_bias_weight: float = 0.25,
                  potential_shaping_enabled: bool = False, potential_shaping_gamma: float = 1.0,
                  potential_shaping_weight: float = 1.0, potential_mode: str = "prob", max_rollout_moves: int = 50,
-                 num_trees: int = 1, leaf_batch: int = 1):
+                 num_trees: int = 1, leaf_batch: int = 1, search_width: int = 0):
         if potential_mode not in {"prob", "logit"}:
             raise ValueError("potential_mode must be either 'prob' or 'logit'.")
         if int(max_rollout_moves) <= 0:
@@ -313,6 +372,10 @@ class MCTSAgent:
         # leaf-batched rollouts: every iteration rolls out `leaf_batch` times from the new leaf (1 = the reference);
         # with the transposition table a batch caches the sum of its rewards
         self.leaf_batch = max(1, int(leaf_batch))
+        # search_width > 0: ONE tree over the whole GPU (WideUCT: `search_width` simulations planned per round, then run
+        # on the whole grid) instead of the reference's sequential iteration -- a different, deterministic schedule for
+        # callers that need one move fast; rollouts or the dummy leaf value only, the transposition table is not used
+        self.search_width = max(0, int(search_width))
         self.seed = 0 if seed is None else int(seed)
         self.move_generator = get_shared_generator()
         self.zobrist_hash = ZobristHash(seed=seed)
@@ -395,6 +458,24 @@ class MCTSAgent:
                 res = eng.search(None, chunk, resume=True)
                 done += chunk
                 torch.cuda.synchronize()
+        elif self.search_width > 0:
+            if self._requires_learned_evaluator and not self.learned_evaluator._is_dummy:
+                raise NotImplementedError("search_width > 0 runs rollouts or the dummy leaf value; fitted models run in the "
+                                          "sequential kernel (search_width=0)")
+            total = max(1, int(self.iterations))
+            key = ("wide", total, self.search_width, self.seed, self.exploration_constant, self.max_rollout_moves)
+            cached = getattr(self, "_wide_cache", None)
+            if cached is not None and cached[0] == key:
+                eng = cached[1]
+                eng.p.tree_offset = self._searches
+            else:
+                eng = WideUCT(total, width=self.search_width, max_rollout_moves=self.max_rollout_moves,
+                              exploration=self.exploration_constant, seed=self.seed, tree_offset=self._searches,
+                              reward_mode=2 if self.leaf_evaluation_enabled else 0, rollout_policy=self.rollout_policy)
+                self._wide_cache = (key, eng)
+            self._searches += 1
+            res = eng.search(root, total)
+            done = total
         else:
             eng = self._engine(max(1, int(self.iterations)))
             res = eng.search(root, int(self.iterations), root_frontiers=frontiers)

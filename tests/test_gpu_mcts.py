@@ -591,12 +591,13 @@ def test_kernel_matches_reference_uct(golden_dir):
         root = dev.to_device(np.atleast_1d(st))
         tt = None
         if sp.get("tt"):
-            tt = tables[name] if sp.get("second") else tables.setdefault(name + tag.split("/")[0], TranspositionTable(max_size=1 << 15))
-            if not sp.get("second"):
-                tables[name] = tt
-        kw = dict(n_trees=1, seed=seed, tree_offset=1 if sp.get("second") else 0, tt=tt.device if tt else None,
-                  zobrist=zob if tt else None)
-        before = tt.device.stats() if tt else None
+            if sp.get("second"):
+                tt = tables[name]                     # the table of the first search of this root (tt1/<name>)
+            else:
+                tt = tables[name] = TranspositionTable(max_size=1 << 15)
+        kw = dict(n_trees=1, seed=seed, tree_offset=1 if sp.get("second") else 0, tt=tt.device if tt is not None else None,
+                  zobrist=zob if tt is not None else None)              # (an empty table is falsy: it has __len__)
+        before = tt.device.stats() if tt is not None else None
         if sp["family"] == "plain":
             eng = DeviceUCT(sp["iterations"], rollout_policy=sp.get("rollout_policy", 0), reward_mode=sp.get("reward_mode", 0), **kw)
             res = eng.search(root, sp["iterations"])

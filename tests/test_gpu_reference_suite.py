@@ -37,4 +37,4 @@ def test_reference_tests_pass_with_the_device_path_installed(tmp_path):
     assert "reference generator class: B200LegalMoveGenerator; shared: B200LegalMoveGenerator" in res["output"], tail
     assert "FastMCTSAgent: B200FastMCTSAgent" in res["output"], tail
     assert res["returncode"] == 0 and res["failed"] == 0 and res["error"] == 0, tail
-    assert res["passed"] >= 110, tail
+    assert res["passed"] >= 105, tail
