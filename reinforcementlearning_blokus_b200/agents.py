@@ -135,7 +135,8 @@ class FastMCTSAgent:
 
     def __init__(self, iterations: int = 30, time_limit: float = 0.5, exploration_constant: float = 1.414,
                  seed: Optional[int] = None, enable_diagnostics: bool = False, diagnostics_sample_interval: int = 100,
-                 rollout_plies: int = 50, leaf_batch: int = 1, search_width: Optional[int] = None):
+                 rollout_plies: int = 50, leaf_batch: int = 1, search_width: Optional[int] = None,
+                 num_trees: Optional[int] = None):
         self.iterations = iterations
         self.time_limit = time_limit
         self.exploration_constant = exploration_constant
@@ -152,6 +153,10 @@ class FastMCTSAgent:
         # planned per round (default: a quarter of the budget, 64..1024).  search_width=0 (or leaf_batch > 1) selects
         # the sequential one-warp / one-CTA search instead.
         self.search_width = search_width
+        # root-parallel trees of the wide search: the simulation budget is split over `num_trees` bandits that are planned
+        # side by side (one planner each) and share the GPU for their rollouts; their root statistics are summed.
+        # Default: one tree per 625 simulations of the budget, at most 8 (5,000 simulations: 8 planners, ~1 ms).
+        self.num_trees = num_trees
         self._thinks = 0
         self._wide_cache = None
 
@@ -178,16 +183,16 @@ class FastMCTSAgent:
         ordered = sorted(legal_moves, key=lambda m: m.to_id())      # rank <-> move (ascending id)
         wide = self.leaf_batch == 1 and (self.search_width is None or int(self.search_width) > 0)
         if wide:
-            W = 1
-            total = max(1, int(self.iterations))
+            W = int(self.num_trees) if self.num_trees else max(1, min(8, int(self.iterations) // 625))    # trees
+            total = max(1, -(-int(self.iterations) // W))         # simulations per tree
             width = int(self.search_width) if self.search_width else max(64, min(1024, total // 4))
-            key = (total, width, self.exploration_constant, self.rollout_plies, self.seed)
+            key = (total, width, W, self.exploration_constant, self.rollout_plies, self.seed)
             if self._wide_cache is not None and self._wide_cache[0] == key:
                 eng = self._wide_cache[1]                         # workspace and tables are kept between moves
-                eng.p.tree_offset = self._thinks
+                eng.p.tree_offset = self._thinks * W
             else:
-                eng = WideUCT(total, width=width, max_rollout_moves=self.rollout_plies, max_depth=1, ucb_variant=1,
-                              exploration=self.exploration_constant, seed=self.seed, tree_offset=self._thinks, reward_mode=1)
+                eng = WideUCT(total, width=width, n_trees=W, max_rollout_moves=self.rollout_plies, max_depth=1, ucb_variant=1,
+                              exploration=self.exploration_constant, seed=self.seed, tree_offset=self._thinks * W, reward_mode=1)
                 self._wide_cache = (key, eng)
         else:
             W = self.leaf_batch
@@ -214,8 +219,8 @@ class FastMCTSAgent:
             if self.enable_diagnostics and done == next_sample:
                 next_sample += interval
                 if done < total:
-                    v = res["visits"][0, :n_root].cpu().numpy()
-                    w = res["reward"][0, :n_root].cpu().numpy()
+                    v = res["visits"][:, :n_root].sum(dim=0).cpu().numpy() if wide else res["visits"][0, :n_root].cpu().numpy()
+                    w = res["reward"][:, :n_root].sum(dim=0).cpu().numpy() if wide else res["reward"][0, :n_root].cpu().numpy()
                     b = int(np.argmax(v))
                     bm = ordered[b]
                     trace.append({"sim": done * W,
@@ -224,8 +229,12 @@ class FastMCTSAgent:
                                   "entropy": float(compute_policy_entropy([int(x) for x in v if x > 0]))})
         if int(res["counts"][0].item()) != n_root:
             raise dev._lib.BlokusB200Error("legal_moves does not match the device's legal-move set for this board")
-        visits = res["visits"][0, :n_root].cpu().numpy()
-        reward = res["reward"][0, :n_root].cpu().numpy()
+        if wide:                                                   # root statistics summed over the trees
+            visits = res["visits"][:, :n_root].sum(dim=0).cpu().numpy()
+            reward = res["reward"][:, :n_root].sum(dim=0).cpu().numpy()
+        else:
+            visits = res["visits"][0, :n_root].cpu().numpy()
+            reward = res["reward"][0, :n_root].cpu().numpy()
         expanded = [r for r in range(n_root) if visits[r] > 0]
         # children were created from the highest rank down; "first child with max visits" = highest rank on ties
         cand = [self._move_dict(ordered[r], visits[r], reward[r] / visits[r]) for r in sorted(expanded, reverse=True)]

@@ -83,6 +83,7 @@ __global__ void k_movegen_bitmap(const bk_state* __restrict__, const uint8_t* __
 
 static cudaError_t bk_init_policies_impl();
 static cudaError_t bk_init_policies() { return bk_init_policies_impl(); }
+static cudaError_t bk_init_wide();
 
 struct DeviceGuard {            // bk_init works on `device` and leaves the caller's current device as it found it
     int prev = -1;
@@ -110,6 +111,7 @@ extern "C" int bk_init(int device) {
     CUDA_TRY(cudaFuncSetAttribute(k_movegen_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_movegen_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_EMIT_SMEM_BYTES));
     CUDA_TRY(bk_init_policies());
+    CUDA_TRY(bk_init_wide());
     if (!cx->tickets) CUDA_TRY(cudaMalloc(&cx->tickets, BK_TICKETS * sizeof(unsigned int)));
     CUDA_TRY(cudaDeviceSynchronize());
     cx->inited = 1;
@@ -1164,6 +1166,10 @@ extern "C" int bk_mcts_search(const bk_state* roots, int n_roots, int n_trees, c
     return BK_OK;
 }
 
+static cudaError_t bk_init_wide() {
+    return cudaFuncSetAttribute(k_wide_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_WIDE_PLAN_SMEM);
+}
+
 extern "C" int64_t bk_mcts_wide_workspace_bytes(const bk_mcts_params* params) {
     if (!params || params->iterations_total <= 0) return 0;
     return (int64_t)wide_layout(params->iterations_total, params->round_width, params->max_depth).total;
@@ -1217,7 +1223,7 @@ extern "C" int bk_mcts_wide_search(const bk_state* roots, int n_roots, int n_tre
         const uint32_t left = target - reached;
         int rounds = (int)((left + L.width - 1) / L.width);
         for (int r = 0; r < rounds; r++) {
-            k_wide_plan<<<n_trees, 32, 0, st>>>(roots, n_roots > 0 ? n_roots : 1, n_trees, *params, ws, fresh, target);
+            k_wide_plan<<<n_trees, BK_WIDE_PLAN_THREADS, BK_WIDE_PLAN_SMEM, st>>>(roots, n_roots > 0 ? n_roots : 1, n_trees, *params, ws, fresh, target);
             fresh = 0;
             if (heur) k_wide_work<1><<<wgrid, BK_MCTS_THREADS, HEUR_SMEM_PER_WARP, st>>>(n_trees, *params, ws);
             else k_wide_work<0><<<wgrid, BK_MCTS_THREADS, 0, st>>>(n_trees, *params, ws);
@@ -1233,7 +1239,7 @@ extern "C" int bk_mcts_wide_search(const bk_state* roots, int n_roots, int n_tre
         reached = lo;
     }
     if (params->iterations == 0 || fresh) {    // nothing ran: still build the root (fresh) and report
-        if (fresh) k_wide_plan<<<n_trees, 32, 0, st>>>(roots, n_roots, n_trees, *params, ws, 1, 0u);
+        if (fresh) k_wide_plan<<<n_trees, BK_WIDE_PLAN_THREADS, BK_WIDE_PLAN_SMEM, st>>>(roots, n_roots, n_trees, *params, ws, 1, 0u);
         k_wide_finish<<<n_trees, 32, 0, st>>>(n_trees, *params, ws, max_root_moves, root_visits,
                                               reinterpret_cast<long long*>(root_reward), root_counts, root_move_ids, status, sims_done);
         LAUNCH_CHECK();

@@ -49,12 +49,12 @@ __host__ __device__ inline WideLayout wide_layout(int sims_total, int width, int
     size_t o = 0;
     L.off_states = o;       o += (size_t)L.max_nodes * sizeof(bk_state);
     L.off_reward = o;       o += (size_t)L.max_nodes * 8;
-    L.off_q = o;            o += (size_t)L.max_nodes * 8;
-    L.off_inv = o;          o += (size_t)L.max_nodes * 8;
     L.table_len = (uint32_t)(T + L.width + 2);              // simulation counts 0 .. T + width (finished + pending)
     L.off_rcp = o;          o += (size_t)L.table_len * 8;
-    L.off_invtab = o;       o += (size_t)L.table_len * 8;
-    L.off_stab = o;         o += (size_t)L.table_len * 8;
+    L.off_q = o;            o += (size_t)L.max_nodes * 4;
+    L.off_inv = o;          o += (size_t)L.max_nodes * 4;
+    L.off_invtab = o;       o += (size_t)L.table_len * 4;
+    L.off_stab = o;         o += (size_t)L.table_len * 4;
     L.off_parent = o;       o += (size_t)L.max_nodes * 4;
     L.off_visits = o;       o += (size_t)L.max_nodes * 4;
     L.off_virt = o;         o += (size_t)L.max_nodes * 4;
@@ -80,17 +80,17 @@ struct WideHeader {            // persistent between the launches of one search 
 static_assert(sizeof(WideHeader) <= 128, "WideHeader must fit its workspace slot");
 
 struct WideView {              // typed pointers into one tree's workspace slice
-    bk_state* states; long long* reward; double* q; double* inv; int32_t* parent; int32_t* visits; int32_t* virt;
+    bk_state* states; long long* reward; float* q; float* inv; int32_t* parent; int32_t* visits; int32_t* virt;
     uint32_t* child_base; uint32_t* pool; uint16_t* n_legal; uint16_t* n_expanded; uint16_t* move_of;
     uint32_t* item_leaf; uint32_t* item_parent; uint16_t* item_rank; WideHeader* hdr;
-    const double* rcp; const double* invtab; const double* stab;
+    const double* rcp; const float* invtab; const float* stab;
 };
 __device__ __forceinline__ WideView wide_view(unsigned char* base, const WideLayout& L) {
     WideView v;
     v.states = reinterpret_cast<bk_state*>(base + L.off_states);
     v.reward = reinterpret_cast<long long*>(base + L.off_reward);
-    v.q = reinterpret_cast<double*>(base + L.off_q);
-    v.inv = reinterpret_cast<double*>(base + L.off_inv);
+    v.q = reinterpret_cast<float*>(base + L.off_q);
+    v.inv = reinterpret_cast<float*>(base + L.off_inv);
     v.parent = reinterpret_cast<int32_t*>(base + L.off_parent);
     v.visits = reinterpret_cast<int32_t*>(base + L.off_visits);
     v.virt = reinterpret_cast<int32_t*>(base + L.off_virt);
@@ -104,16 +104,18 @@ __device__ __forceinline__ WideView wide_view(unsigned char* base, const WideLay
     v.item_rank = reinterpret_cast<uint16_t*>(base + L.off_item_rank);
     v.hdr = reinterpret_cast<WideHeader*>(base + L.off_header);
     v.rcp = reinterpret_cast<const double*>(base + L.off_rcp);
-    v.invtab = reinterpret_cast<const double*>(base + L.off_invtab);
-    v.stab = reinterpret_cast<const double*>(base + L.off_stab);
+    v.invtab = reinterpret_cast<const float*>(base + L.off_invtab);
+    v.stab = reinterpret_cast<const float*>(base + L.off_stab);
     return v;
 }
 
-// Selection terms.  Everything expensive is tabulated once per search (k_wide_tables): for n = finished + pending
-// simulations of a child and N of its parent
-//     u = q + s[N] * inv[n],   q = (w * unit) * rcp[m],   rcp[m] = 1/m,   inv[n] = 1/sqrt(n),   s[N] = c * sqrt(L(N))
-// (m = finished simulations of the child, w their reward sum)
-// so that a walk is loads, one multiply-add per child and one warp arg-max.
+// Selection terms.  Everything expensive is tabulated once per search (k_wide_tables) in float64 and rounded to float32:
+// for m finished simulations of a child with reward sum w, n = m + its pending ones and N of its parent
+//     u = fma(s[N], inv[n], q)   in float32,
+//     q = float((w * unit) * rcp[m]),  rcp[m] = 1/m,  inv[n] = float(1/sqrt(n)),  s[N] = float(c * sqrt(L(N)))
+// so that a walk is loads, one fused multiply-add per child and one warp arg-max.  (Single precision on purpose: the walks
+// are one long dependent chain on a single warp, and float64 arithmetic has several times the latency; q is a mean of
+// integer rewards below 2^7, 24 bits resolve differences far below the exploration term.)
 __global__ void __launch_bounds__(256)
 k_wide_tables(int n_trees, bk_mcts_params prm, unsigned char* __restrict__ workspace) {
     const int tree = blockIdx.y;
@@ -121,27 +123,56 @@ k_wide_tables(int n_trees, bk_mcts_params prm, unsigned char* __restrict__ works
     const WideLayout L = wide_layout(prm.iterations_total, prm.round_width, prm.max_depth);
     unsigned char* base = workspace + (size_t)tree * L.total;
     double* rcp = reinterpret_cast<double*>(base + L.off_rcp);
-    double* inv = reinterpret_cast<double*>(base + L.off_invtab);
-    double* stab = reinterpret_cast<double*>(base + L.off_stab);
+    float* inv = reinterpret_cast<float*>(base + L.off_invtab);
+    float* stab = reinterpret_cast<float*>(base + L.off_stab);
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < L.table_len; n += gridDim.x * blockDim.x) {
         const double dn = (double)(n ? n : 1u);
         rcp[n] = __ddiv_rn(1.0, dn);
-        inv[n] = __ddiv_rn(1.0, sqrt(dn));
-        stab[n] = __dmul_rn(prm.exploration, sqrt(__dmul_rn(log(dn), prm.ucb_variant ? 2.0 : 1.0)));
+        inv[n] = __double2float_rn(__ddiv_rn(1.0, sqrt(dn)));
+        stab[n] = __double2float_rn(__dmul_rn(prm.exploration, sqrt(__dmul_rn(log(dn), prm.ucb_variant ? 2.0 : 1.0))));
     }
 }
 
-// 64-bit key whose unsigned order is the order of the doubles (finite values and infinities)
-__device__ __forceinline__ unsigned long long wide_key(double u) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(u);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+// 32-bit key whose unsigned order is the order of the floats (finite values and infinities; never 0)
+__device__ __forceinline__ uint32_t wide_key(float u) {
+    const uint32_t b = __float_as_uint(u);
+    return (b >> 31) ? ~b : (b | 0x80000000u);
 }
 
-// ---- PLAN: one warp per tree --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+// ---- PLAN: one CTA per tree ----------------------------------------------------------------------------------------------
+// The walks of a round are one dependent chain (each walk sees the pending counts of the walks before it), so the time of
+// a round is (number of walks) x (latency of one walk).  Two things keep that latency short:
+//   * a shared-memory image of the first BK_WIDE_NC nodes -- the root, all its children (created first: nodes 1..n) and the
+//     earliest grandchildren; a flat bandit never has more -- loaded at the start of the round; pending counts and
+//     exploration terms of these nodes are written back in one sweep at the end; later nodes are read from global memory;
+//   * BK_WIDE_PLAN_THREADS threads score the children of a node together (one child per thread up to 256 children; a node
+//     with few children is scored by every warp redundantly, which needs no exchange), two warp reductions + one barrier
+//     + two warp reductions give the first maximum; everything after the choice (claiming the move, the item, the pending
+//     counts along the path) is warp 0's work, and one barrier ends the walk.
+#define BK_WIDE_NC 2049
+// Measured on B200 (profiles/r02_wide_latency.md): one warp 0.65 us per walk; eight warps sharing the scoring 0.8 us -- the
+// two barriers per walk cost more than the shorter scoring loop saves, the walk is latency-bound outside the loop.  So the
+// planner is ONE warp (the cooperative path stays compiled for wider CTAs); callers that want more than one planner run
+// several root-parallel trees side by side (n_trees > 1: one planner CTA each, the work grid shared).
+#define BK_WIDE_PLAN_THREADS 32
+#define BK_WIDE_PLAN_WARPS (BK_WIDE_PLAN_THREADS / 32)
+#define BK_WIDE_SOLO (BK_WIDE_PLAN_THREADS == 32 ? 0xFFFFFFFFu : 64u)   /* children up to which every warp scores all of them */
+struct WideSmem {
+    float q[BK_WIDE_NC], inv[BK_WIDE_NC];
+    int32_t vis[BK_WIDE_NC], virt[BK_WIDE_NC], par[BK_WIDE_NC];
+    uint32_t cb[BK_WIDE_NC];
+    uint16_t nl[BK_WIDE_NC], ne[BK_WIDE_NC], mv[BK_WIDE_NC];
+    uint32_t cand_key[2][BK_WIDE_PLAN_WARPS], cand_k[2][BK_WIDE_PLAN_WARPS];
+    uint32_t n_nodes, pool_used, overflow, stop;
+};
+#define BK_WIDE_PLAN_SMEM ((int)sizeof(WideSmem))
+
+__global__ void __launch_bounds__(BK_WIDE_PLAN_THREADS)
 k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mcts_params prm, unsigned char* __restrict__ workspace,
             int fresh, uint32_t sims_target) {
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) unsigned char plan_smem[];
+    WideSmem& S = *reinterpret_cast<WideSmem*>(plan_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tree = blockIdx.x;
     if (tree >= n_trees) return;
     const WideLayout L = wide_layout(prm.iterations_total, prm.round_width, prm.max_depth);
@@ -150,101 +181,167 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
     const double unit = prm.reward_mode == 2 ? 0.5 : 1.0;
 
     if (fresh) {
-        WarpState s;
-        load_state(roots + (tree % n_roots), lane, s);
-        uint32_t A, C; make_masks(s, s.to_move, lane, A, C);
-        const Totals t0 = gen_totals<1>(A, C, sel4(s.used, s.to_move), lane);
-        store_state(V.states + 0, lane, s);
-        const int32_t rs = board_score_of(s, s.to_move);
-        if (lane == 0) {
-            V.parent[0] = -1; V.visits[0] = 0; V.virt[0] = 0; V.reward[0] = 0; V.child_base[0] = BK_WIDE_NONE;
-            V.n_legal[0] = (uint16_t)t0.n; V.n_expanded[0] = 0; V.move_of[0] = 0xFFFF; V.q[0] = 0.0; V.inv[0] = 0.0;
-            hdr->n_nodes = 1; hdr->pool_used = 0; hdr->sims_done = 0; hdr->round = 0; hdr->round_items = 0; hdr->ticket = 0;
-            hdr->sims_base = 0; hdr->overflow = 0; hdr->root_player = s.to_move; hdr->root_score = rs; hdr->inited = 1;
+        if (warp == 0) {
+            WarpState s;
+            load_state(roots + (tree % n_roots), lane, s);
+            uint32_t A, C; make_masks(s, s.to_move, lane, A, C);
+            const Totals t0 = gen_totals<BK_MCTS_MAX_WARPS>(A, C, sel4(s.used, s.to_move), lane);
+            store_state(V.states + 0, lane, s);
+            const int32_t rs = board_score_of(s, s.to_move);
+            if (lane == 0) {
+                V.parent[0] = -1; V.visits[0] = 0; V.virt[0] = 0; V.reward[0] = 0; V.child_base[0] = BK_WIDE_NONE;
+                V.n_legal[0] = (uint16_t)t0.n; V.n_expanded[0] = 0; V.move_of[0] = 0xFFFF; V.q[0] = 0.0f; V.inv[0] = 0.0f;
+                hdr->n_nodes = 1; hdr->pool_used = 0; hdr->sims_done = 0; hdr->round = 0; hdr->round_items = 0; hdr->ticket = 0;
+                hdr->sims_base = 0; hdr->overflow = 0; hdr->root_player = s.to_move; hdr->root_score = rs; hdr->inited = 1;
+            }
         }
-        __syncwarp();
+        __threadfence_block();
+        __syncthreads();
     }
+    uint32_t n_nodes = hdr->n_nodes, pool_used = hdr->pool_used, overflow = hdr->overflow;
     // ---- the previous round is complete: drop its pending counts and refresh the selection terms along its paths
     const uint32_t prev = hdr->round_items;
-    for (uint32_t i = lane; i < prev; i += 32) {
+    for (uint32_t i = tid; i < prev; i += BK_WIDE_PLAN_THREADS) {
         for (int32_t v = (int32_t)V.item_leaf[i]; v > 0; v = V.parent[v]) {      // the root is nobody's child: no terms
             const int32_t n = V.visits[v];
             V.virt[v] = 0;
-            V.q[v] = __dmul_rn(__dmul_rn((double)V.reward[v], unit), V.rcp[n]);
+            V.q[v] = __double2float_rn(__dmul_rn(__dmul_rn((double)V.reward[v], unit), V.rcp[n]));
             V.inv[v] = V.invtab[n];
         }
     }
-    __syncwarp();
-    if (lane == 0) V.virt[0] = 0;
-    uint32_t n_nodes = hdr->n_nodes, pool_used = hdr->pool_used, overflow = hdr->overflow;
+    __threadfence_block();
+    __syncthreads();
+    // ---- shared-memory image of the first nodes
+    const uint32_t nc = n_nodes < BK_WIDE_NC ? n_nodes : BK_WIDE_NC;
+    for (uint32_t v = tid; v < nc; v += BK_WIDE_PLAN_THREADS) {
+        S.q[v] = V.q[v]; S.inv[v] = V.inv[v]; S.vis[v] = V.visits[v]; S.virt[v] = 0; S.par[v] = V.parent[v];
+        S.cb[v] = V.child_base[v]; S.nl[v] = V.n_legal[v]; S.ne[v] = V.n_expanded[v]; S.mv[v] = V.move_of[v];
+    }
+    if (tid == 0) { S.n_nodes = n_nodes; S.pool_used = pool_used; S.overflow = overflow; S.stop = 0; }
+    __syncthreads();
     const uint32_t sims_done = hdr->sims_done;
     const uint32_t room = sims_target > sims_done ? sims_target - sims_done : 0u;
     const uint32_t want_items = overflow ? 0u : (room < L.width ? room : L.width);
-    uint32_t n_items = 0;
-    __syncwarp();
-    while (n_items < want_items) {
+    uint32_t n_items = 0, buf = 0;
+    for (; n_items < want_items; n_items++) {
+        // ---- descent: all threads, uniform control flow
         uint32_t node = 0, depth = 0;
         bool may_expand = false, pending = false;
         for (;;) {
-            const uint32_t nl = V.n_legal[node], ne = V.n_expanded[node];
+            const bool in = node < BK_WIDE_NC;
+            const uint32_t nl = in ? S.nl[node] : V.n_legal[node], ne = in ? S.ne[node] : V.n_expanded[node];
             if (nl == BK_WIDE_PENDING) { pending = true; break; }        // created in this round: a leaf until the round ends
             may_expand = ne < nl && (prm.max_depth <= 0 || (int)depth < prm.max_depth);
             if (may_expand || ne == 0) break;
-            const double s = V.stab[V.visits[node] + V.virt[node]];
-            const uint32_t cb = V.child_base[node];
-            double best = 0.0; uint32_t best_k = BK_WIDE_NONE;
-            for (uint32_t k = lane; k < ne; k += 32) {
-                const uint32_t ch = V.pool[cb + k];
-                const double u = __dadd_rn(V.q[ch], __dmul_rn(s, V.inv[ch]));
-                if (best_k == BK_WIDE_NONE || u > best) { best = u; best_k = k; }
+            const int32_t big_n = in ? S.vis[node] + S.virt[node] : V.visits[node] + V.virt[node];
+            const float s = __ldg(V.stab + big_n);
+            const uint32_t cb = in ? S.cb[node] : V.child_base[node];
+            const bool solo = ne <= BK_WIDE_SOLO;                        // every warp scores all children: no exchange
+            const uint32_t first = solo ? (uint32_t)lane : (uint32_t)tid, step = solo ? 32u : (uint32_t)BK_WIDE_PLAN_THREADS;
+            float best = 0.0f; uint32_t best_k = BK_WIDE_NONE;
+            if (node == 0) {
+                // the root's children are nodes 1 .. ne in creation order (nothing else is created while it has untried moves)
+                for (uint32_t k = first; k < ne; k += step) {
+                    const float u = __fmaf_rn(s, S.inv[k + 1], S.q[k + 1]);
+                    if (best_k == BK_WIDE_NONE || u > best) { best = u; best_k = k; }
+                }
+            } else {
+                for (uint32_t k = first; k < ne; k += step) {
+                    const uint32_t ch = V.pool[cb + k];
+                    const bool cin = ch < BK_WIDE_NC;
+                    const float u = __fmaf_rn(s, cin ? S.inv[ch] : V.inv[ch], cin ? S.q[ch] : V.q[ch]);
+                    if (best_k == BK_WIDE_NONE || u > best) { best = u; best_k = k; }
+                }
             }
-            // first maximum over the warp: largest key, then smallest k (three integer reductions)
-            const unsigned long long key = best_k == BK_WIDE_NONE ? 0ull : wide_key(best);
-            const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-            const uint32_t mh = __reduce_max_sync(BK_FULL, hi);
-            const uint32_t ml = __reduce_max_sync(BK_FULL, hi == mh ? lo : 0u);
-            const uint32_t kk = __reduce_min_sync(BK_FULL, (hi == mh && lo == ml) ? best_k : BK_WIDE_NONE);
-            node = V.pool[cb + kk];
+            // first maximum: largest key, then smallest k
+            uint32_t key = best_k == BK_WIDE_NONE ? 0u : wide_key(best);
+            uint32_t mk = __reduce_max_sync(BK_FULL, key);
+            uint32_t kk = __reduce_min_sync(BK_FULL, key == mk ? best_k : BK_WIDE_NONE);
+            if (!solo) {
+                if (lane == 0) { S.cand_key[buf][warp] = mk; S.cand_k[buf][warp] = kk; }
+                __syncthreads();
+                key = lane < BK_WIDE_PLAN_WARPS ? S.cand_key[buf][lane] : 0u;
+                const uint32_t ck = lane < BK_WIDE_PLAN_WARPS ? S.cand_k[buf][lane] : BK_WIDE_NONE;
+                mk = __reduce_max_sync(BK_FULL, key);
+                kk = __reduce_min_sync(BK_FULL, key == mk ? ck : BK_WIDE_NONE);
+                buf ^= 1u;
+            }
+            node = node == 0 ? kk + 1 : V.pool[cb + kk];
             depth++;
         }
-        uint32_t leaf = node, par = BK_WIDE_NONE, rank = 0;
-        if (pending) {                                                   // another simulation of a child that is being built
-            par = (uint32_t)V.parent[node]; rank = V.move_of[node];      // (its rank sits in move_of until the work kernel runs)
-        } else if (may_expand) {
-            const uint32_t nl = V.n_legal[node], ne = V.n_expanded[node];
-            uint32_t cb = V.child_base[node];
-            if (cb == BK_WIDE_NONE) {
-                const uint32_t remaining = (uint32_t)prm.iterations_total - (sims_done + n_items);
-                const uint32_t want = nl < remaining ? nl : remaining;
-                cb = pool_used;
-                if (pool_used + want > L.pool_slots) overflow = 1;
-                pool_used += want;
+        // ---- the rest of the walk is warp 0's
+        if (warp == 0) {
+            uint32_t leaf = node, par = BK_WIDE_NONE, rank = 0;
+            bool stop = false;
+            if (pending) {                                               // another simulation of a child that is being built
+                const bool in = node < BK_WIDE_NC;                       // (its rank sits in move_of until the work kernel runs)
+                par = (uint32_t)(in ? S.par[node] : V.parent[node]); rank = in ? S.mv[node] : V.move_of[node];
+            } else if (may_expand) {
+                const bool in = node < BK_WIDE_NC;
+                const uint32_t nl = in ? S.nl[node] : V.n_legal[node], ne = in ? S.ne[node] : V.n_expanded[node];
+                uint32_t cb = in ? S.cb[node] : V.child_base[node];
+                if (cb == BK_WIDE_NONE) {
+                    const uint32_t remaining = (uint32_t)prm.iterations_total - (sims_done + n_items);
+                    const uint32_t want = nl < remaining ? nl : remaining;
+                    cb = pool_used;
+                    if (pool_used + want > L.pool_slots) overflow = 1;
+                    pool_used += want;
+                }
+                if (n_nodes >= L.max_nodes) overflow = 1;
+                if (overflow) stop = true;
+                else {
+                    const uint32_t child = n_nodes++;
+                    rank = nl - 1 - ne;
+                    __syncwarp();                                        // every lane has read ne / cb before they change
+                    if (lane == 0) {
+                        V.child_base[node] = cb; V.pool[cb + ne] = child; V.n_expanded[node] = (uint16_t)(ne + 1);
+                        V.parent[child] = (int32_t)node; V.visits[child] = 0; V.virt[child] = 0; V.reward[child] = 0;
+                        V.child_base[child] = BK_WIDE_NONE; V.n_legal[child] = BK_WIDE_PENDING; V.n_expanded[child] = 0;
+                        V.move_of[child] = (uint16_t)rank; V.q[child] = 0.0f; V.inv[child] = 0.0f;
+                        if (in) { S.cb[node] = cb; S.ne[node] = (uint16_t)(ne + 1); }
+                        if (child < BK_WIDE_NC) {
+                            S.par[child] = (int32_t)node; S.vis[child] = 0; S.virt[child] = 0; S.cb[child] = BK_WIDE_NONE;
+                            S.nl[child] = BK_WIDE_PENDING; S.ne[child] = 0; S.mv[child] = (uint16_t)rank; S.q[child] = 0.0f; S.inv[child] = 0.0f;
+                        }
+                    }
+                    leaf = child; par = node;
+                    __syncwarp();
+                }
             }
-            if (n_nodes >= L.max_nodes) overflow = 1;
-            if (overflow) break;
-            const uint32_t child = n_nodes++;
-            rank = nl - 1 - ne;
-            if (lane == 0) {
-                V.child_base[node] = cb; V.pool[cb + ne] = child; V.n_expanded[node] = (uint16_t)(ne + 1);
-                V.parent[child] = (int32_t)node; V.visits[child] = 0; V.virt[child] = 0; V.reward[child] = 0;
-                V.child_base[child] = BK_WIDE_NONE; V.n_legal[child] = BK_WIDE_PENDING; V.n_expanded[child] = 0;
-                V.move_of[child] = (uint16_t)rank; V.q[child] = 0.0; V.inv[child] = 0.0;
+            if (!stop) {
+                if (lane == 0) { V.item_leaf[n_items] = leaf; V.item_parent[n_items] = par; V.item_rank[n_items] = (uint16_t)rank; }
+                // one more pending simulation on every node of the path; Q stays the mean of the finished simulations
+                for (int32_t v = (int32_t)leaf; v >= 0;) {
+                    if (v < BK_WIDE_NC) {
+                        const int32_t pend = S.virt[v] + 1;
+                        const float iv = __ldg(V.invtab + S.vis[v] + pend);
+                        const int32_t up = S.par[v];
+                        __syncwarp();
+                        if (lane == 0) { S.virt[v] = pend; if (v > 0) S.inv[v] = iv; }
+                        v = up;
+                    } else {
+                        const int32_t pend = V.virt[v] + 1;
+                        const float iv = __ldg(V.invtab + V.visits[v] + pend);
+                        const int32_t up = V.parent[v];
+                        __syncwarp();
+                        if (lane == 0) { V.virt[v] = pend; V.inv[v] = iv; }
+                        v = up;
+                    }
+                }
             }
-            leaf = child; par = node;
+            if (lane == 0) { S.n_nodes = n_nodes; S.pool_used = pool_used; S.overflow = overflow; S.stop = stop ? 1u : 0u; }
         }
-        if (lane == 0) {
-            V.item_leaf[n_items] = leaf; V.item_parent[n_items] = par; V.item_rank[n_items] = (uint16_t)rank;
-            // one more pending simulation on every node of the path
-            for (int32_t v = (int32_t)leaf; v >= 0; v = V.parent[v]) {
-                const int32_t pend = V.virt[v] + 1;
-                V.virt[v] = pend;
-                if (v > 0) V.inv[v] = V.invtab[V.visits[v] + pend];     // Q stays the mean of the finished simulations
-            }
-        }
-        n_items++;
-        __syncwarp();
+        __threadfence_block();
+        __syncthreads();
+        n_nodes = S.n_nodes; pool_used = S.pool_used; overflow = S.overflow;
+        if (S.stop) break;
     }
-    if (lane == 0) {
+    // ---- write the round's pending counts and exploration terms of the imaged nodes back
+    {
+        const uint32_t nc2 = n_nodes < BK_WIDE_NC ? n_nodes : BK_WIDE_NC;
+        for (uint32_t v = tid; v < nc2; v += BK_WIDE_PLAN_THREADS) { V.virt[v] = S.virt[v]; if (v > 0) V.inv[v] = S.inv[v]; }
+    }
+    if (tid == 0) {
         hdr->n_nodes = n_nodes; hdr->pool_used = pool_used; hdr->overflow = overflow;
         hdr->round = hdr->round + 1; hdr->round_items = n_items; hdr->ticket = 0; hdr->sims_base = sims_done;
         hdr->sims_done = sims_done + n_items;

@@ -35,10 +35,13 @@ if DEVICE:
     FastMCTSAgent(iterations=64, time_limit=0.05).think(_g.board, _p, _g.get_legal_moves(_p), 20)
 
 
-def pytest_report_header(config):
-    import engine.move_generator as mg
-    return ["reference generator class: %s; shared: %s" % (mg.LegalMoveGenerator.__name__, type(mg.get_shared_generator()).__name__),
-            "FastMCTSAgent: %s" % __import__("agents.fast_mcts_agent").fast_mcts_agent.FastMCTSAgent.__name__]
+import engine.move_generator as _mg
+import engine.board as _eb
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "install_report.txt"), "w") as _f:
+    _f.write("generator class: %s; shared: %s; FastMCTSAgent: %s; MCTSAgent: %s; Board.can_place_piece: %s" % (
+        _mg.LegalMoveGenerator.__name__, type(_mg.get_shared_generator()).__name__,
+        __import__("agents.fast_mcts_agent").fast_mcts_agent.FastMCTSAgent.__name__,
+        __import__("mcts.mcts_agent").mcts_agent.MCTSAgent.__name__, _eb.Board.can_place_piece.__name__))
 '''
 
 
@@ -66,4 +69,10 @@ def run(modules: Sequence[str], scratch: str, device: bool, timeout: int = 1500,
     counts = {k: 0 for k in ("passed", "failed", "error", "skipped")}
     for n, k in re.findall(r"(\d+) (passed|failed|errors?|skipped)", out.strip().splitlines()[-1] if out.strip() else ""):
         counts[k.rstrip("s") if k.startswith("error") else k] = int(n)
-    return {"returncode": proc.returncode, "output": out, **counts}
+    report = ""
+    try:
+        with open(os.path.join(scratch, "install_report.txt")) as f:
+            report = f.read().strip()
+    except OSError:
+        pass
+    return {"returncode": proc.returncode, "output": out, "report": report, **counts}

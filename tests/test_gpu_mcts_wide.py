@@ -91,17 +91,26 @@ def test_agents_use_the_wide_search(golden_dir):
     legal = get_shared_generator().get_legal_moves(board, player)
     ids = sorted(m.to_id() for m in legal)
     st = board.to_packed()
-    # think(): 1,000 simulations, width = a quarter of the budget; one chunk of four rounds
-    out = FastMCTSAgent(iterations=1000, time_limit=30.0, seed=5).think(board, player, legal, 30000)
-    want = orc.mcts_wide(st, [1000], 250, seed=5, tree_id=0, max_depth=1, ucb_variant=1, reward_mode=1)
-    n = want["n_root"]
-    best = max(range(n - 1, -1, -1), key=lambda r: want["visits"][r])
-    assert out["move"].to_id() == ids[best]
-    assert out["stats"]["nodesEvaluated"] == 1000
-    top = {(t["piece_id"], t["orientation"], t["anchor_row"], t["anchor_col"]): t["visits"] for t in out["stats"]["topMoves"]}
+    # think(): the budget is split over root-parallel trees (one planner each), width = a quarter of a tree's share;
+    # the root statistics of the trees are summed
     from reinforcementlearning_blokus_b200 import Move
-    for key, v in top.items():
-        assert v == want["visits"][ids.index(Move(*key).to_id())]
+    n = len(ids)
+    for budget in (400, 1000, 5000):
+        agent = FastMCTSAgent(iterations=budget, time_limit=30.0, seed=5)
+        out = agent.think(board, player, legal, 30000)
+        per_tree, width, trees = agent._wide_cache[0][:3]
+        assert trees == max(1, min(8, budget // 625)) and per_tree * trees >= budget
+        tot = np.zeros(n, dtype=np.int64)
+        chunk = max(FastMCTSAgent.CHUNK, 4 * width)             # think() checks the clock between chunks of four rounds
+        calls = [min(chunk, per_tree - lo) for lo in range(0, per_tree, chunk)]
+        for k in range(trees):
+            w = orc.mcts_wide(st, calls, width, seed=5, tree_id=k, max_depth=1, ucb_variant=1, reward_mode=1)
+            assert w["n_root"] == n
+            tot += w["visits"][:n]
+        assert out["stats"]["nodesEvaluated"] == per_tree * trees == int(tot.sum())
+        assert out["move"].to_id() == ids[max(range(n - 1, -1, -1), key=lambda r: tot[r])]
+        for t in out["stats"]["topMoves"]:
+            assert t["visits"] == tot[ids.index(Move(t["piece_id"], t["orientation"], t["anchor_row"], t["anchor_col"]).to_id())]
     # the sequential search stays available
     seq = FastMCTSAgent(iterations=200, time_limit=30.0, seed=5, search_width=0).think(board, player, legal, 30000)
     w2 = orc.mcts_search(st, 200, seed=5, tree_id=0, max_depth=1, ucb_variant=1, reward_mode=1)
