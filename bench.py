@@ -334,6 +334,44 @@ def run_cuda(args) -> None:
         mcts["mcts_heuristic_rollout_sims_per_sec_per_gpu"] = ht * iters / (m0.elapsed_time(m1) * 1e-3)
         del heng
 
+    # ---- STRONG scaling of ONE move: a fixed budget split over 16 root-parallel wide trees, 16 / N per GPU,
+    # one all-reduce of the root statistics; the merged result is the same for every N (checked by the checksum below)
+    if not args.no_extras and 16 % world == 0:
+        from reinforcementlearning_blokus_b200 import dist as bdist
+
+        mid = dev.playout(64, seed=0xB10C05, max_turns=24, want_final=True)["final_states"][17:18].contiguous()
+        strong = {}
+        for tag, sims, kw in (("uct_heuristic_rollouts_16384_sims", 16384, dict(rollout_policy=dev.POLICY_HEURISTIC)),
+                              ("flat_uniform_rollouts_8192_sims", 8192, dict(max_depth=1, ucb_variant=1, reward_mode=1))):
+            rp = bdist.RootParallelWide(sims, 16, seed=SEED, **kw)
+            out = rp.search(mid)                                  # warm-up (allocations, NCCL channel setup)
+            rp.search(mid, search_index=1)
+            barrier()
+            reps, t_search, t_merge = 5, 0.0, 0.0
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            for k in range(reps):
+                rp.eng.p.tree_offset = rp.rank * rp.trees_per_rank
+                barrier()
+                a.record(stream)
+                res = rp.eng.search(mid, rp.per_tree)
+                b.record(stream)
+                v, w = bdist.merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0))
+                c.record(stream)
+                torch.cuda.synchronize()
+                t_search += a.elapsed_time(b)
+                t_merge += b.elapsed_time(c)
+            tt = torch.tensor([t_search / reps, t_merge / reps], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            n_root = out["n_root"]
+            strong[tag] = {"ms_per_move": float(tt[0] + tt[1]), "search_ms": float(tt[0]), "merge_us": float(tt[1]) * 1e3,
+                           "trees_total": 16, "trees_per_gpu": 16 // world, "sims_per_tree": rp.per_tree, "round_width": rp.width,
+                           "best_rank": int(torch.argmax(v[:n_root]).item()),
+                           "visits_checksum": int((v[:n_root] * torch.arange(1, n_root + 1, device=v.device)).sum().item())}
+            del rp
+        if mcts is not None:
+            mcts["mcts_strong_scaling_one_move"] = strong
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -118,3 +118,32 @@ def root_parallel_search(root_state: torch.Tensor, sims_total: int, trees_per_ra
     v, w = merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0), group=group)
     return {"rank_of_best": pick_move(v, n_root), "visits": v[:n_root], "reward": w[:n_root], "n_root": n_root,
             "sims": iters * trees}
+
+
+class RootParallelWide:
+    """STRONG scaling of one move: a fixed simulation budget split over `total_trees` root-parallel WIDE trees
+    (mcts.WideUCT: each tree is itself spread over its GPU), `total_trees / world_size` of them on every rank, one
+    all-reduce of the root statistics.  Tree t always has global index search_index * total_trees + t, so the merged
+    result is the same for every world size that divides total_trees."""
+
+    def __init__(self, sims_total: int, total_trees: int, seed: int, width: int = 0, group=None, **wide_kwargs):
+        from .mcts import WideUCT
+
+        self.rank, self.ws = world()
+        if total_trees % self.ws:
+            raise ValueError("total_trees must be a multiple of the world size")
+        self.group = group
+        self.total_trees = int(total_trees)
+        self.trees_per_rank = self.total_trees // self.ws
+        self.per_tree = max(1, int(sims_total) // self.total_trees)
+        self.width = int(width) if width else max(64, min(1024, self.per_tree // 4))
+        self.eng = WideUCT(self.per_tree, width=self.width, n_trees=self.trees_per_rank, seed=seed,
+                           tree_offset=self.rank * self.trees_per_rank, **wide_kwargs)
+
+    def search(self, root_state: torch.Tensor, search_index: int = 0) -> Dict[str, object]:
+        self.eng.p.tree_offset = int(search_index) * self.total_trees + self.rank * self.trees_per_rank
+        res = self.eng.search(root_state, self.per_tree)
+        n_root = int(res["counts"][0].item())
+        v, w = merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0), group=self.group)
+        return {"rank_of_best": pick_move(v, n_root), "visits": v[:n_root], "reward": w[:n_root], "n_root": n_root,
+                "sims": self.per_tree * self.total_trees}
