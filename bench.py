@@ -411,15 +411,28 @@ def run_cuda(args) -> None:
         dist.destroy_process_group()
 
 
+def _playout_constants():
+    """ncu-measured constants of k_playout<0,false> (warp instructions per playout, DRAM bytes per launch) with the hash
+    of the kernel sources they were measured on; `stale` when the kernel has changed since (tools/playout_traffic.py
+    regenerates the file from an ncu capture)."""
+    from reinforcementlearning_blokus_b200 import build
+
+    for name in ("r02_playout_traffic.json", "r01_playout_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            try:
+                with open(p) as f:
+                    d = json.load(f)
+            except Exception:
+                continue
+            d["file"] = "profiles/" + name
+            d["stale"] = d.get("kernel_source_hash") != build.playout_source_hash()
+            return d
+    return {}
+
+
 def _traffic_from_profiles():
-    p = os.path.join(ROOT, "profiles", "r01_playout_traffic.json")
-    if os.path.exists(p):
-        try:
-            with open(p) as f:
-                return json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
+    return _playout_constants().get("dram_bytes_per_launch")
 
 
 def _int_roofline(n, per_launch_s, clocks, sm_max):
@@ -431,14 +444,10 @@ def _int_roofline(n, per_launch_s, clocks, sm_max):
     peak = 148 * 4 * sm_mhz * 1e6
     res["peak"] = peak
     res["peak_source"] = f"148 SMs x 4 SMSP x 1 warp-instr/clk x {sm_mhz:.0f} MHz (median under load)"
-    p = os.path.join(ROOT, "profiles", "r01_playout_traffic.json")
-    wi = ALG_WARP_INSTR_PER_PLAYOUT
-    if os.path.exists(p):
-        try:
-            with open(p) as f:
-                wi = json.load(f).get("warp_instr_per_playout", wi)
-        except Exception:
-            pass
+    consts = _playout_constants()
+    wi = consts.get("warp_instr_per_playout", ALG_WARP_INSTR_PER_PLAYOUT)
+    res["constants_from"] = consts.get("file")
+    res["stale"] = bool(consts.get("stale", True))       # True: the kernel sources changed since the ncu capture
     if wi:
         res["warp_instr_per_playout"] = wi
         res["achieved"] = wi * n / per_launch_s

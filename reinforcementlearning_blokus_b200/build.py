@@ -40,6 +40,21 @@ def _source_hash() -> str:
     return h.hexdigest()
 
 
+PLAYOUT_KERNEL_SOURCES = ["blokus_b200.cu", "movegen_core.cuh", "orient_gen.cuh", "tables_gen.h"]
+
+
+def playout_source_hash() -> str:
+    """Hash of the files k_playout<0,false> is compiled from: profiles/*_playout_traffic.json records the hash its
+    instruction / DRAM-byte constants were measured with, and bench.py flags them as stale when it differs."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in PLAYOUT_KERNEL_SOURCES:
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def needs_build() -> bool:
     """True when the library is missing or was built from other sources (content hash, not mtimes: the tree is
     copied to the GPU box and a copy does not keep modification times in order)."""

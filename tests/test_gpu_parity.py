@@ -303,17 +303,26 @@ def test_exclusive_scan_sizes():
         assert np.array_equal(got, want), n
 
 
-def test_legality_sweep_small():
-    """A 30,000-state slice of the configs[2] sweep (tools/legality_sweep.py runs the 10^6 version)."""
+def test_legality_sweep_million():
+    """BASELINE.json configs[2] at its stated size: 10^6 synthetic states (every game stage, terminal states included),
+    the device's ascending move list of the side to move against the oracle's frontier+bitboard generator byte for
+    byte, every 1000th state also against the naive generator (0.1 s of GPU time, ~10-20 s of oracle time on the host
+    cores; tools/legality_sweep.py runs 10^7)."""
     import importlib.util
 
     spec = importlib.util.spec_from_file_location(
         "legality_sweep", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "legality_sweep.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    res = mod.sweep(30000, seed=77)
-    assert res["states"] == 30000 and res["mismatches"] == 0 and res["naive_mismatches"] == 0
-    assert res["terminal_states"] > 0 and res["max_moves"] > 500
+    res = mod.sweep(1_000_000, seed=77)
+    assert res["states"] == 1_000_000 and res["mismatches"] == 0 and res["naive_mismatches"] == 0
+    assert res["terminal_states"] > 0 and res["max_moves"] > 800 and res["total_moves"] > 150_000_000
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        import json
+
+        with open(os.path.join(out, "legality_sweep_1M.json"), "w") as f:
+            json.dump(res, f)
 
 
 def test_abi_error_codes_and_empty_batches():
@@ -354,17 +363,17 @@ def test_abi_error_codes_and_empty_batches():
     assert torch.equal(again["final_states"], fin) and (again["trace"].cpu().numpy() == 0xFFFF).all()
 
 
-def test_playout_replay_sweep_small():
-    """tools/playout_sweep.py at test size: every move of 3,000 uniform and 400 heuristic games equals the oracle's
-    (profiles/r01_playout_replay_sweep.json holds the 50,000 + 5,000 game run)."""
+def test_playout_replay_sweep():
+    """tools/playout_sweep.py: every move and the final scores of 12,000 uniform and 1,200 heuristic whole games equal
+    the oracle's replay (profiles/r01w_playout_replay_sweep.json holds a 200,000 + 30,000 game run)."""
     import importlib.util
 
     spec = importlib.util.spec_from_file_location(
         "playout_sweep", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "playout_sweep.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    u = mod.sweep(3000, seed=7, policy=0, first_game=123456)
-    h = mod.sweep(400, seed=7, policy=1, first_game=654321)
+    u = mod.sweep(12000, seed=7, policy=0, first_game=123456)
+    h = mod.sweep(1200, seed=7, policy=1, first_game=654321)
     assert u["mismatches"] == 0 and h["mismatches"] == 0
     assert h["mean_score"] > u["mean_score"]
 
