@@ -79,7 +79,7 @@ extern "C" const char* bk_version(void) { return "blokus_b200 r2 sm_100a (row-sl
 __global__ void k_movegen_emit(const bk_state* __restrict__, const uint8_t* __restrict__, int, const uint32_t* __restrict__,
                                uint32_t, uint32_t* __restrict__, uint16_t* __restrict__);
 __global__ void k_movegen_bitmap(const bk_state* __restrict__, const uint8_t* __restrict__, int, uint32_t* __restrict__);
-#define BK_EMIT_SMEM_BYTES (8 * (32 * 57 * 4 + 32 * 4))
+#define BK_EMIT_SMEM_BYTES (8 * (32 * 60 * 4))
 
 static cudaError_t bk_init_policies_impl();
 static cudaError_t bk_init_policies() { return bk_init_policies_impl(); }
@@ -140,15 +140,20 @@ k_movegen_count(const bk_state* __restrict__ states, const uint8_t* __restrict__
     }
 }
 
-// Ascending move ids.  Phase 1 writes the legal-anchor rows of all 91 orientations to shared memory
-// (word w = o*20 + row, so a set bit `col` of word w is move id 20*w + col).  Phase 2 gives every lane a
-// contiguous slice of 57 words: lane-local prefix counts go into bits 20..30 of the words and one warp scan
-// yields the lane bases.  Phase 3 locates list position k with two binary searches (owner lane, then word), so
-// lane L writes positions L, L+32, ...: every lane extracts the same number of moves and the global stores are
-// coalesced, with no staging buffer.
-#define EMIT_WORDS_PER_LANE 57            /* 32 * 57 = 1824 >= 1820 */
+// Ascending move ids.  The legal-anchor rows of an orientation (word w = o*20 + row; bit `col` of word w is move id
+// 20*w + col) are sparse: ~9 % of the 1 820 words of a mid-game state hold a move.  The sink therefore appends only
+// the NON-EMPTY rows to a list in shared memory while the generator runs -- one ballot per orientation tells every
+// lane where its row goes, and the list comes out in ascending id order.  Then the entries are dealt out evenly
+// (lane j takes entries j*per .. (j+1)*per), one warp scan of the lanes' move counts gives their list positions and
+// every lane writes the ids of its entries.  No zeroing, no pass over empty words, no search.  (A uniform branch around
+// the append -- REDUX.OR of the rows first -- was measured slower: 0.33 vs 0.47 G generations/s; the compiler predicates
+// the ten instructions of the append, which is cheaper than 91 more reductions.)
+// (Round 1 staged all 1 820 words and located every list position with two binary searches: 1 885 warp instructions
+// per state, LSU pipe 56 %; a first rewrite with contiguous 60-word slices per lane still spent 55 % of its 1 549
+// instructions in lock-step bit loops over mostly empty words -- profiles/r02_emit_ncu.md.)
+#define EMIT_WORDS_PER_LANE 60            /* 32 * 60 = 1920 >= 1820 (row staging of the bitmap generator) */
 #define EMIT_ROW_WORDS (32 * EMIT_WORDS_PER_LANE)
-#define EMIT_SMEM_PER_WARP (EMIT_ROW_WORDS * 4 + 32 * 4)
+#define EMIT_SMEM_PER_WARP (EMIT_ROW_WORDS * 4)
 static_assert(BK_EMIT_SMEM_BYTES == BK_WARPS * EMIT_SMEM_PER_WARP, "emit shared-memory size");
 
 struct SmemRowSink {
@@ -160,14 +165,30 @@ struct SmemRowSink {
     template <int G0, int NG, int PID> __device__ __forceinline__ void flush() {}
 };
 
-__global__ void __launch_bounds__(BK_THREADS)
+struct NonEmptyRowSink {               // list[k] = (word index << 20) | row bits, ascending word index
+    static constexpr bool kRows = true;
+    uint32_t* list; uint32_t lane, below, n;
+    __device__ __forceinline__ void begin(uint32_t* l, int lane_) { list = l; lane = (uint32_t)lane_; below = (1u << lane_) - 1u; n = 0; }
+    template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) {
+        const uint32_t m = __ballot_sync(BK_FULL, L != 0u);
+        if (m) {
+            if (L) list[n + __popc(m & below)] = ((uint32_t)(O * 20 + (int)lane) << 20) | L;
+            n += __popc(m);
+        }
+    }
+    template <int G0, int NG, int PID> __device__ __forceinline__ void flush() {}
+};
+
+#ifndef BK_EMIT_CTAS
+#define BK_EMIT_CTAS 3
+#endif
+__global__ void __launch_bounds__(BK_THREADS, BK_EMIT_CTAS)
 k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ players, int n,
                const uint32_t* __restrict__ offsets, uint32_t cap, uint32_t* __restrict__ counts_out,
                uint16_t* __restrict__ ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint32_t* rows = reinterpret_cast<uint32_t*>(smem_raw + (size_t)wib * EMIT_SMEM_PER_WARP);
-    uint32_t* lane_base = rows + EMIT_ROW_WORDS;
+    uint32_t* list = reinterpret_cast<uint32_t*>(smem_raw + (size_t)wib * EMIT_SMEM_PER_WARP);   // <= 1 820 entries
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     uint64_t word = warp < n ? fetch_state_word(states + warp, lane) : 0ull;
@@ -177,45 +198,34 @@ k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ 
         word = next;
         const uint32_t p = players ? (players[i] & 3u) : s.to_move;
         uint32_t A, C; make_masks(s, p, lane, A, C);
-#pragma unroll
-        for (int k = 0; k < EMIT_WORDS_PER_LANE; k++) rows[k * 32 + lane] = 0;   // spent pieces are never visited
-        __syncwarp();
-        SmemRowSink sink; sink.rows = rows; sink.lane = lane;
+        NonEmptyRowSink sink; sink.begin(list, lane);
         bk_gen_all(A, C, sel4(s.used, p), sink);
         __syncwarp();
-        uint32_t* mine = rows + lane * EMIT_WORDS_PER_LANE;
+        const uint32_t ne = sink.n;                              // non-empty rows (uniform)
+        const uint32_t per = (ne + 31u) >> 5;
+        const uint32_t lo = min((uint32_t)lane * per, ne), hi = min(lo + per, ne);
         uint32_t cnt = 0;
-#pragma unroll
-        for (int k = 0; k < EMIT_WORDS_PER_LANE; k++) {
-            const uint32_t bits = mine[k];
-            mine[k] = bits | (cnt << 20);
-            cnt += __popc(bits);
-        }
+        for (uint32_t e = lo; e < hi; e++) cnt += __popc(list[e] & BK_ROWMASK);
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(BK_FULL, incl, d); if (lane >= d) incl += v; }
         const uint32_t total = __reduce_add_sync(BK_FULL, cnt);
-        lane_base[lane] = incl - cnt;
         // CSR mode: state i owns ids[offsets[i] .. offsets[i+1]);  fixed mode (offsets == NULL): state i owns
         // ids[i*cap .. (i+1)*cap) and a longer list is truncated (counts_out still reports the full length).
         const size_t base = offsets ? (size_t)offsets[i] : (size_t)i * cap;
         const uint32_t limit = offsets ? total : (total < cap ? total : cap);
         if (counts_out && lane == 0) counts_out[i] = total;
-        __syncwarp();
-        for (uint32_t k = lane; k < limit; k += 32) {
-            uint32_t L = 0;                                  // owner lane: the last one whose base is <= k
-#pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) if (lane_base[L + step] <= k) L += step;
-            const uint32_t rem = k - lane_base[L];
-            const uint32_t* words = rows + L * EMIT_WORDS_PER_LANE;
-            uint32_t w = 0;                                  // last word whose prefix is <= rem: it holds the move
-#pragma unroll
-            for (int step = 32; step >= 1; step >>= 1)
-                if (w + step < EMIT_WORDS_PER_LANE && (words[w + step] >> 20) <= rem) w += step;
-            const uint32_t wd = words[w];
-            uint32_t bits = wd & BK_ROWMASK;
-            for (uint32_t skip = rem - (wd >> 20); skip; skip--) bits &= bits - 1;
-            ids[base + k] = (uint16_t)((L * EMIT_WORDS_PER_LANE + w) * 20u + (__ffs(bits) - 1));
+        uint32_t pos = incl - cnt;                               // this lane's first list position
+        uint16_t* out = ids + base;
+        for (uint32_t e = lo; e < hi; e++) {
+            const uint32_t w = list[e];
+            const uint32_t id0 = (w >> 20) * 20u;
+            uint32_t bits = w & BK_ROWMASK;
+            do {
+                const uint32_t c = __ffs(bits) - 1; bits &= bits - 1;
+                if (pos < limit) out[pos] = (uint16_t)(id0 + c);
+                pos++;
+            } while (bits);
         }
         __syncwarp();
     }
@@ -811,7 +821,7 @@ extern "C" int bk_movegen_emit(const bk_state* states, const uint8_t* players, i
                                uint16_t* move_ids, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && (n == 0 || (states && offsets && move_ids)), "bk_movegen_emit: null buffer");
     if (n == 0) return BK_OK;
-    k_movegen_emit<<<grid_for(cx, n, 3), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, offsets, 0u, nullptr, move_ids);
+    k_movegen_emit<<<grid_for(cx, n, BK_EMIT_CTAS), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, offsets, 0u, nullptr, move_ids);
     LAUNCH_CHECK();
     return BK_OK;
 }
@@ -820,7 +830,7 @@ extern "C" int bk_movegen_fixed(const bk_state* states, const uint8_t* players, 
                                 uint16_t* move_ids, void* stream) {
     REQUIRE_INIT(); REQUIRE(n >= 0 && cap > 0 && (n == 0 || (states && counts && move_ids)), "bk_movegen_fixed: bad argument");
     if (n == 0) return BK_OK;
-    k_movegen_emit<<<grid_for(cx, n, 3), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, nullptr, cap, counts, move_ids);
+    k_movegen_emit<<<grid_for(cx, n, BK_EMIT_CTAS), BK_THREADS, BK_WARPS * EMIT_SMEM_PER_WARP, as_stream(stream)>>>(states, players, n, nullptr, cap, counts, move_ids);
     LAUNCH_CHECK();
     return BK_OK;
 }
