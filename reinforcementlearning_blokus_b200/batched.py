@@ -84,8 +84,9 @@ def selfplay_mcts(n_games: int, iterations: int, *, seed: int = 0, trees_per_gam
                   game_offset: int = 0, max_turns: int = 96, want_policy: bool = False) -> Dict[str, torch.Tensor]:
     """Self-play where EVERY move of every game is chosen by UCT search -- the league's data generator
     (configs/stage3_selfplay_gpu.yaml feeds such games to training) as device batches: per turn one launch searches the
-    current position of all n_games games (tree k searches game k % n_games; `trees_per_game` root-parallel trees per
-    game, their root statistics summed), the most visited move is played (ties: the reference's rule for one tree,
+    current position of all n_games games (`trees_per_game` root-parallel trees per game, laid out game-major, their
+    root statistics summed; tree j of global game G on turn t always draws from Philox stream id
+    ((G + t * 2^24) * trees_per_game + j), whatever the batch or shard size), the most visited move is played (ties: the reference's rule for one tree,
     first child in creation order = highest rank), and games whose mover has no move pass
     (analytics/tournament/arena_runner.py:653-695).
 
@@ -106,22 +107,28 @@ def selfplay_mcts(n_games: int, iterations: int, *, seed: int = 0, trees_per_gam
         running = alive != 0
         if not bool(running.any()):
             break
-        # every (game, turn) pair gets its own block of Philox streams
-        eng.p.tree_offset = (int(game_offset) + t * (1 << 24)) * int(trees_per_game)
-        res = eng.search(games.states, iterations)
-        visits = res["visits"].view(trees_per_game, n_games, -1).sum(dim=0)
+        # every (game, turn) pair gets its own block of Philox streams; trees are game-major (tree k searches root k)
+        tpg = int(trees_per_game)
+        eng.p.tree_offset = (int(game_offset) + t * (1 << 24)) * tpg
+        roots = games.states if tpg == 1 else games.states.repeat_interleave(tpg, dim=0).contiguous()
+        res = eng.search(roots, iterations)
+        visits = res["visits"].view(n_games, tpg, -1).sum(dim=1)
         # most visited root move, ties to the highest rank; unexpanded ranks have 0 visits
         key = visits.to(torch.int64) * MAX_ROOT_MOVES + rank_weight[None, : visits.shape[1]]
         best = key.argmax(dim=1)
-        ids = res["moves"][:n_games].view(torch.int16).gather(1, best[:, None]).view(torch.uint16)[:, 0]
-        has_move = (res["counts"][:n_games] > 0) & running
+        moves_g = res["moves"].view(n_games, tpg, -1)[:, 0].contiguous()       # the move ids by rank are the same in every tree
+        counts_g = res["counts"].view(n_games, tpg)[:, 0]
+        ids = moves_g.view(torch.int16).gather(1, best[:, None]).view(torch.uint16)[:, 0]
+        has_move = (counts_g > 0) & running
         move = torch.where(has_move, ids.to(torch.int32), torch.full_like(ids, PASS, dtype=torch.int32))
         move16 = move.to(torch.int16).view(torch.uint16).contiguous()      # 0..36399 and 0xFFFF survive the round trip
+        before = games.states.clone()
         ok, _ = games.step(move16)
+        games.states = torch.where(running[:, None], games.states, before)  # a finished game is not touched any more
         trace[:, t] = torch.where(running, move, trace[:, t])
         turns += running.to(torch.int32)
         if want_policy:
-            policy.append((visits.clone(), res["moves"][:n_games].clone()))
+            policy.append((visits.clone(), moves_g.clone()))
     gs, bs = games.scores()
     out = {"trace": trace.to(torch.int16).view(torch.uint16), "game_scores": gs, "board_scores": bs, "turns": turns,
            "final_states": games.states}

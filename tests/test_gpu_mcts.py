@@ -278,6 +278,14 @@ def test_batched_mcts_selfplay():
     c = batched.selfplay_mcts(4, 16, seed=2, trees_per_game=3, leaf_batch=4, want_policy=True, max_turns=6)
     v0, m0 = c["policy"][0]
     assert v0.shape[0] == 4 and int(v0[0].sum()) == 3 * 16 * 4 and len(c["policy"]) == 6
+    # a game's streams depend on its GLOBAL index only: games 2..3 of a 4-game batch == a 2-game batch at offset 2
+    d = batched.selfplay_mcts(2, 16, seed=2, trees_per_game=3, leaf_batch=4, max_turns=6, game_offset=2)
+    assert torch.equal(c["trace"][2:, :6], d["trace"][:, :6])
+    # a finished game is left alone while the slower games of the batch go on (its side to move does not keep rotating)
+    e = batched.selfplay_mcts(6, 8, seed=21)
+    solo = [batched.selfplay_mcts(1, 8, seed=21, game_offset=g) for g in range(6)]
+    for g in range(6):
+        assert torch.equal(e["final_states"][g], solo[g]["final_states"][0]) and torch.equal(e["trace"][g], solo[g]["trace"][0])
 
 
 def _logreg_artifact(golden_dir, tmp_path, scaler=True):
