@@ -155,7 +155,7 @@ class FastMCTSAgent:
         self.search_width = search_width
         # root-parallel trees of the wide search: the simulation budget is split over `num_trees` bandits that are planned
         # side by side (one planner each) and share the GPU for their rollouts; their root statistics are summed.
-        # Default: one tree per 625 simulations of the budget, at most 8 (5,000 simulations: 8 planners, ~1 ms).
+        # Default: one tree per 625 simulations of the budget (rounded), at most 8 (5,000 simulations: 8 planners, ~1 ms).
         self.num_trees = num_trees
         self._thinks = 0
         self._wide_cache = None
@@ -183,7 +183,7 @@ class FastMCTSAgent:
         ordered = sorted(legal_moves, key=lambda m: m.to_id())      # rank <-> move (ascending id)
         wide = self.leaf_batch == 1 and (self.search_width is None or int(self.search_width) > 0)
         if wide:
-            W = int(self.num_trees) if self.num_trees else max(1, min(8, int(self.iterations) // 625))    # trees
+            W = int(self.num_trees) if self.num_trees else max(1, min(8, (int(self.iterations) + 312) // 625))    # trees
             total = max(1, -(-int(self.iterations) // W))         # simulations per tree
             width = int(self.search_width) if self.search_width else max(64, min(1024, total // 4))
             key = (total, width, W, self.exploration_constant, self.rollout_plies, self.seed)
@@ -227,19 +227,19 @@ class FastMCTSAgent:
                                   "bestActionId": f"{bm.piece_id}-{bm.orientation}-{bm.anchor_row}-{bm.anchor_col}",
                                   "bestQMean": float(w[b] / v[b]) if v[b] > 0 else 0.0,
                                   "entropy": float(compute_policy_entropy([int(x) for x in v if x > 0]))})
-        if int(res["counts"][0].item()) != n_root:
+        # one read-back: summed root statistics (over the trees of the wide search) and the device's legal-move count
+        sel = slice(None) if wide else slice(0, 1)
+        both = torch.cat([res["visits"][sel, :n_root].sum(dim=0, dtype=torch.int64), res["reward"][sel, :n_root].sum(dim=0),
+                          res["counts"][:1].to(torch.int64)]).cpu().numpy()
+        if int(both[-1]) != n_root:
             raise dev._lib.BlokusB200Error("legal_moves does not match the device's legal-move set for this board")
-        if wide:                                                   # root statistics summed over the trees
-            visits = res["visits"][:, :n_root].sum(dim=0).cpu().numpy()
-            reward = res["reward"][:, :n_root].sum(dim=0).cpu().numpy()
-        else:
-            visits = res["visits"][0, :n_root].cpu().numpy()
-            reward = res["reward"][0, :n_root].cpu().numpy()
-        expanded = [r for r in range(n_root) if visits[r] > 0]
+        visits, reward = both[:n_root], both[n_root:2 * n_root]
         # children were created from the highest rank down; "first child with max visits" = highest rank on ties
-        cand = [self._move_dict(ordered[r], visits[r], reward[r] / visits[r]) for r in sorted(expanded, reverse=True)]
-        cand.sort(key=lambda x: x["visits"], reverse=True)
-        top_moves = cand[:10]
+        ranks_desc = np.arange(n_root - 1, -1, -1)
+        ranks_desc = ranks_desc[visits[ranks_desc] > 0]
+        by_visits = ranks_desc[np.argsort(-visits[ranks_desc], kind="stable")]
+        expanded = [int(r) for r in ranks_desc[::-1]]
+        top_moves = [self._move_dict(ordered[r], visits[r], reward[r] / visits[r]) for r in by_visits[:10]]
         spent_ms = int((time.perf_counter() - start) * 1000)
         done *= W                                                  # from here on: simulations
         if done < 5:        # fast_mcts_agent.py:179-191: too few simulations -> quick heuristic pick
@@ -247,7 +247,7 @@ class FastMCTSAgent:
                           key=lambda m: abs(m.anchor_row - 9.5) + abs(m.anchor_col - 9.5))[0]
             return {"move": pick, "stats": {"timeBudgetMs": time_budget_ms, "timeSpentMs": spent_ms,
                                             "nodesEvaluated": max(done, 1), "maxDepthReached": 2, "topMoves": top_moves}}
-        best_rank = max(sorted(expanded, reverse=True), key=lambda r: visits[r]) if expanded else 0
+        best_rank = int(by_visits[0]) if len(by_visits) else 0
         entropy = compute_policy_entropy([int(visits[r]) for r in expanded]) if self.enable_diagnostics else 0.0
         n_exp = len(expanded)
         diagnostics = None

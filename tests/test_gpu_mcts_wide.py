@@ -99,7 +99,7 @@ def test_agents_use_the_wide_search(golden_dir):
         agent = FastMCTSAgent(iterations=budget, time_limit=30.0, seed=5)
         out = agent.think(board, player, legal, 30000)
         per_tree, width, trees = agent._wide_cache[0][:3]
-        assert trees == max(1, min(8, budget // 625)) and per_tree * trees >= budget
+        assert trees == max(1, min(8, (budget + 312) // 625)) and per_tree * trees >= budget
         tot = np.zeros(n, dtype=np.int64)
         chunk = max(FastMCTSAgent.CHUNK, 4 * width)             # think() checks the clock between chunks of four rounds
         calls = [min(chunk, per_tree - lo) for lo in range(0, per_tree, chunk)]
@@ -122,3 +122,23 @@ def test_agents_use_the_wide_search(golden_dir):
         w3 = orc.mcts_wide(st, [400], 128, seed=8, tree_id=0, rollout_policy=pol)
         assert np.array_equal(r["visits"], w3["visits"][:n]) and np.array_equal(r["reward"], w3["reward"][:n])
         assert agent.select_action(board, player, legal) in legal
+
+
+def test_wide_search_degenerate_roots(golden_dir):
+    """A root whose player cannot move (every simulation re-simulates the root) and roots with very few moves (the
+    tree is exhausted early and later walks keep landing on terminal nodes)."""
+    z = np.load(os.path.join(golden_dir, "random_states.npz"))
+    states = z["states"].view(STATE_DTYPE).reshape(-1)
+    picked = {}
+    for s in states:
+        n = len(orc.OracleBoard.from_packed(s).legal_moves(int(s["to_move"])))
+        if n <= 3 and n not in picked:
+            picked[n] = s
+    assert 0 in picked and len(picked) >= 2
+    for n, root in sorted(picked.items()):
+        for kw in (dict(), dict(max_depth=1, ucb_variant=1, reward_mode=1)):
+            want = orc.mcts_wide(root, [150], 64, seed=4, **kw)
+            res = WideUCT(150, width=64, seed=4, **kw).search(dev.to_device(np.atleast_1d(root)), 150)
+            assert int(res["counts"][0]) == want["n_root"] == n
+            assert int(res["sims_done"][0]) == 150 and int(res["status"][0]) == 0
+            _same(res, want)
