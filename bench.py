@@ -405,6 +405,11 @@ def run_cuda(args) -> None:
         line["extras"] = dict(mcts or {})
     if world == 1 and not args.no_extras:
         line["extras"].update(_extras(dev, torch, n))
+        # the one HBM-bound kernel of the path: the legal-anchor bitmap generator (256 B in, 7 280 B out per state)
+        gps = line["extras"]["movegen_bitmap_gens_per_sec"]
+        line["roofline_movegen_bitmap"] = {"bound": "hbm", "kernel": "k_movegen_bitmap", "achieved": gps * (256 + 7280) / 1e9,
+                                           "peak": hbm_peak, "unit": "GB/s", "frac": gps * (256 + 7280) / 1e9 / hbm_peak,
+                                           "peak_source": peak_src, "bytes_per_state": 256 + 7280}
         line["cpu_baseline"] = _cpu_baseline()
     _emit(line)
     if world > 1:
@@ -547,6 +552,18 @@ def _extras(dev, torch, n):
             eng.search(root, iters)
             torch.cuda.synchronize()
             ex[tag] = round(timeit(lambda: eng.search(root, iters), reps=3), 3)
+        # the same move searched by the whole GPU (K6, the round-synchronous search; what FastMCTSAgent.think runs): one tree,
+        # eight root-parallel trees for the 5,000-simulation /think budget, and the full tree with HeuristicAgent rollouts
+        from reinforcementlearning_blokus_b200.mcts import WideUCT
+
+        flat = dict(max_depth=1, ucb_variant=1, reward_mode=1)
+        for tag, sims, trees, kw in (("mcts_move_1000_sims_ms_wide_1tree", 1000, 1, flat), ("mcts_move_1000_sims_ms_wide_2trees", 500, 2, flat),
+                                     ("mcts_move_5000_sims_ms_wide_8trees", 625, 8, flat),
+                                     ("mcts_move_1000_sims_ms_wide_uct_heuristic_rollouts", 1000, 1, dict(rollout_policy=dev.POLICY_HEURISTIC))):
+            weng = WideUCT(sims, width=max(64, min(1024, sims // 4)), n_trees=trees, seed=SEED, **kw)
+            weng.search(root, sims)
+            ex[tag] = round(timeit(lambda: weng.search(root, sims), reps=5), 3)
+            del weng
         # UCT with learned leaf evaluation in the kernel (reward_mode 3: a pairwise logistic win-probability model on the
         # 34 snapshot features of every new leaf instead of a rollout); synthetic weights, trees from the empty board
         wts = torch.from_numpy(np.random.default_rng(0).normal(0.0, 0.05, 35))
