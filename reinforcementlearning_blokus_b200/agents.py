@@ -180,7 +180,9 @@ class FastMCTSAgent:
                                          "timeSpentMs": int((time.perf_counter() - start) * 1000),
                                          "nodesEvaluated": 1, "maxDepthReached": 1,
                                          "topMoves": [dict(self._move_dict(m, 1, 0.0), q_value=0.0)]}}
-        ordered = sorted(legal_moves, key=lambda m: m.to_id())      # rank <-> move (ascending id)
+        # rank <-> move: ascending id.  The generator's own list says so itself; anything else is sorted here
+        ids_known = getattr(legal_moves, "ascending_ids", None)
+        ordered = legal_moves if ids_known is not None and len(ids_known) == len(legal_moves) else sorted(legal_moves, key=lambda m: m.to_id())
         wide = self.leaf_batch == 1 and (self.search_width is None or int(self.search_width) > 0)
         if wide:
             W = int(self.num_trees) if self.num_trees else max(1, min(8, (int(self.iterations) + 312) // 625))    # trees

@@ -82,6 +82,26 @@ class Piece:
         self.size = P.PIECE_SIZES[pid]
 
 
+class MoveList(list):
+    """The list get_legal_moves returns: a plain list of Move objects that also remembers that it is in ascending
+    canonical id order (``ascending_ids``: the ids as a numpy array), so that agents handed this very list do not have to
+    recompute and sort 200+ ids per call.  Any copy or slice is an ordinary list again."""
+
+    ascending_ids: Optional[np.ndarray] = None
+
+    def _forget(name):                     # any in-place change makes it an ordinary list again
+        def method(self, *a, **k):
+            self.ascending_ids = None
+            return getattr(list, name)(self, *a, **k)
+        method.__name__ = name
+        return method
+
+    for _n in ("__setitem__", "__delitem__", "__iadd__", "__imul__", "append", "extend", "insert", "pop", "remove", "clear",
+               "sort", "reverse"):
+        locals()[_n] = _forget(_n)
+    del _n, _forget
+
+
 class LegalMoveGenerator:
     """Drop-in for the reference generator; stateless apart from the immutable shape caches."""
 
@@ -102,7 +122,9 @@ class LegalMoveGenerator:
         g, cell = np.divmod(ids, P.NUM_CELLS)
         pid, ori = _ORIENT_PIECE[g].tolist(), _ORIENT_INDEX[g].tolist()
         row, col = np.divmod(cell, P.BOARD_SIZE)
-        return [Move(a, b, c, d) for a, b, c, d in zip(pid, ori, row.tolist(), col.tolist())]
+        out = MoveList(Move(a, b, c, d) for a, b, c, d in zip(pid, ori, row.tolist(), col.tolist()))
+        out.ascending_ids = ids
+        return out
 
     # the reference exposes its variants under these names; tests and benchmarks call them directly
     _get_legal_moves_naive = get_legal_moves

@@ -275,3 +275,24 @@ def test_snapshot_rows_schema():
     assert (r["checkpoint_index"], r["checkpoint_ply"], r["turn_index"], r["player_id"], r["player_name"], r["agent_name"]) == (1, 16, 17, 2, "BLUE", "b")
     assert r["current_player_id"] == 17 % 4 + 1 and r["label_is_winner"] == 1 and r["winner_ids_json"] == "[2, 3]" and r["is_tie"] is True
     assert r["frontier_size"] == float(feats[0, 1, 1, 0]) and rows[-1]["winner_id"] == 1 and rows[-1]["final_rank"] == 4
+
+
+def test_move_list_forgets_its_order_when_changed():
+    """get_legal_moves returns a list that knows it is in ascending id order (agents skip re-sorting it); any in-place
+    change or copy makes it an ordinary list again."""
+    import random
+
+    from reinforcementlearning_blokus_b200.move_generator import MoveList
+
+    def fresh():
+        m = MoveList([10, 20, 30, 40])
+        m.ascending_ids = np.array([10, 20, 30, 40])
+        return m
+
+    assert fresh().ascending_ids is not None
+    assert getattr(fresh()[:2], "ascending_ids", None) is None and getattr(list(fresh()), "ascending_ids", None) is None
+    for change in (lambda m: random.Random(0).shuffle(m), lambda m: m.sort(reverse=True), lambda m: m.pop(), lambda m: m.append(5),
+                   lambda m: m.reverse(), lambda m: m.__setitem__(0, 1), lambda m: m.remove(20), lambda m: m.extend([1])):
+        m = fresh()
+        change(m)
+        assert m.ascending_ids is None
