@@ -684,6 +684,57 @@ def gen_mcts_deep(seed=42):
     print("mcts", len(names), "searches")
 
 
+def gen_mcts_gbt(seed=42):
+    """The evaluator's other artifact type, "pairwise_gbt_phase" (mcts/learned_evaluator.py:112-127), through the
+    unmodified MCTSAgent with leaf evaluation: an "early" phase model plus a fallback model (used for the mid-game
+    root), scikit-learn GradientBoostingClassifier fitted on pairwise.npz.  The artifact is stored flattened
+    (reinforcementlearning_blokus_b200.winprob.flatten_gbt_phase_models -- checked against scikit-learn on its own in
+    tests/test_host_logic.py) next to the searches; added to the entries gen_mcts wrote."""
+    import tempfile
+
+    import joblib
+    from sklearn.ensemble import GradientBoostingClassifier
+
+    from analytics.winprob.features import SNAPSHOT_FEATURE_COLUMNS
+    from mcts.mcts_agent import MCTSAgent, MCTSNode
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from reinforcementlearning_blokus_b200.winprob import flatten_gbt_phase_models
+
+    path = os.path.join(HERE, "mcts.npz")
+    out = {k: v for k, v in np.load(path).items()}
+    names = [str(n) for n in out["names"] if not str(n).startswith("gbt/")]
+    z = np.load(os.path.join(HERE, "pairwise.npz"))
+    early = GradientBoostingClassifier(n_estimators=24, max_depth=3, random_state=0).fit(z["X"], z["label"])
+    fallback = GradientBoostingClassifier(n_estimators=40, max_depth=2, learning_rate=0.2, random_state=1).fit(z["X"][::2], z["label"][::2])
+    artifact = {"model_type": "pairwise_gbt_phase", "feature_columns": list(SNAPSHOT_FEATURE_COLUMNS),
+                "phase_models": {"early": early}, "fallback_model": fallback}
+    out["gbt_model"] = flatten_gbt_phase_models(artifact)
+    roots = [("empty", Board()), ("kat1_40", generate_random_valid_state(40, seed=40)[0])]
+    with tempfile.TemporaryDirectory() as td, _AscendingGenerator():
+        art = os.path.join(td, "gbt.pkl")
+        joblib.dump(artifact, art)
+        for name, board in roots:
+            player = board.current_player
+            ag = MCTSAgent(iterations=80, rollout_agent=PhiloxIndexAgent(seed), use_transposition_table=False, seed=seed,
+                           learned_model_path=art, leaf_evaluation_enabled=True)
+            root = MCTSNode(board, player)
+            ag._run_mcts_with_iterations(root)
+            tag = "gbt/" + name
+            mv, vis, rew = _root_children(root)
+            out[tag + "/state"] = np.frombuffer(_packed_for(board, player).tobytes(), dtype=np.uint8)
+            out[tag + "/frontier"] = _frontier_bytes(board)
+            out[tag + "/moves"], out[tag + "/visits"], out[tag + "/reward"] = mv, vis, rew
+            out[tag + "/digest"] = _tree_digest(root)
+            out[tag + "/tt"] = np.array([0, 0], dtype=np.int64)
+            out[tag + "/best"] = np.array([move_id(root.get_best_move())], dtype=np.uint16)
+            names.append(tag)
+            print(tag, "children", len(mv), "digest", out[tag + "/digest"].tolist(), "reward sum", float(rew.sum()), flush=True)
+    out["names"] = np.array(names)
+    np.savez_compressed(path, **out)
+    print("mcts", len(names), "searches")
+
+
 def _packed_for(board: Board, player: Player) -> np.ndarray:
     s = pack(board)
     s["to_move"] = player.value - 1
@@ -767,8 +818,8 @@ def random_state_from_packed(s) -> Board:
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise", "mcts", "mcts_deep", "telemetry"]
+    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise", "mcts", "mcts_deep", "mcts_gbt", "telemetry"]
     for w in which:
         {"tables": gen_tables, "kat1": gen_kat1, "kat2": gen_kat2, "random": gen_random_states,
          "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic, "mobility": gen_mobility,
-         "snapshots": gen_snapshots, "pairwise": gen_pairwise, "mcts": gen_mcts, "mcts_deep": gen_mcts_deep, "telemetry": gen_telemetry}[w]()
+         "snapshots": gen_snapshots, "pairwise": gen_pairwise, "mcts": gen_mcts, "mcts_deep": gen_mcts_deep, "mcts_gbt": gen_mcts_gbt, "telemetry": gen_telemetry}[w]()

@@ -610,7 +610,9 @@ def test_kernel_matches_reference_uct(golden_dir):
             eng = DeviceUCT(sp["iterations"], rollout_policy=sp.get("rollout_policy", 0), reward_mode=sp.get("reward_mode", 0), **kw)
             res = eng.search(root, sp["iterations"])
         elif sp["family"] == "learned":
-            eng = DeviceUCT(sp["iterations"], reward_mode=3, leaf_model=model, progressive_bias_weight=sp.get("bias_weight", 0.0), **kw)
+            kind = sp.get("model_kind", 0)
+            eng = DeviceUCT(sp["iterations"], reward_mode=3, leaf_model=torch.from_numpy(z["gbt_model"].copy()) if kind else model,
+                            leaf_model_kind=kind, progressive_bias_weight=sp.get("bias_weight", 0.0), **kw)
             res = eng.search(root, sp["iterations"], root_frontiers=_frontier_words(fr))
         else:
             eng = DeviceUCT(sp["iterations"], reward_mode=4, leaf_model=model, max_rollout_moves=6, shaping_weight=2.0,

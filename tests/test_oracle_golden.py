@@ -208,7 +208,7 @@ def test_uct_matches_reference(golden_dir):
     zt = orc.zobrist_table(seed)
     model = z["model"]
     tables = {}
-    assert len(names) >= 40
+    assert len(names) >= 48
     for tag in names:
         sp = U.spec(tag)
         name = tag.split("/")[1]
@@ -224,8 +224,9 @@ def test_uct_matches_reference(golden_dir):
             w = orc.mcts_search(st, sp["iterations"], seed=seed, rollout_policy=sp.get("rollout_policy", 0),
                                 reward_mode=sp.get("reward_mode", 0), **kw)
         elif sp["family"] == "learned":
-            w = orc.mcts_search_learned(st, sp["iterations"], seed=seed, model=model, root_frontier=fr,
-                                        bias_weight=sp.get("bias_weight", 0.0), **kw)
+            kind = sp.get("model_kind", 0)
+            w = orc.mcts_search_learned(st, sp["iterations"], seed=seed, model=z["gbt_model"] if kind else model, root_frontier=fr,
+                                        bias_weight=sp.get("bias_weight", 0.0), model_kind=kind, **kw)
         else:
             w = orc.mcts_search_shaped(st, sp["iterations"], seed=seed, model=model, root_frontier=fr, max_rollout_moves=6,
                                        shaping_weight=2.0, shaping_gamma=0.9, potential_mode=sp["potential_mode"], **kw)

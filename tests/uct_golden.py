@@ -35,6 +35,7 @@ def spec(tag):
         "bias": dict(iterations=80, family="learned", tt=True, bias_weight=0.25),
         "shape_prob": dict(iterations=40, family="shaped", potential_mode=0),
         "shape_logit": dict(iterations=40, family="shaped", potential_mode=1),
+        "gbt": dict(iterations=80, family="learned", model_kind=1),          # pairwise_gbt_phase artifact, leaf evaluation
         "deep_uct": dict(iterations=300, family="plain"),
         "deep_tt": dict(iterations=300, family="plain", tt=True),
         "deep_heur": dict(iterations=150, family="plain", rollout_policy=1, tt=True),
