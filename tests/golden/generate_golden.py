@@ -735,6 +735,51 @@ def gen_mcts_gbt(seed=42):
     print("mcts", len(names), "searches")
 
 
+def gen_heuristic_games(count=6, seed=42):
+    """Complete games where EVERY move is chosen by the unmodified HeuristicAgent.select_action (agents/heuristic_agent.py:
+    39-66: its scores, its softmax), with only its RandomState replaced by the Philox categorical draw of turn t
+    (stream 0 of (seed, game), the playout kernel's stream) -- the arena loop of analytics/tournament/arena_runner.py:653-695."""
+    from agents.heuristic_agent import HeuristicAgent as _H
+
+    traces = np.full((count, 96), 0xFFFF, dtype=np.uint16)
+    gsc = np.zeros((count, 4), dtype=np.int32)
+    turns = np.zeros(count, dtype=np.int32)
+
+    class TurnChoice(_PhiloxChoice):
+        def choice(self, n, p):
+            r = draw(self.seed, self.tree, self.n, 0)          # stream 0, draw number = turn (set by the loop below)
+            order = np.concatenate([np.arange(L, n, 32) for L in range(min(32, n))])
+            cdf = np.cumsum(np.asarray(p, dtype=np.float64)[order])
+            k = int(np.searchsorted(cdf, cdf[-1] * (r * 2.0 ** -32), side="right"))
+            return int(order[min(k, n - 1)])
+
+    for gi in range(count):
+        game = BlokusGame(enable_telemetry=False)
+        agent = _H(seed=seed)
+        agent.rng = TurnChoice(seed, gi)
+        t = 0
+        while not game.is_game_over() and t < 96:
+            pl = game.get_current_player()
+            legal = game.get_legal_moves(pl)
+            if not legal:
+                game.board._update_current_player()
+                game._check_game_over()
+                t += 1
+                continue
+            legal.sort(key=move_id)
+            agent.rng.n = t
+            mv = agent.select_action(game.board, pl, legal)
+            assert game.make_move(mv, pl)
+            traces[gi, t] = move_id(mv)
+            t += 1
+        res = game.get_game_result()
+        gsc[gi] = [res.scores[p + 1] for p in range(4)]
+        turns[gi] = t
+        print("heuristic game", gi, "turns", t, "scores", gsc[gi].tolist(), flush=True)
+    np.savez_compressed(os.path.join(HERE, "heuristic_games.npz"), seed=np.array([seed], dtype=np.uint64), traces=traces,
+                        game_scores=gsc, turns=turns)
+
+
 def _packed_for(board: Board, player: Player) -> np.ndarray:
     s = pack(board)
     s["to_move"] = player.value - 1
@@ -818,8 +863,8 @@ def random_state_from_packed(s) -> Board:
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise", "mcts", "mcts_deep", "mcts_gbt", "telemetry"]
+    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise", "mcts", "mcts_deep", "mcts_gbt", "heuristic_games", "telemetry"]
     for w in which:
         {"tables": gen_tables, "kat1": gen_kat1, "kat2": gen_kat2, "random": gen_random_states,
          "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic, "mobility": gen_mobility,
-         "snapshots": gen_snapshots, "pairwise": gen_pairwise, "mcts": gen_mcts, "mcts_deep": gen_mcts_deep, "mcts_gbt": gen_mcts_gbt, "telemetry": gen_telemetry}[w]()
+         "snapshots": gen_snapshots, "pairwise": gen_pairwise, "mcts": gen_mcts, "mcts_deep": gen_mcts_deep, "mcts_gbt": gen_mcts_gbt, "heuristic_games": gen_heuristic_games, "telemetry": gen_telemetry}[w]()

@@ -186,6 +186,16 @@ def test_playout_matches_reference_games(golden_dir):
     assert np.array_equal(_np(r["final_states"]), z["finals"])
 
 
+def test_heuristic_playouts_match_reference_games(golden_dir):
+    """bk_playout(policy = HeuristicAgent) against whole games played by the reference's own HeuristicAgent
+    (tests/golden/heuristic_games.npz): same moves, same final scores."""
+    z = np.load(os.path.join(golden_dir, "heuristic_games.npz"))
+    n = len(z["traces"])
+    r = dev.playout(n, seed=int(z["seed"][0]), policy=dev.POLICY_HEURISTIC, want_trace=True)
+    assert np.array_equal(_np(r["trace"]), z["traces"])
+    assert np.array_equal(_np(r["game_scores"]), z["game_scores"])
+
+
 def test_playout_matches_oracle_and_is_batch_independent():
     seed, n, off = 20261018, 256, 1000
     r = dev.playout(n, seed=seed, game_offset=off, want_trace=True, want_choice=True, want_final=True)

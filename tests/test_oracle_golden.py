@@ -235,3 +235,15 @@ def test_uct_matches_reference(golden_dir):
             assert [tt.hits(), tt.size()] == z[tag + "/tt"].tolist(), tag
     for t in tables.values():
         t.close()
+
+
+def test_heuristic_policy_games_match_reference(golden_dir):
+    """Whole games played by the reference's HeuristicAgent.select_action (its scores, its softmax; only the categorical
+    draw is Philox, tests/golden/generate_golden.py gen_heuristic_games): the oracle's heuristic-policy playout picks the
+    same ~430 moves and ends on the same scores."""
+    z = np.load(os.path.join(golden_dir, "heuristic_games.npz"))
+    seed = int(z["seed"][0])
+    for g in range(len(z["traces"])):
+        o = orc.playout(seed, g, policy=1)
+        assert np.array_equal(o["trace"], z["traces"][g]), g
+        assert np.array_equal(o["game_scores"], z["game_scores"][g]) and o["turns"] == int(z["turns"][g])
