@@ -780,6 +780,27 @@ def gen_heuristic_games(count=6, seed=42):
                         game_scores=gsc, turns=turns)
 
 
+def gen_tt_eviction():
+    """mcts/zobrist.py TranspositionTable with a small max_size: a sequence of puts (one of them overwrites an old key)
+    and what is left afterwards -- pins the evict-oldest-tenth rule (:196-200) and dict semantics of put."""
+    from mcts.zobrist import TranspositionTable
+
+    rng = np.random.default_rng(0)
+    keys = [int(k) for k in rng.integers(1, 2**63, size=160)]
+    tt = TranspositionTable(max_size=50)
+    ops = []
+    for i, k in enumerate(keys):
+        tt.put(k, {"reward": float(i)})
+        ops.append([k, float(i)])
+        if i in (30, 77, 120):
+            tt.put(keys[i - 28], {"reward": -float(i)})          # overwrite an entry that may or may not still be there
+            ops.append([keys[i - 28], -float(i)])
+    left = {str(k): v["reward"] for k, v in tt.table.items()}
+    with open(os.path.join(HERE, "tt_eviction.json"), "w") as f:
+        json.dump({"max_size": 50, "ops": ops, "left": left, "order": [str(k) for k in tt.table]}, f)
+    print("tt_eviction", len(ops), "puts,", len(left), "entries left")
+
+
 def _packed_for(board: Board, player: Player) -> np.ndarray:
     s = pack(board)
     s["to_move"] = player.value - 1
@@ -863,8 +884,8 @@ def random_state_from_packed(s) -> Board:
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise", "mcts", "mcts_deep", "mcts_gbt", "heuristic_games", "telemetry"]
+    which = sys.argv[1:] or ["tables", "kat1", "kat2", "random", "games", "zobrist", "heuristic", "mobility", "snapshots", "pairwise", "mcts", "mcts_deep", "mcts_gbt", "heuristic_games", "tt_eviction", "telemetry"]
     for w in which:
         {"tables": gen_tables, "kat1": gen_kat1, "kat2": gen_kat2, "random": gen_random_states,
          "games": gen_games, "zobrist": gen_zobrist, "heuristic": gen_heuristic, "mobility": gen_mobility,
-         "snapshots": gen_snapshots, "pairwise": gen_pairwise, "mcts": gen_mcts, "mcts_deep": gen_mcts_deep, "mcts_gbt": gen_mcts_gbt, "heuristic_games": gen_heuristic_games, "telemetry": gen_telemetry}[w]()
+         "snapshots": gen_snapshots, "pairwise": gen_pairwise, "mcts": gen_mcts, "mcts_deep": gen_mcts_deep, "mcts_gbt": gen_mcts_gbt, "heuristic_games": gen_heuristic_games, "tt_eviction": gen_tt_eviction, "telemetry": gen_telemetry}[w]()

@@ -628,3 +628,20 @@ def test_kernel_matches_reference_uct(golden_dir):
             first = 0 if not sp.get("second") else int(z["tt1/" + name + "/tt"][0])
             assert after["hits"] - before["hits"] == want_hits - first, tag
             assert after["size"] == want_size, tag
+
+
+def test_device_table_eviction_matches_reference(golden_dir):
+    """The same 163 puts of the reference's TranspositionTable(max_size=50) through the device table (mcts.TranspositionTable:
+    evict_if_full + bk_tt_put): same keys and values left."""
+    import json
+
+    with open(os.path.join(golden_dir, "tt_eviction.json")) as f:
+        fx = json.load(f)
+    tt = TranspositionTable(max_size=fx["max_size"])
+    for key, reward in fx["ops"]:
+        tt.put(int(key), {"reward": reward})
+    assert len(tt) == len(fx["left"])
+    for key, reward in fx["left"].items():
+        assert tt.get(int(key)) == {"reward": reward}
+    gone = [k for k, _ in fx["ops"] if str(k) not in fx["left"]]
+    assert gone and all(tt.get(int(k)) is None for k in gone[:40])

@@ -247,3 +247,23 @@ def test_heuristic_policy_games_match_reference(golden_dir):
         o = orc.playout(seed, g, policy=1)
         assert np.array_equal(o["trace"], z["traces"][g]), g
         assert np.array_equal(o["game_scores"], z["game_scores"][g]) and o["turns"] == int(z["turns"][g])
+
+
+def test_transposition_table_eviction_matches_reference(golden_dir):
+    """mcts/zobrist.py:188-202 run by the reference on 163 puts into a 50-entry table (tests/golden/tt_eviction.json): the
+    oracle's table -- evict the max_size // 10 entries inserted first when full, overwriting keeps an entry's place --
+    ends with the same keys and values."""
+    with open(os.path.join(golden_dir, "tt_eviction.json")) as f:
+        fx = json.load(f)
+    t = orc.OracleTT(8)
+    for key, reward in fx["ops"]:
+        if t.size() >= fx["max_size"]:
+            t.evict_oldest(fx["max_size"] // 10)
+        t.put(int(key), reward)
+    assert t.size() == len(fx["left"])
+    for key, reward in fx["left"].items():
+        assert t.get(int(key)) == reward
+    for key, _ in fx["ops"]:
+        if str(key) not in fx["left"]:
+            assert t.get(int(key)) is None
+    t.close()
