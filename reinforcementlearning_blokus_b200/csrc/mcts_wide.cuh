@@ -163,6 +163,7 @@ struct WideSmem {
     uint32_t cb[BK_WIDE_NC];
     uint16_t nl[BK_WIDE_NC], ne[BK_WIDE_NC], mv[BK_WIDE_NC];
     uint32_t cand_key[2][BK_WIDE_PLAN_WARPS], cand_k[2][BK_WIDE_PLAN_WARPS];
+    uint16_t give[2048], first[2048];       // flat batch rounds: walks given to root child k, position of its first item
     uint32_t n_nodes, pool_used, overflow, stop;
 };
 #define BK_WIDE_PLAN_SMEM ((int)sizeof(WideSmem))
@@ -223,6 +224,112 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
     const uint32_t room = sims_target > sims_done ? sims_target - sims_done : 0u;
     const uint32_t want_items = overflow ? 0u : (room < L.width ? room : L.width);
     uint32_t n_items = 0, buf = 0;
+    // ---- a flat bandit whose root is fully expanded gets the whole round dealt out at once.  With the exploration scale
+    // frozen at the round's final count, s = stab[finished + W], the value of giving child k one more walk when it already
+    // has j of this round is u_k(j) = fma(s, invtab[m_k + j], q_k), non-increasing in j, and the sequential rule "the next
+    // walk goes to the first maximal child" picks exactly the W largest values (ties: lower k first, then lower j).  That
+    // set is found without walking: a bit-by-bit search for the largest key T with #{(k, j): key(u_k(j)) >= T} >= W, every
+    // child's count by a binary search over j; children take everything above T and the values equal to T are shared out in
+    // child order.  Cost O(children * log W * 32) per round instead of O(W * children).  The items are numbered child by child.
+    if (prm.max_depth == 1 && want_items > 0 && S.nl[0] != BK_WIDE_PENDING && S.nl[0] > 0 && S.ne[0] == S.nl[0] && S.nl[0] <= 2048) {
+        if (warp == 0) {
+            const uint32_t ne0 = S.ne[0], W = want_items;
+            const float s = __ldg(V.stab + S.vis[0] + (int32_t)W);
+            // walks of child k whose key is >= tau: first j with key(u_k(j)) < tau (keys do not increase with j)
+            auto count_ge = [&](uint32_t k, uint32_t tau) -> uint32_t {
+                const float q = S.q[k + 1];
+                const float* it = V.invtab + S.vis[k + 1];
+                if (wide_key(__fmaf_rn(s, __ldg(it), q)) < tau) return 0u;
+                uint32_t lo = 1, hi = W;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (wide_key(__fmaf_rn(s, __ldg(it + mid), q)) >= tau) lo = mid + 1; else hi = mid;
+                }
+                return lo;
+            };
+            // the same for all children, eight per lane at a time: eight independent searches keep eight table loads in flight
+            auto total_ge = [&](uint32_t tau) -> uint32_t {
+                uint32_t t = 0;
+                for (uint32_t base = lane; base < ne0; base += 256u) {
+                    uint32_t lo[8], hi[8]; float q[8]; const float* it[8];
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        const uint32_t k = base + 32u * (uint32_t)r;
+                        const bool valid = k < ne0;
+                        q[r] = valid ? S.q[k + 1] : 0.0f;
+                        it[r] = V.invtab + (valid ? S.vis[k + 1] : 1);
+                        const bool any = valid && wide_key(__fmaf_rn(s, __ldg(it[r]), q[r])) >= tau;
+                        lo[r] = any ? 1u : 0u; hi[r] = any ? W : 0u;
+                    }
+                    bool more = true;
+                    while (more) {
+                        more = false;
+#pragma unroll
+                        for (int r = 0; r < 8; r++) {
+                            if (lo[r] < hi[r]) {
+                                const uint32_t mid = (lo[r] + hi[r]) >> 1;
+                                if (wide_key(__fmaf_rn(s, __ldg(it[r] + mid), q[r])) >= tau) lo[r] = mid + 1; else hi[r] = mid;
+                                more = true;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 8; r++) t += lo[r];
+                }
+                return __reduce_add_sync(BK_FULL, t);
+            };
+            // the threshold lies between the smallest last value and the largest first value of the children
+            uint32_t kmax = 0, kmin = 0xFFFFFFFFu;
+            for (uint32_t k = lane; k < ne0; k += 32) {
+                const float q = S.q[k + 1];
+                const float* it = V.invtab + S.vis[k + 1];
+                kmax = max(kmax, wide_key(__fmaf_rn(s, __ldg(it), q)));
+                kmin = min(kmin, wide_key(__fmaf_rn(s, __ldg(it + (W - 1u)), q)));
+            }
+            kmax = __reduce_max_sync(BK_FULL, kmax); kmin = __reduce_min_sync(BK_FULL, kmin);
+            uint32_t tau = kmin, top = kmax;                                             // total_ge(kmin) = children * W >= W
+            while (tau < top) {
+                const uint32_t mid = tau + ((top - tau + 1u) >> 1);
+                if (total_ge(mid) >= W) tau = mid; else top = mid - 1u;
+            }
+            const uint32_t above = tau == 0xFFFFFFFFu ? 0u : total_ge(tau + 1u);      // walks with a key strictly above tau
+            uint32_t left = W - above, at = 0;                                           // still to share out; next item position
+            for (uint32_t row = 0; row * 32u < ne0; row++) {
+                const uint32_t k = row * 32u + (uint32_t)lane;
+                uint32_t hi_cnt = 0, eq = 0;
+                if (k < ne0) {
+                    hi_cnt = tau == 0xFFFFFFFFu ? 0u : count_ge(k, tau + 1u);
+                    eq = count_ge(k, tau) - hi_cnt;
+                }
+                uint32_t incl = eq;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(BK_FULL, incl, d); if (lane >= d) incl += v; }
+                const uint32_t before = incl - eq;                                       // equal-valued walks of lower children in this row
+                const uint32_t take = before >= left ? 0u : (eq < left - before ? eq : left - before);
+                const uint32_t mine = hi_cnt + take;
+                const uint32_t row_eq = __shfl_sync(BK_FULL, incl, 31);
+                left -= row_eq < left ? row_eq : left;
+                uint32_t pincl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(BK_FULL, pincl, d); if (lane >= d) pincl += v; }
+                if (k < ne0) {
+                    S.give[k] = (uint16_t)mine; S.first[k] = (uint16_t)(at + pincl - mine);
+                    if (mine) { S.virt[k + 1] = (int32_t)mine; S.inv[k + 1] = __ldg(V.invtab + S.vis[k + 1] + (int32_t)mine); }
+                }
+                at += __shfl_sync(BK_FULL, pincl, 31);
+            }
+            __syncwarp();
+            // items: position t belongs to the last child whose first position is <= t
+            for (uint32_t t = lane; t < W; t += 32) {
+                uint32_t lo = 0, hi = ne0 - 1;
+                while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (S.first[mid] <= t) lo = mid; else hi = mid - 1; }
+                V.item_leaf[t] = lo + 1; V.item_parent[t] = BK_WIDE_NONE; V.item_rank[t] = 0;
+            }
+            if (lane == 0) S.virt[0] += (int32_t)W;
+        }
+        n_items = want_items;
+        __syncthreads();
+    }
     for (; n_items < want_items; n_items++) {
         // ---- descent: all threads, uniform control flow
         uint32_t node = 0, depth = 0;
