@@ -323,7 +323,7 @@ def run_cuda(args) -> None:
                 "mcts_root_visits_total": int(v.sum().item()), "mcts_collective": "1 all_reduce(int64[2,2048]) per search"}
         # the reference's default rollout policy (HeuristicAgent softmax, mcts_agent.py:275-276), no collective
         del eng
-        ht = 2 * 2072                       # two waves of 14 one-warp trees per SM
+        ht = 2 * 148 * 20                   # two waves of 20 one-warp trees per SM (BK_MCTS_HEUR_CTAS_PER_SM)
         heng = DeviceUCT(iters, n_trees=ht, seed=SEED, tree_offset=rank * ht, rollout_policy=dev.POLICY_HEURISTIC)
         heng.search(root, iters)
         torch.cuda.synchronize()

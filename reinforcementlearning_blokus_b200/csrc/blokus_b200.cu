@@ -453,9 +453,12 @@ k_scores(const bk_state* __restrict__ states, int n, int32_t* __restrict__ gs, i
 #ifndef BK_PLAYOUT_MIRROR
 #define BK_PLAYOUT_MIRROR true
 #endif
+#ifndef BK_PLAYOUT_HEUR_MIN_BLOCKS
+#define BK_PLAYOUT_HEUR_MIN_BLOCKS 3
+#endif
 // POLICY 2 = one policy per seat and game (arena match-ups): seat_policies[i] packs the policy of player p in byte p.
 template <int POLICY, bool TRACE = true>
-__global__ void __launch_bounds__(BK_PLAYOUT_THREADS, POLICY == 0 ? BK_PLAYOUT_MIN_BLOCKS : 2)
+__global__ void __launch_bounds__(BK_PLAYOUT_THREADS, POLICY == 0 ? BK_PLAYOUT_MIN_BLOCKS : BK_PLAYOUT_HEUR_MIN_BLOCKS)
 k_playout(unsigned int* __restrict__ ticket, const uint32_t* __restrict__ seat_policies, const bk_state* __restrict__ start, int n, uint64_t seed, uint64_t game_offset, int first_turn, int max_turns,
                   int32_t* __restrict__ gs, int32_t* __restrict__ bs, uint16_t* __restrict__ trace,
                   uint16_t* __restrict__ choice, bk_state* __restrict__ finals) {
@@ -517,7 +520,7 @@ k_playout(unsigned int* __restrict__ ticket, const uint32_t* __restrict__ seat_p
                     }
                 } else {
                     uint32_t id = 0, idx = 0;
-                    const uint32_t nmoves = heuristic_pick(s, p, philox_word(rnd, t), hs, lane, id, idx);
+                    const uint32_t nmoves = heuristic_pick(s, p, philox_word(rnd, t), hs, lane, ch != nullptr, id, idx);
                     if (nmoves == 0) {
                         dead |= 1u << p;
                     } else if (probing) {
@@ -966,7 +969,7 @@ extern "C" int bk_playout(const bk_state* start_states, int n, uint64_t seed, ui
         k_playout<0><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, 0, as_stream(stream)>>>(
             ticket, nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     } else {
-        pcap = (long long)cx->sms * 2;
+        pcap = (long long)cx->sms * BK_PLAYOUT_HEUR_MIN_BLOCKS;
         k_playout<1><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, BK_HEUR_PLAYOUT_SMEM, as_stream(stream)>>>(
             ticket, nullptr, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice, final_states);
     }
@@ -986,7 +989,7 @@ extern "C" int bk_playout_seats(const bk_state* start_states, int n, uint64_t se
     const int pw = BK_PLAYOUT_THREADS / 32;
     unsigned int* ticket = nullptr;
     CUDA_TRY(fresh_ticket(cx, as_stream(stream), &ticket));
-    long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)cx->sms * 2;
+    long long pneed = ((long long)n + pw - 1) / pw, pcap = (long long)cx->sms * BK_PLAYOUT_HEUR_MIN_BLOCKS;
     k_playout<2><<<(int)(pneed < pcap ? pneed : pcap), BK_PLAYOUT_THREADS, BK_HEUR_PLAYOUT_SMEM, as_stream(stream)>>>(
         ticket, seat_policies, start_states, n, seed, game_offset, first_turn, max_turns, game_scores, board_scores, trace, choice,
         final_states);

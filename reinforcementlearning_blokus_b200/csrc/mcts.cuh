@@ -96,7 +96,7 @@ __device__ __forceinline__ int32_t board_score_of(const WarpState& s, uint32_t q
 // heuristic rollouts: 14 KB of list scratch per warp allows 14 one-warp CTAs per SM (16 KB each with the static part
 // and the per-CTA reservation, 228 KB per SM); the register cap that goes with it is 146
 #ifndef BK_MCTS_HEUR_CTAS_PER_SM
-#define BK_MCTS_HEUR_CTAS_PER_SM 14
+#define BK_MCTS_HEUR_CTAS_PER_SM 20
 #endif
 
 // BATCH = false: one warp per tree (CTA of 32 threads), the reference's one-rollout-per-iteration search.
@@ -353,7 +353,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                                 uint32_t id = 0, idx = 0;
                                 const uint32_t before_draws = draws;
                                 const uint32_t rnd = next_draw();
-                                if (heuristic_pick(s, p, rnd, hs, lane, id, idx) == 0) { draws = before_draws; break; }
+                                if (heuristic_pick(s, p, rnd, hs, lane, false, id, idx) == 0) { draws = before_draws; break; }
                                 o = (int)(id / 400u); row = (int)((id % 400u) / 20u); col = (int)(id % 20u);
                             } else {
                                 uint32_t A, C; make_masks(s, p, lane, A, C);
@@ -400,7 +400,7 @@ k_mcts(unsigned int* __restrict__ ticket, const bk_state* __restrict__ roots, in
                         // a turn without a move consumes no draw: peek, then commit
                         const uint32_t before_draws = draws;
                         const uint32_t rnd = next_draw();
-                        if (heuristic_pick(s, p, rnd, hs, lane, id, idx) == 0) { draws = before_draws; break; }
+                        if (heuristic_pick(s, p, rnd, hs, lane, false, id, idx) == 0) { draws = before_draws; break; }
                         place_move(s, p, (int)(id / 400u), (int)((id % 400u) / 20u), (int)(id % 20u), lane);
                         continue;
                     }

@@ -513,7 +513,7 @@ k_wide_work(int n_trees, bk_mcts_params prm, unsigned char* __restrict__ workspa
                     uint32_t id = 0, idx = 0;
                     const uint32_t before_draws = draws;
                     const uint32_t rnd = next_draw();
-                    if (heuristic_pick(s, p, rnd, 0u, lane, id, idx) == 0) { draws = before_draws; break; }
+                    if (heuristic_pick(s, p, rnd, 0u, lane, false, id, idx) == 0) { draws = before_draws; break; }
                     place_move(s, p, (int)(id / 400u), (int)((id % 400u) / 20u), (int)(id % 20u), lane);
                     continue;
                 }

@@ -500,18 +500,32 @@ class PhiloxIndexAgent:
         self.seed = seed
 
 
+def _device_order(ids):
+    """Cumulative order of the device's categorical draw (csrc/heuristic.cuh): the moves are grouped into entries (anchor row,
+    orientation), entries numbered row by row; lane L of 32 owns entries L, L+32, ... (columns ascending inside an entry);
+    the cumulative sum runs over lane 0's moves, then lane 1's, ...  `ids` = ascending move ids; returns indices into it."""
+    ids = np.asarray(ids, dtype=np.int64)
+    o, row, col = ids // 400, (ids % 400) // 20, ids % 20
+    _, entry = np.unique(row * 128 + o, return_inverse=True)         # entry number in (row, orientation) order
+    return np.lexsort((col, entry, entry % 32))
+
+
 class _PhiloxChoice:
     """Stands in for HeuristicAgent.rng (agents/heuristic_agent.py:29,65): choice(n, p=probs) turns the next Philox
     draw of stream 1 into a categorical sample.  The probabilities are the reference's own softmax; the cumulative
-    order is the device's (32 interleaved lanes: all moves k = L mod 32 of lane 0, then lane 1, ...)."""
+    order is the device's (_device_order; `ids` = the ascending move ids of the list the probabilities belong to, set by
+    the caller before select_action runs)."""
+
+    stream = 1
 
     def __init__(self, seed: int, tree: int = 0):
-        self.seed, self.tree, self.n = seed, tree, 0
+        self.seed, self.tree, self.n, self.ids = seed, tree, 0, None
 
     def choice(self, n, p):
-        r = draw(self.seed, self.tree, self.n, 1)
+        r = draw(self.seed, self.tree, self.n, self.stream)
         self.n += 1
-        order = np.concatenate([np.arange(L, n, 32) for L in range(min(32, n))])
+        assert self.ids is not None and len(self.ids) == n
+        order = _device_order(self.ids)
         cdf = np.cumsum(np.asarray(p, dtype=np.float64)[order])
         target = cdf[-1] * (r * 2.0 ** -32)
         k = int(np.searchsorted(cdf, target, side="right"))
@@ -605,7 +619,12 @@ def gen_mcts(iterations=200, seed=42):
         for name, board in roots[:3]:
             from agents.heuristic_agent import HeuristicAgent as _H
 
-            h = _H(seed=seed)
+            class _HIds(_H):                       # hands the move ids of the list to the draw; select_action itself is the reference's
+                def select_action(self, board, player, legal_moves):
+                    self.rng.ids = [move_id(m) for m in legal_moves]
+                    return super().select_action(board, player, legal_moves)
+
+            h = _HIds(seed=seed)
             h.rng = _PhiloxChoice(seed)
             ag = MCTSAgent(iterations=60, rollout_agent=h, use_transposition_table=False, seed=seed)
             record("heur/%s" % name, board, board.current_player, ag, 60)
@@ -675,7 +694,12 @@ def gen_mcts_deep(seed=42):
             record("deep_uct/" + name, board, player, ag, 300)
             ag = MCTSAgent(iterations=300, rollout_agent=PhiloxIndexAgent(seed), use_transposition_table=True, seed=seed)
             record("deep_tt/" + name, board, player, ag, 300)
-            h = _H(seed=seed)
+            class _HIds(_H):                       # hands the move ids of the list to the draw; select_action itself is the reference's
+                def select_action(self, board, player, legal_moves):
+                    self.rng.ids = [move_id(m) for m in legal_moves]
+                    return super().select_action(board, player, legal_moves)
+
+            h = _HIds(seed=seed)
             h.rng = _PhiloxChoice(seed)
             ag = MCTSAgent(iterations=150, rollout_agent=h, use_transposition_table=True, seed=seed)
             record("deep_heur/" + name, board, player, ag, 150)
@@ -746,12 +770,7 @@ def gen_heuristic_games(count=6, seed=42):
     turns = np.zeros(count, dtype=np.int32)
 
     class TurnChoice(_PhiloxChoice):
-        def choice(self, n, p):
-            r = draw(self.seed, self.tree, self.n, 0)          # stream 0, draw number = turn (set by the loop below)
-            order = np.concatenate([np.arange(L, n, 32) for L in range(min(32, n))])
-            cdf = np.cumsum(np.asarray(p, dtype=np.float64)[order])
-            k = int(np.searchsorted(cdf, cdf[-1] * (r * 2.0 ** -32), side="right"))
-            return int(order[min(k, n - 1)])
+        stream = 0                                             # stream 0, draw number = turn (set by the loop below)
 
     for gi in range(count):
         game = BlokusGame(enable_telemetry=False)
@@ -768,6 +787,7 @@ def gen_heuristic_games(count=6, seed=42):
                 continue
             legal.sort(key=move_id)
             agent.rng.n = t
+            agent.rng.ids = [move_id(m) for m in legal]
             mv = agent.select_action(game.board, pl, legal)
             assert game.make_move(mv, pl)
             traces[gi, t] = move_id(mv)
