@@ -99,8 +99,11 @@ __device__ __forceinline__ double heur_weight(const uint8_t* __restrict__ vmap, 
 // pointers are rebuilt from the extern array HERE so that the compiler knows their address space: handed over as plain
 // pointers they compiled to generic LD.E / ST.E with 64-bit address arithmetic, and those loads were the kernel's
 // long-scoreboard stalls (profiles/r01r_all_kernels_ncu.md: 51 % issue-active, 1.8 long-scoreboard stalls per issue).
-__device__ __noinline__ uint32_t heuristic_pick(const WarpState s, uint32_t p, uint32_t r, uint32_t scratch_off, int lane,
-                                                bool want_idx, uint32_t& id_out, uint32_t& idx_out) {
+// Inlined: every kernel instantiation has exactly one call site, and out of line the callee spilled 88 bytes at the
+// playout kernel's 80 registers and rebuilt the global-memory descriptors of its table loads (4 R2UR) for every move
+// (6.6 -> 7.4 M playouts/s, 6.7 -> 7.5 M heuristic-rollout simulations/s when it was inlined).
+__device__ __forceinline__ uint32_t heuristic_pick(const WarpState& s, uint32_t p, uint32_t r, uint32_t scratch_off, int lane,
+                                                          bool want_idx, uint32_t& id_out, uint32_t& idx_out) {
     extern __shared__ __align__(16) unsigned char heur_dyn_smem[];
     HeurScratch sc; sc.bind(heur_dyn_smem + scratch_off);
     uint32_t A, C; make_masks(s, p, lane, A, C);
