@@ -30,6 +30,13 @@
 /* per warp: private lists, allowed rows, cell bytes */
 #define HEUR_SMEM_PER_WARP (HEUR_PRIV_WORDS * 4 + 32 * 4 + 400)
 static_assert(HEUR_SMEM_PER_WARP % 16 == 0, "heuristic scratch keeps 16-byte alignment per warp");
+// -DBK_HEUR_CHECK builds the policy with its own bounds checks (compute-sanitizer is not available on the GPU pool): every
+// shared-memory and table index is tested and a violation traps the kernel (tools/heuristic_variants.py runs such a build).
+#ifdef BK_HEUR_CHECK
+#define HEUR_ASSERT(c) do { if (!(c)) __trap(); } while (0)
+#else
+#define HEUR_ASSERT(c) do { } while (0)
+#endif
 
 __device__ double g_e1[400];                 // exp(0.5 * (1 - dist(anchor, centre)/max_dist))   (heuristic_agent.py:185-198)
 __device__ double g_e2[HEUR_E2_SIZE];        // exp((i - 10) / 4)
@@ -74,8 +81,12 @@ struct HeurScratch {
 struct HeurPrivSink {
     static constexpr bool kRows = false;
     uint32_t a;        // shared-memory address of this lane's next free slot
+#ifdef BK_HEUR_CHECK
+    uint32_t a_end;
+#endif
     template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) {
         if (L) {
+            HEUR_ASSERT(a < a_end && (L >> 20) == 0u);
             asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(L | ((uint32_t)O << 20)) : "memory");
             a += 80u;
         }
@@ -86,9 +97,12 @@ struct HeurPrivSink {
 // softmax weight of the move of orientation table entry `tb` anchored at `cell`
 __device__ __forceinline__ double heur_weight(const uint8_t* __restrict__ vmap, uint32_t cell, const uint2 tb) {
     const uint8_t* v = vmap + cell;
+    HEUR_ASSERT(cell + (tb.x & 0xFFu) < 400u && cell + ((tb.x >> 8) & 0xFFu) < 400u && cell + ((tb.x >> 16) & 0xFFu) < 400u &&
+                cell + (tb.x >> 24) < 400u && cell + (tb.y & 0xFFu) < 400u);
     const uint32_t v0 = v[tb.x & 0xFFu];
     const uint32_t sum = v0 + v[(tb.x >> 8) & 0xFFu] + v[(tb.x >> 16) & 0xFFu] + v[tb.x >> 24] + v[tb.y & 0xFFu];
     const uint32_t idx = sum + (tb.y >> 16) - ((tb.y >> 8) & 0xFFu) * v0;
+    HEUR_ASSERT(idx < HEUR_E2_SIZE);
     return __dmul_rn(__ldg(g_e2 + idx), __ldg(g_e1 + cell));
 }
 
@@ -111,6 +125,10 @@ __device__ __forceinline__ uint32_t heuristic_pick(const WarpState& s, uint32_t 
     sc.arows[lane] = A;
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(sc.priv + lane);
     HeurPrivSink sink; sink.a = a0;
+#ifdef BK_HEUR_CHECK
+    sink.a_end = a0 + 80u * BK_TBL_ORIENTS;
+    HEUR_ASSERT(scratch_off % 16u == 0u);
+#endif
     bk_gen_all<HeurPrivSink, true>(A, C, sel4(s.used, p), sink);
     const uint32_t cnt = (sink.a - a0) / 80u;                               // this lane's entries
     uint32_t incl = cnt;
@@ -149,7 +167,9 @@ __device__ __forceinline__ uint32_t heuristic_pick(const WarpState& s, uint32_t 
         uint32_t src = 0;                                    // owner: the last lane whose base is <= gg
 #pragma unroll
         for (int step = 16; step >= 1; step >>= 1) { const uint32_t b = __shfl_sync(BK_FULL, base, src + step); if (b <= gg) src += step; }
+        HEUR_ASSERT(src < 20u && gg - __shfl_sync(BK_FULL, base, src) < __shfl_sync(BK_FULL, cnt, src));
         const uint32_t e = sc.priv[(gg - __shfl_sync(BK_FULL, base, src)) * 20u + src];
+        HEUR_ASSERT((e >> 20) < BK_TBL_ORIENTS && (e & BK_ROWMASK) != 0u);
         uint32_t bits = g < E ? (e & BK_ROWMASK) : 0u;
         const uint2 tb = __ldg(g_orient_off + (e >> 20));
         const uint32_t cell0 = src * 20u + 19u;
@@ -176,7 +196,9 @@ __device__ __forceinline__ uint32_t heuristic_pick(const WarpState& s, uint32_t 
         uint32_t src = 0;
 #pragma unroll
         for (int step = 16; step >= 1; step >>= 1) { const uint32_t b = __shfl_sync(BK_FULL, base, src + step); if (b <= g) src += step; }
+        HEUR_ASSERT(src < 20u && g - __shfl_sync(BK_FULL, base, src) < __shfl_sync(BK_FULL, cnt, src));
         const uint32_t e = sc.priv[(g - __shfl_sync(BK_FULL, base, src)) * 20u + src];
+        HEUR_ASSERT((e >> 20) < BK_TBL_ORIENTS && (e & BK_ROWMASK) != 0u);
         uint32_t bits = e & BK_ROWMASK;
         const uint2 tb = __ldg(g_orient_off + (e >> 20));
         pick_o = e >> 20; pick_row = src;
