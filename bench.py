@@ -343,31 +343,39 @@ def run_cuda(args) -> None:
         strong = {}
         for tag, sims, kw in (("uct_heuristic_rollouts_16384_sims", 16384, dict(rollout_policy=dev.POLICY_HEURISTIC)),
                               ("flat_uniform_rollouts_8192_sims", 8192, dict(max_depth=1, ucb_variant=1, reward_mode=1))):
-            rp = bdist.RootParallelWide(sims, 16, seed=SEED, **kw)
-            out = rp.search(mid)                                  # warm-up (allocations, NCCL channel setup)
+            rp = bdist.RootParallelWide(sims, 16, seed=SEED, **kw)   # merge = one kernel over NVLink peer memory
+            out = rp.search(mid)                                  # warm-up (allocations, window mapping)
             rp.search(mid, search_index=1)
+            n_root = out["n_root"]
+            bdist.merge_root_stats(out["visits"], out["reward"])  # NCCL channel setup for the comparison below
             barrier()
-            reps, t_search, t_merge = 5, 0.0, 0.0
-            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            reps, t_search, t_merge, t_nccl = 5, 0.0, 0.0, 0.0
+            a, b, c, d = (torch.cuda.Event(enable_timing=True) for _ in range(4))
             for k in range(reps):
                 rp.eng.p.tree_offset = rp.rank * rp.trees_per_rank
                 barrier()
                 a.record(stream)
                 res = rp.eng.search(mid, rp.per_tree)
                 b.record(stream)
-                v, w = bdist.merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0))
+                v, w = rp.peer.merge(res["visits"], res["reward"], n_root, check=False)
                 c.record(stream)
+                v2, w2 = bdist.merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0))   # the NCCL way, for comparison
+                d.record(stream)
                 torch.cuda.synchronize()
+                assert int(rp.peer.status.item()) == 0 and torch.equal(v, v2[:n_root]) and torch.equal(w, w2[:n_root])
                 t_search += a.elapsed_time(b)
                 t_merge += b.elapsed_time(c)
-            tt = torch.tensor([t_search / reps, t_merge / reps], dtype=torch.float64, device="cuda")
+                t_nccl += c.elapsed_time(d)
+            tt = torch.tensor([t_search / reps, t_merge / reps, t_nccl / reps], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            n_root = out["n_root"]
             strong[tag] = {"ms_per_move": float(tt[0] + tt[1]), "search_ms": float(tt[0]), "merge_us": float(tt[1]) * 1e3,
+                           "merge": "bk_root_merge_p2p (one kernel, 64-bit atomics on NVLink peer memory)",
+                           "merge_us_nccl_all_reduce": float(tt[2]) * 1e3,
                            "trees_total": 16, "trees_per_gpu": 16 // world, "sims_per_tree": rp.per_tree, "round_width": rp.width,
                            "best_rank": int(torch.argmax(v[:n_root]).item()),
                            "visits_checksum": int((v[:n_root] * torch.arange(1, n_root + 1, device=v.device)).sum().item())}
+            rp.peer.close()
             del rp
         if mcts is not None:
             mcts["mcts_strong_scaling_one_move"] = strong

@@ -1279,3 +1279,116 @@ extern "C" int bk_heuristic_scores_weighted(const bk_state* states, const uint8_
     LAUNCH_CHECK();
     return BK_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Root-parallel merge over peer memory (one process per GPU; windows mapped through CUDA IPC)
+// ---------------------------------------------------------------------------------------------
+// Window layout in 64-bit words: two slots of [visits[capacity], reward[capacity]] (merge e uses slot e & 1), then the two
+// arrival counters.  A slot is cleared by its owner after it has been read; it is written again two merges later, and a
+// peer can only be that far ahead after the owner has taken part in the merge in between, i.e. after this kernel ended.
+#define BK_P2P_MAX_WORLD 16
+struct P2PPeers { unsigned long long* w[BK_P2P_MAX_WORLD]; };
+
+__global__ void __launch_bounds__(1024)
+k_root_merge_p2p(const int32_t* __restrict__ visits, const int64_t* __restrict__ reward, int n_trees, int stride, int n, int capacity,
+                 int rank, int world, P2PPeers peers, unsigned long long epoch, long long timeout_cycles,
+                 int64_t* __restrict__ merged, int32_t* __restrict__ status) {
+    __shared__ int s_ok;
+    const unsigned slot = (unsigned)(epoch & 1ull);
+    const unsigned long long target = (epoch / 2ull + 1ull) * (unsigned long long)world;
+    const size_t slot_base = (size_t)slot * 2u * (size_t)capacity;
+    // 1. this rank's sums over its trees, added into every rank's window (own included)
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
+        const int which = i >= n, k = i - which * n;
+        long long v = 0;
+        for (int t = 0; t < n_trees; t++)
+            v += which ? (long long)reward[(size_t)t * stride + k] : (long long)visits[(size_t)t * stride + k];
+        const size_t at = slot_base + (size_t)which * capacity + k;
+        for (int p = 0; p < world; p++) {
+            const int q = (rank + 1 + p) % world;                        // ranks start with different peers
+            atomicAdd_system(peers.w[q] + at, (unsigned long long)v);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. arrival: one increment per rank and window; wait for `world` arrivals at the own window
+    if (threadIdx.x == 0) {
+        for (int p = 0; p < world; p++) atomicAdd_system(peers.w[(rank + 1 + p) % world] + 4u * (size_t)capacity + slot, 1ull);
+        volatile unsigned long long* mine = peers.w[rank] + 4u * (size_t)capacity + slot;
+        const long long t0 = clock64();
+        int ok = 1;
+        while (*mine < target) {
+            if (clock64() - t0 > timeout_cycles) { ok = 0; break; }
+            __nanosleep(200);
+        }
+        s_ok = ok;
+    }
+    __syncthreads();
+    __threadfence_system();
+    // 3. read the merged sums and clear the slot for the merge after the next
+    volatile unsigned long long* own = peers.w[rank];
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
+        const int which = i >= n, k = i - which * n;
+        const size_t at = slot_base + (size_t)which * capacity + k;
+        merged[(size_t)which * n + k] = (int64_t)own[at];
+        own[at] = 0ull;
+    }
+    __threadfence_system();
+    if (threadIdx.x == 0) *status = s_ok ? 0 : 1;
+}
+
+extern "C" int bk_p2p_window_create(int capacity, void** window, unsigned char* handle_host) {
+    REQUIRE_INIT(); REQUIRE(window && handle_host, "bk_p2p_window_create: null output");
+    REQUIRE(capacity >= 1 && capacity <= 2048, "bk_p2p_window_create: capacity must be in [1, 2048]");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    const size_t bytes = (4u * (size_t)capacity + 2u) * sizeof(unsigned long long);
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(p); return fail(BK_ERR_CUDA, "bk_p2p_window_create: %s", cudaGetErrorString(e)); }
+    memcpy(handle_host, &h, sizeof(h));
+    *window = p;
+    return BK_OK;
+}
+extern "C" int bk_p2p_window_open(const unsigned char* handle_host, void** peer_window) {
+    REQUIRE_INIT(); REQUIRE(handle_host && peer_window, "bk_p2p_window_open: null argument");
+    cudaIpcMemHandle_t h; memcpy(&h, handle_host, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(peer_window, h, cudaIpcMemLazyEnablePeerAccess));
+    return BK_OK;
+}
+extern "C" int bk_p2p_window_close(void* peer_window) {
+    if (peer_window) CUDA_TRY(cudaIpcCloseMemHandle(peer_window));
+    return BK_OK;
+}
+extern "C" int bk_p2p_window_destroy(void* window) {
+    if (window) CUDA_TRY(cudaFree(window));
+    return BK_OK;
+}
+extern "C" int bk_root_merge_p2p(const int32_t* root_visits, const int64_t* root_reward, int n_trees, int stride, int n, int capacity,
+                                 int rank, int world, void* const* windows_host, uint64_t epoch, int timeout_ms, int64_t* merged,
+                                 int32_t* status, void* stream) {
+    REQUIRE_INIT();
+    REQUIRE(root_visits && root_reward && windows_host && merged && status, "bk_root_merge_p2p: null buffer");
+    REQUIRE(world >= 1 && world <= BK_P2P_MAX_WORLD && rank >= 0 && rank < world, "bk_root_merge_p2p: rank / world out of range (world <= 16)");
+    REQUIRE(n_trees >= 1 && n >= 0 && n <= capacity && n <= stride && capacity <= 2048, "bk_root_merge_p2p: n, stride or capacity out of range");
+    P2PPeers peers;
+    for (int p = 0; p < BK_P2P_MAX_WORLD; p++) peers.w[p] = p < world ? reinterpret_cast<unsigned long long*>(windows_host[p]) : nullptr;
+    for (int p = 0; p < world; p++) REQUIRE(peers.w[p] != nullptr, "bk_root_merge_p2p: null window");
+    static int khz_of[BK_MAX_DEVICES];                  // cudaDevAttrClockRate is a slow query (about a millisecond): asked once per device
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (khz_of[dev] == 0) {
+        int q = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&q, cudaDevAttrClockRate, dev));
+        khz_of[dev] = q > 0 ? q : 2000000;
+    }
+    const int khz = khz_of[dev];
+    const long long timeout_cycles = (long long)(timeout_ms > 0 ? timeout_ms : 2000) * (long long)(khz > 0 ? khz : 2000000);
+    k_root_merge_p2p<<<1, 1024, 0, as_stream(stream)>>>(root_visits, root_reward, n_trees, stride, n, capacity, rank, world, peers,
+                                                        (unsigned long long)epoch, timeout_cycles, merged, status);
+    LAUNCH_CHECK();
+    return BK_OK;
+}

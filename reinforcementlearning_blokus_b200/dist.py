@@ -7,12 +7,15 @@ Two things shard:
   * root-parallel MCTS -- every rank searches its own trees from the same root with rank-distinct tree
     indices, then ONE all-reduce(sum) of the root visit / reward vectors (int64, <= 2048 entries each) and
     every rank picks the same move.  The reference has no such step (it is single-process); the merge rule is
-    the standard root-parallel one: most summed visits, lowest move id on ties.
+    the standard root-parallel one: most summed visits, lowest move id on ties.  On GPUs the all-reduce is replaced by
+    ``PeerRootMerge``: one kernel per rank that sums its trees and adds the sums into every rank's window over NVLink peer
+    memory (bk_root_merge_p2p) -- same integer sums, no NCCL launch on the move's critical path.
 """
 
 from __future__ import annotations
 
-from typing import Dict, Tuple
+import ctypes as C
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -120,18 +123,96 @@ def root_parallel_search(root_state: torch.Tensor, sims_total: int, trees_per_ra
             "sims": iters * trees}
 
 
+class PeerRootMerge:
+    """The exchange step of a root-parallel search as ONE kernel per rank over NVLink peer memory (include/blokus_b200.h,
+    bk_root_merge_p2p): every rank owns a window (cudaMalloc + CUDA IPC handle), maps the windows of the others, and per
+    merge adds the sums over its own trees into all windows with 64-bit atomics, signals, waits for the other ranks inside
+    the kernel and reads its own window.  The handles travel once, at construction, through ``all_gather_object``.
+    Results are the integer sums ``merge_root_stats`` returns.  One process per GPU; every rank must call ``merge`` the same
+    number of times (the epoch is part of the protocol)."""
+
+    def __init__(self, capacity: int = 2048, group=None, timeout_ms: int = 2000):
+        from . import _lib
+        from . import device as dev
+
+        self.rank, self.ws = world()
+        if self.ws > 16:
+            raise ValueError("PeerRootMerge supports up to 16 ranks")
+        self.capacity, self.timeout_ms, self.epoch = int(capacity), int(timeout_ms), 0
+        self.lib = dev._lib_for(None)
+        self._check = _lib.check
+        own, handle = C.c_void_p(), C.create_string_buffer(64)
+        self._check(self.lib.bk_p2p_window_create(self.capacity, C.byref(own), handle))
+        self.own = own.value
+        handles = [None] * self.ws
+        if self.ws > 1:
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.windows = (C.c_void_p * self.ws)()
+        self._opened = []
+        for r in range(self.ws):
+            if r == self.rank:
+                self.windows[r] = self.own
+            else:
+                peer = C.c_void_p()
+                self._check(self.lib.bk_p2p_window_open(handles[r], C.byref(peer)))
+                self.windows[r] = peer.value
+                self._opened.append(peer.value)
+        self.merged = torch.zeros((2, self.capacity), dtype=torch.int64, device="cuda")
+        self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        if self.ws > 1:
+            dist.barrier(group=group)          # nobody pushes before every window is mapped everywhere
+
+    def merge(self, visits: torch.Tensor, reward: torch.Tensor, n: int, check: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """visits [n_trees, stride] int32, reward [n_trees, stride] int64 (a search's root outputs), n root moves ->
+        (visits, reward) int64[n] summed over all trees of all ranks.  ``check`` reads the status word back (one
+        4-byte copy); a caller that synchronises anyway can pass False and test ``self.status`` itself."""
+        from . import device as dev
+
+        if visits.dtype != torch.int32 or reward.dtype != torch.int64 or visits.shape != reward.shape or visits.dim() != 2:
+            raise ValueError("PeerRootMerge.merge: visits int32 [trees, stride] and reward int64 [trees, stride] expected")
+        n = int(n)
+        if not 0 <= n <= min(self.capacity, visits.shape[1]):
+            raise ValueError("PeerRootMerge.merge: n out of range")
+        self._check(self.lib.bk_root_merge_p2p(visits.data_ptr(), reward.data_ptr(), int(visits.shape[0]), int(visits.stride(0)), n,
+                                               self.capacity, self.rank, self.ws, self.windows, self.epoch, self.timeout_ms,
+                                               self.merged.data_ptr(), self.status.data_ptr(), dev._stream()))
+        self.epoch += 1
+        out = self.merged.view(-1)[: 2 * n].view(2, n)
+        if check and int(self.status.item()) != 0:
+            raise RuntimeError("PeerRootMerge: the other ranks did not arrive within %d ms" % self.timeout_ms)
+        return out[0], out[1]
+
+    def close(self) -> None:
+        torch.cuda.synchronize()
+        for p in self._opened:
+            self.lib.bk_p2p_window_close(p)
+        self._opened = []
+        if self.own:
+            self.lib.bk_p2p_window_destroy(self.own)
+            self.own = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class RootParallelWide:
     """STRONG scaling of one move: a fixed simulation budget split over `total_trees` root-parallel WIDE trees
     (mcts.WideUCT: each tree is itself spread over its GPU), `total_trees / world_size` of them on every rank, one
-    all-reduce of the root statistics.  Tree t always has global index search_index * total_trees + t, so the merged
-    result is the same for every world size that divides total_trees."""
+    exchange of the root statistics -- ``merge="p2p"``: PeerRootMerge (one kernel over NVLink peer memory, the default on
+    GPUs), ``merge="nccl"``: torch.distributed all-reduce.  Tree t always has global index search_index * total_trees + t,
+    so the merged result is the same for every world size that divides total_trees."""
 
-    def __init__(self, sims_total: int, total_trees: int, seed: int, width: int = 0, group=None, **wide_kwargs):
+    def __init__(self, sims_total: int, total_trees: int, seed: int, width: int = 0, group=None, merge: str = "p2p", **wide_kwargs):
         from .mcts import WideUCT
 
         self.rank, self.ws = world()
         if total_trees % self.ws:
             raise ValueError("total_trees must be a multiple of the world size")
+        if merge not in ("p2p", "nccl"):
+            raise ValueError("merge must be 'p2p' or 'nccl'")
         self.group = group
         self.total_trees = int(total_trees)
         self.trees_per_rank = self.total_trees // self.ws
@@ -139,11 +220,18 @@ class RootParallelWide:
         self.width = int(width) if width else max(64, min(1024, self.per_tree // 4))
         self.eng = WideUCT(self.per_tree, width=self.width, n_trees=self.trees_per_rank, seed=seed,
                            tree_offset=self.rank * self.trees_per_rank, **wide_kwargs)
+        self.peer = PeerRootMerge(capacity=int(self.eng.visits.shape[1]), group=group) if merge == "p2p" else None
+
+    def merge(self, res: Dict[str, torch.Tensor], n_root: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.peer is not None:
+            return self.peer.merge(res["visits"], res["reward"], n_root)
+        v, w = merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0), group=self.group)
+        return v[:n_root], w[:n_root]
 
     def search(self, root_state: torch.Tensor, search_index: int = 0) -> Dict[str, object]:
         self.eng.p.tree_offset = int(search_index) * self.total_trees + self.rank * self.trees_per_rank
         res = self.eng.search(root_state, self.per_tree)
         n_root = int(res["counts"][0].item())
-        v, w = merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0), group=self.group)
-        return {"rank_of_best": pick_move(v, n_root), "visits": v[:n_root], "reward": w[:n_root], "n_root": n_root,
+        v, w = self.merge(res, n_root)
+        return {"rank_of_best": pick_move(v, n_root), "visits": v, "reward": w, "n_root": n_root,
                 "sims": self.per_tree * self.total_trees}

@@ -254,3 +254,36 @@ def test_two_devices_in_one_process():
             assert torch.equal(outs[d][0], got[0]) and torch.equal(outs[d][1], got[1])
         outs[d] = got
     assert torch.equal(outs[0][0], outs[1][0])
+
+
+def test_peer_root_merge_single_rank():
+    """bk_root_merge_p2p with one rank: the merged statistics are the sums over the rank's own trees (the slots alternate
+    and are cleared after every merge, so repeated merges of different sizes stay exact)."""
+    from reinforcementlearning_blokus_b200 import dist as bdist
+
+    peer = bdist.PeerRootMerge(capacity=2048)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for it in range(12):
+        n_trees, n = 1 + it % 4, (1, 58, 237, 2048)[it % 4]
+        vis = torch.randint(0, 1 << 20, (n_trees, 2048), generator=g, device="cuda", dtype=torch.int32)
+        rew = torch.randint(-(1 << 40), 1 << 40, (n_trees, 2048), generator=g, device="cuda", dtype=torch.int64)
+        v, w = peer.merge(vis, rew, n)
+        assert torch.equal(v, vis.sum(dim=0, dtype=torch.int64)[:n]) and torch.equal(w, rew.sum(dim=0)[:n])
+    with pytest.raises(ValueError):
+        peer.merge(vis.to(torch.int64), rew, 5)
+    peer.close()
+
+
+def test_peer_root_merge_two_ranks():
+    """Two processes, two GPUs (torchrun, NCCL for the comparison): 200 merges over NVLink peer memory equal the all-reduce
+    on every rank (tools/p2p_merge_check.py exits non-zero otherwise)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                           "--master-port", "29631", "tools/p2p_merge_check.py"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
