@@ -304,15 +304,18 @@ def run_cuda(args) -> None:
         trees, iters = 4 * 3552, 256        # four waves of 24 one-warp trees per SM, handed out by a ticket counter
         root = dev.to_device(empty_states(1))
         eng = DeviceUCT(iters, n_trees=trees, seed=SEED, tree_offset=rank * trees)
+        peer = bdist.PeerRootMerge()                  # windows over NVLink peer memory (CUDA IPC), mapped once
         res = eng.search(root, iters)                 # warm-up (search and merge: the first reduction loads torch kernels)
-        bdist.merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0))
+        n_root0 = int(res["counts"][0].item())
+        peer.merge(res["visits"], res["reward"], n_root0)
         barrier()
         m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         m0.record(stream)
         res = eng.search(root, iters)
-        v, w = bdist.merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0))
+        v, w = peer.merge(res["visits"], res["reward"], n_root0, check=False)    # sums over this rank's trees, then ONE kernel
         m1.record(stream)
         barrier()
+        assert int(peer.status.item()) == 0
         ms_m = m0.elapsed_time(m1)
         if world > 1:
             t = torch.tensor([ms_m], dtype=torch.float64, device="cuda")
@@ -320,9 +323,10 @@ def run_cuda(args) -> None:
             ms_m = float(t.item())
         mcts = {"mcts_sims_per_sec": world * trees * iters / (ms_m * 1e-3), "mcts_trees_per_gpu": trees,
                 "mcts_iterations_per_tree": iters, "mcts_rollout_plies": 50,
-                "mcts_root_visits_total": int(v.sum().item()), "mcts_collective": "1 all_reduce(int64[2,2048]) per search"}
+                "mcts_root_visits_total": int(v.sum().item()), "mcts_collective": "1 bk_root_merge_p2p per search (int64[2,n_root] added into every rank's window over NVLink peer memory)"}
         # the reference's default rollout policy (HeuristicAgent softmax, mcts_agent.py:275-276), no collective
-        del eng
+        peer.close()
+        del eng, peer
         ht = 2 * 148 * 20                   # two waves of 20 one-warp trees per SM (BK_MCTS_HEUR_CTAS_PER_SM)
         heng = DeviceUCT(iters, n_trees=ht, seed=SEED, tree_offset=rank * ht, rollout_policy=dev.POLICY_HEURISTIC)
         heng.search(root, iters)

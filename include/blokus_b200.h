@@ -312,8 +312,9 @@ int bk_mcts_wide_search(const bk_state* roots, int n_roots, int n_trees, const b
  * A window is created by its owner (cudaMalloc + cudaIpcGetMemHandle), its 64-byte handle travels to the other processes
  * by any host channel, and they map it with bk_p2p_window_open.
  *   bk_p2p_window_create : `capacity` = largest number of root moves (<= 2048); *window = device pointer, handle_host[64]
- *   bk_root_merge_p2p    : root_visits [n_trees][stride] int32, root_reward [n_trees][stride] int64 (outputs of
- *                          bk_mcts_search / bk_mcts_wide_search), n = number of root moves; windows_host = host array of
+ *   bk_root_merge_p2p    : root_visits [n_trees][stride] int32 (or int64 when visits_are_int64: sums the caller has already
+ *                          taken over many trees), root_reward [n_trees][stride] int64 (outputs of bk_mcts_search /
+ *                          bk_mcts_wide_search; one CTA adds up the trees, so keep n_trees small), n = number of root moves; windows_host = host array of
  *                          `world` device pointers in rank order (own window at [rank]); epoch = 0, 1, 2, ... the same on
  *                          every rank, +1 per merge; merged [2][n] int64 (visits, reward); status = 0, or 1 if the peers
  *                          did not arrive within timeout_ms (merged is then undefined).  One process per GPU. */
@@ -321,7 +322,7 @@ int bk_p2p_window_create(int capacity, void** window, unsigned char* handle_host
 int bk_p2p_window_open(const unsigned char* handle_host, void** peer_window);
 int bk_p2p_window_close(void* peer_window);
 int bk_p2p_window_destroy(void* window);
-int bk_root_merge_p2p(const int32_t* root_visits, const int64_t* root_reward, int n_trees, int stride, int n, int capacity,
+int bk_root_merge_p2p(const void* root_visits, int visits_are_int64, const int64_t* root_reward, int n_trees, int stride, int n, int capacity,
                       int rank, int world, void* const* windows_host, uint64_t epoch, int timeout_ms, int64_t* merged,
                       int32_t* status, void* stream);
 

@@ -66,7 +66,7 @@ PROTOTYPES = {
     "bk_p2p_window_open": (_i32, [_vp, C.POINTER(_vp)]),
     "bk_p2p_window_close": (_i32, [_vp]),
     "bk_p2p_window_destroy": (_i32, [_vp]),
-    "bk_root_merge_p2p": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _u64, _i32, _vp, _vp, _vp]),
+    "bk_root_merge_p2p": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _u64, _i32, _vp, _vp, _vp]),
 }
 
 

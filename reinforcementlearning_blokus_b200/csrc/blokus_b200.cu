@@ -1290,7 +1290,7 @@ extern "C" int bk_heuristic_scores_weighted(const bk_state* states, const uint8_
 struct P2PPeers { unsigned long long* w[BK_P2P_MAX_WORLD]; };
 
 __global__ void __launch_bounds__(1024)
-k_root_merge_p2p(const int32_t* __restrict__ visits, const int64_t* __restrict__ reward, int n_trees, int stride, int n, int capacity,
+k_root_merge_p2p(const void* __restrict__ visits, int visits_i64, const int64_t* __restrict__ reward, int n_trees, int stride, int n, int capacity,
                  int rank, int world, P2PPeers peers, unsigned long long epoch, long long timeout_cycles,
                  int64_t* __restrict__ merged, int32_t* __restrict__ status) {
     __shared__ int s_ok;
@@ -1302,7 +1302,9 @@ k_root_merge_p2p(const int32_t* __restrict__ visits, const int64_t* __restrict__
         const int which = i >= n, k = i - which * n;
         long long v = 0;
         for (int t = 0; t < n_trees; t++)
-            v += which ? (long long)reward[(size_t)t * stride + k] : (long long)visits[(size_t)t * stride + k];
+            v += which ? (long long)reward[(size_t)t * stride + k]
+                       : (visits_i64 ? (long long)static_cast<const int64_t*>(visits)[(size_t)t * stride + k]
+                                     : (long long)static_cast<const int32_t*>(visits)[(size_t)t * stride + k]);
         const size_t at = slot_base + (size_t)which * capacity + k;
         for (int p = 0; p < world; p++) {
             const int q = (rank + 1 + p) % world;                        // ranks start with different peers
@@ -1367,7 +1369,7 @@ extern "C" int bk_p2p_window_destroy(void* window) {
     if (window) CUDA_TRY(cudaFree(window));
     return BK_OK;
 }
-extern "C" int bk_root_merge_p2p(const int32_t* root_visits, const int64_t* root_reward, int n_trees, int stride, int n, int capacity,
+extern "C" int bk_root_merge_p2p(const void* root_visits, int visits_are_int64, const int64_t* root_reward, int n_trees, int stride, int n, int capacity,
                                  int rank, int world, void* const* windows_host, uint64_t epoch, int timeout_ms, int64_t* merged,
                                  int32_t* status, void* stream) {
     REQUIRE_INIT();
@@ -1387,7 +1389,7 @@ extern "C" int bk_root_merge_p2p(const int32_t* root_visits, const int64_t* root
     }
     const int khz = khz_of[dev];
     const long long timeout_cycles = (long long)(timeout_ms > 0 ? timeout_ms : 2000) * (long long)(khz > 0 ? khz : 2000000);
-    k_root_merge_p2p<<<1, 1024, 0, as_stream(stream)>>>(root_visits, root_reward, n_trees, stride, n, capacity, rank, world, peers,
+    k_root_merge_p2p<<<1, 1024, 0, as_stream(stream)>>>(root_visits, visits_are_int64, root_reward, n_trees, stride, n, capacity, rank, world, peers,
                                                         (unsigned long long)epoch, timeout_cycles, merged, status);
     LAUNCH_CHECK();
     return BK_OK;

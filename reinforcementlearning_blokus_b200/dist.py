@@ -105,9 +105,10 @@ def pick_move(visits: torch.Tensor, n_root: int) -> int:
 
 def root_parallel_search(root_state: torch.Tensor, sims_total: int, trees_per_rank: int, seed: int,
                          max_rollout_moves: int = 50, exploration: float = 1.414, search_index: int = 0,
-                         group=None) -> Dict[str, object]:
-    """sims_total simulations split evenly over world_size * trees_per_rank trees; one all-reduce; every rank
-    returns the same {"rank_of_best", "visits", "reward", "n_root", "sims"}."""
+                         group=None, peer: Optional["PeerRootMerge"] = None) -> Dict[str, object]:
+    """sims_total simulations split evenly over world_size * trees_per_rank trees; one exchange (``peer`` = a
+    PeerRootMerge: one kernel over NVLink peer memory; None: all-reduce); every rank returns the same
+    {"rank_of_best", "visits", "reward", "n_root", "sims"}."""
     from .mcts import DeviceUCT
 
     rank, ws = world()
@@ -118,7 +119,10 @@ def root_parallel_search(root_state: torch.Tensor, sims_total: int, trees_per_ra
                     seed=seed, tree_offset=search_index * trees + rank * trees_per_rank)
     res = eng.search(root_state, iters)
     n_root = int(res["counts"][0].item())
-    v, w = merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0), group=group)
+    if peer is not None:
+        v, w = peer.merge(res["visits"], res["reward"], n_root)
+    else:
+        v, w = merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0), group=group)
     return {"rank_of_best": pick_move(v, n_root), "visits": v[:n_root], "reward": w[:n_root], "n_root": n_root,
             "sims": iters * trees}
 
@@ -164,18 +168,21 @@ class PeerRootMerge:
 
     def merge(self, visits: torch.Tensor, reward: torch.Tensor, n: int, check: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """visits [n_trees, stride] int32, reward [n_trees, stride] int64 (a search's root outputs), n root moves ->
-        (visits, reward) int64[n] summed over all trees of all ranks.  ``check`` reads the status word back (one
-        4-byte copy); a caller that synchronises anyway can pass False and test ``self.status`` itself."""
+        (visits, reward) int64[n] summed over all trees of all ranks.  More than 32 trees are first added up by torch (the
+        kernel is one CTA).  ``check`` reads the status word back (one 4-byte copy); a caller that synchronises anyway can
+        pass False and test ``self.status`` itself."""
         from . import device as dev
 
-        if visits.dtype != torch.int32 or reward.dtype != torch.int64 or visits.shape != reward.shape or visits.dim() != 2:
-            raise ValueError("PeerRootMerge.merge: visits int32 [trees, stride] and reward int64 [trees, stride] expected")
+        if visits.dtype not in (torch.int32, torch.int64) or reward.dtype != torch.int64 or visits.shape != reward.shape or visits.dim() != 2:
+            raise ValueError("PeerRootMerge.merge: visits int32/int64 [trees, stride] and reward int64 [trees, stride] expected")
         n = int(n)
         if not 0 <= n <= min(self.capacity, visits.shape[1]):
             raise ValueError("PeerRootMerge.merge: n out of range")
-        self._check(self.lib.bk_root_merge_p2p(visits.data_ptr(), reward.data_ptr(), int(visits.shape[0]), int(visits.stride(0)), n,
-                                               self.capacity, self.rank, self.ws, self.windows, self.epoch, self.timeout_ms,
-                                               self.merged.data_ptr(), self.status.data_ptr(), dev._stream()))
+        if visits.shape[0] > 32:
+            visits, reward = visits.sum(dim=0, dtype=torch.int64, keepdim=True), reward.sum(dim=0, keepdim=True)
+        self._check(self.lib.bk_root_merge_p2p(visits.data_ptr(), int(visits.dtype == torch.int64), reward.data_ptr(), int(visits.shape[0]),
+                                               int(visits.stride(0)), n, self.capacity, self.rank, self.ws, self.windows, self.epoch,
+                                               self.timeout_ms, self.merged.data_ptr(), self.status.data_ptr(), dev._stream()))
         self.epoch += 1
         out = self.merged.view(-1)[: 2 * n].view(2, n)
         if check and int(self.status.item()) != 0:

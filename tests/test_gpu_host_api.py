@@ -269,8 +269,15 @@ def test_peer_root_merge_single_rank():
         rew = torch.randint(-(1 << 40), 1 << 40, (n_trees, 2048), generator=g, device="cuda", dtype=torch.int64)
         v, w = peer.merge(vis, rew, n)
         assert torch.equal(v, vis.sum(dim=0, dtype=torch.int64)[:n]) and torch.equal(w, rew.sum(dim=0)[:n])
+    # many trees: torch adds them up first and the kernel takes int64 visit sums
+    vis = torch.randint(0, 1 << 20, (100, 2048), generator=g, device="cuda", dtype=torch.int32)
+    rew = torch.randint(-(1 << 40), 1 << 40, (100, 2048), generator=g, device="cuda", dtype=torch.int64)
+    v, w = peer.merge(vis, rew, 237)
+    assert torch.equal(v, vis.sum(dim=0, dtype=torch.int64)[:237]) and torch.equal(w, rew.sum(dim=0)[:237])
     with pytest.raises(ValueError):
-        peer.merge(vis.to(torch.int64), rew, 5)
+        peer.merge(vis.to(torch.int16), rew, 5)
+    with pytest.raises(ValueError):
+        peer.merge(vis, rew, 4096)
     peer.close()
 
 
