@@ -171,11 +171,13 @@ int bk_scores(const bk_state* states, int n, int32_t* game_scores /*[n][4]*/,
 /* Game i (global index game_offset+i) starts from start_states[i] (NULL: the empty board) and plays
  * turns first_turn, first_turn+1, ... (passes count as turns): turn t of game g draws
  * r = word t%4 of philox4x32_10(key=seed, ctr=(g_lo,g_hi,t/4,0)) and plays the ((uint64)r*n_legal)>>32-th move of the
- * ascending list; a player with no move passes; the game stops once no player can move or when
+ * ascending list (policy BK_POLICY_UNIFORM; with BK_POLICY_HEURISTIC the same word r is the categorical draw over the
+ * softmax of HeuristicAgent's move scores, cumulative order as documented in csrc/heuristic.cuh and restated by the oracle);
+ * a player with no move passes; the game stops once no player can move or when
  * t reaches max_turns (0 = BK_MAX_TURNS).  A game played in segments [0,a), [a,b), ... through
  * final_states is the same game as one call.  Outputs (each may be NULL): game_scores/board_scores [n][4],
  * trace [n][BK_MAX_TURNS] move ids by turn (BK_PASS = pass/pad; slots < first_turn are left untouched),
- * choice [n][BK_MAX_TURNS] chosen indices, final_states [n]. */
+ * choice [n][BK_MAX_TURNS] rank of each chosen move in the ascending legal-move list, final_states [n]. */
 int bk_playout(const bk_state* start_states, int n, uint64_t seed, uint64_t game_offset,
                int policy, int first_turn, int max_turns, int32_t* game_scores, int32_t* board_scores,
                uint16_t* trace, uint16_t* choice, bk_state* final_states, void* stream);
