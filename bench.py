@@ -570,7 +570,7 @@ def _extras(dev, torch, n):
 
         flat = dict(max_depth=1, ucb_variant=1, reward_mode=1)
         for tag, sims, trees, kw in (("mcts_move_1000_sims_ms_wide_1tree", 1000, 1, flat), ("mcts_move_1000_sims_ms_wide_2trees", 500, 2, flat),
-                                     ("mcts_move_5000_sims_ms_wide_8trees", 625, 8, flat),
+                                     ("mcts_move_5000_sims_ms_wide_8trees", 625, 8, flat), ("mcts_move_5000_sims_ms_wide_2trees", 2500, 2, flat),
                                      ("mcts_move_1000_sims_ms_wide_uct_heuristic_rollouts", 1000, 1, dict(rollout_policy=dev.POLICY_HEURISTIC))):
             weng = WideUCT(sims, width=max(64, min(1024, sims // 4)), n_trees=trees, seed=SEED, **kw)
             weng.search(root, sims)

@@ -155,7 +155,9 @@ class FastMCTSAgent:
         self.search_width = search_width
         # root-parallel trees of the wide search: the simulation budget is split over `num_trees` bandits that are planned
         # side by side (one planner each) and share the GPU for their rollouts; their root statistics are summed.
-        # Default: one tree per 625 simulations of the budget (rounded), at most 8 (5,000 simulations: 8 planners, ~1 ms).
+        # Default: one tree per 2,500 simulations of the budget (rounded), at most 8.  (A round costs about the same whatever
+        # its width since the flat rounds are dealt out at once, so extra planners no longer buy time; fewer, larger bandits
+        # adapt better.  Round 2 began with one tree per 625 simulations, when a planner walked every simulation.)
         self.num_trees = num_trees
         self._thinks = 0
         self._wide_cache = None
@@ -185,7 +187,7 @@ class FastMCTSAgent:
         ordered = legal_moves if ids_known is not None and len(ids_known) == len(legal_moves) else sorted(legal_moves, key=lambda m: m.to_id())
         wide = self.leaf_batch == 1 and (self.search_width is None or int(self.search_width) > 0)
         if wide:
-            W = int(self.num_trees) if self.num_trees else max(1, min(8, (int(self.iterations) + 312) // 625))    # trees
+            W = int(self.num_trees) if self.num_trees else max(1, min(8, (int(self.iterations) + 1250) // 2500))  # trees
             total = max(1, -(-int(self.iterations) // W))         # simulations per tree
             width = int(self.search_width) if self.search_width else max(64, min(1024, total // 4))
             key = (total, width, W, self.exploration_constant, self.rollout_plies, self.seed)

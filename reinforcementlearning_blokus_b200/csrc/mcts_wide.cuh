@@ -139,6 +139,10 @@ __device__ __forceinline__ uint32_t wide_key(float u) {
     return (b >> 31) ? ~b : (b | 0x80000000u);
 }
 
+__device__ __forceinline__ float wide_unkey(uint32_t k) {
+    return __uint_as_float((k >> 31) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
 // ---- PLAN: one CTA per tree ----------------------------------------------------------------------------------------------
 // The walks of a round are one dependent chain (each walk sees the pending counts of the walks before it), so the time of
 // a round is (number of walks) x (latency of one walk).  Two things keep that latency short:
@@ -222,67 +226,128 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
     __syncthreads();
     const uint32_t sims_done = hdr->sims_done;
     const uint32_t room = sims_target > sims_done ? sims_target - sims_done : 0u;
-    const uint32_t want_items = overflow ? 0u : (room < L.width ? room : L.width);
+    uint32_t want_items = overflow ? 0u : (room < L.width ? room : L.width);
     uint32_t n_items = 0, buf = 0;
-    // ---- a flat bandit whose root is fully expanded gets the whole round dealt out at once.  With the exploration scale
-    // frozen at the round's final count, s = stab[finished + W], the value of giving child k one more walk when it already
-    // has j of this round is u_k(j) = fma(s, invtab[m_k + j], q_k), non-increasing in j, and the sequential rule "the next
-    // walk goes to the first maximal child" picks exactly the W largest values (ties: lower k first, then lower j).  That
+    // ---- while the root has untried moves every walk stops there and claims the next one (no selection happens), so these
+    // walks are written down at once: children n_nodes, n_nodes + 1, ... with ranks nl-1-ne, nl-2-ne, ... -- exactly what the
+    // walks below would do one after the other (0.6 us each; a 237-move root costs 150 us that way).
+    static_assert(BK_WIDE_PLAN_WARPS == 1, "the batched root expansions are written for one planner warp");
+    if (n_items < want_items && !overflow && S.nl[0] != BK_WIDE_PENDING && S.ne[0] < S.nl[0]) {
+        if (warp == 0) {
+            const uint32_t nl = S.nl[0], ne = S.ne[0];
+            uint32_t cb = S.cb[0];
+            if (cb == BK_WIDE_NONE) {
+                const uint32_t remaining = (uint32_t)prm.iterations_total - (sims_done + n_items);
+                const uint32_t want = nl < remaining ? nl : remaining;
+                cb = pool_used;
+                if (pool_used + want > L.pool_slots) overflow = 1;
+                pool_used += want;
+            }
+            uint32_t e = min(want_items - n_items, nl - ne);
+            bool stop = false;
+            if (overflow) { e = 0; stop = true; }
+            else if (n_nodes + e > L.max_nodes) { e = L.max_nodes - n_nodes; overflow = 1; stop = true; }   // the walk after the last fitting one
+            const float inv1 = __ldg(V.invtab + 1);
+            __syncwarp();
+            for (uint32_t i = lane; i < e; i += 32u) {
+                const uint32_t child = n_nodes + i, k = ne + i, rank = nl - 1u - k;
+                V.pool[cb + k] = child;
+                V.parent[child] = 0; V.visits[child] = 0; V.virt[child] = 0; V.reward[child] = 0;
+                V.child_base[child] = BK_WIDE_NONE; V.n_legal[child] = BK_WIDE_PENDING; V.n_expanded[child] = 0;
+                V.move_of[child] = (uint16_t)rank; V.q[child] = 0.0f; V.inv[child] = 0.0f;
+                if (child < BK_WIDE_NC) {
+                    S.par[child] = 0; S.vis[child] = 0; S.virt[child] = 1; S.cb[child] = BK_WIDE_NONE;
+                    S.nl[child] = BK_WIDE_PENDING; S.ne[child] = 0; S.mv[child] = (uint16_t)rank; S.q[child] = 0.0f; S.inv[child] = inv1;
+                } else { V.virt[child] = 1; V.inv[child] = inv1; }
+                V.item_leaf[n_items + i] = child; V.item_parent[n_items + i] = 0u; V.item_rank[n_items + i] = (uint16_t)rank;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (e > 0) { V.child_base[0] = cb; S.cb[0] = cb; }
+                V.n_expanded[0] = (uint16_t)(ne + e); S.ne[0] = (uint16_t)(ne + e);
+                S.virt[0] += (int32_t)e;
+                S.n_nodes = n_nodes + e; S.pool_used = pool_used; S.overflow = overflow; S.stop = stop ? 1u : 0u;
+            }
+            n_items += e;
+        }
+        __threadfence_block();
+        __syncthreads();
+        n_nodes = S.n_nodes; pool_used = S.pool_used; overflow = S.overflow;
+        if (S.stop) want_items = n_items;
+    }
+    // ---- a flat bandit whose root is fully expanded -- at the start of the round, or once this round's expansions are
+    // written down -- gets the rest of the round dealt out at once.  With the exploration scale frozen at the round's final
+    // count, s = stab[finished + pending + W], the value of giving child k one more walk when it already has j of them is
+    // u_k(j) = fma(s, invtab[m_k + p_k + j], q_k) (m finished, p pending simulations; a child created in this round has m = 0,
+    // p = 1, q = 0), non-increasing in j, and the sequential rule "the next walk goes to the first maximal child" picks
+    // exactly the W largest values (ties: lower k first, then lower j).  That
     // set is found without walking: a bit-by-bit search for the largest key T with #{(k, j): key(u_k(j)) >= T} >= W, every
     // child's count by a binary search over j; children take everything above T and the values equal to T are shared out in
     // child order.  Cost O(children * log W * 32) per round instead of O(W * children).  The items are numbered child by child.
-    if (prm.max_depth == 1 && want_items > 0 && S.nl[0] != BK_WIDE_PENDING && S.nl[0] > 0 && S.ne[0] == S.nl[0] && S.nl[0] <= 2048) {
+    if (prm.max_depth == 1 && n_items < want_items && S.nl[0] != BK_WIDE_PENDING && S.nl[0] > 0 && S.ne[0] == S.nl[0] && S.nl[0] <= 2048) {
         if (warp == 0) {
-            const uint32_t ne0 = S.ne[0], W = want_items;
-            const float s = __ldg(V.stab + S.vis[0] + (int32_t)W);
-            // walks of child k whose key is >= tau: first j with key(u_k(j)) < tau (keys do not increase with j)
+            const uint32_t ne0 = S.ne[0], W = want_items - n_items, item0 = n_items;
+            const float s = __ldg(V.stab + S.vis[0] + S.virt[0] + (int32_t)W);
+            // walks of child k whose key is >= tau: first j with key(u_k(j)) < tau (keys do not increase with j).  The
+            // boundary is GUESSED in closed form -- fma(s, 1/sqrt(m + j), q) >= t  <=>  m + j <= (s / (t - q))^2 up to rounding --
+            // and then settled with the real table values (the answer is the exact boundary of the monotone predicate, the
+            // same a binary search finds), which takes two or three dependent loads instead of log2(W).
+            const float inv_s = s > 0.0f ? 1.0f / s : 0.0f;
+            auto guess = [&](float q, int32_t m, float t) -> uint32_t {
+                const float x = (t - q) * inv_s;                           // needs 1/sqrt(m + j) >= x
+                if (!(x > 0.0f) || !(s > 0.0f)) return W;                  // every j qualifies (or s == 0: settled below)
+                const float r = 1.0f / (x * x) - (float)m + 1.0f;
+                return r <= 0.0f ? 0u : (r >= (float)W ? W : (uint32_t)r);
+            };
+            // one step towards the boundary in [lo, hi] (ok(j) for j < lo, !ok(j) for j >= hi): test the guess or its left neighbour
+            auto settle_step = [&](const float* it, float q, uint32_t tau, uint32_t& lo, uint32_t& hi, uint32_t& g, int step) {
+                if (step >= 6) g = (lo + hi) >> 1;                         // a bad guess: plain bisection from here
+                g = g < lo ? lo : (g > hi ? hi : g);
+                const uint32_t j = g == hi ? g - 1u : g;                   // g == hi > lo: is the left neighbour still in?
+                const bool in = wide_key(__fmaf_rn(s, __ldg(it + j), q)) >= tau;
+                if (g == hi) { if (in) lo = hi; else { hi = g - 1u; g = hi; } }
+                else if (in) { lo = g + 1u; g = lo; }
+                else { hi = g; if (g > lo) g = g - 1u; }
+            };
             auto count_ge = [&](uint32_t k, uint32_t tau) -> uint32_t {
                 const float q = S.q[k + 1];
-                const float* it = V.invtab + S.vis[k + 1];
-                if (wide_key(__fmaf_rn(s, __ldg(it), q)) < tau) return 0u;
-                uint32_t lo = 1, hi = W;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (wide_key(__fmaf_rn(s, __ldg(it + mid), q)) >= tau) lo = mid + 1; else hi = mid;
-                }
+                const int32_t m = S.vis[k + 1] + S.virt[k + 1];
+                uint32_t lo = 0, hi = W, g = guess(q, m, wide_unkey(tau));
+                for (int step = 0; lo < hi; step++) settle_step(V.invtab + m, q, tau, lo, hi, g, step);
                 return lo;
             };
-            // the same for all children, eight per lane at a time: eight independent searches keep eight table loads in flight
+            // the same for all children, eight per lane at a time: eight independent chains keep eight table loads in flight
             auto total_ge = [&](uint32_t tau) -> uint32_t {
-                uint32_t t = 0;
+                const float t = wide_unkey(tau);
+                uint32_t sum = 0;
                 for (uint32_t base = lane; base < ne0; base += 256u) {
-                    uint32_t lo[8], hi[8]; float q[8]; const float* it[8];
+                    uint32_t lo[8], hi[8], g[8]; float q[8]; const float* it[8];
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
                         const uint32_t k = base + 32u * (uint32_t)r;
                         const bool valid = k < ne0;
+                        const int32_t m = valid ? S.vis[k + 1] + S.virt[k + 1] : 1;
                         q[r] = valid ? S.q[k + 1] : 0.0f;
-                        it[r] = V.invtab + (valid ? S.vis[k + 1] : 1);
-                        const bool any = valid && wide_key(__fmaf_rn(s, __ldg(it[r]), q[r])) >= tau;
-                        lo[r] = any ? 1u : 0u; hi[r] = any ? W : 0u;
+                        it[r] = V.invtab + m;
+                        lo[r] = 0u; hi[r] = valid ? W : 0u; g[r] = guess(q[r], m, t);
                     }
                     bool more = true;
-                    while (more) {
+                    for (int step = 0; more; step++) {
                         more = false;
 #pragma unroll
-                        for (int r = 0; r < 8; r++) {
-                            if (lo[r] < hi[r]) {
-                                const uint32_t mid = (lo[r] + hi[r]) >> 1;
-                                if (wide_key(__fmaf_rn(s, __ldg(it[r] + mid), q[r])) >= tau) lo[r] = mid + 1; else hi[r] = mid;
-                                more = true;
-                            }
-                        }
+                        for (int r = 0; r < 8; r++)
+                            if (lo[r] < hi[r]) { settle_step(it[r], q[r], tau, lo[r], hi[r], g[r], step); more = true; }
                     }
 #pragma unroll
-                    for (int r = 0; r < 8; r++) t += lo[r];
+                    for (int r = 0; r < 8; r++) sum += lo[r];
                 }
-                return __reduce_add_sync(BK_FULL, t);
+                return __reduce_add_sync(BK_FULL, sum);
             };
             // the threshold lies between the smallest last value and the largest first value of the children
             uint32_t kmax = 0, kmin = 0xFFFFFFFFu;
             for (uint32_t k = lane; k < ne0; k += 32) {
                 const float q = S.q[k + 1];
-                const float* it = V.invtab + S.vis[k + 1];
+                const float* it = V.invtab + S.vis[k + 1] + S.virt[k + 1];
                 kmax = max(kmax, wide_key(__fmaf_rn(s, __ldg(it), q)));
                 kmin = min(kmin, wide_key(__fmaf_rn(s, __ldg(it + (W - 1u)), q)));
             }
@@ -314,7 +379,7 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(BK_FULL, pincl, d); if (lane >= d) pincl += v; }
                 if (k < ne0) {
                     S.give[k] = (uint16_t)mine; S.first[k] = (uint16_t)(at + pincl - mine);
-                    if (mine) { S.virt[k + 1] = (int32_t)mine; S.inv[k + 1] = __ldg(V.invtab + S.vis[k + 1] + (int32_t)mine); }
+                    if (mine) { S.virt[k + 1] += (int32_t)mine; S.inv[k + 1] = __ldg(V.invtab + S.vis[k + 1] + S.virt[k + 1]); }
                 }
                 at += __shfl_sync(BK_FULL, pincl, 31);
             }
@@ -323,7 +388,9 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
             for (uint32_t t = lane; t < W; t += 32) {
                 uint32_t lo = 0, hi = ne0 - 1;
                 while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (S.first[mid] <= t) lo = mid; else hi = mid - 1; }
-                V.item_leaf[t] = lo + 1; V.item_parent[t] = BK_WIDE_NONE; V.item_rank[t] = 0;
+                const bool pend = S.nl[lo + 1] == BK_WIDE_PENDING;       // created in this round: the work kernel re-derives it
+                V.item_leaf[item0 + t] = lo + 1; V.item_parent[item0 + t] = pend ? 0u : BK_WIDE_NONE;
+                V.item_rank[item0 + t] = pend ? S.mv[lo + 1] : (uint16_t)0;
             }
             if (lane == 0) S.virt[0] += (int32_t)W;
         }

@@ -99,7 +99,7 @@ def test_agents_use_the_wide_search(golden_dir):
         agent = FastMCTSAgent(iterations=budget, time_limit=30.0, seed=5)
         out = agent.think(board, player, legal, 30000)
         per_tree, width, trees = agent._wide_cache[0][:3]
-        assert trees == max(1, min(8, (budget + 312) // 625)) and per_tree * trees >= budget
+        assert trees == max(1, min(8, (budget + 1250) // 2500)) and per_tree * trees >= budget
         tot = np.zeros(n, dtype=np.int64)
         chunk = max(FastMCTSAgent.CHUNK, 4 * width)             # think() checks the clock between chunks of four rounds
         calls = [min(chunk, per_tree - lo) for lo in range(0, per_tree, chunk)]
