@@ -142,7 +142,7 @@ class PeerRootMerge:
         self.rank, self.ws = world()
         if self.ws > 16:
             raise ValueError("PeerRootMerge supports up to 16 ranks")
-        self.capacity, self.timeout_ms, self.epoch = int(capacity), int(timeout_ms), 0
+        self.capacity, self.timeout_ms, self.epoch, self.group = int(capacity), int(timeout_ms), 0, group
         self.lib = dev._lib_for(None)
         self._check = _lib.check
         own, handle = C.c_void_p(), C.create_string_buffer(64)
@@ -189,18 +189,22 @@ class PeerRootMerge:
             raise RuntimeError("PeerRootMerge: the other ranks did not arrive within %d ms" % self.timeout_ms)
         return out[0], out[1]
 
-    def close(self) -> None:
+    def close(self, collective: bool = True) -> None:
+        """Unmap the peers' windows, then free the own one.  ``collective`` (every rank calls close): a barrier in between,
+        so that no window is freed while another process still has it mapped."""
         torch.cuda.synchronize()
         for p in self._opened:
             self.lib.bk_p2p_window_close(p)
         self._opened = []
         if self.own:
+            if collective and self.ws > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)
             self.lib.bk_p2p_window_destroy(self.own)
             self.own = None
 
     def __del__(self):
         try:
-            self.close()
+            self.close(collective=False)
         except Exception:
             pass
 
