@@ -27,6 +27,7 @@
 #define BK_WIDE_NONE 0xFFFFFFFFu
 #define BK_WIDE_STREAM 0x57u        /* Philox stream id of the wide search's rollouts */
 #define BK_WIDE_MAX_WIDTH 4096
+#define BK_WIDE_DEAL_MIN 256u       /* full trees: walks left in the round from which the root deals them out at once */
 #define BK_WIDE_PENDING 0xFFFFu     /* n_legal of a node whose state the current round is still building */
 
 struct WideLayout {
@@ -275,8 +276,8 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
         n_nodes = S.n_nodes; pool_used = S.pool_used; overflow = S.overflow;
         if (S.stop) want_items = n_items;
     }
-    // ---- a flat bandit whose root is fully expanded -- at the start of the round, or once this round's expansions are
-    // written down -- gets the rest of the round dealt out at once.  With the exploration scale frozen at the round's final
+    // ---- a root that is fully expanded -- at the start of the round, or once this round's expansions are written down --
+    // deals the rest of the round's walks out to its children at once (flat bandit: that is the whole walk).  With the exploration scale frozen at the round's final
     // count, s = stab[finished + pending + W], the value of giving child k one more walk when it already has j of them is
     // u_k(j) = fma(s, invtab[m_k + p_k + j], q_k) (m finished, p pending simulations; a child created in this round has m = 0,
     // p = 1, q = 0), non-increasing in j, and the sequential rule "the next walk goes to the first maximal child" picks
@@ -284,7 +285,12 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
     // set is found without walking: a bit-by-bit search for the largest key T with #{(k, j): key(u_k(j)) >= T} >= W, every
     // child's count by a binary search over j; children take everything above T and the values equal to T are shared out in
     // child order.  Cost O(children * log W * 32) per round instead of O(W * children).  The items are numbered child by child.
-    if (prm.max_depth == 1 && n_items < want_items && S.nl[0] != BK_WIDE_PENDING && S.nl[0] > 0 && S.ne[0] == S.nl[0] && S.nl[0] <= 2048) {
+    const bool flat = prm.max_depth == 1;
+    bool dealt = false;                                              // full tree: walk i of the round starts at root child item_leaf[i]
+    // (the dealing costs 60-100 us whatever the width and saves about 0.35 us per walk of a full tree, 0.65 us of a flat one:
+    //  full trees use it for rounds of at least BK_WIDE_DEAL_MIN walks -- part of the schedule, the oracle has the same rule)
+    if (n_items < want_items && (flat || want_items - n_items >= BK_WIDE_DEAL_MIN) && S.nl[0] != BK_WIDE_PENDING && S.nl[0] > 0 &&
+        S.ne[0] == S.nl[0] && S.nl[0] <= 2048) {
         if (warp == 0) {
             const uint32_t ne0 = S.ne[0], W = want_items - n_items, item0 = n_items;
             const float s = __ldg(V.stab + S.vis[0] + S.virt[0] + (int32_t)W);
@@ -379,7 +385,7 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(BK_FULL, pincl, d); if (lane >= d) pincl += v; }
                 if (k < ne0) {
                     S.give[k] = (uint16_t)mine; S.first[k] = (uint16_t)(at + pincl - mine);
-                    if (mine) { S.virt[k + 1] += (int32_t)mine; S.inv[k + 1] = __ldg(V.invtab + S.vis[k + 1] + S.virt[k + 1]); }
+                    if (flat && mine) { S.virt[k + 1] += (int32_t)mine; S.inv[k + 1] = __ldg(V.invtab + S.vis[k + 1] + S.virt[k + 1]); }
                 }
                 at += __shfl_sync(BK_FULL, pincl, 31);
             }
@@ -392,14 +398,18 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
                 V.item_leaf[item0 + t] = lo + 1; V.item_parent[item0 + t] = pend ? 0u : BK_WIDE_NONE;
                 V.item_rank[item0 + t] = pend ? S.mv[lo + 1] : (uint16_t)0;
             }
-            if (lane == 0) S.virt[0] += (int32_t)W;
+            if (flat && lane == 0) S.virt[0] += (int32_t)W;
         }
-        n_items = want_items;
+        // The flat bandit is done with the round.  In a full tree the dealing replaces only the ROOT's selection: walk i goes
+        // on below the child it was dealt to (item_leaf[i] holds that child until the walk writes its own leaf there), one
+        // after the other as before -- the scan of all root children per walk is what is saved.
+        if (flat) n_items = want_items; else dealt = true;
+        __threadfence_block();
         __syncthreads();
     }
     for (; n_items < want_items; n_items++) {
         // ---- descent: all threads, uniform control flow
-        uint32_t node = 0, depth = 0;
+        uint32_t node = dealt ? V.item_leaf[n_items] : 0u, depth = dealt ? 1u : 0u;
         bool may_expand = false, pending = false;
         for (;;) {
             const bool in = node < BK_WIDE_NC;

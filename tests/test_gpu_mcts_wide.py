@@ -52,6 +52,22 @@ def test_wide_search_heuristic_rollouts_and_short_rollouts(golden_dir):
         _same(res, want)
 
 
+def test_wide_full_tree_rounds_dealt_at_the_root(golden_dir):
+    """Full trees with rounds of at least 256 walks: a fully expanded root deals the round's walks out to its children at once
+    (threshold search, exploration scale frozen for the round) and every walk goes on below its child -- restated by the
+    oracle as the greedy choice.  Wide rounds, resumed calls, uniform and HeuristicAgent rollouts, short rollouts."""
+    for ri, root in enumerate(_roots(golden_dir)[:4]):
+        for kw in (dict(max_rollout_moves=6), dict(max_rollout_moves=4, rollout_policy=1), dict(reward_mode=2)):
+            calls = [700, 640] if ri % 2 else [1340]
+            want = orc.mcts_wide(root, calls, 512, seed=21 + ri, tree_id=2, **kw)
+            eng = WideUCT(sum(calls), width=512, seed=21 + ri, tree_offset=2, **kw)
+            res = None
+            for ci, c in enumerate(calls):
+                res = eng.search(dev.to_device(np.atleast_1d(root)) if ci == 0 else None, c, resume=ci > 0)
+            _same(res, want)
+            assert int(res["sims_done"][0]) == want["sims"] == sum(calls)
+
+
 def test_wide_search_resumes_and_runs_several_trees(golden_dir):
     roots_np = _roots(golden_dir)[:3]
     roots = dev.to_device(np.stack(roots_np))
