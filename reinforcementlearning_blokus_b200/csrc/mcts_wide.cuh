@@ -27,7 +27,7 @@
 #define BK_WIDE_NONE 0xFFFFFFFFu
 #define BK_WIDE_STREAM 0x57u        /* Philox stream id of the wide search's rollouts */
 #define BK_WIDE_MAX_WIDTH 4096
-#define BK_WIDE_DEAL_MIN 256u       /* full trees: walks left in the round from which the root deals them out at once */
+#define BK_WIDE_DEAL_MIN 128u       /* full trees: walks left in the round from which the root deals them out at once */
 #define BK_WIDE_PENDING 0xFFFFu     /* n_legal of a node whose state the current round is still building */
 
 struct WideLayout {
@@ -287,7 +287,8 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
     // child order.  Cost O(children * log W * 32) per round instead of O(W * children).  The items are numbered child by child.
     const bool flat = prm.max_depth == 1;
     bool dealt = false;                                              // full tree: walk i of the round starts at root child item_leaf[i]
-    // (the dealing costs 60-100 us whatever the width and saves about 0.35 us per walk of a full tree, 0.65 us of a flat one:
+    uint32_t dealt0 = 0;                                             // position of the first dealt walk
+    // (the dealing costs 60-100 us whatever the width and saves most of a walk's 0.65-0.85 us:
     //  full trees use it for rounds of at least BK_WIDE_DEAL_MIN walks -- part of the schedule, the oracle has the same rule)
     if (n_items < want_items && (flat || want_items - n_items >= BK_WIDE_DEAL_MIN) && S.nl[0] != BK_WIDE_PENDING && S.nl[0] > 0 &&
         S.ne[0] == S.nl[0] && S.nl[0] <= 2048) {
@@ -403,11 +404,69 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
         // The flat bandit is done with the round.  In a full tree the dealing replaces only the ROOT's selection: walk i goes
         // on below the child it was dealt to (item_leaf[i] holds that child until the walk writes its own leaf there), one
         // after the other as before -- the scan of all root children per walk is what is saved.
-        if (flat) n_items = want_items; else dealt = true;
+        if (flat) n_items = want_items; else { dealt = true; dealt0 = n_items; }
         __threadfence_block();
         __syncthreads();
     }
     for (; n_items < want_items; n_items++) {
+        // ---- a dealt round: the walks of one root child are consecutive.  While that child has untried moves each of them
+        // stops there and claims the next one; while it is itself being built each of them is one more simulation of it.
+        // Either way the walks need no selection and are written down at once (what they would do one after the other).
+        if (dealt) {
+            const uint32_t nd = V.item_leaf[n_items], k = nd - 1u;            // a root child: node k + 1 < BK_WIDE_NC
+            if (n_items == dealt0 + S.first[k] && warp == 0) {
+                const uint32_t g = S.give[k], nl = S.nl[nd], ne = S.ne[nd];
+                uint32_t e = 0;
+                bool stop = false;
+                if (nl == BK_WIDE_PENDING) {
+                    e = g;
+                    const uint16_t rank = S.mv[nd];
+                    for (uint32_t i = lane; i < e; i += 32u) {
+                        V.item_leaf[n_items + i] = nd; V.item_parent[n_items + i] = 0u; V.item_rank[n_items + i] = rank;
+                    }
+                } else if (ne < nl && (prm.max_depth <= 0 || 1 < prm.max_depth)) {
+                    uint32_t cb = S.cb[nd];
+                    if (cb == BK_WIDE_NONE) {
+                        const uint32_t remaining = (uint32_t)prm.iterations_total - (sims_done + n_items);
+                        const uint32_t want = nl < remaining ? nl : remaining;
+                        cb = pool_used;
+                        if (pool_used + want > L.pool_slots) overflow = 1;
+                        pool_used += want;
+                    }
+                    e = min(g, nl - ne);
+                    if (overflow) { e = 0; stop = true; }
+                    else if (n_nodes + e > L.max_nodes) { e = L.max_nodes - n_nodes; overflow = 1; stop = true; }
+                    const float inv1 = __ldg(V.invtab + 1);
+                    __syncwarp();
+                    for (uint32_t i = lane; i < e; i += 32u) {
+                        const uint32_t child = n_nodes + i, kk = ne + i, rank = nl - 1u - kk;
+                        V.pool[cb + kk] = child;
+                        V.parent[child] = (int32_t)nd; V.visits[child] = 0; V.reward[child] = 0;
+                        V.child_base[child] = BK_WIDE_NONE; V.n_legal[child] = BK_WIDE_PENDING; V.n_expanded[child] = 0;
+                        V.move_of[child] = (uint16_t)rank; V.q[child] = 0.0f;
+                        if (child < BK_WIDE_NC) {
+                            V.virt[child] = 0; V.inv[child] = 0.0f;
+                            S.par[child] = (int32_t)nd; S.vis[child] = 0; S.virt[child] = 1; S.cb[child] = BK_WIDE_NONE;
+                            S.nl[child] = BK_WIDE_PENDING; S.ne[child] = 0; S.mv[child] = (uint16_t)rank; S.q[child] = 0.0f; S.inv[child] = inv1;
+                        } else { V.virt[child] = 1; V.inv[child] = inv1; }
+                        V.item_leaf[n_items + i] = child; V.item_parent[n_items + i] = nd; V.item_rank[n_items + i] = (uint16_t)rank;
+                    }
+                    __syncwarp();
+                    if (lane == 0 && e > 0) { V.child_base[nd] = cb; S.cb[nd] = cb; V.n_expanded[nd] = (uint16_t)(ne + e); S.ne[nd] = (uint16_t)(ne + e); }
+                    n_nodes += e;
+                }
+                if (e > 0 || stop) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        S.virt[nd] += (int32_t)e; S.inv[nd] = __ldg(V.invtab + S.vis[nd] + S.virt[nd]); S.virt[0] += (int32_t)e;
+                        S.n_nodes = n_nodes; S.pool_used = pool_used; S.overflow = overflow;
+                    }
+                    __syncwarp();
+                    if (stop) { n_items += e; break; }
+                    if (e > 0) { n_items += e - 1u; continue; }              // (the loop adds the last one)
+                }
+            }
+        }
         // ---- descent: all threads, uniform control flow
         uint32_t node = dealt ? V.item_leaf[n_items] : 0u, depth = dealt ? 1u : 0u;
         bool may_expand = false, pending = false;

@@ -53,7 +53,7 @@ def test_wide_search_heuristic_rollouts_and_short_rollouts(golden_dir):
 
 
 def test_wide_full_tree_rounds_dealt_at_the_root(golden_dir):
-    """Full trees with rounds of at least 256 walks: a fully expanded root deals the round's walks out to its children at once
+    """Full trees with rounds of at least 128 walks: a fully expanded root deals the round's walks out to its children at once
     (threshold search, exploration scale frozen for the round) and every walk goes on below its child -- restated by the
     oracle as the greedy choice.  Wide rounds, resumed calls, uniform and HeuristicAgent rollouts, short rollouts."""
     for ri, root in enumerate(_roots(golden_dir)[:4]):
