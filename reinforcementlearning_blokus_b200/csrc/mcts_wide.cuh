@@ -360,11 +360,14 @@ k_wide_plan(const bk_state* __restrict__ roots, int n_roots, int n_trees, bk_mct
             }
             kmax = __reduce_max_sync(BK_FULL, kmax); kmin = __reduce_min_sync(BK_FULL, kmin);
             uint32_t tau = kmin, top = kmax;                                             // total_ge(kmin) = children * W >= W
+            bool exact = false;                                                          // a key with exactly W values at or above it
             while (tau < top) {
                 const uint32_t mid = tau + ((top - tau + 1u) >> 1);
-                if (total_ge(mid) >= W) tau = mid; else top = mid - 1u;
+                const uint32_t c = total_ge(mid);
+                if (c == W) { tau = mid - 1u; exact = true; break; }                     // those W values ARE the W largest: done
+                if (c > W) tau = mid; else top = mid - 1u;
             }
-            const uint32_t above = tau == 0xFFFFFFFFu ? 0u : total_ge(tau + 1u);      // walks with a key strictly above tau
+            const uint32_t above = exact ? W : (tau == 0xFFFFFFFFu ? 0u : total_ge(tau + 1u));   // walks with a key strictly above tau
             uint32_t left = W - above, at = 0;                                           // still to share out; next item position
             for (uint32_t row = 0; row * 32u < ne0; row++) {
                 const uint32_t k = row * 32u + (uint32_t)lane;
