@@ -26,7 +26,7 @@ dev.replay_snapshots(tr, (8, 16, 24, 32, 40, 48, 56, 64))
 roots = dev.to_device(empty_states(1))
 DeviceUCT(256, n_trees=3552, seed=42).search(roots, 256)
 # short launches for the two kernels whose counter passes came back as nan in round 1 (185 ms launches under replay)
-DeviceUCT(24, n_trees=2072, seed=42, rollout_policy=dev.POLICY_HEURISTIC).search(roots, 24)          # k_mcts<1,false,false>
+DeviceUCT(24, n_trees=2960, seed=42, rollout_policy=dev.POLICY_HEURISTIC).search(roots, 24)          # k_mcts<1,false,false>
 DeviceUCT(16, n_trees=444, seed=42, leaf_batch=8).search(roots, 16)                                  # k_mcts<0,true,false>
 import numpy as np
 w = torch.from_numpy(np.random.default_rng(0).normal(0, 0.05, 35))
