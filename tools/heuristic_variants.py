@@ -1,5 +1,10 @@
 """Heuristic-policy playouts/s and UCT-with-heuristic-rollouts sims/s of the library BLOKUS_B200_LIB points at (tuning aid).
-usage: python tools/heuristic_variants.py [trees_per_sm]"""
+usage: python tools/heuristic_variants.py [trees_per_sm]
+
+A variant is built next to the product library, e.g. the self-checking build of profiles/r02p_heuristic_bounds_check.json:
+  cd reinforcementlearning_blokus_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared \
+      -Xcompiler -fPIC -DBK_HEUR_CHECK -o ../../build_variants/h_check.so blokus_b200.cu
+  BLOKUS_B200_LIB=build_variants/h_check.so python tools/heuristic_variants.py 20"""
 import json
 import os
 import sys
