@@ -18,6 +18,13 @@
 //                  (re-derive the claimed move by rank, place it, count its legal moves), roll out with the Philox stream
 //                  of (seed, tree, simulation number), add visit and reward to the leaf and all its ancestors (integer
 //                  atomics: order-independent, hence deterministic).
+//           DEALT ROUNDS  walks that need no selection are not walked: while the root has untried moves every walk claims the
+//                  next one, so they are written down in one sweep; and a root that is fully expanded hands the rest of the
+//                  round (flat bandit: always; full tree: from BK_WIDE_DEAL_MIN walks) to its children at once -- the W largest
+//                  values of the children's non-increasing sequences u_k(j) with the exploration scale frozen at the round's
+//                  final count, i.e. the greedy "next walk to the first maximal child", found by a threshold search.  A flat
+//                  bandit is then done; in a full tree walk i goes on below its child, child after child, and runs of
+//                  expansions at one child are again written down at once.
 //   The result depends on (seed, tree id, width, the sequence of search calls) only -- not on the grid or the SM count.
 //
 // Restated sequentially in oracle/blokus_oracle.c (orc_mcts_wide); tests/test_gpu_mcts_wide.py compares bit for bit.
