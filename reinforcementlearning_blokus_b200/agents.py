@@ -219,7 +219,8 @@ class FastMCTSAgent:
                 n = min(n, next_sample - done)          # land exactly on the sampling points (:164-175)
             res = eng.search(root if done == 0 else None, n, resume=done > 0)
             done += n
-            torch.cuda.current_stream().synchronize()
+            if not wide:                                  # (bk_mcts_wide_search returns when its rounds have finished)
+                torch.cuda.current_stream().synchronize()
             if self.enable_diagnostics and done == next_sample:
                 next_sample += interval
                 if done < total:

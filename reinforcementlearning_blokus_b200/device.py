@@ -42,7 +42,14 @@ def _lib_for(t: Optional[torch.Tensor] = None):
     return _lib.init(cur)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (the raw query is ~20 us cheaper per call than
+    building a torch.cuda.Stream object, which matters for one-move latencies of a millisecond)."""
+    if _raw_stream is not None:
+        return int(_raw_stream(torch.cuda.current_device()))
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -214,7 +214,7 @@ class DeviceUCT:
             self.zobrist.device_table().data_ptr() if self.zobrist is not None else None,
             self.workspace.data_ptr(), self.ws_bytes, self.max_root_moves,
             self.visits.data_ptr(), self.reward.data_ptr(), self.counts.data_ptr(), self.moves.data_ptr(),
-            self.status.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            self.status.data_ptr(), dev._stream()))
         dev._count()
         self.iterations_done += iterations
         reward = self.reward.view(torch.float64) if self.p.reward_mode >= 3 else self.reward
@@ -273,7 +273,7 @@ class WideUCT:
         _lib.check(self.lib.bk_mcts_wide_search(
             self._roots.data_ptr(), self._roots.shape[0], self.n_trees, C.byref(self.p), self.workspace.data_ptr(), self.ws_bytes,
             self.max_root_moves, self.visits.data_ptr(), self.reward.data_ptr(), self.counts.data_ptr(), self.moves.data_ptr(),
-            self.status.data_ptr(), self.done.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            self.status.data_ptr(), self.done.data_ptr(), dev._stream()))
         rounds = -(-int(sims) // self.width) + 1
         dev._count(2 * rounds + 1)
         self.sims_done += int(sims)
