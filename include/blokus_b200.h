@@ -319,7 +319,7 @@ int bk_mcts_wide_search(const bk_state* roots, int n_roots, int n_trees, const b
  *                          bk_mcts_wide_search; one CTA adds up the trees, so keep n_trees small), n = number of root moves; windows_host = host array of
  *                          `world` device pointers in rank order (own window at [rank]); epoch = 0, 1, 2, ... the same on
  *                          every rank, +1 per merge; merged [2][n] int64 (visits, reward); status = 0, or 1 if the peers
- *                          did not arrive within timeout_ms (merged is then undefined).  One process per GPU. */
+ *                          did not arrive within timeout_ms (<= 0: 20 s; merged is then undefined).  One process per GPU. */
 int bk_p2p_window_create(int capacity, void** window, unsigned char* handle_host);
 int bk_p2p_window_open(const unsigned char* handle_host, void** peer_window);
 int bk_p2p_window_close(void* peer_window);

@@ -165,18 +165,21 @@ struct SmemRowSink {
     template <int G0, int NG, int PID> __device__ __forceinline__ void flush() {}
 };
 
-struct NonEmptyRowSink {               // list[k] = (word index << 20) | row bits, ascending word index
-    static constexpr bool kRows = true;
-    uint32_t* list; uint32_t lane, below, n;
-    __device__ __forceinline__ void begin(uint32_t* l, int lane_) { list = l; lane = (uint32_t)lane_; below = (1u << lane_) - 1u; n = 0; }
+struct NonEmptyRowSink {               // list[k] = (word index << 20) | MIRRORED row bits (bit j = column 19 - j), ascending word index
+    static constexpr bool kRows = false;  // rows as the mirrored generator makes them: no BREV per orientation, the extraction decodes
+    uint32_t a0, a, lane20, below;        // a = 32-bit shared-memory address of the next free slot (see HeurPrivSink on why)
+    __device__ __forceinline__ void begin(uint32_t* l, int lane_) {
+        a0 = a = (uint32_t)__cvta_generic_to_shared(l); lane20 = (uint32_t)lane_ << 20; below = (1u << lane_) - 1u;
+    }
     template <int O, int SLOT, int GI> __device__ __forceinline__ void put(uint32_t L) {
         const uint32_t m = __ballot_sync(BK_FULL, L != 0u);
         if (m) {
-            if (L) list[n + __popc(m & below)] = ((uint32_t)(O * 20 + (int)lane) << 20) | L;
-            n += __popc(m);
+            if (L) asm volatile("st.shared.u32 [%0], %1;" :: "r"(a + 4u * (uint32_t)__popc(m & below)), "r"(L + lane20 + ((uint32_t)(O * 20) << 20)) : "memory");
+            a += 4u * (uint32_t)__popc(m);
         }
     }
     template <int G0, int NG, int PID> __device__ __forceinline__ void flush() {}
+    __device__ __forceinline__ uint32_t count() const { return (a - a0) >> 2; }
 };
 
 #ifndef BK_EMIT_CTAS
@@ -199,9 +202,9 @@ k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ 
         const uint32_t p = players ? (players[i] & 3u) : s.to_move;
         uint32_t A, C; make_masks(s, p, lane, A, C);
         NonEmptyRowSink sink; sink.begin(list, lane);
-        bk_gen_all(A, C, sel4(s.used, p), sink);
+        bk_gen_all<NonEmptyRowSink, true>(A, C, sel4(s.used, p), sink);
         __syncwarp();
-        const uint32_t ne = sink.n;                              // non-empty rows (uniform)
+        const uint32_t ne = sink.count();                        // non-empty rows (uniform)
         const uint32_t per = (ne + 31u) >> 5;
         const uint32_t lo = min((uint32_t)lane * per, ne), hi = min(lo + per, ne);
         uint32_t cnt = 0;
@@ -221,9 +224,9 @@ k_movegen_emit(const bk_state* __restrict__ states, const uint8_t* __restrict__ 
             const uint32_t w = list[e];
             const uint32_t id0 = (w >> 20) * 20u;
             uint32_t bits = w & BK_ROWMASK;
-            do {
-                const uint32_t c = __ffs(bits) - 1; bits &= bits - 1;
-                if (pos < limit) out[pos] = (uint16_t)(id0 + c);
+            do {                                                 // columns ascending = mirrored bits from the top
+                const uint32_t j = 31u - (uint32_t)__clz(bits); bits ^= 1u << j;
+                if (pos < limit) out[pos] = (uint16_t)(id0 + 19u - j);
                 pos++;
             } while (bits);
         }
@@ -1388,7 +1391,7 @@ extern "C" int bk_root_merge_p2p(const void* root_visits, int visits_are_int64, 
         khz_of[dev] = q > 0 ? q : 2000000;
     }
     const int khz = khz_of[dev];
-    const long long timeout_cycles = (long long)(timeout_ms > 0 ? timeout_ms : 2000) * (long long)(khz > 0 ? khz : 2000000);
+    const long long timeout_cycles = (long long)(timeout_ms > 0 ? timeout_ms : 20000) * (long long)(khz > 0 ? khz : 2000000);
     k_root_merge_p2p<<<1, 1024, 0, as_stream(stream)>>>(root_visits, visits_are_int64, root_reward, n_trees, stride, n, capacity, rank, world, peers,
                                                         (unsigned long long)epoch, timeout_cycles, merged, status);
     LAUNCH_CHECK();

@@ -135,7 +135,7 @@ class PeerRootMerge:
     Results are the integer sums ``merge_root_stats`` returns.  One process per GPU; every rank must call ``merge`` the same
     number of times (the epoch is part of the protocol)."""
 
-    def __init__(self, capacity: int = 2048, group=None, timeout_ms: int = 2000):
+    def __init__(self, capacity: int = 2048, group=None, timeout_ms: int = 20000):
         from . import _lib
         from . import device as dev
 
