@@ -297,92 +297,95 @@ def run_cuda(args) -> None:
     # ---- root-parallel MCTS (the third part of BASELINE.json's metric): every rank searches its own trees from
     # the empty board (50-ply rollouts), then ONE all-reduce of the root statistics (dist.merge_root_stats)
     mcts = None
-    if not args.no_extras:
-        from reinforcementlearning_blokus_b200 import dist as bdist
-        from reinforcementlearning_blokus_b200.mcts import DeviceUCT
+    try:   # the search extras must never take the headline line down with them (a failure is reported in `extras`)
+        if not args.no_extras:
+            from reinforcementlearning_blokus_b200 import dist as bdist
+            from reinforcementlearning_blokus_b200.mcts import DeviceUCT
 
-        trees, iters = 4 * 3552, 256        # four waves of 24 one-warp trees per SM, handed out by a ticket counter
-        root = dev.to_device(empty_states(1))
-        eng = DeviceUCT(iters, n_trees=trees, seed=SEED, tree_offset=rank * trees)
-        peer = bdist.PeerRootMerge()                  # windows over NVLink peer memory (CUDA IPC), mapped once
-        res = eng.search(root, iters)                 # warm-up (search and merge: the first reduction loads torch kernels)
-        n_root0 = int(res["counts"][0].item())
-        peer.merge(res["visits"], res["reward"], n_root0)
-        barrier()
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m0.record(stream)
-        res = eng.search(root, iters)
-        v, w = peer.merge(res["visits"], res["reward"], n_root0, check=False)    # sums over this rank's trees, then ONE kernel
-        m1.record(stream)
-        barrier()
-        assert int(peer.status.item()) == 0
-        ms_m = m0.elapsed_time(m1)
-        if world > 1:
-            t = torch.tensor([ms_m], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_m = float(t.item())
-        mcts = {"mcts_sims_per_sec": world * trees * iters / (ms_m * 1e-3), "mcts_trees_per_gpu": trees,
-                "mcts_iterations_per_tree": iters, "mcts_rollout_plies": 50,
-                "mcts_root_visits_total": int(v.sum().item()), "mcts_collective": "1 bk_root_merge_p2p per search (int64[2,n_root] added into every rank's window over NVLink peer memory)"}
-        # the reference's default rollout policy (HeuristicAgent softmax, mcts_agent.py:275-276), no collective
-        peer.close()
-        del eng, peer
-        ht = 2 * 148 * 20                   # two waves of 20 one-warp trees per SM (BK_MCTS_HEUR_CTAS_PER_SM)
-        heng = DeviceUCT(iters, n_trees=ht, seed=SEED, tree_offset=rank * ht, rollout_policy=dev.POLICY_HEURISTIC)
-        heng.search(root, iters)
-        torch.cuda.synchronize()
-        m0.record(stream)
-        heng.search(root, iters)
-        m1.record(stream)
-        torch.cuda.synchronize()
-        mcts["mcts_heuristic_rollout_sims_per_sec_per_gpu"] = ht * iters / (m0.elapsed_time(m1) * 1e-3)
-        del heng
-
-    # ---- STRONG scaling of ONE move: a fixed budget split over 16 root-parallel wide trees, 16 / N per GPU,
-    # one all-reduce of the root statistics; the merged result is the same for every N (checked by the checksum below)
-    if not args.no_extras and 16 % world == 0:
-        from reinforcementlearning_blokus_b200 import dist as bdist
-
-        mid = dev.playout(64, seed=0xB10C05, max_turns=24, want_final=True)["final_states"][17:18].contiguous()
-        strong = {}
-        for tag, sims, kw in (("uct_heuristic_rollouts_16384_sims", 16384, dict(rollout_policy=dev.POLICY_HEURISTIC)),
-                              ("flat_uniform_rollouts_8192_sims", 8192, dict(max_depth=1, ucb_variant=1, reward_mode=1))):
-            rp = bdist.RootParallelWide(sims, 16, seed=SEED, **kw)   # merge = one kernel over NVLink peer memory
-            out = rp.search(mid)                                  # warm-up (allocations, window mapping)
-            rp.search(mid, search_index=1)
-            n_root = out["n_root"]
-            bdist.merge_root_stats(out["visits"], out["reward"])  # NCCL channel setup for the comparison below
+            trees, iters = 4 * 3552, 256        # four waves of 24 one-warp trees per SM, handed out by a ticket counter
+            root = dev.to_device(empty_states(1))
+            eng = DeviceUCT(iters, n_trees=trees, seed=SEED, tree_offset=rank * trees)
+            peer = bdist.PeerRootMerge()                  # windows over NVLink peer memory (CUDA IPC), mapped once
+            res = eng.search(root, iters)                 # warm-up (search and merge: the first reduction loads torch kernels)
+            n_root0 = int(res["counts"][0].item())
+            peer.merge(res["visits"], res["reward"], n_root0)
             barrier()
-            reps, t_search, t_merge, t_nccl = 5, 0.0, 0.0, 0.0
-            a, b, c, d = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-            for k in range(reps):
-                rp.eng.p.tree_offset = rp.rank * rp.trees_per_rank
-                barrier()
-                a.record(stream)
-                res = rp.eng.search(mid, rp.per_tree)
-                b.record(stream)
-                v, w = rp.peer.merge(res["visits"], res["reward"], n_root, check=False)
-                c.record(stream)
-                v2, w2 = bdist.merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0))   # the NCCL way, for comparison
-                d.record(stream)
-                torch.cuda.synchronize()
-                assert int(rp.peer.status.item()) == 0 and torch.equal(v, v2[:n_root]) and torch.equal(w, w2[:n_root])
-                t_search += a.elapsed_time(b)
-                t_merge += b.elapsed_time(c)
-                t_nccl += c.elapsed_time(d)
-            tt = torch.tensor([t_search / reps, t_merge / reps, t_nccl / reps], dtype=torch.float64, device="cuda")
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record(stream)
+            res = eng.search(root, iters)
+            v, w = peer.merge(res["visits"], res["reward"], n_root0, check=False)    # sums over this rank's trees, then ONE kernel
+            m1.record(stream)
+            barrier()
+            assert int(peer.status.item()) == 0
+            ms_m = m0.elapsed_time(m1)
             if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            strong[tag] = {"ms_per_move": float(tt[0] + tt[1]), "search_ms": float(tt[0]), "merge_us": float(tt[1]) * 1e3,
-                           "merge": "bk_root_merge_p2p (one kernel, 64-bit atomics on NVLink peer memory)",
-                           "merge_us_nccl_all_reduce": float(tt[2]) * 1e3,
-                           "trees_total": 16, "trees_per_gpu": 16 // world, "sims_per_tree": rp.per_tree, "round_width": rp.width,
-                           "best_rank": int(torch.argmax(v[:n_root]).item()),
-                           "visits_checksum": int((v[:n_root] * torch.arange(1, n_root + 1, device=v.device)).sum().item())}
-            rp.peer.close()
-            del rp
-        if mcts is not None:
-            mcts["mcts_strong_scaling_one_move"] = strong
+                t = torch.tensor([ms_m], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_m = float(t.item())
+            mcts = {"mcts_sims_per_sec": world * trees * iters / (ms_m * 1e-3), "mcts_trees_per_gpu": trees,
+                    "mcts_iterations_per_tree": iters, "mcts_rollout_plies": 50,
+                    "mcts_root_visits_total": int(v.sum().item()), "mcts_collective": "1 bk_root_merge_p2p per search (int64[2,n_root] added into every rank's window over NVLink peer memory)"}
+            # the reference's default rollout policy (HeuristicAgent softmax, mcts_agent.py:275-276), no collective
+            peer.close()
+            del eng, peer
+            ht = 2 * 148 * 20                   # two waves of 20 one-warp trees per SM (BK_MCTS_HEUR_CTAS_PER_SM)
+            heng = DeviceUCT(iters, n_trees=ht, seed=SEED, tree_offset=rank * ht, rollout_policy=dev.POLICY_HEURISTIC)
+            heng.search(root, iters)
+            torch.cuda.synchronize()
+            m0.record(stream)
+            heng.search(root, iters)
+            m1.record(stream)
+            torch.cuda.synchronize()
+            mcts["mcts_heuristic_rollout_sims_per_sec_per_gpu"] = ht * iters / (m0.elapsed_time(m1) * 1e-3)
+            del heng
+
+        # ---- STRONG scaling of ONE move: a fixed budget split over 16 root-parallel wide trees, 16 / N per GPU,
+        # one all-reduce of the root statistics; the merged result is the same for every N (checked by the checksum below)
+        if not args.no_extras and 16 % world == 0:
+            from reinforcementlearning_blokus_b200 import dist as bdist
+
+            mid = dev.playout(64, seed=0xB10C05, max_turns=24, want_final=True)["final_states"][17:18].contiguous()
+            strong = {}
+            for tag, sims, kw in (("uct_heuristic_rollouts_16384_sims", 16384, dict(rollout_policy=dev.POLICY_HEURISTIC)),
+                                  ("flat_uniform_rollouts_8192_sims", 8192, dict(max_depth=1, ucb_variant=1, reward_mode=1))):
+                rp = bdist.RootParallelWide(sims, 16, seed=SEED, **kw)   # merge = one kernel over NVLink peer memory
+                out = rp.search(mid)                                  # warm-up (allocations, window mapping)
+                rp.search(mid, search_index=1)
+                n_root = out["n_root"]
+                bdist.merge_root_stats(out["visits"], out["reward"])  # NCCL channel setup for the comparison below
+                barrier()
+                reps, t_search, t_merge, t_nccl = 5, 0.0, 0.0, 0.0
+                a, b, c, d = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+                for k in range(reps):
+                    rp.eng.p.tree_offset = rp.rank * rp.trees_per_rank
+                    barrier()
+                    a.record(stream)
+                    res = rp.eng.search(mid, rp.per_tree)
+                    b.record(stream)
+                    v, w = rp.peer.merge(res["visits"], res["reward"], n_root, check=False)
+                    c.record(stream)
+                    v2, w2 = bdist.merge_root_stats(res["visits"].sum(dim=0), res["reward"].sum(dim=0))   # the NCCL way, for comparison
+                    d.record(stream)
+                    torch.cuda.synchronize()
+                    assert int(rp.peer.status.item()) == 0 and torch.equal(v, v2[:n_root]) and torch.equal(w, w2[:n_root])
+                    t_search += a.elapsed_time(b)
+                    t_merge += b.elapsed_time(c)
+                    t_nccl += c.elapsed_time(d)
+                tt = torch.tensor([t_search / reps, t_merge / reps, t_nccl / reps], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                strong[tag] = {"ms_per_move": float(tt[0] + tt[1]), "search_ms": float(tt[0]), "merge_us": float(tt[1]) * 1e3,
+                               "merge": "bk_root_merge_p2p (one kernel, 64-bit atomics on NVLink peer memory)",
+                               "merge_us_nccl_all_reduce": float(tt[2]) * 1e3,
+                               "trees_total": 16, "trees_per_gpu": 16 // world, "sims_per_tree": rp.per_tree, "round_width": rp.width,
+                               "best_rank": int(torch.argmax(v[:n_root]).item()),
+                               "visits_checksum": int((v[:n_root] * torch.arange(1, n_root + 1, device=v.device)).sum().item())}
+                rp.peer.close()
+                del rp
+            if mcts is not None:
+                mcts["mcts_strong_scaling_one_move"] = strong
+    except Exception as exc:      # noqa: BLE001 -- reported, not hidden: the line carries the message
+        mcts = dict(mcts or {}, mcts_extras_error=repr(exc)[:300])
 
     if rank != 0:
         if world > 1:
@@ -416,12 +419,16 @@ def run_cuda(args) -> None:
     if not args.no_extras:
         line["extras"] = dict(mcts or {})
     if world == 1 and not args.no_extras:
-        line["extras"].update(_extras(dev, torch, n))
+        try:
+            line["extras"].update(_extras(dev, torch, n))
+        except Exception as exc:      # noqa: BLE001 -- same rule: report it in the line, keep the headline
+            line["extras"]["extras_error"] = repr(exc)[:300]
         # the one HBM-bound kernel of the path: the legal-anchor bitmap generator (256 B in, 7 280 B out per state)
-        gps = line["extras"]["movegen_bitmap_gens_per_sec"]
-        line["roofline_movegen_bitmap"] = {"bound": "hbm", "kernel": "k_movegen_bitmap", "achieved": gps * (256 + 7280) / 1e9,
-                                           "peak": hbm_peak, "unit": "GB/s", "frac": gps * (256 + 7280) / 1e9 / hbm_peak,
-                                           "peak_source": peak_src, "bytes_per_state": 256 + 7280}
+        gps = line["extras"].get("movegen_bitmap_gens_per_sec")
+        if gps is not None:
+            line["roofline_movegen_bitmap"] = {"bound": "hbm", "kernel": "k_movegen_bitmap", "achieved": gps * (256 + 7280) / 1e9,
+                                               "peak": hbm_peak, "unit": "GB/s", "frac": gps * (256 + 7280) / 1e9 / hbm_peak,
+                                               "peak_source": peak_src, "bytes_per_state": 256 + 7280}
         line["cpu_baseline"] = _cpu_baseline()
     _emit(line)
     if world > 1:
