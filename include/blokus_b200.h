@@ -100,6 +100,15 @@ int bk_movegen_emit(const bk_state* states, const uint8_t* players, int n,
 int bk_movegen_fixed(const bk_state* states, const uint8_t* players, int n, uint32_t cap,
                      uint32_t* counts, uint16_t* move_ids, void* stream);
 
+/* ONE board with HOST buffers -- LegalMoveGenerator.get_legal_moves(board, player) for a single position
+ * (engine/move_generator.py:130-151; the protocol of benchmarks/benchmark_move_generation.py:136-224): copies the 256-byte
+ * state up, generates the side to move's ascending id list, copies it back and waits for the stream.  state_host: the
+ * packed state with `to_move` set to the player asked for; state_dev (256 B) and list_dev (capacity*2 + 8 bytes) are the
+ * caller's device staging; list_host receives capacity uint16 ids followed by the uint32 count (a count above capacity means
+ * the list was truncated).  Page-locked host buffers make the copies asynchronous. */
+int bk_legal_moves_host(const bk_state* state_host, bk_state* state_dev, void* list_dev, void* list_host, int capacity,
+                        void* stream);
+
 /* One-pass CSR: after bk_movegen_fixed (ids in rows of `cap` slots, full lengths in counts) and bk_exclusive_scan_u32 of
  * min(counts, cap), copy every row's ids to its CSR range move_ids[offsets[i] .. offsets[i+1]).  Rows longer than cap
  * must be regenerated with bk_movegen_emit (the host wrapper does that when it happens). */

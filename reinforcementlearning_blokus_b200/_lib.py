@@ -36,6 +36,7 @@ PROTOTYPES = {
     "bk_exclusive_scan_u32": (_i32, [_vp, _i32, _vp, _vp]),
     "bk_movegen_emit": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "bk_movegen_fixed": (_i32, [_vp, _vp, _i32, _u32, _vp, _vp, _vp]),
+    "bk_legal_moves_host": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "bk_can_place_mask": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "bk_movegen_bitmap": (_i32, [_vp, _vp, _i32, _vp, _vp]),
     "bk_compact_rows": (_i32, [_vp, _u32, _vp, _i32, _vp, _vp]),

@@ -841,6 +841,24 @@ extern "C" int bk_movegen_fixed(const bk_state* states, const uint8_t* players, 
     return BK_OK;
 }
 
+// One board, host buffers in and out: the three steps of a single get_legal_moves call in one entry point (the copies are
+// asynchronous when the host buffers are page-locked; the call returns after the stream has drained).
+extern "C" int bk_legal_moves_host(const bk_state* state_host, bk_state* state_dev, void* list_dev, void* list_host, int capacity,
+                                   void* stream) {
+    REQUIRE_INIT();
+    REQUIRE(state_host && state_dev && list_dev && list_host && capacity > 0 && capacity <= 32768, "bk_legal_moves_host: bad argument");
+    cudaStream_t st = as_stream(stream);
+    const size_t list_bytes = (size_t)capacity * sizeof(uint16_t);
+    CUDA_TRY(cudaMemcpyAsync(state_dev, state_host, sizeof(bk_state), cudaMemcpyHostToDevice, st));
+    k_movegen_emit<<<1, 32, EMIT_SMEM_PER_WARP, st>>>(state_dev, nullptr, 1, nullptr, (uint32_t)capacity,
+                                                      reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(list_dev) + list_bytes),
+                                                      static_cast<uint16_t*>(list_dev));
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(list_host, list_dev, list_bytes + 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return BK_OK;
+}
+
 // Fixed-capacity rows -> CSR: state i's first (offsets[i+1] - offsets[i]) ids move from slots[i*cap ...] to ids[offsets[i] ...].
 __global__ void __launch_bounds__(BK_THREADS)
 k_compact_rows(const uint16_t* __restrict__ slots, uint32_t cap, const uint32_t* __restrict__ offsets, int n,

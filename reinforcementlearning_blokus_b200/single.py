@@ -28,6 +28,7 @@ class _Ctx:
         if not torch.cuda.is_available():
             raise dev._lib.BlokusB200Error("no CUDA device: blokus_b200 has no CPU fallback")
         d = torch.device("cuda", torch.cuda.current_device())
+        self.lib = dev._lib_for(None)
         self.h_state = torch.empty((1, STATE_BYTES), dtype=torch.uint8).pin_memory()
         self.d_state = torch.empty((1, STATE_BYTES), dtype=torch.uint8, device=d)
         self.d_player = torch.empty(1, dtype=torch.uint8, device=d)
@@ -69,10 +70,12 @@ def legal_move_ids(state_np, player: int) -> np.ndarray:
     """Ascending move ids of one packed state for `player` (0..3): one upload, one kernel, one download."""
     with _lock:
         c = _get()
-        c.upload_as_mover(state_np, player)
-        dev.movegen_fixed(c.d_state, MAX_MOVES, None, out=(c.d_counts, c.d_ids))
-        c.h_list.copy_(c.d_list, non_blocking=True)       # 8 KB: cheaper than a second round trip for the exact length
-        torch.cuda.current_stream().synchronize()
+        c.h_state_np[0] = np.frombuffer(np.asarray(state_np).tobytes(), dtype=np.uint8)
+        c.h_state_np[0, 240] = player                     # the player rides in the state's side-to-move byte
+        # upload, kernel, download (8 KB: cheaper than a second round trip for the exact length) and the wait in ONE C call
+        dev._lib.check(c.lib.bk_legal_moves_host(c.h_state.data_ptr(), c.d_state.data_ptr(), c.d_list.data_ptr(), c.h_list.data_ptr(),
+                                                 MAX_MOVES, dev._stream()))
+        dev._count(1)
         n = int(c.h_count_np[0])
         if n > MAX_MOVES:
             raise dev._lib.BlokusB200Error(f"{n} legal moves exceed the single-state buffer ({MAX_MOVES})")
