@@ -93,8 +93,8 @@ __device__ __forceinline__ int32_t board_score_of(const WarpState& s, uint32_t q
 #ifndef BK_MCTS_CTAS_PER_SM
 #define BK_MCTS_CTAS_PER_SM 24
 #endif
-// heuristic rollouts: 14 KB of list scratch per warp allows 14 one-warp CTAs per SM (16 KB each with the static part
-// and the per-CTA reservation, 228 KB per SM); the register cap that goes with it is 146
+// heuristic rollouts: 7.8 KB of list scratch per warp (round 1: 14 KB, which capped this at 14); measured on B200 with the
+// policy inlined: 6.9 M simulations/s at 16 one-warp CTAs per SM, 7.5 M at 20 (96 registers), 7.5 M at 24 (80 registers, spills)
 #ifndef BK_MCTS_HEUR_CTAS_PER_SM
 #define BK_MCTS_HEUR_CTAS_PER_SM 20
 #endif
